@@ -1,0 +1,164 @@
+/* mcsim.h — C ABI of libmcsim_b200.so, the B200 drop-in for the rollout path of
+ * einsteinguang/interactive_highway_simulation's precompiled `mc_sim_highway` module.
+ *
+ * Every entry point replaces one Python-visible function of that module (binding table
+ * in mc_sim_highway.so `init_module_mc_sim_highway` 0xc2bf0; callers in the reference's
+ * behaviors.py).  Plain pointers and sizes only; the caller owns every buffer; return
+ * value 0 = ok, negative = error (mcs_last_error() gives the text).  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails with MCS_ERR_CUDA.
+ *
+ *   reference (Python name → C++ symbol @ address)                          → here
+ *   simulationMultiThread → python_converter::simulationMultiThreadWrapper
+ *       0xbddd0 → runMultiThreads 0xbb910 → runMTimes 0xc28c0 → Simulation::run 0x10e790
+ *                                                                           → mcs_rollouts*
+ *   Simulation(...).run() / agentsStatesHistory()  0x10e790 / 0xef540       → mcs_trajectories
+ *   laneChangeMobilBehavior → laneChangeBehaviorMOBILWrapper 0xb9960        → mcs_decide_mobil
+ *   fixedDirectionLaneChangeBehavior → customizedLaneChangeBehaviorWrapper  → mcs_decide_fixed_direction
+ *   fixedGapMergingBehavior → customizedMergingBehaviorWrapper              → mcs_decide_fixed_gap
+ *   closestGapMergingBehavior → closestGapMergingBehaviorWrapper            → mcs_decide_closest_gap
+ *   MapMultiLane(list[Corridor]) 0x109f00 + Environment(map, list[Agent]) 0x10c6c0
+ *                                                                           → mcs_scene_create
+ */
+#ifndef MCSIM_H
+#define MCSIM_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enumerations (the reference passes these as std::string) ---- */
+enum { MCS_LANE_MAIN = 0, MCS_LANE_MERGING = 1, MCS_LANE_EXIT = 2, MCS_LANE_OTHER = 3 };
+enum { MCS_BEH_IDM = 0, MCS_BEH_IDM_LC = 1, MCS_BEH_MERGING = 2, MCS_BEH_EXIT = 3, MCS_BEH_OTHER = 4 };
+/* ego command: "keep_lane" "acc" "dcc" "left" "right"; anything else = INVALID */
+enum { MCS_ACT_KEEP_LANE = 0, MCS_ACT_ACC = 1, MCS_ACT_DCC = 2, MCS_ACT_LEFT = 3, MCS_ACT_RIGHT = 4, MCS_ACT_INVALID = 5 };
+/* Agent::commitToDecision: "not_decided" "keep_lane" "left" "right" */
+enum { MCS_COMMIT_NOT_DECIDED = 0, MCS_COMMIT_KEEP_LANE = 1, MCS_COMMIT_LEFT = 2, MCS_COMMIT_RIGHT = 3 };
+
+enum {
+  MCS_OK = 0,
+  MCS_ERR_ARG = -1,      /* bad pointer / size / enum */
+  MCS_ERR_CUDA = -2,     /* no device, launch or copy failure */
+  MCS_ERR_CAPACITY = -3, /* scene larger than the compiled limits (MCS_MAX_*) */
+  MCS_ERR_SCENE = -4     /* an agent's lane is unknown where the reference would crash */
+};
+
+#define MCS_MAX_AGENTS 256   /* vehicles per rollout  */
+#define MCS_MAX_LANES 8      /* corridors per scene   */
+#define MCS_GROUPS 8         /* runMultiThreads' hard-coded thread count (0xbb952) */
+
+/* ---- value types (layout = the reference's memory order) ---- */
+typedef struct mcs_corridor {
+  int32_t id;
+  int32_t type;      /* MCS_LANE_* */
+  double left[4];    /* Line left:   p1.x p1.y p2.x p2.y  (Corridor+0x38) */
+  double right[4];   /* Line right                         (Corridor+0x58) */
+  double center[4];  /* Line center                        (Corridor+0x78) */
+  double v_limit;    /* Corridor+0x98 */
+} mcs_corridor;
+
+typedef struct mcs_agent {
+  int32_t id;
+  int32_t behavior;              /* MCS_BEH_* */
+  double x, y, v, vy, vd, a, l, w; /* Agent ctor order: x y vx vy vd a l w */
+  double idm[6];                 /* accMax minDis accMin accCom aEmergency thw (memory order) */
+  double rss[6];                 /* rTimeOther rTimeEgo aMinBrake aMaxBrake aSoft dSoft */
+  double yp[7];                  /* bias a b c politenessFactor deltaA biasA */
+  int32_t commit;                /* MCS_COMMIT_*; Python may set Agent.commitToDecision (behaviors.py:77) */
+  int32_t commit_keep_lane_step; /* Agent.commitKeepLaneStep */
+  int32_t target_lane_id;        /* Agent.targetLaneId (-1 = none) */
+  int32_t reserved;
+} mcs_agent;
+
+typedef struct mcs_sim_param { /* SimParameter(dt, steps, minSteps) */
+  double dt;
+  int32_t steps;
+  int32_t min_steps;
+} mcs_sim_param;
+
+typedef struct mcs_candidate { /* one simulationMultiThread call: (egoId, action, gapId) */
+  int32_t ego_id;
+  int32_t action;  /* MCS_ACT_* */
+  int32_t gap_id;  /* -2 = n/a, -1 = last gap, else vehicle id */
+  int32_t reserved;
+} mcs_candidate;
+
+typedef struct mcs_feature { /* BehaviorFeature, same field order as the reference struct */
+  double fallBackRate, successRate, utility, comfort, expectedStepRatio, utilityObjects, comfortObjects;
+  int32_t fromNSims;
+  int32_t reserved;
+} mcs_feature;
+
+typedef struct mcs_status { /* StatusOneSim of one rollout + bookkeeping; 64 bytes */
+  double utility, comfort, utilityObjects, comfortObjects;
+  int32_t finishStep;
+  int32_t executedSteps;  /* steps actually simulated (≤ steps) */
+  uint32_t draws;         /* random draws consumed, incl. the N aggressive-flag draws */
+  uint8_t finish, fallBack, ok, overflow;
+  int32_t reserved[4];
+} mcs_status;
+
+typedef struct mcs_action { double ax, vy; } mcs_action;
+
+typedef struct mcs_action_with_type { /* ActionWithType */
+  double ax, vy;
+  int32_t commit;                /* MCS_COMMIT_* */
+  int32_t commit_keep_lane_step;
+  int32_t target_lane_id;
+  int32_t reserved;
+} mcs_action_with_type;
+
+typedef struct mcs_scene mcs_scene; /* opaque: map + agents resident in HBM */
+
+/* ---- lifetime ---- */
+int mcs_device_count(void);
+const char* mcs_last_error(void);
+const char* mcs_version(void);
+
+/* MapMultiLane(corridors) + list[Agent] → device-resident scene (structure-of-arrays).  `device` = CUDA ordinal. */
+int mcs_scene_create(const mcs_corridor* corridors, int n_corridors, const mcs_agent* agents, int n_agents,
+                     int device, mcs_scene** out);
+int mcs_scene_destroy(mcs_scene* scene);
+/* agent visit order (std::unordered_map iteration order the reference walks) and neighbour lane ids, for tests */
+int mcs_scene_visit_order(const mcs_scene* scene, int32_t* order_out, int n);
+
+/* ---- simulationMultiThread, batched over candidates ----
+ * For each candidate c: MCS_GROUPS groups × n_per_group rollouts; rollout r (0-based over the
+ * candidate's groups*n_per_group rollouts, offset by first_rollout) draws from the stream
+ * mcs_rollout_key(seed + c, r).  features_out[c] = mean over groups of the per-group means,
+ * exactly as runMTimes/runMultiThreads combine them.  Host buffers in and out. */
+int mcs_rollouts(mcs_scene* scene, const mcs_candidate* candidates, int n_candidates, const mcs_sim_param* param,
+                 int n_per_group, uint64_t seed, mcs_feature* features_out, mcs_status* status_out /* may be NULL;
+                 else n_candidates*MCS_GROUPS*n_per_group records */);
+
+/* Sharded form: simulate only rollouts [first, first+count) of every candidate and return their
+ * statuses (count per candidate); the caller (one rank per GPU) gathers and calls mcs_reduce_features. */
+int mcs_rollouts_range(mcs_scene* scene, const mcs_candidate* candidates, int n_candidates, const mcs_sim_param* param,
+                       uint64_t seed, int64_t first, int64_t count, mcs_status* status_out);
+/* Fixed-order two-level mean (host, pure function): statuses = n_candidates × (groups*n_per_group). */
+int mcs_reduce_features(const mcs_status* statuses, int n_candidates, int groups, int n_per_group, int steps,
+                        mcs_feature* features_out);
+
+/* Device-resident variant used by the throughput benchmark: results stay in HBM
+ * (d_status_out = device pointer or NULL to keep only the per-block vehicle-step counters).
+ * Returns total executed vehicle-steps through *vehicle_steps_out after synchronising. */
+int mcs_rollouts_device(mcs_scene* scene, const mcs_candidate* candidates, int n_candidates, const mcs_sim_param* param,
+                        uint64_t seed, int64_t first, int64_t count, void* d_status_out, void* cuda_stream,
+                        float* kernel_ms_out, uint64_t* vehicle_steps_out);
+
+/* ---- Simulation.run() + agentsStatesHistory() for one rollout ----
+ * states_out: [n_agents][steps+1][4] (x y v a), agent order = input order; n_states_out = states per agent */
+int mcs_trajectories(mcs_scene* scene, const mcs_candidate* candidate, const mcs_sim_param* param, uint64_t seed,
+                     int64_t rollout, double* states_out, int32_t* n_states_out, mcs_status* status_out);
+
+/* ---- single decisions (the reference's per-step Python-facing wrappers) ---- */
+int mcs_decide_mobil(mcs_scene* scene, int32_t agent_id, const mcs_action* idm_action, int require_rss,
+                     uint64_t seed, mcs_action_with_type* out);
+int mcs_decide_fixed_direction(mcs_scene* scene, int32_t agent_id, int32_t action, mcs_action* out);
+int mcs_decide_fixed_gap(mcs_scene* scene, int32_t agent_id, int32_t direction, int32_t gap_id, mcs_action* out);
+int mcs_decide_closest_gap(mcs_scene* scene, int32_t agent_id, int32_t direction, mcs_action* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCSIM_H */

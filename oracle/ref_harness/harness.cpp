@@ -19,6 +19,7 @@
 //         [<commit> <keepStep> <targetLane>]
 //   sim <dt> <steps> <minSteps>
 //   rng counter <key> | rng libc <seed>
+//   math mcs | math libm                 which exp/pow the binary gets (default mcs = include/mcsim_math.h)
 //   run <egoId> <action> <gapId> [hist] [dump]   one fresh Simulation, one rollout
 //   rollouts <egoId> <action> <gapId> <first> <count> <seed> [hist]
 //                                       fresh Simulation per rollout r, key = mcs_rollout_key(seed, r)
@@ -33,6 +34,7 @@
 // Every answer is one line starting with the command name; doubles are printed with %.17g.
 #include "ref_abi.hpp"
 #include "../../include/mcsim_rng.h"
+#include "../../include/mcsim_math.h"
 
 #include <chrono>
 #include <iostream>
@@ -50,6 +52,22 @@ static long g_reseed_after_build = -1;  // libc mode: srand(seed) again once the
 static thread_local uint64_t g_draws = 0;
 static int (*real_rand)(void) = nullptr;
 static FILE* g_trace = nullptr;
+
+// libm interposition: the binary's pow@plt / exp@plt bind here (-rdynamic).  math mode 0 routes them
+// to include/mcsim_math.h (the pinned definitions shared with the product), 1 to the platform libm.
+static int g_math = 0;
+static double (*real_pow)(double, double) = nullptr;
+static double (*real_exp)(double) = nullptr;
+extern "C" double pow(double x, double y) {
+  if (g_math == 0 && y == 4.0) return mcs_pow4(x);
+  if (!real_pow) real_pow = reinterpret_cast<double (*)(double, double)>(dlsym(RTLD_NEXT, "pow"));
+  return real_pow(x, y);
+}
+extern "C" double exp(double x) {
+  if (g_math == 0) return mcs_exp(x);
+  if (!real_exp) real_exp = reinterpret_cast<double (*)(double)>(dlsym(RTLD_NEXT, "exp"));
+  return real_exp(x);
+}
 
 extern "C" int rand(void) {
   g_draws++;
@@ -239,6 +257,7 @@ int main(int argc, char** argv) {
       if (in >> a.commit >> a.keepStep >> a.targetLane) a.hasCommit = true;
       g_agents.push_back(a);
     } else if (cmd == "sim") { in >> g_sim.dt >> g_sim.steps >> g_sim.minSteps; }
+    else if (cmd == "math") { std::string m; in >> m; g_math = (m == "libm") ? 1 : 0; }
     else if (cmd == "rng") {
       std::string m; unsigned long long s; in >> m >> s;
       g_reseed_after_build = -1;
