@@ -1,0 +1,144 @@
+"""Thin ctypes layer over libmcsim_b200.so (C ABI in include/mcsim.h).
+
+There is no CPU implementation behind this module: if the CUDA library is missing or no B200 is
+visible, every compute entry point raises.  (The CPU restatement under oracle/ is test infrastructure
+and is never imported here.)
+"""
+import ctypes as C
+import os
+
+from . import _abi as abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmcsim_b200.so")
+
+EXPORTS = [
+    "mcs_device_count", "mcs_last_error", "mcs_version", "mcs_scene_create", "mcs_scene_destroy",
+    "mcs_scene_visit_order", "mcs_rollouts", "mcs_rollouts_range", "mcs_reduce_features", "mcs_rollouts_device",
+    "mcs_trajectories", "mcs_decide_mobil", "mcs_decide_fixed_direction", "mcs_decide_fixed_gap",
+    "mcs_decide_closest_gap",
+]
+
+
+class McsimError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libmcsim_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libmcsim_b200.so once; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise McsimError(abi.MCS_ERR_CUDA, "%s not built — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                            "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    L.mcs_device_count.restype = C.c_int
+    L.mcs_last_error.restype = C.c_char_p
+    L.mcs_version.restype = C.c_char_p
+    L.mcs_scene_create.restype = C.c_int
+    L.mcs_scene_create.argtypes = [P(abi.Corridor), C.c_int, P(abi.Agent), C.c_int, C.c_int, P(C.c_void_p)]
+    L.mcs_scene_destroy.restype = C.c_int
+    L.mcs_scene_destroy.argtypes = [C.c_void_p]
+    L.mcs_scene_visit_order.restype = C.c_int
+    L.mcs_scene_visit_order.argtypes = [C.c_void_p, P(C.c_int32), C.c_int]
+    L.mcs_rollouts.restype = C.c_int
+    L.mcs_rollouts.argtypes = [C.c_void_p, P(abi.Candidate), C.c_int, P(abi.SimParam), C.c_int, C.c_uint64,
+                               P(abi.Feature), P(abi.Status)]
+    L.mcs_rollouts_range.restype = C.c_int
+    L.mcs_rollouts_range.argtypes = [C.c_void_p, P(abi.Candidate), C.c_int, P(abi.SimParam), C.c_uint64, C.c_int64,
+                                     C.c_int64, P(abi.Status)]
+    L.mcs_reduce_features.restype = C.c_int
+    L.mcs_reduce_features.argtypes = [P(abi.Status), C.c_int, C.c_int, C.c_int, C.c_int, P(abi.Feature)]
+    L.mcs_rollouts_device.restype = C.c_int
+    L.mcs_rollouts_device.argtypes = [C.c_void_p, P(abi.Candidate), C.c_int, P(abi.SimParam), C.c_uint64, C.c_int64,
+                                      C.c_int64, C.c_void_p, C.c_void_p, P(C.c_float), P(C.c_uint64)]
+    L.mcs_trajectories.restype = C.c_int
+    L.mcs_trajectories.argtypes = [C.c_void_p, P(abi.Candidate), P(abi.SimParam), C.c_uint64, C.c_int64,
+                                   P(C.c_double), P(C.c_int32), P(abi.Status)]
+    L.mcs_decide_mobil.restype = C.c_int
+    L.mcs_decide_mobil.argtypes = [C.c_void_p, C.c_int32, P(abi.Action), C.c_int, C.c_uint64, P(abi.ActionWithType)]
+    L.mcs_decide_fixed_direction.restype = C.c_int
+    L.mcs_decide_fixed_direction.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(abi.Action)]
+    L.mcs_decide_fixed_gap.restype = C.c_int
+    L.mcs_decide_fixed_gap.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, P(abi.Action)]
+    L.mcs_decide_closest_gap.restype = C.c_int
+    L.mcs_decide_closest_gap.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(abi.Action)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise McsimError(rc, lib().mcs_last_error().decode("utf-8", "replace"))
+
+
+class DeviceScene:
+    """A MapMultiLane + list[Agent] resident on one GPU (mcs_scene_create)."""
+
+    def __init__(self, corridors, agents, device=0):
+        self._h = C.c_void_p()
+        self.n_agents = len(agents)
+        self.n_corridors = len(corridors)
+        self._corridors = corridors   # keep the ctypes arrays alive
+        self._agents = agents
+        check(lib().mcs_scene_create(corridors, len(corridors), agents, len(agents), device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().mcs_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def visit_order(self):
+        out = (C.c_int32 * self.n_agents)()
+        check(lib().mcs_scene_visit_order(self._h, out, self.n_agents))
+        return list(out)
+
+    def rollouts(self, candidates, sim_param, n_per_group, seed, want_status=False):
+        nc = len(candidates)
+        feats = (abi.Feature * nc)()
+        st = None
+        if want_status:
+            st = (abi.Status * (nc * abi.MCS_GROUPS * n_per_group))()
+        check(lib().mcs_rollouts(self._h, candidates, nc, C.byref(sim_param), n_per_group, seed, feats, st))
+        return feats, st
+
+    def rollouts_range(self, candidates, sim_param, seed, first, count):
+        nc = len(candidates)
+        st = (abi.Status * (nc * count))()
+        check(lib().mcs_rollouts_range(self._h, candidates, nc, C.byref(sim_param), seed, first, count, st))
+        return st
+
+    def rollouts_device(self, candidates, sim_param, seed, first, count, d_status_ptr=None):
+        ms = C.c_float()
+        steps = C.c_uint64()
+        check(lib().mcs_rollouts_device(self._h, candidates, len(candidates), C.byref(sim_param), seed, first, count,
+                                        d_status_ptr, None, C.byref(ms), C.byref(steps)))
+        return ms.value, steps.value
+
+    def trajectories(self, candidate, sim_param, seed, rollout):
+        n = self.n_agents
+        buf = (C.c_double * (n * (sim_param.steps + 1) * 4))()
+        ns = C.c_int32()
+        st = abi.Status()
+        check(lib().mcs_trajectories(self._h, C.byref(candidate), C.byref(sim_param), seed, rollout, buf, C.byref(ns),
+                                     C.byref(st)))
+        return buf, ns.value, st
+
+
+def reduce_features(statuses, n_candidates, groups, n_per_group, steps):
+    feats = (abi.Feature * n_candidates)()
+    check(lib().mcs_reduce_features(statuses, n_candidates, groups, n_per_group, steps, feats))
+    return feats

@@ -1,0 +1,746 @@
+// Rollout kernel for sm_100a: one thread block per Monte-Carlo rollout, one thread per vehicle.
+//
+// Replaces the reference's Simulation::run (mc_sim_highway.so 0x10e790) and everything it calls:
+//   idmAccFrontBack 0xebc30, idmBehaviorAndYieldingToMergingAgents 0x104200, laneChangeBehaviorMOBIL 0xf42d0,
+//   laneChangeProbability 0xe19f0, rssSafe 0xb8950, customizedLaneChangeBehavior 0xf5e30,
+//   Environment::{matchAgentsOnCorridor 0x10b810, frontAgent 0xe2670, followingAgent 0xe2920, neighborAgents 0xe8240}.
+//
+// Design (B200): the path is FP64-latency/issue bound, not HBM bound — a rollout reads the scene once
+// (L2-resident, shared by every block) and writes one 64-byte record.  Vehicle state lives in registers;
+// only what neighbours gather (x, v, plus static l / vd / IDM parameters) is staged in shared memory.
+// The reference's per-lane std::vector<AgentPtr> (sorted only when lane membership changes, searched by
+// binary search every step) is a byte array of slots per lane in shared memory with exactly those
+// semantics.  MOBIL (≈90 % of the arithmetic, needed by ≈1 vehicle in 11 per step) is compacted: vehicles
+// that need it queue in shared memory and the first nTasks threads of the block evaluate them, so whole
+// warps skip it.  Random draws come from the counter stream of include/mcsim_rng.h at the index the
+// reference's sequential loop would have consumed them (block-wide exclusive scan of per-vehicle counts).
+//
+// Arithmetic is written in the operation order of the reference machine code and compiled with
+// -fmad=false: results are bit-identical to the reference binary given the same exp/pow (mcsim_math.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mcsim.h"
+#include "../../include/mcsim_math.h"
+#include "../../include/mcsim_rng.h"
+#include "scene.hpp"
+
+namespace mcs {
+
+struct LaneDev {
+  double leftY, rightY, centerY, vLimit, endX;
+  int id, type, leftIdx, rightIdx, leftmost, pad;
+};
+
+struct SceneDev {
+  int n, n_pad, n_lanes, has_exit_lanes;
+  const double* f;          // F_COUNT * n_pad
+  const int32_t* i;         // I_COUNT * n_pad
+  const uint8_t* lane_vec;  // n_pad
+  int lane_start[MCS_MAX_LANES + 1];
+  LaneDev lanes[MCS_MAX_LANES];
+};
+
+struct CandDev { int ego_slot, action, gap_id, target_lane_id, ok, pad[3]; };
+
+struct LaunchParams {
+  double dt;
+  int steps, min_steps;
+  uint64_t seed;      // stream of candidate c = mcs_rollout_key(seed + c, rollout)
+  int64_t first;      // first rollout index
+  int64_t count;      // rollouts per candidate in this launch
+  int n_cand;
+  mcs_status* status; // [n_cand][count]
+  double* traj;       // optional [n_cand][count][n][steps+1][4] in INPUT agent order, or nullptr
+  int32_t* traj_n;    // optional [n_cand][count]
+  unsigned long long* vehicle_steps;  // optional global counter
+};
+
+#define MCS_MINSD(a, b) (((a) < (b)) ? (a) : (b))   /* x86 vminsd: second source when not less / unordered */
+#define MCS_MAXSD(a, b) (((a) > (b)) ? (a) : (b))
+
+struct IdmP { double accMax, minDis, accMin, accCom, thw; };
+
+// shared-memory view of one rollout
+struct Smem {
+  double* x;       // [n_pad] current longitudinal position
+  double* v;       // [n_pad]
+  double* l;       // [n_pad] static
+  double* vd;      // [n_pad] static
+  double* idm;     // [5][n_pad] static: accMax minDis accMin accCom thw
+  double* mob;     // [6][n_pad] MOBIL geometry results per vehicle: accNewL accNewR dNewL dNewR deltaOld (+1 spare)
+  double* chist;   // [steps+2] ego comfort samples
+  double* csort;   // [steps+2] the same, sorted descending
+  double* red;     // [16] reduction scratch
+  int* scan;       // [n_pad/32 + 1]
+  int* cnt;        // [MCS_MAX_LANES + 1] lane counts / starts
+  int* flags;      // [8] block flags
+  int* tasks;      // [n_pad] MOBIL task queue
+  uint8_t* lane;   // [n_pad] lane slot of each vehicle (0xff = none)
+  uint8_t* vec;    // [n_pad] concatenated per-lane vectors
+  uint8_t* mflag;  // [n_pad] MOBIL flags per vehicle
+};
+
+__device__ __forceinline__ IdmP load_idm(const Smem& s, int np, int k) {
+  IdmP p;
+  p.accMax = s.idm[k]; p.minDis = s.idm[np + k]; p.accMin = s.idm[2 * np + k]; p.accCom = s.idm[3 * np + k];
+  p.thw = s.idm[4 * np + k];
+  return p;
+}
+
+// idmAccFrontBack 0xebc30: fronts (slots, -1 = null), back slot or -1.  pw = pow(egoV/vd, 4) supplied by the caller.
+__device__ __forceinline__ double idm_acc(const Smem& s, const IdmP& p, int f0, int f1, int back, double egoX,
+                                          double egoV, double egoL, double pw) {
+  const double freeAcc = (1.0 - pw) * p.accMax;
+  const double na = -p.accMax;
+  const double sq = sqrt(na * p.accCom);
+  const double sq2 = sq + sq;
+  const double dDes = (egoV * p.thw + p.minDis) * 0.7;
+  bool any = false;
+  double d = 0.0;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int f = q == 0 ? f0 : f1;
+    if (f < 0) continue;
+    const double gap = (s.x[f] - egoX) - (egoL + s.l[f]) * 0.5;
+    double term;
+    if (gap > 0.0) {
+      const double dv = (egoV - s.v[f]) * egoV;
+      double t = dv / sq2 + dDes;
+      t = MCS_MAXSD(t, 0.0);
+      t = t / gap;
+      term = (t * t) * na;
+    } else {
+      term = -10000000000.0;
+    }
+    if (!any) { d = term; any = true; }
+    else d = MCS_MINSD(term, d);
+  }
+  double sum = any ? d + 0.0 : 0.0;
+  if (back >= 0) {
+    const double bv = s.v[back];
+    const double gap = (s.x[back] - egoX) - (egoL + s.l[back]) * 0.5;
+    if (0.0 > gap) {
+      const double dDesB = (bv * p.thw + p.minDis) * 0.7;
+      const double dv = (bv - egoV) * egoV;
+      double t = dv / sq2 + dDesB;
+      t = MCS_MAXSD(t, 0.0);
+      t = t / gap;
+      sum = sum + (t * t) * p.accMax;
+    } else {
+      sum = sum + 10000000000.0;
+    }
+  }
+  const double r = MCS_MINSD(sum + freeAcc, p.accMax);
+  return MCS_MAXSD(p.accMin, r);
+}
+
+// std::upper_bound over lane vector [lo, lo+n): first position whose x > key (frontAgent 0xe27e0-0xe2820)
+__device__ __forceinline__ int lane_upper(const Smem& s, int lo, int n, double key) {
+  int first = 0, len = n;
+  while (len > 0) {
+    const int half = len >> 1, mid = first + half;
+    if (s.x[s.vec[lo + mid]] > key) len = half;
+    else { first = mid + 1; len = len - half - 1; }
+  }
+  return first;
+}
+// std::lower_bound: first position whose x >= key (neighborAgents 0xe8680-0xe86b1)
+__device__ __forceinline__ int lane_lower(const Smem& s, int lo, int n, double key) {
+  int first = 0, len = n;
+  while (len > 0) {
+    const int half = len >> 1, mid = first + half;
+    if (s.x[s.vec[lo + mid]] >= key) len = half;
+    else { first = mid + 1; len = len - half - 1; }
+  }
+  return first;
+}
+// reverse-iterator upper_bound with key > elem (followingAgent 0xe2aa8-0xe2ad4): answer is element first-1, 0 = none
+__device__ __forceinline__ int lane_reverse(const Smem& s, int lo, int n, double key) {
+  int first = n, len = n;
+  while (len > 0) {
+    const int half = len >> 1, mid = first - half;
+    if (key > s.x[s.vec[lo + mid - 1]]) len = half;
+    else { first = mid - 1; len = len - half - 1; }
+  }
+  return first;
+}
+
+// rssSafe 0xb8950 with optionals given as slots (-1 = nullopt); rTOther/rTEgo/aMin/aMax of the evaluating vehicle
+__device__ __forceinline__ bool rss_safe(const Smem& s, int leader, int follower, double ex, double ev, double el,
+                                         double rTOther, double rTEgo, double aMin, double aMax) {
+  if (leader < 0 && follower < 0) return true;
+  if (leader >= 0) {
+    const double fGap = (s.x[leader] - ex) - (s.l[leader] + el) * 0.5;
+    const double fV = s.v[leader];
+    double d = (ev * ev) / (aMin * -2.0) + ev * rTEgo;
+    d = d + (fV * fV) / (aMax + aMax);
+    d = MCS_MAXSD(0.0, d);
+    if (d > fGap) return false;
+    if (follower < 0) return true;
+  }
+  const double bGap = (s.l[follower] + el) * 0.5 + (s.x[follower] - ex);
+  const double bV = s.v[follower];
+  double d = (bV * bV) / (aMin * -2.0) + bV * rTOther;
+  d = d + (ev * ev) / (aMax + aMax);
+  d = MCS_MAXSD(0.0, d);
+  return !(d > -bGap);
+}
+
+// laneChangeProbability 0xe19f0
+__device__ __forceinline__ void lane_change_probability(double p[3], double q0, double q1, double q2, bool leftOk, bool rightOk) {
+  const double wP = MCS_MAXSD(p[2], p[0]) * 1.5 + 0.5;
+  const double wQ = MCS_MAXSD(q2, q0) * 1.5 + 0.5;
+  double L = 0.0, R = 0.0;
+  if (leftOk) L = p[0] * wP + q0 * wQ;
+  const double K = wP * p[1] + wQ * q1;
+  if (rightOk) R = p[2] * wP + q2 * wQ;
+  const double S = (L + K) + R;
+  p[0] = L / S; p[1] = K / S; p[2] = R / S;
+}
+
+// lateral centring 0x10441b-0x10447f
+__device__ __forceinline__ double centering_vy(double y, double centerY) {
+  const double dy = y - centerY;
+  const double ady = fabs(dy);
+  double m = 0.1;
+  if (!(0.1 > ady)) m = MCS_MINSD(1.3, ady);
+  return ((-dy) / (ady + 1e-10)) * m;
+}
+
+// RSS emergency test 0x104988-0x1049f9
+__device__ __forceinline__ bool rss_emergency(const Smem& s, int front, double ex, double ev, double el, double rTEgo,
+                                              double aMin, double aMax) {
+  const double gap = (s.x[front] - ex) - (s.l[front] + el) * 0.5;
+  const double fv = s.v[front];
+  double d = (ev * ev) / (aMin * -2.0) + ev * rTEgo;
+  d = d + (fv * fv) / (aMax + aMax);
+  d = MCS_MAXSD(0.0, d);
+  return gap < d;
+}
+
+// lane-change prior, first match of an agent that had no lane at scene creation (0x10bb97-0x10bd8a)
+__device__ __forceinline__ void prior_from_offset(double y, double vy, double centerY, double out[3]) {
+  const double d = ((y - centerY) * 0.333 + 0.6805 * vy) - 0.01;
+  double t;
+  t = d - 1.04; const double e1 = mcs_exp(((-t) * t) / 0.055);
+  t = d - 0.35; const double e2 = mcs_exp(((-t) * t) / 0.055);
+  t = d - 0.7; const double e3 = mcs_exp(((-t) * t) / 0.07);
+  const double a = (0.8 * e1 + 0.8 * e2) + e3 * 0.65;
+  t = 1.04 + d; const double e4 = mcs_exp(((-t) * t) / 0.055);
+  t = 0.35 + d; const double e5 = mcs_exp(((-t) * t) / 0.055);
+  t = 0.7 + d; const double e6 = mcs_exp(((-t) * t) / 0.07);
+  const double c = (0.75 * e4 + 0.75 * e5) + e6 * 0.6;
+  const double b = mcs_exp(((-d) * d) / 0.055) * 2.5;
+  const double sum = (a + b) + c;
+  out[0] = a / sum; out[1] = b / sum; out[2] = c / sum;
+}
+
+// MOBIL flag bits (Smem::mflag)
+enum { MF_STRICT_L = 1, MF_RELAX_L = 2, MF_STRICT_R = 4, MF_RELAX_R = 8, MF_CAN_L = 16, MF_CAN_R = 32 };
+
+// side neighbours of vehicle at x in lane `ln`: leader = first with x_elem >= x, follower = last with x_elem < x
+__device__ __forceinline__ void side_leader_follower(const Smem& s, const int* laneStart, int ln, double x, int& leader,
+                                                     int& follower) {
+  const int lo = laneStart[ln], n = laneStart[ln + 1] - lo;
+  const int f = lane_lower(s, lo, n, x);
+  leader = f < n ? s.vec[lo + f] : -1;
+  const int r = lane_reverse(s, lo, n, x);
+  follower = r > 0 ? s.vec[lo + r - 1] : -1;
+}
+
+// The part of laneChangeBehaviorMOBIL (0xf44c9-0xf4dde, 0xf5259-0xf584e) that does not depend on the vehicle's own
+// IDM action: accelerations in the neighbour lanes, follower deltas, RSS gates.  Executed for vehicle `k` by
+// whichever thread picked the task; results go to shared memory.
+__device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc, const int* laneStart, int np, int k,
+                                               int front, int back) {
+  const int ln = s.lane[k];
+  const LaneDev& L = sc.lanes[ln];
+  const double ex = s.x[k], ev = s.v[k], el = s.l[k], evd = s.vd[k];
+  const IdmP pe = load_idm(s, np, k);
+  const double rTOther = sc.f[(size_t)F_RSS_RTOTHER * np + k], rTEgo = sc.f[(size_t)F_RSS_RTEGO * np + k];
+  const double aMin = sc.f[(size_t)F_RSS_AMIN * np + k], aMax = sc.f[(size_t)F_RSS_AMAX * np + k];
+  const bool canL = L.leftIdx >= 0 && sc.lanes[L.leftIdx].type == MCS_LANE_MAIN;
+  const bool canR = L.rightIdx >= 0 && sc.lanes[L.rightIdx].type == MCS_LANE_MAIN;
+  int mf = (canL ? MF_CAN_L : 0) | (canR ? MF_CAN_R : 0);
+  double deltaOld = 0.0;
+  if (back >= 0) {
+    const IdmP pb = load_idm(s, np, back);
+    const double bx = s.x[back], bv = s.v[back], bl = s.l[back];
+    const double pw = mcs_pow4(bv / s.vd[back]);
+    const double withEgo = idm_acc(s, pb, front, k, -1, bx, bv, bl, pw);
+    const double without = idm_acc(s, pb, front, -1, -1, bx, bv, bl, pw);
+    deltaOld = without - withEgo;
+  }
+  double accNewL = 0.0, accNewR = 0.0, dNewL = 0.0, dNewR = 0.0;
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const bool can = side == 0 ? canL : canR;
+    if (!can) continue;
+    const int sl = side == 0 ? L.leftIdx : L.rightIdx;
+    int leader, follower;
+    side_leader_follower(s, laneStart, sl, ex, leader, follower);
+    const double vdCap = MCS_MINSD(evd, 1.1 * sc.lanes[sl].vLimit);
+    const double accNew = idm_acc(s, pe, leader, -1, follower, ex, ev, el, mcs_pow4(ev / vdCap));
+    const bool strict = rss_safe(s, leader, follower, ex, ev, el, rTOther, rTEgo, aMin, aMax);
+    const bool relax = rss_safe(s, leader, follower, ex, ev, el, rTOther, rTEgo, -10.0, -1.0);
+    double dNew = 0.0;
+    if (follower >= 0) {
+      const IdmP pn = load_idm(s, np, follower);
+      const double nx = s.x[follower], nv = s.v[follower], nl = s.l[follower];
+      const double pw = mcs_pow4(nv / s.vd[follower]);
+      const double without = idm_acc(s, pn, leader, -1, -1, nx, nv, nl, pw);
+      const double withEgo = idm_acc(s, pn, leader, k, -1, nx, nv, nl, pw);
+      dNew = withEgo - without;
+    }
+    if (side == 0) { accNewL = accNew; dNewL = dNew; mf |= (strict ? MF_STRICT_L : 0) | (relax ? MF_RELAX_L : 0); }
+    else { accNewR = accNew; dNewR = dNew; mf |= (strict ? MF_STRICT_R : 0) | (relax ? MF_RELAX_R : 0); }
+  }
+  s.mob[k] = accNewL; s.mob[np + k] = accNewR; s.mob[2 * np + k] = dNewL; s.mob[3 * np + k] = dNewR;
+  s.mob[4 * np + k] = deltaOld;
+  s.mflag[k] = (uint8_t)mf;
+}
+
+// block-wide exclusive scan of one int per thread; blockDim.x multiple of 32, ≤ 256
+__device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) scratch[w] = inc;
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  int base = 0, tot = 0;
+  for (int q = 0; q < nw; ++q) {
+    const int c = scratch[q];
+    if (q < w) base += c;
+    tot += c;
+  }
+  total = tot;
+  __syncthreads();
+  return base + inc - v;
+}
+
+template <bool kTraj>
+__global__ void __launch_bounds__(256) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int np = sc.n_pad, n = sc.n, k = threadIdx.x;
+  const int cand = blockIdx.y;
+  const int64_t ridx = (int64_t)blockIdx.x;           // rollout within this launch
+  const CandDev cd = cands[cand];
+  mcs_status* st_out = lp.status + ((size_t)cand * lp.count + ridx);
+
+  // ---- carve shared memory
+  Smem s;
+  {
+    unsigned char* p = smem_raw;
+    s.x = (double*)p; p += sizeof(double) * np;
+    s.v = (double*)p; p += sizeof(double) * np;
+    s.l = (double*)p; p += sizeof(double) * np;
+    s.vd = (double*)p; p += sizeof(double) * np;
+    s.idm = (double*)p; p += sizeof(double) * 5 * np;
+    s.mob = (double*)p; p += sizeof(double) * 6 * np;
+    s.chist = (double*)p; p += sizeof(double) * ((lp.steps + 2) & ~1);
+    s.csort = (double*)p; p += sizeof(double) * ((lp.steps + 2) & ~1);
+    s.red = (double*)p; p += sizeof(double) * 16;
+    s.scan = (int*)p; p += sizeof(int) * 16;
+    s.cnt = (int*)p; p += sizeof(int) * 16;
+    s.flags = (int*)p; p += sizeof(int) * 8;
+    s.tasks = (int*)p; p += sizeof(int) * np;
+    s.lane = p; p += np;
+    s.vec = p; p += np;
+    s.mflag = p; p += np;
+  }
+  int* laneStart = s.cnt;  // [n_lanes + 1]
+
+  if (!cd.ok) {           // setEgoAgentIdAndDrivingBehavior failed: the reference runs nothing (runMTimes 0xc2935)
+    if (k == 0) { mcs_status z; memset(&z, 0, sizeof z); *st_out = z; }
+    return;
+  }
+  const bool live = k < n;
+  const uint64_t key = mcs_rollout_key(lp.seed + (uint64_t)cand, (uint64_t)(lp.first + ridx));
+
+  // ---- per-vehicle registers
+  const double* F = sc.f;
+  const int32_t* I = sc.i;
+  double x = 0, y = 0, v = 0, vy = 0;
+  double el = 0, evd = 1, a0 = 0;
+  double rTEgo = 0, aMin = -1, aMax = -1;
+  int lane = -1, beh = MCS_BEH_OTHER, commit = 0, keepStep = 0, targetLane = -1, inputIdx = 0;
+  bool aggressive = false;
+  const bool isEgo = live && k == cd.ego_slot;
+  bool reached = false;
+  if (live) {
+    x = F[(size_t)F_X * np + k]; y = F[(size_t)F_Y * np + k]; v = F[(size_t)F_V * np + k]; vy = F[(size_t)F_VY * np + k];
+    a0 = F[(size_t)F_A * np + k]; el = F[(size_t)F_L * np + k]; evd = F[(size_t)F_VD * np + k];
+    rTEgo = F[(size_t)F_RSS_RTEGO * np + k]; aMin = F[(size_t)F_RSS_AMIN * np + k]; aMax = F[(size_t)F_RSS_AMAX * np + k];
+    lane = I[(size_t)I_LANE * np + k]; beh = I[(size_t)I_BEH * np + k]; commit = I[(size_t)I_COMMIT * np + k];
+    keepStep = I[(size_t)I_KEEPSTEP * np + k]; targetLane = I[(size_t)I_TARGETLANE * np + k];
+    inputIdx = I[(size_t)I_INPUT * np + k];
+    // Agent ctor draw (0xf89e6): draw index = position in the INPUT list
+    aggressive = ((double)mcs_rand31(key, (uint64_t)inputIdx) / 2147483647.0) > 0.8;
+    if (isEgo) targetLane = cd.target_lane_id;
+  }
+  const int beh0 = live ? I[(size_t)I_BEH0 * np + k] : 0;
+  double prior0 = live ? F[(size_t)F_PRIOR_L * np + k] : 0, prior1 = live ? F[(size_t)F_PRIOR_K * np + k] : 0,
+         prior2 = live ? F[(size_t)F_PRIOR_R * np + k] : 0;
+  // stage what neighbours gather
+  s.x[k] = x; s.v[k] = v; s.l[k] = el; s.vd[k] = evd;
+  s.idm[k] = live ? F[(size_t)F_IDM_ACCMAX * np + k] : 1.0;
+  s.idm[np + k] = live ? F[(size_t)F_IDM_MINDIS * np + k] : 0.0;
+  s.idm[2 * np + k] = live ? F[(size_t)F_IDM_ACCMIN * np + k] : 0.0;
+  s.idm[3 * np + k] = live ? F[(size_t)F_IDM_ACCCOM * np + k] : -1.0;
+  s.idm[4 * np + k] = live ? F[(size_t)F_IDM_THW * np + k] : 0.0;
+  s.lane[k] = (uint8_t)(lane < 0 ? 0xff : lane);
+  s.vec[k] = sc.lane_vec[k];
+  if (k <= sc.n_lanes) laneStart[k] = sc.lane_start[k];
+  if (k < 8) s.flags[k] = 0;
+  __syncthreads();
+
+  // statistics (Simulation::run 0x10ee71-0x10f49a) accumulated on the fly in history order
+  double sumAbsA = fabs(a0), sumV = v;
+  double prevA = a0;
+  bool fallBack = false;
+  double sumU = 0.0, thwAcc = 0.0;
+  int thwCnt = 0, nStates = 1;
+  if (isEgo) {
+    const double r = v / evd;
+    double u = r;
+    if (!(evd >= v)) u = MCS_MAXSD(0.9, 1.0 - (r - 1.0));
+    sumU = u;
+    s.chist[0] = a0 > 0.0 ? fabs(a0) * 0.5 : fabs(a0);
+  }
+  if (kTraj && live) {
+    double* t = lp.traj + ((((size_t)cand * lp.count + ridx) * n + inputIdx) * (size_t)(lp.steps + 1)) * 4;
+    t[0] = x; t[1] = y; t[2] = v; t[3] = a0;
+  }
+  uint64_t drawCtr = (uint64_t)n;   // draws 0..n-1 were the ctor flags
+  int finishStep = lp.steps;
+  bool finish = false;
+  int step = 0;
+  bool unsupported = false;
+
+  while (lp.steps > step) {
+    // ================= plan, part A: own-lane search, IDM, draw counts =================
+    double ax = 0.0, avy = 0.0;
+    int front = -1, back = -1;
+    bool needMobil = false, noise = false, egoCustom = false;
+    int nDraw = 0;
+    const bool hasLane = live && lane >= 0;
+    double pwOwn = 0.0, centerY = 0.0, vLimit = 0.0;
+    if (hasLane) {
+      const LaneDev& L = sc.lanes[lane];
+      centerY = L.centerY; vLimit = L.vLimit;
+      const int lo = laneStart[lane], cnt = laneStart[lane + 1] - lo;
+      const int fpos = lane_upper(s, lo, cnt, x);
+      front = fpos < cnt ? s.vec[lo + fpos] : -1;
+      // yielding candidates (right lane of type merging, exit agents on the left main lane) are not handled yet
+      if ((L.rightIdx >= 0 && sc.lanes[L.rightIdx].type == MCS_LANE_MERGING) ||
+          (sc.has_exit_lanes && L.leftIdx >= 0 && sc.lanes[L.leftIdx].type == MCS_LANE_MAIN)) unsupported = true;
+      if (isEgo) {
+        const bool lr = cd.action == MCS_ACT_LEFT || cd.action == MCS_ACT_RIGHT;
+        if ((beh == MCS_BEH_IDM || beh == MCS_BEH_IDM_LC) && !(lr && reached)) egoCustom = true;
+        else if (beh == MCS_BEH_MERGING || beh == MCS_BEH_EXIT) { if (!reached) unsupported = true; }
+      } else if (beh == MCS_BEH_IDM_LC) {
+        noise = true;
+        const bool canL = L.leftIdx >= 0 && sc.lanes[L.leftIdx].type == MCS_LANE_MAIN;
+        const bool canR = L.rightIdx >= 0 && sc.lanes[L.rightIdx].type == MCS_LANE_MAIN;
+        needMobil = !(commit == MCS_COMMIT_KEEP_LANE && keepStep <= 9) && (canL || canR);
+      } else if (beh == MCS_BEH_IDM) {
+        noise = true;
+      } else {
+        unsupported = true;
+      }
+      if (needMobil) {
+        const int bpos = lane_reverse(s, lo, cnt, x);
+        back = bpos > 0 ? s.vec[lo + bpos - 1] : -1;
+      }
+    }
+    // compaction: queue MOBIL tasks
+    int nTasks;
+    {
+      const int pos = block_exclusive_scan(needMobil ? 1 : 0, s.scan, nTasks);
+      if (needMobil) s.tasks[pos] = k | (front & 0xff) << 8 | (back & 0xff) << 16 | ((front < 0) ? 1 << 24 : 0) | ((back < 0) ? 1 << 25 : 0);
+    }
+    __syncthreads();
+    for (int t = k; t < nTasks; t += blockDim.x) {
+      const int rec = s.tasks[t];
+      const int vk = rec & 0xff;
+      const int vf = (rec >> 24 & 1) ? -1 : (rec >> 8 & 0xff);
+      const int vb = (rec >> 25 & 1) ? -1 : (rec >> 16 & 0xff);
+      mobil_geometry(s, sc, laneStart, np, vk, vf, vb);
+    }
+    __syncthreads();
+    // draw counts: [noise][MOBIL decision draw]
+    bool mobilDraw = false;
+    if (needMobil) {
+      const int mf = s.mflag[k];
+      const int laneId = sc.lanes[lane].id;
+      const bool contL = commit == MCS_COMMIT_LEFT && targetLane != laneId && (mf & MF_RELAX_L);
+      const bool contR = commit == MCS_COMMIT_RIGHT && targetLane != laneId && (mf & MF_RELAX_R);
+      mobilDraw = !(contL || contR);
+    }
+    nDraw = (noise ? 1 : 0) + (mobilDraw ? 1 : 0);
+    int totalDraws;
+    const uint64_t drawBase = drawCtr + (uint64_t)block_exclusive_scan(nDraw, s.scan, totalDraws);
+    drawCtr += (uint64_t)totalDraws;
+
+    // ================= plan, part B: actions =================
+    double thwPush = 0.0;
+    bool pushThw = false;
+    if (hasLane) {
+      const IdmP pe = load_idm(s, np, k);
+      if (front >= 0) thwPush = (((s.x[front] - x) - (s.l[front] + el) * 0.5) / v) / pe.thw;
+      else thwPush = 1.0;
+      pushThw = true;
+      avy = centering_vy(y, centerY);
+      if (egoCustom) {
+        // customizedLaneChangeBehavior 0xf5e30
+        const double vdCap = MCS_MINSD(evd, 1.1 * vLimit);
+        const int cmd = cd.action;
+        if (cmd == MCS_ACT_KEEP_LANE || cmd == MCS_ACT_ACC || cmd == MCS_ACT_DCC) {
+          IdmP p = pe;
+          double vdd = vdCap;
+          if (cmd == MCS_ACT_DCC) { p.thw = pe.thw + pe.thw; vdd = 0.8 * vdCap; }
+          if (cmd == MCS_ACT_ACC) { p.thw = 0.9; vdd = 1.1 * vdCap; }
+          ax = idm_acc(s, p, front, -1, -1, x, v, el, mcs_pow4(v / vdd));
+          if (front >= 0 && rss_emergency(s, front, x, v, el, rTEgo, aMin, aMax)) ax = aMin;
+        } else {
+          const bool emergency = front >= 0 && rss_emergency(s, front, x, v, el, rTEgo, aMin, aMax);
+          const LaneDev& L = sc.lanes[lane];
+          const int sl = cmd == MCS_ACT_LEFT ? L.leftIdx : L.rightIdx;
+          if (sl >= 0 && sc.lanes[sl].type == MCS_LANE_MAIN) {
+            int leader, follower;
+            side_leader_follower(s, laneStart, sl, x, leader, follower);
+            ax = idm_acc(s, pe, leader, front, follower, x, v, el, mcs_pow4(v / vdCap));
+            if (emergency) ax = aMin;
+            const double rTOther = F[(size_t)F_RSS_RTOTHER * np + k];
+            if (rss_safe(s, leader, follower, x, v, el, rTOther, rTEgo, aMin, aMax)) {
+              const double m = MCS_MINSD(1.0, 0.17 * v);
+              avy = m * (cmd == MCS_ACT_LEFT ? 1.0 : -1.0);
+            }
+          } else {
+            ax = emergency ? aMin : 0.0;
+          }
+        }
+      } else {
+        // idmBehaviorAndYieldingToMergingAgents 0x104200 (no yielding candidates in supported scenes)
+        double vdd = evd;
+        if (isEgo) vdd = MCS_MINSD(evd, 1.1 * vLimit);
+        const double pw = mcs_pow4(v / vdd);
+        const double axFront = idm_acc(s, pe, front, -1, -1, x, v, el, pw);
+        IdmP py = pe;
+        py.accMax = F[(size_t)F_IDMY_ACCMAX * np + k]; py.accMin = F[(size_t)F_IDMY_ACCMIN * np + k];
+        const double axY = idm_acc(s, py, -1, -1, -1, x, v, el, pw);
+        ax = MCS_MINSD(axY, axFront);
+        if (noise) ax = ax + ((double)mcs_rand31(key, drawBase) / 2147483647.0 - 0.5);
+        if (front >= 0 && rss_emergency(s, front, x, v, el, rTEgo, aMin, aMax)) ax = aMin;
+        if (beh == MCS_BEH_IDM_LC && !isEgo) {
+          // laneChangeBehaviorMOBIL 0xf42d0, decision part
+          if (commit == MCS_COMMIT_KEEP_LANE && keepStep <= 9) {
+            keepStep = keepStep + 1;
+          } else if (needMobil) {
+            const int mf = s.mflag[k];
+            const bool canL = mf & MF_CAN_L, canR = mf & MF_CAN_R;
+            const bool strictL = mf & MF_STRICT_L, relaxL = mf & MF_RELAX_L, strictR = mf & MF_STRICT_R, relaxR = mf & MF_RELAX_R;
+            const double accNewL = s.mob[k], accNewR = s.mob[np + k], dNewL = s.mob[2 * np + k], dNewR = s.mob[3 * np + k];
+            const double deltaOld = s.mob[4 * np + k];
+            const double pf = F[(size_t)F_YP_PF * np + k], dA = F[(size_t)F_YP_DA * np + k], bA = F[(size_t)F_YP_BA * np + k];
+            const double axIdm = ax, vyIdm = avy;
+            double axLeft = axIdm, vyLeft = vyIdm, axRight = 0.0, vyRight = 0.0;
+            double incL = -10000000000.0, incR = -10000000000.0;
+            if (canL) {
+              axLeft = (axIdm == aMin) ? axIdm : accNewL;
+              vyLeft = MCS_MINSD(1.0, 0.17 * v);
+              incL = (((dNewL + deltaOld) * pf + (accNewL - axIdm)) - dA) - bA;
+            }
+            if (canR) {
+              axRight = accNewR;
+              vyRight = MCS_MAXSD(-1.0, -0.17 * v);
+              incR = (((dNewR + deltaOld) * pf + (accNewR - axIdm)) - dA) + bA;
+            }
+            const LaneDev& L = sc.lanes[lane];
+            if (commit == MCS_COMMIT_LEFT && targetLane != L.id && relaxL) { ax = axLeft; avy = vyLeft; }
+            else if (commit == MCS_COMMIT_RIGHT && targetLane != L.id && relaxR) { ax = axRight; avy = vyRight; }
+            else {
+              keepStep = 0;
+              const double eL = mcs_exp(incL), eR = mcs_exp(incR);
+              const double denom = (1.0 + eL) + eR;
+              double p[3];
+              p[0] = eL / denom; p[2] = eR / denom; p[1] = (1.0 - p[0]) - p[2];
+              if (commit == MCS_COMMIT_NOT_DECIDED && nStates <= 1) {
+                if (aggressive) lane_change_probability(p, prior0, prior1, prior2, relaxL, relaxR);
+                else {
+                  const bool r = strictR ? true : ((prior2 >= 0.5) && relaxR);
+                  const bool l = strictL ? true : ((prior0 >= 0.5) && relaxL);
+                  lane_change_probability(p, prior0, prior1, prior2, l, r);
+                }
+              } else if (aggressive) lane_change_probability(p, 0.0, 0.0, 0.0, relaxL, relaxR);
+              else lane_change_probability(p, 0.0, 0.0, 0.0, strictL, strictR);
+              double pL = p[0];
+              if (el > 6.0) {
+                pL = pL * 0.5;
+                if (L.leftIdx >= 0 && sc.lanes[L.leftIdx].leftmost) pL = 0.0;
+                const double k2 = p[1] + p[1], r2 = p[2] + p[2];
+                const double S = (k2 + pL) + r2;
+                p[1] = k2 / S; p[2] = r2 / S;
+              }
+              const double u = (double)mcs_rand31(key, drawBase + 1) / 2147483647.0;
+              if (pL > u && canL) { commit = MCS_COMMIT_LEFT; targetLane = sc.lanes[L.leftIdx].id; ax = axLeft; avy = vyLeft; }
+              else if (pL + p[2] > u && canR) { commit = MCS_COMMIT_RIGHT; targetLane = sc.lanes[L.rightIdx].id; ax = axRight; avy = vyRight; }
+              else { commit = MCS_COMMIT_KEEP_LANE; targetLane = -1; }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();   // every read of the pre-step x / v is done
+
+    // ================= integrate (0x10ea36-0x10eb80) =================
+    double acc = 0.0;
+    if (live) {
+      double v1 = ax * lp.dt + v;
+      if (0.0 > v1) {
+        v = 0.0; x = 0.0 * lp.dt + x; vy = avy; y = avy * lp.dt + y; acc = 0.0; v1 = 0.0;
+      } else {
+        v = v1; x = v1 * lp.dt + x; vy = avy; y = avy * lp.dt + y; acc = (v1 == 0.0) ? 0.0 : ax;
+      }
+      s.x[k] = x; s.v[k] = v;
+      sumAbsA = sumAbsA + fabs(acc); sumV = sumV + v;
+      if (isEgo) {
+        if (aMin == prevA && aMin == acc) fallBack = true;
+        const double r = v / evd;
+        double u = r;
+        if (!(evd >= v)) u = MCS_MAXSD(0.9, 1.0 - (r - 1.0));
+        sumU = sumU + u;
+        s.chist[nStates] = acc > 0.0 ? fabs(acc) * 0.5 : fabs(acc);
+        if (pushThw) { if (0.9 > thwPush && thwPush > 0.0) thwAcc = (thwPush + thwAcc) - 0.9; thwCnt++; }
+      }
+      prevA = acc;
+      if (kTraj) {
+        double* t = lp.traj + ((((size_t)cand * lp.count + ridx) * n + inputIdx) * (size_t)(lp.steps + 1) + nStates) * 4;
+        t[0] = x; t[1] = y; t[2] = v; t[3] = acc;
+      }
+    }
+    nStates++;
+
+    // ================= matchAgentsOnCorridor (0x10b810) =================
+    bool changed = false;
+    if (live) {
+      bool stay = false;
+      if (lane >= 0) { const LaneDev& L = sc.lanes[lane]; stay = L.leftY >= y && y >= L.rightY; }
+      if (!stay) {
+        changed = true;
+        for (int j = 0; j < sc.n_lanes; ++j) {
+          const LaneDev& L = sc.lanes[j];
+          if (!(L.leftY >= y && y >= L.rightY)) continue;
+          const bool first = lane < 0;
+          lane = j;
+          if (L.type == MCS_LANE_MAIN && beh == MCS_BEH_MERGING) beh = MCS_BEH_IDM_LC;
+          if (L.type == MCS_LANE_EXIT && beh == MCS_BEH_EXIT) beh = MCS_BEH_IDM;
+          if (first) { double p[3]; prior_from_offset(y, vy, L.centerY, p); prior0 = p[0]; prior1 = p[1]; prior2 = p[2]; }
+          break;
+        }
+        s.lane[k] = (uint8_t)(lane < 0 ? 0xff : lane);
+      }
+      if (isEgo && !reached && lane >= 0) reached = sc.lanes[lane].id == targetLane;
+    }
+    const int anyChanged = __syncthreads_or(changed ? 1 : 0);   // also publishes the new x / v / lane
+    if (anyChanged) {
+      // rebuild per-lane vectors: members in slot (visit) order, stable ascending x  (0x10be30-0x10c1a5)
+      int rank = 0;
+      const int myLane = live ? (int)s.lane[k] : 0xff;
+      if (k < MCS_MAX_LANES + 1) s.scan[k] = 0;
+      __syncthreads();
+      if (myLane != 0xff) {
+        for (int j = 0; j < n; ++j) {
+          const double xj = s.x[j];
+          rank += (s.lane[j] == myLane && (xj < x || (xj == x && j < k))) ? 1 : 0;
+        }
+        atomicAdd(&s.scan[myLane], 1);
+      }
+      __syncthreads();
+      if (k == 0) {
+        int run = 0;
+        for (int j = 0; j < sc.n_lanes; ++j) { laneStart[j] = run; run += s.scan[j]; }
+        laneStart[sc.n_lanes] = run;
+      }
+      __syncthreads();
+      if (myLane != 0xff) s.vec[laneStart[myLane] + rank] = (uint8_t)k;
+    }
+    // ================= termination (0x10edd0-0x10ee10) =================
+    if (isEgo) s.flags[0] = reached ? 1 : 0;
+    __syncthreads();
+    const bool egoReached = s.flags[0] != 0;
+    if (egoReached) {
+      finish = true;
+      finishStep = min(finishStep, step);
+      if (lp.min_steps <= step) break;
+    }
+    step++;
+  }
+
+  // ================= outcome statistics (0x10ee20-0x10f64d) =================
+  const int executed = nStates - 1;
+  const int fs = max(finishStep, (int)(1.0 / lp.dt));
+  double utilO = 1e300, comfO = 1e300;   // min identity; replaced by 1.0 when the rollout has no objects
+  if (live && !isEgo) {
+    const double cnt = (double)nStates;
+    const double meanV = sumV / cnt;
+    comfO = (sumAbsA / cnt) / aMin + 1.0;
+    utilO = (meanV >= evd) ? 1.0 : meanV / evd;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double u2 = __shfl_xor_sync(0xffffffffu, utilO, o), c2 = __shfl_xor_sync(0xffffffffu, comfO, o);
+    utilO = MCS_MINSD(u2, utilO); comfO = MCS_MINSD(c2, comfO);
+  }
+  if ((k & 31) == 0) { s.red[(k >> 5) * 2] = utilO; s.red[(k >> 5) * 2 + 1] = comfO; }
+  // ego comfort: mean over the k largest samples of 1 + c/aMin, summed in descending order (0x10f1c3-0x10f49a)
+  __syncthreads();
+  {
+    const int ns = nStates;
+    double* sorted = s.csort;
+    for (int t = k; t < ns; t += blockDim.x) {
+      const double c = s.chist[t];
+      int rank = 0;
+      for (int j = 0; j < ns; ++j) { const double cj = s.chist[j]; rank += (cj > c || (cj == c && j < t)) ? 1 : 0; }
+      sorted[rank] = c;
+    }
+  }
+  __syncthreads();
+  if (isEgo) {
+    const int nw = blockDim.x >> 5;
+    double uo = s.red[0], co = s.red[1];
+    for (int q = 1; q < nw; ++q) { uo = MCS_MINSD(s.red[2 * q], uo); co = MCS_MINSD(s.red[2 * q + 1], co); }
+    if (n <= 1) { uo = 1.0; co = 1.0; }
+    mcs_status st;
+    memset(&st, 0, sizeof st);
+    st.utilityObjects = uo; st.comfortObjects = co;
+    const double util = sumU / (double)nStates;
+    const double thwTerm = thwCnt > 0 ? thwAcc / (double)thwCnt : 0.0;
+    st.utility = util + thwTerm;
+    const int kk = (int)((double)nStates * 0.2);
+    double sumC = 0.0;
+    for (int t = 0; t < kk; ++t) sumC = sumC + (s.csort[t] / aMin + 1.0);
+    st.comfort = sumC / (double)kk;
+    st.finishStep = fs; st.executedSteps = executed; st.draws = (uint32_t)drawCtr;
+    st.finish = finish ? 1 : 0;
+    if (beh0 == MCS_BEH_MERGING || beh0 == MCS_BEH_EXIT) st.fallBack = (2.0 > v) ? 1 : 0;
+    else st.fallBack = fallBack ? 1 : 0;
+    st.ok = 1;
+    st.overflow = 0;
+    *st_out = st;
+    if (kTraj && lp.traj_n) lp.traj_n[(size_t)cand * lp.count + ridx] = nStates;
+    if (lp.vehicle_steps) atomicAdd(lp.vehicle_steps, (unsigned long long)executed * (unsigned long long)n);
+  }
+  if (__syncthreads_or(unsupported ? 1 : 0)) {
+    if (isEgo) st_out->overflow = 2;   // scene uses a behaviour this build does not implement: caller must fail loudly
+  }
+}
+
+}  // namespace mcs
