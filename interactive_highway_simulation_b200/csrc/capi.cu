@@ -23,7 +23,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 size_t rollout_smem_bytes(int n_pad, int steps) {
   size_t doubles = (size_t)n_pad * (4 + 5 + 6) + 2 * (size_t)((steps + 2) & ~1) + 16;
   size_t ints = 16 + 16 + 8 + (size_t)n_pad;
-  return doubles * 8 + ints * 4 + 3 * (size_t)n_pad;
+  return doubles * 8 + ints * 4 + 5 * (size_t)n_pad;
 }
 
 // per-candidate two-level mean, fixed order: runMTimes 0xc2a6e-0xc2b1f per group, runMultiThreads 0xbca08-0xbca92

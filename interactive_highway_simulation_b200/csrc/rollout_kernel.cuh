@@ -79,7 +79,8 @@ struct Smem {
   int* tasks;      // [n_pad] MOBIL task queue
   uint8_t* lane;   // [n_pad] lane slot of each vehicle (0xff = none)
   uint8_t* vec;    // [n_pad] concatenated per-lane vectors
-  uint8_t* mflag;  // [n_pad] MOBIL flags per vehicle
+  uint8_t* mflag;  // [2][n_pad] MOBIL flags per vehicle (left part, right part)
+  uint8_t* pos;    // [n_pad] position of each vehicle inside vec
 };
 
 __device__ __forceinline__ IdmP load_idm(const Smem& s, int np, int k) {
@@ -251,41 +252,42 @@ __device__ __forceinline__ void side_leader_follower(const Smem& s, const int* l
 }
 
 // The part of laneChangeBehaviorMOBIL (0xf44c9-0xf4dde, 0xf5259-0xf584e) that does not depend on the vehicle's own
-// IDM action: accelerations in the neighbour lanes, follower deltas, RSS gates.  Executed for vehicle `k` by
-// whichever thread picked the task; results go to shared memory.
+// IDM action: accelerations in the neighbour lanes, follower deltas, RSS gates.  A vehicle's evaluation is three
+// independent sub-tasks (part 0: old follower, part 1: left lane, part 2: right lane) executed by whichever
+// threads picked them from the queue; results go to shared memory.
 __device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc, const int* laneStart, int np, int k,
-                                               int front, int back) {
+                                               int front, int back, int part) {
   const int ln = s.lane[k];
   const LaneDev& L = sc.lanes[ln];
-  const double ex = s.x[k], ev = s.v[k], el = s.l[k], evd = s.vd[k];
-  const IdmP pe = load_idm(s, np, k);
-  const double rTOther = sc.f[(size_t)F_RSS_RTOTHER * np + k], rTEgo = sc.f[(size_t)F_RSS_RTEGO * np + k];
-  const double aMin = sc.f[(size_t)F_RSS_AMIN * np + k], aMax = sc.f[(size_t)F_RSS_AMAX * np + k];
-  const bool canL = L.leftIdx >= 0 && sc.lanes[L.leftIdx].type == MCS_LANE_MAIN;
-  const bool canR = L.rightIdx >= 0 && sc.lanes[L.rightIdx].type == MCS_LANE_MAIN;
-  int mf = (canL ? MF_CAN_L : 0) | (canR ? MF_CAN_R : 0);
-  double deltaOld = 0.0;
-  if (back >= 0) {
-    const IdmP pb = load_idm(s, np, back);
-    const double bx = s.x[back], bv = s.v[back], bl = s.l[back];
-    const double pw = mcs_pow4(bv / s.vd[back]);
-    const double withEgo = idm_acc(s, pb, front, k, -1, bx, bv, bl, pw);
-    const double without = idm_acc(s, pb, front, -1, -1, bx, bv, bl, pw);
-    deltaOld = without - withEgo;
+  if (part == 0) {
+    double deltaOld = 0.0;
+    if (back >= 0) {
+      const IdmP pb = load_idm(s, np, back);
+      const double bx = s.x[back], bv = s.v[back], bl = s.l[back];
+      const double pw = mcs_pow4(bv / s.vd[back]);
+      const double withEgo = idm_acc(s, pb, front, k, -1, bx, bv, bl, pw);
+      const double without = idm_acc(s, pb, front, -1, -1, bx, bv, bl, pw);
+      deltaOld = without - withEgo;
+    }
+    s.mob[4 * np + k] = deltaOld;
+    return;
   }
-  double accNewL = 0.0, accNewR = 0.0, dNewL = 0.0, dNewR = 0.0;
-#pragma unroll
-  for (int side = 0; side < 2; ++side) {
-    const bool can = side == 0 ? canL : canR;
-    if (!can) continue;
-    const int sl = side == 0 ? L.leftIdx : L.rightIdx;
+  const int side = part - 1;
+  const int sl = side == 0 ? L.leftIdx : L.rightIdx;
+  const bool can = sl >= 0 && sc.lanes[sl].type == MCS_LANE_MAIN;
+  int mf = 0;
+  double accNew = 0.0, dNew = 0.0;
+  if (can) {
+    const double ex = s.x[k], ev = s.v[k], el = s.l[k], evd = s.vd[k];
+    const IdmP pe = load_idm(s, np, k);
+    const double rTOther = sc.f[(size_t)F_RSS_RTOTHER * np + k], rTEgo = sc.f[(size_t)F_RSS_RTEGO * np + k];
+    const double aMin = sc.f[(size_t)F_RSS_AMIN * np + k], aMax = sc.f[(size_t)F_RSS_AMAX * np + k];
     int leader, follower;
     side_leader_follower(s, laneStart, sl, ex, leader, follower);
     const double vdCap = MCS_MINSD(evd, 1.1 * sc.lanes[sl].vLimit);
-    const double accNew = idm_acc(s, pe, leader, -1, follower, ex, ev, el, mcs_pow4(ev / vdCap));
+    accNew = idm_acc(s, pe, leader, -1, follower, ex, ev, el, mcs_pow4(ev / vdCap));
     const bool strict = rss_safe(s, leader, follower, ex, ev, el, rTOther, rTEgo, aMin, aMax);
     const bool relax = rss_safe(s, leader, follower, ex, ev, el, rTOther, rTEgo, -10.0, -1.0);
-    double dNew = 0.0;
     if (follower >= 0) {
       const IdmP pn = load_idm(s, np, follower);
       const double nx = s.x[follower], nv = s.v[follower], nl = s.l[follower];
@@ -294,12 +296,12 @@ __device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc
       const double withEgo = idm_acc(s, pn, leader, k, -1, nx, nv, nl, pw);
       dNew = withEgo - without;
     }
-    if (side == 0) { accNewL = accNew; dNewL = dNew; mf |= (strict ? MF_STRICT_L : 0) | (relax ? MF_RELAX_L : 0); }
-    else { accNewR = accNew; dNewR = dNew; mf |= (strict ? MF_STRICT_R : 0) | (relax ? MF_RELAX_R : 0); }
+    mf = side == 0 ? (MF_CAN_L | (strict ? MF_STRICT_L : 0) | (relax ? MF_RELAX_L : 0))
+                   : (MF_CAN_R | (strict ? MF_STRICT_R : 0) | (relax ? MF_RELAX_R : 0));
   }
-  s.mob[k] = accNewL; s.mob[np + k] = accNewR; s.mob[2 * np + k] = dNewL; s.mob[3 * np + k] = dNewR;
-  s.mob[4 * np + k] = deltaOld;
-  s.mflag[k] = (uint8_t)mf;
+  s.mob[side * np + k] = accNew;
+  s.mob[(2 + side) * np + k] = dNew;
+  s.mflag[side * np + k] = (uint8_t)mf;
 }
 
 // block-wide exclusive scan of one int per thread; blockDim.x multiple of 32, ≤ 256
@@ -326,7 +328,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int& to
 }
 
 template <bool kTraj>
-__global__ void __launch_bounds__(256) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp) {
+__global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int np = sc.n_pad, n = sc.n, k = threadIdx.x;
   const int cand = blockIdx.y;
@@ -353,7 +355,8 @@ __global__ void __launch_bounds__(256) rollout_kernel(const SceneDev sc, const C
     s.tasks = (int*)p; p += sizeof(int) * np;
     s.lane = p; p += np;
     s.vec = p; p += np;
-    s.mflag = p; p += np;
+    s.mflag = p; p += 2 * np;
+    s.pos = p; p += np;
   }
   int* laneStart = s.cnt;  // [n_lanes + 1]
 
@@ -397,9 +400,14 @@ __global__ void __launch_bounds__(256) rollout_kernel(const SceneDev sc, const C
   s.idm[4 * np + k] = live ? F[(size_t)F_IDM_THW * np + k] : 0.0;
   s.lane[k] = (uint8_t)(lane < 0 ? 0xff : lane);
   s.vec[k] = sc.lane_vec[k];
+  int oldLane = lane;           // lane whose vector currently holds this vehicle
+  int myPos = 0;                // its position in s.vec
   if (k <= sc.n_lanes) laneStart[k] = sc.lane_start[k];
   if (k < 8) s.flags[k] = 0;
   __syncthreads();
+  if (k < laneStart[sc.n_lanes]) s.pos[s.vec[k]] = (uint8_t)k;
+  __syncthreads();
+  myPos = s.pos[k];
 
   // statistics (Simulation::run 0x10ee71-0x10f49a) accumulated on the fly in history order
   double sumAbsA = fabs(a0), sumV = v;
@@ -467,18 +475,19 @@ __global__ void __launch_bounds__(256) rollout_kernel(const SceneDev sc, const C
       if (needMobil) s.tasks[pos] = k | (front & 0xff) << 8 | (back & 0xff) << 16 | ((front < 0) ? 1 << 24 : 0) | ((back < 0) ? 1 << 25 : 0);
     }
     __syncthreads();
-    for (int t = k; t < nTasks; t += blockDim.x) {
-      const int rec = s.tasks[t];
+    for (int t = k; t < 3 * nTasks; t += blockDim.x) {
+      const int part = t / nTasks;                 // neighbouring threads run the same part: less divergence
+      const int rec = s.tasks[t - part * nTasks];
       const int vk = rec & 0xff;
       const int vf = (rec >> 24 & 1) ? -1 : (rec >> 8 & 0xff);
       const int vb = (rec >> 25 & 1) ? -1 : (rec >> 16 & 0xff);
-      mobil_geometry(s, sc, laneStart, np, vk, vf, vb);
+      mobil_geometry(s, sc, laneStart, np, vk, vf, vb, part);
     }
     __syncthreads();
     // draw counts: [noise][MOBIL decision draw]
     bool mobilDraw = false;
     if (needMobil) {
-      const int mf = s.mflag[k];
+      const int mf = s.mflag[k] | s.mflag[np + k];
       const int laneId = sc.lanes[lane].id;
       const bool contL = commit == MCS_COMMIT_LEFT && targetLane != laneId && (mf & MF_RELAX_L);
       const bool contR = commit == MCS_COMMIT_RIGHT && targetLane != laneId && (mf & MF_RELAX_R);
@@ -544,7 +553,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const SceneDev sc, const C
           if (commit == MCS_COMMIT_KEEP_LANE && keepStep <= 9) {
             keepStep = keepStep + 1;
           } else if (needMobil) {
-            const int mf = s.mflag[k];
+            const int mf = s.mflag[k] | s.mflag[np + k];
             const bool canL = mf & MF_CAN_L, canR = mf & MF_CAN_R;
             const bool strictL = mf & MF_STRICT_L, relaxL = mf & MF_RELAX_L, strictR = mf & MF_STRICT_R, relaxR = mf & MF_RELAX_R;
             const double accNewL = s.mob[k], accNewR = s.mob[np + k], dNewL = s.mob[2 * np + k], dNewR = s.mob[3 * np + k];
@@ -651,26 +660,83 @@ __global__ void __launch_bounds__(256) rollout_kernel(const SceneDev sc, const C
     }
     const int anyChanged = __syncthreads_or(changed ? 1 : 0);   // also publishes the new x / v / lane
     if (anyChanged) {
-      // rebuild per-lane vectors: members in slot (visit) order, stable ascending x  (0x10be30-0x10c1a5)
-      int rank = 0;
-      const int myLane = live ? (int)s.lane[k] : 0xff;
+      // The reference rebuilds every lane vector (members in visit order) and std::sorts it by x (0x10be30-0x10c1a5):
+      // the result is "members ordered by (x, slot)".  Vehicles that kept their lane are already in that order unless
+      // two of them passed through each other since the last rebuild, so the usual case only has to splice the few
+      // movers in: rank = old rank - leavers ahead + arrivals ahead.  An order inversion anywhere falls back to ranking
+      // every vehicle against every other one.
+      const int newLane = live ? (int)s.lane[k] : 0xff;
+      const int oldL = oldLane < 0 ? 0xff : oldLane;
+      const bool inVec = live && oldL != 0xff;
+      const bool mover = live && newLane != oldL;
+      bool inversion = false;
+      if (inVec && myPos > laneStart[oldL]) {
+        const int pj = s.vec[myPos - 1];
+        const double xp = s.x[pj];
+        inversion = xp > x || (xp == x && pj > k);
+      }
+      if (k == 0) s.flags[1] = 0;
       if (k < MCS_MAX_LANES + 1) s.scan[k] = 0;
-      __syncthreads();
-      if (myLane != 0xff) {
-        for (int j = 0; j < n; ++j) {
-          const double xj = s.x[j];
-          rank += (s.lane[j] == myLane && (xj < x || (xj == x && j < k))) ? 1 : 0;
+      const int anyInv = __syncthreads_or(inversion ? 1 : 0);
+      int rank = 0;
+      if (anyInv) {
+        if (newLane != 0xff) {
+          for (int j = 0; j < n; ++j) {
+            const double xj = s.x[j];
+            rank += (s.lane[j] == newLane && (xj < x || (xj == x && j < k))) ? 1 : 0;
+          }
+          atomicAdd(&s.scan[newLane], 1);
         }
-        atomicAdd(&s.scan[myLane], 1);
+      } else {
+        if (mover) {
+          const int slot = atomicAdd(&s.flags[1], 1);
+          s.tasks[slot] = k | (inVec ? myPos : 0) << 8 | oldL << 16 | newLane << 24;
+        }
+        __syncthreads();
+        const int nm = s.flags[1];
+        if (!mover && inVec) {
+          rank = myPos - laneStart[oldL];
+          for (int q = 0; q < nm; ++q) {
+            const int rec = s.tasks[q];
+            const int mk = rec & 0xff, mpos = rec >> 8 & 0xff, mold = rec >> 16 & 0xff, mnew = rec >> 24 & 0xff;
+            if (mold == oldL && mpos < myPos) rank--;
+            if (mnew == oldL) { const double xm = s.x[mk]; rank += (xm < x || (xm == x && mk < k)) ? 1 : 0; }
+          }
+        } else if (mover && newLane != 0xff) {
+          // members of the destination lane with a smaller (x, slot) key: binary search in its (ordered) old vector
+          const int lo = laneStart[newLane], cntL = laneStart[newLane + 1] - lo;
+          int first = 0, len = cntL;
+          while (len > 0) {
+            const int half = len >> 1, mid = first + half;
+            const int j = s.vec[lo + mid];
+            const double xj = s.x[j];
+            if (xj < x || (xj == x && j < k)) { first = mid + 1; len = len - half - 1; }
+            else len = half;
+          }
+          rank = first;
+          for (int q = 0; q < nm; ++q) {
+            const int rec = s.tasks[q];
+            const int mk = rec & 0xff, mpos = rec >> 8 & 0xff, mold = rec >> 16 & 0xff, mnew = rec >> 24 & 0xff;
+            if (mold == newLane && mpos < lo + first) rank--;
+            if (mnew == newLane && mk != k) { const double xm = s.x[mk]; rank += (xm < x || (xm == x && mk < k)) ? 1 : 0; }
+          }
+        }
+        if (newLane != 0xff && (mover || !inVec)) atomicAdd(&s.scan[newLane], 1);      // arrivals
+        if (mover && inVec) atomicSub(&s.scan[oldL], 1);                               // leavers
       }
       __syncthreads();
       if (k == 0) {
         int run = 0;
+        for (int j = 0; j < sc.n_lanes; ++j) {
+          const int c = anyInv ? s.scan[j] : (laneStart[j + 1] - laneStart[j]) + s.scan[j];
+          s.scan[j] = c;
+        }
         for (int j = 0; j < sc.n_lanes; ++j) { laneStart[j] = run; run += s.scan[j]; }
         laneStart[sc.n_lanes] = run;
       }
       __syncthreads();
-      if (myLane != 0xff) s.vec[laneStart[myLane] + rank] = (uint8_t)k;
+      if (newLane != 0xff) { myPos = laneStart[newLane] + rank; s.vec[myPos] = (uint8_t)k; }
+      oldLane = newLane == 0xff ? -1 : newLane;
     }
     // ================= termination (0x10edd0-0x10ee10) =================
     if (isEgo) s.flags[0] = reached ? 1 : 0;
