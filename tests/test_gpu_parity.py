@@ -1,0 +1,182 @@
+"""Parity tests proper: the CUDA rollout path, called through the C ABI (libmcsim_b200.so), against
+  (1) the oracle on the same seeded inputs,
+  (2) the committed golden vectors the reference binary produced,
+  (3) size-independent properties at BASELINE.json's full sizes.
+Everything is bit-exact (==): statuses, draw counts, per-step trajectories, reduced features."""
+import ctypes as C
+import random
+
+import pytest
+
+import golden_io
+from interactive_highway_simulation_b200 import _abi as abi
+from scenes import ACTIONS, STATUS_KEYS, lane_change_cases, probe_scene, same
+
+pytestmark = pytest.mark.gpu
+
+ROLLOUT_CASES = golden_io.load_all("rollouts")
+
+
+@pytest.fixture(scope="module")
+def gpu(backend_lib):
+    assert backend_lib.lib().mcs_device_count() > 0, "no CUDA device: the rollout path has no CPU fallback"
+    return backend_lib
+
+
+def status_dict(g):
+    return dict(ok=g.ok, finish=g.finish, fallBack=g.fallBack, finishStep=g.finishStep, utility=g.utility, comfort=g.comfort,
+                utilityObjects=g.utilityObjects, comfortObjects=g.comfortObjects, draws=g.draws, executedSteps=g.executedSteps)
+
+
+def check_against_oracle(gpu, oracle, s, ego, dt, steps, min_steps, seed, count, tag, traj_rollouts=2, gap=-2, actions=ACTIONS):
+    ds = gpu.DeviceScene(s.c_corridors(), s.c_agents())
+    try:
+        for act in actions:
+            cand = (abi.Candidate * 1)(abi.Candidate(ego, abi.ACTIONS[act], gap, 0))
+            sp = abi.SimParam(dt, steps, min_steps)
+            st = ds.rollouts_range(cand, sp, seed, 0, count)
+            o, _ = oracle.rollouts(s, ego, act, gap, dt, steps, min_steps, seed, 0, count, hist=True)
+            for i in range(count):
+                g = status_dict(st[i])
+                if g["ok"] == 0 and o[i]["ok"] == 0:
+                    continue
+                for k in STATUS_KEYS + ("executedSteps",):
+                    assert same(g[k], o[i][k]), (tag, act, "rollout", i, k, g[k], o[i][k])
+            for r in range(min(traj_rollouts, count)):
+                if st[r].ok == 0:
+                    continue
+                buf, ns, _ = ds.trajectories(cand[0], sp, seed, r)
+                for ai, a in enumerate(s.agents):
+                    ho = o[r]["hist"][a["id"]]
+                    assert ns == len(ho)
+                    for t in range(ns):
+                        base = (ai * (steps + 1) + t) * 4
+                        assert tuple(buf[base:base + 4]) == ho[t], (tag, act, "rollout", r, "agent", a["id"], "t", t)
+    finally:
+        ds.close()
+
+
+def test_probe_scene_against_oracle(gpu, oracle):
+    check_against_oracle(gpu, oracle, probe_scene(), 0, 0.3, 40, 30, 7, 32, "probe")
+
+
+@pytest.mark.parametrize("case", lane_change_cases(10), ids=lambda c: c[0])
+def test_random_lane_change_scenes_against_oracle(gpu, oracle, case):
+    tag, s, ego, dt, steps, min_steps, seed = case
+    check_against_oracle(gpu, oracle, s, ego, dt, steps, min_steps, seed, 12, tag)
+
+
+@pytest.mark.parametrize("case", ROLLOUT_CASES, ids=golden_io.ids(ROLLOUT_CASES))
+def test_against_reference_golden_vectors(gpu, case):
+    """The CUDA path against what the reference's machine code returned (no oracle in between)."""
+    s = golden_io.scene_of(case)
+    ds = gpu.DeviceScene(s.c_corridors(), s.c_agents())
+    try:
+        cand = (abi.Candidate * 1)(abi.Candidate(case["ego"], abi.ACTIONS[case["action"]], case["gap"], 0))
+        sp = abi.SimParam(case["dt"], case["steps"], case["min_steps"])
+        st = ds.rollouts_range(cand, sp, case["seed"], case["first"], case["count"])
+        for i, r in enumerate(case["rollouts"]):
+            g = status_dict(st[i])
+            if g["ok"] == 0 and r["ok"] == 0:
+                continue
+            for k in STATUS_KEYS:
+                assert same(g[k], r[k]), (case["tag"], "rollout", i, k, g[k], r[k])
+            if "hist" in r:
+                buf, ns, _ = ds.trajectories(cand[0], sp, case["seed"], case["first"] + i)
+                for ai, a in enumerate(s.agents):
+                    hr = r["hist"][str(a["id"])]
+                    assert ns == len(hr)
+                    for t in range(ns):
+                        base = (ai * (case["steps"] + 1) + t) * 4
+                        assert tuple(buf[base:base + 4]) == tuple(hr[t]), (case["tag"], i, a["id"], t)
+    finally:
+        ds.close()
+
+
+def test_features_two_level_mean(gpu, oracle):
+    """simulationMultiThread semantics: 8 groups x n rollouts, mean of per-group means in fixed order; batched over
+    candidates in one launch, and identical to the sharded path (mcs_rollouts_range + mcs_reduce_features)."""
+    s = probe_scene()
+    ds = gpu.DeviceScene(s.c_corridors(), s.c_agents())
+    try:
+        cands = (abi.Candidate * 5)(*[abi.Candidate(0, abi.ACTIONS[a], -2, 0) for a in ACTIONS])
+        sp = abi.SimParam(0.3, 40, 30)
+        n = 20
+        feats, st = ds.rollouts(cands, sp, n, 77, want_status=True)
+        for c, act in enumerate(ACTIONS):
+            o, ost = oracle.rollouts(s, 0, act, -2, 0.3, 40, 30, 77 + c, 0, 8 * n)
+            want = oracle.reduce(ost, 8, n, 40)
+            for f, _ in abi.Feature._fields_:
+                assert same(getattr(feats[c], f), getattr(want, f)), (act, f)
+        # sharded: two halves of the rollout range, gathered, reduced on the host
+        half = 4 * n
+        a = ds.rollouts_range(cands, sp, 77, 0, half)
+        b = ds.rollouts_range(cands, sp, 77, half, half)
+        allst = (abi.Status * (5 * 8 * n))()
+        for c in range(5):
+            for i in range(half):
+                allst[c * 8 * n + i] = a[c * half + i]
+                allst[c * 8 * n + half + i] = b[c * half + i]
+        red = gpu.reduce_features(allst, 5, 8, n, 40)
+        for c in range(5):
+            for f, _ in abi.Feature._fields_:
+                assert same(getattr(red[c], f), getattr(feats[c], f)), (c, f)
+    finally:
+        ds.close()
+
+
+def test_invalid_candidates_yield_zero_sims(gpu):
+    """Unknown ego id / command without a neighbour lane: the reference returns fromNSims = 0 (so:0xc2b80)."""
+    s = probe_scene()
+    ds = gpu.DeviceScene(s.c_corridors(), s.c_agents())
+    try:
+        cands = (abi.Candidate * 3)(abi.Candidate(999, abi.ACTIONS["keep_lane"], -2, 0),
+                                    abi.Candidate(5, abi.ACTIONS["left"], -2, 0),      # agent 5 drives in the leftmost lane
+                                    abi.Candidate(0, abi.ACT_INVALID, -2, 0))
+        feats, _ = ds.rollouts(cands, abi.SimParam(0.3, 40, 30), 2, 1)
+        assert [f.fromNSims for f in feats] == [0, 0, 0]
+    finally:
+        ds.close()
+
+
+def test_capacity_and_argument_errors(gpu):
+    s = probe_scene()
+    cs, as_ = s.c_corridors(), s.c_agents()
+    h = C.c_void_p()
+    assert gpu.lib().mcs_scene_create(cs, len(cs), as_, 0, 0, C.byref(h)) == abi.MCS_ERR_ARG          # empty agent list
+    big = (abi.Agent * (abi.MCS_MAX_AGENTS + 1))()
+    for i, a in enumerate(big):
+        a.id = i
+    assert gpu.lib().mcs_scene_create(cs, len(cs), big, len(big), 0, C.byref(h)) == abi.MCS_ERR_CAPACITY
+    assert gpu.lib().mcs_scene_create(cs, len(cs), as_, len(as_), 99, C.byref(h)) == abi.MCS_ERR_CUDA  # no such device
+
+
+def test_full_size_properties(gpu, oracle):
+    """BASELINE.json configs[4] shape (256 vehicles x 100 steps): determinism, shard-independence, draw accounting and
+    a spot check of a few rollouts against the oracle."""
+    from interactive_highway_simulation_b200 import synthetic
+    corridors, agents, ego = synthetic.lane_change_scene(256, 4, seed=0)
+    ds = gpu.DeviceScene(corridors, agents)
+    try:
+        cand = (abi.Candidate * 1)(abi.Candidate(ego, abi.ACTIONS["keep_lane"], -2, 0))
+        sp = abi.SimParam(0.3, 100, 100)
+        R = 2048
+        a = ds.rollouts_range(cand, sp, 2026, 0, R)
+        b = ds.rollouts_range(cand, sp, 2026, 0, R)
+        assert bytes(a) == bytes(b)                                      # idempotent / deterministic
+        c = ds.rollouts_range(cand, sp, 2026, R - 64, 128)              # a shard that straddles the first batch
+        for i in range(64):
+            assert bytes(a[R - 64 + i]) == bytes(c[i])                   # a rollout depends only on (seed, index)
+        for i in range(R):
+            assert a[i].ok == 1 and a[i].executedSteps == 100 and a[i].finish == 1
+            assert 256 + 255 * 100 <= a[i].draws <= 256 + 2 * 255 * 100   # ctor flags + noise (+ MOBIL) draws
+        ms, vsteps = ds.rollouts_device(cand, sp, 2026, 0, R)
+        assert vsteps == R * 256 * 100                                   # checksum of executed vehicle-steps
+        ost = (abi.Status * 3)()
+        rc = oracle.lib.orc_rollouts(corridors, len(corridors), agents, len(agents), C.byref(cand[0]), C.byref(sp), 2026,
+                                     1000, 3, ost, None, None)
+        assert rc == 0
+        for i in range(3):
+            assert bytes(a[1000 + i])[:48] == bytes(ost[i])[:48], i
+    finally:
+        ds.close()
