@@ -673,8 +673,302 @@ Action customized_lane_change(Env& e, int idx, int cmd) {
   return {axT, vy};
 }
 
-Action customized_merging(Env& e, int idx, int cmd, int gapId);     // defined below
-Action merging_closest_gap(Env& e, int idx, int direction);         // defined below
+// ---------------------------------------------------------------------------------------------
+// merging / exit: gap selection and gap execution
+
+// idmAccFrontBack(IdmParam, vector<IdmMatch> fronts, IdmMatch back, v, vd)  so:0xeb8d0-0xebbfd
+// (differs from the Agent overload above: accMin where that one uses -accMax)
+struct Match { int id; double dis, v; };
+double idm_acc_match(const Idm& p, const Match* fronts, int nf, const Match& back, double v, double vd) {
+  double freeAcc = (1.0 - POW4(v / vd)) * p.accMax;
+  bool any = false;
+  double d = 0.0;
+  for (int k = 0; k < nf; ++k) {
+    const Match& m = fronts[k];
+    if (m.id < 0) continue;
+    double term;
+    if (m.dis > 0.0) {
+      double dv = (v - m.v) * v;
+      double dDes = (v * p.thw + p.minDis) * 0.7;
+      double s = std::sqrt(p.accMin * p.accCom);
+      double t = MAXSD(dv / (s + s) + dDes, 0.0);
+      t = t / m.dis;
+      term = (t * t) * p.accMin;
+    } else {
+      term = -10000000000.0;
+    }
+    if (!any) { d = term; any = true; }
+    else d = MINSD(term, d);
+  }
+  double sum = any ? d + 0.0 : 0.0;
+  if (back.id >= 0) {
+    if (0.0 > back.dis) {
+      double dDes = (back.v * p.thw + p.minDis) * 0.7;
+      double dv = (back.v - v) * v;
+      double s = std::sqrt(p.accMin * p.accCom);
+      double t = MAXSD(dv / (s + s) + dDes, 0.0);
+      t = t / back.dis;
+      sum = sum + (t * t) * p.accMax;
+    } else {
+      sum = sum + 10000000000.0;
+    }
+  }
+  double r = MINSD(sum + freeAcc, p.accMax);
+  return MAXSD(p.accMin, r);
+}
+
+struct Opt { bool has; double v; };
+
+// rssSafeRelax(optional gapFF, vFF, gapF, vF, gapB, vB, egoV, vd, RSSParam, IdmParam)  so:0xb9210-0xb95e4
+// two look-ahead iterations of one second each: RSS-style checks with estimated (not worst-case) decelerations,
+// then the ego is advanced with the IdmMatch IDM and the gaps are updated.
+bool rss_safe_relax(Opt g1, Opt v1o, Opt g3, Opt v3o, Opt g5, Opt v5o, double egoV, double vd, const Rss& r, const Idm& idm) {
+  Match back{-1, 0.0, 0.0};
+  double v = egoV;
+  if (g5.has) back = Match{1, g5.v, v5o.v};
+  int id3 = -1, id1 = -1;
+  double gap3 = 0.0, v3 = 0.0, gap1 = 0.0, v1 = 0.0;
+  if (g3.has) { gap3 = g3.v; v3 = v3o.v; id3 = 1; }
+  if (g1.has) { gap1 = g1.v; v1 = v1o.v; id1 = 1; }
+  for (int it = 2;; it = 1) {
+    const double aMaxHalf = r.aMax * 0.5;
+    double a3 = aMaxHalf;                                  // so:0xb92fc-0xb934f: deceleration the front vehicle needs behind its own leader
+    if (id1 == 1) {
+      double num = (-0.5 * v3) * v3;
+      double den = (v1 * v1) / (r.aMax * -2.0);
+      den = den + (gap1 - gap3);
+      den = den - v3 * r.rTOther;
+      den = MAXSD(den, 0.01);
+      a3 = num / den;
+      a3 = MAXSD(r.aMax, a3);
+      a3 = MINSD(aMaxHalf, a3);
+    }
+    double aEgo = aMaxHalf;
+    if (id3 != -1) {                                       // so:0xb9358-0xb93ce
+      double q = (v3 * v3) / (a3 + a3);
+      double vr = v * r.rTEgo;
+      double d = (v * v) / (-2.0 * r.aMin);
+      d = d + vr;
+      d = d + q;
+      d = MAXSD(0.0, d);
+      double num = (v * -0.5) * v;
+      double den = (v3 * v3) / (r.aMax * -2.0);
+      den = den + gap3;
+      den = den - vr;
+      den = MAXSD(den, 0.01);
+      double ae = num / den;
+      ae = MAXSD(r.aMax, ae);
+      aEgo = MINSD(aMaxHalf, ae);
+      if (d > gap3) return false;
+    }
+    if (back.id >= 0) {                                    // so:0xb93d8-0xb9425
+      double q = (v * v) / (aEgo + aEgo);
+      double d = (back.v * back.v) / (-2.0 * r.aMin);
+      d = d + back.v * r.rTOther;
+      d = d + q;
+      d = MAXSD(0.0, d);
+      if (d > -back.dis) return false;
+    }
+    Match fm{id3, gap3, v3};                               // so:0xb942b-0xb94a6
+    double acc = idm_acc_match(idm, &fm, 1, back, v, vd);
+    double s = acc * 0.5 + v;
+    v = MAXSD(0.0, v + acc);
+    s = MAXSD(s, 0.0);
+    if (id1 != -1) gap1 = (v1 + gap1) - s;
+    if (id3 != -1) gap3 = (v3 + gap3) - s;
+    if (back.id >= 0) {                                    // so:0xb952c-0xb955b
+      double nb = ((back.v + back.dis) - r.dSoft * 0.5) - s;
+      back.dis = nb;
+      back.v = MAXSD(back.v - r.dSoft, 0.0);
+    }
+    if (it == 1) return true;
+  }
+}
+
+// timeToReachGap(xBack, vBack, xFront, vFront, xEgo, vEgo, vTarget)  so:0xe1630-0xe19dc
+double time_to_reach_gap(double xB, double vB, double xF, double vF, double xE, double vE, double vT) {
+  const double a = (vT - vE) / 5.0;
+  if (xB > xE) {                                           // gap ahead: catch up with acceleration clamp(a, 0.5, 2)
+    const double acc = (a > 2.0) ? 2.0 : MAXSD(0.5, a);
+    const double dv = vB - vE;
+    const double dx = xB - xE;
+    const double inv = 1.0 / acc;
+    const double disc = dx * (acc + acc) + dv * dv;
+    const double sq = std::sqrt(disc);
+    const double r1 = (dv + sq) * inv;
+    const double r2 = (dv - sq) * inv;
+    return MAXSD(r1, r2);
+  }
+  if (xE > xF) {                                           // gap behind: fall back with 2 m/s^2
+    const double m = vE - vF;
+    const double dv = vF - vE;
+    const double disc = dv * dv - (xF - xE) * 4.0;
+    const double sq = std::sqrt(disc);
+    const double r1 = (m + sq) * 0.5;
+    const double r2 = (m - sq) * 0.5;
+    return MAXSD(r1, r2);
+  }
+  // alongside the gap: time to reach half the speed of the closer gap vehicle (sic)
+  const double X = (std::fabs(vB - vE) < std::fabs(vF - vE)) ? vB : vF;
+  double acc = a;
+  if (a > 2.0) acc = 2.0;
+  else if (0.5 > a) acc = 0.5;
+  const double h = X * 0.5;
+  if (vE > h) return 0.0;
+  const double t = h - vE;
+  return (t + t) / acc;
+}
+
+// common tail of customizedMergingBehavior (so:0xf7227-0xf72e8, 0xf7610) and mergingBehaviorClosestGap
+// (so:0xff0df-0xff10e, 0xff5a8, 0xff5e0): drift towards the target lane while the vehicle's edge is more than 0.5 m
+// inside its own lane; past that point only when the gap is safe and the target lane has started, otherwise back off.
+Action merge_tail(const Agent& a, double sign, bool far, bool lateral, double targetStartX, double ax) {
+  const double m = a.v * 0.17;
+  const bool toward = far || (lateral && a.x >= targetStartX);
+  double vy;
+  if (toward) vy = (m > 1.0) ? sign : m * sign;
+  else vy = ((m > 1.0) ? -1.0 : -m) * sign;
+  return {ax, vy};
+}
+
+bool far_from_boundary(const Agent& a, const Corr& c, bool left) {
+  if (left) return -0.5 > (a.w * 0.5 + a.y) - c.leftY;     // so:0xf727c-0xf7294 / 0xfe956-0xfe97a
+  return (a.y - a.w * 0.5) - c.rightY > 0.5;               // so:0xf7640-0xf7654 / 0xff267-0xff283
+}
+
+// Neighbor::left() so:0xeae70 / right(): the side's [BB, B, F, FF] without the nulls
+int side_vector(Env& e, int idx, int laneId, int out[4]) {
+  int nb[4], n = 0;
+  side_neighbors(e, idx, laneId, nb);
+  for (int k = 0; k < 4; ++k) if (nb[k] >= 0) out[n++] = nb[k];
+  return n;
+}
+
+Opt front_gap(const Env& e, const Agent& a, int j) {   // (o.x - a.x) - (a.l + o.l)/2
+  if (j < 0) return Opt{false, 0.0};
+  const Agent& o = e.agents[j];
+  return Opt{true, (o.x - a.x) - (o.l + a.l) * 0.5};
+}
+Opt back_gap(const Env& e, const Agent& a, int j) {    // (a.l + o.l)/2 + (o.x - a.x)
+  if (j < 0) return Opt{false, 0.0};
+  const Agent& o = e.agents[j];
+  return Opt{true, (o.l + a.l) * 0.5 + (o.x - a.x)};
+}
+Opt speed_of(const Env& e, int j) { return j < 0 ? Opt{false, 0.0} : Opt{true, e.agents[j].v}; }
+
+// shared by both: RSS emergency towards the own leader, room left on the own lane, choice of ax  so:0xf7155-0xf7224 / 0xff02e-0xff0df
+Action merge_finish(Env& e, Agent& a, const Corr& c, const Corr& tc, int front, bool left, bool safe, double axGap) {
+  double brake = (a.v * a.v) / (a.rss.aMin * -2.0) + a.v * a.rss.rTEgo;
+  bool restrict_ = false;
+  if (front >= 0) {
+    const Agent& f = e.agents[front];
+    double gap = (f.x - a.x) - (f.l + a.l) * 0.5;
+    double d = (f.v * f.v) / (a.rss.aMax + a.rss.aMax) + brake;
+    d = MAXSD(0.0, d);
+    if (d > gap) restrict_ = true;
+  }
+  if (!restrict_) {
+    bool room = (c.centerX2 - a.x) - 15.0 >= brake;
+    if (!room && !safe) restrict_ = true;
+  }
+  const double ax = restrict_ ? a.rss.aMin : axGap;
+  const bool lateral = restrict_ ? false : safe;
+  return merge_tail(a, left ? 1.0 : -1.0, far_from_boundary(a, c, left), lateral, tc.centerX1, ax);
+}
+
+// customizedMergingBehavior(env, ego, direction, gapId)  so:0xf6ba0-0xf7788
+Action customized_merging(Env& e, int idx, int cmd, int gapId) {
+  Agent& a = e.agents[idx];
+  if (a.lanes.empty()) return {0.0, 0.0};                             // so:0xf73e0 "is not matched!"
+  Corr* cp = e.corrById(a.lane());
+  if (!cp) return {0.0, 0.0};
+  const Corr c = *cp;
+  int front = front_agent(e, idx);
+  push_thw_ratio(a, e, front);
+  const bool left = cmd == MCS_ACT_LEFT;                              // anything but "left" is "right" (so:0xf6cbe)
+  if (!(left ? c.hasLeft : c.hasRight)) { e.error = true; return {0.0, 0.0}; }   // binary prints, then reads a missing corridor
+  const int side = left ? c.leftId : c.rightId;
+  int g = -1, gf = -1, gff = -1;
+  auto git = (gapId == -1) ? e.agentIdx.end() : e.agentIdx.find(gapId);
+  if (git != e.agentIdx.end()) {                                      // so:0xf6d46-0xf6e59
+    g = git->second;
+    gf = front_agent(e, g);
+    if (gf >= 0) gff = front_agent(e, gf);
+  } else {                                                            // -1 or unknown id: "go to last gap" so:0xf7488-0xf754f, 0xf7660
+    int v[4];
+    int n = side_vector(e, idx, side, v);
+    if (n >= 1) gf = v[0];
+    if (n >= 2) gff = v[1];
+  }
+  if (e.error) return {0.0, 0.0};
+  const double vdCap = MINSD(a.vd, 1.1 * c.vLimit);
+  bool safe = rss_safe_relax(front_gap(e, a, gff), speed_of(e, gff), front_gap(e, a, gf), speed_of(e, gf),
+                             back_gap(e, a, g), speed_of(e, g), a.v, vdCap, a.rss, a.idm);
+  Corr* tcp = e.corrById(side);
+  if (!tcp) return {0.0, 0.0};
+  const Corr tc = *tcp;
+  int f3[3] = {gf, gff, front};                                       // so:0xf707a-0xf70d9
+  double axGap = idm_acc(e, a.idm, f3, 3, g, a.x, a.v, a.l, vdCap);
+  return merge_finish(e, a, c, tc, front, left, safe, axGap);
+}
+
+// mergingBehaviorClosestGap(env, agent, direction)  so:0xfe660-0xff6cf
+Action merging_closest_gap(Env& e, int idx, int direction) {
+  Agent& a = e.agents[idx];
+  if (a.lanes.empty()) return {0.0, 0.0};
+  Corr* cp = e.corrById(a.lane());
+  if (!cp) return {0.0, 0.0};
+  const Corr c = *cp;
+  int front = front_agent(e, idx);
+  push_thw_ratio(a, e, front);
+  double vd = a.vd;
+  if (a.isEgo) vd = MINSD(vd, 1.1 * c.vLimit);                        // so:0xfe757-0xfe77e
+  double axFront = idm_acc(e, a.idm, &front, 1, -1, a.x, a.v, a.l, vd);
+  const bool left = direction == MCS_ACT_LEFT;
+  if (!(left ? c.hasLeft : c.hasRight)) { e.error = true; return {0.0, 0.0}; }
+  const int side = left ? c.leftId : c.rightId;
+  Corr* tcp = e.corrById(side);
+  if (!tcp) return {0.0, 0.0};
+  const Corr tc = *tcp;
+  const bool far = far_from_boundary(a, c, left);
+  int v[4];
+  const int n = side_vector(e, idx, side, v);
+  if (e.error) return {0.0, 0.0};
+  if (n == 0) {                                                       // so:0xff2bf-0xff2f6, 0xff540
+    if (a.x >= tc.centerX1 || far) return merge_tail(a, left ? 1.0 : -1.0, true, false, 0.0, axFront);
+    return {axFront, 0.0};
+  }
+  double cost[5];                                                     // std::map<int,double>: gap k lies behind v[k]
+  {
+    const Agent& first = e.agents[v[0]];
+    const Agent& last = e.agents[v[n - 1]];
+    cost[0] = time_to_reach_gap(-10000000000.0, 0.0, first.x - (first.l + a.l) * 0.5, first.v, a.x, a.v, vd);
+    cost[n] = time_to_reach_gap((last.l + a.l) * 0.5 + last.x, last.v, 10000000000.0, 100.0, a.x, a.v, vd);
+    for (int i = 0; i + 1 < n; ++i) {
+      const Agent& B = e.agents[v[i]];
+      const Agent& F = e.agents[v[i + 1]];
+      cost[i + 1] = time_to_reach_gap((a.l + B.l) * 0.5 + B.x, B.v, F.x - (a.l + F.l) * 0.5, F.v, a.x, a.v, vd);
+    }
+  }
+  int k = 0;
+  for (int j = 1; j <= n; ++j) if (cost[k] > cost[j]) k = j;          // so:0xfed88-0xfedaf
+  int gf = -1, gff = -1, g = -1;
+  double axGap;
+  if (k == 0) {                                                       // so:0xff370-0xff4c8
+    gf = v[0]; if (n >= 2) gff = v[1];
+    axGap = idm_acc(e, a.idm, &gf, 1, -1, a.x, a.v, a.l, vd);
+  } else if (k == n) {                                                // so:0xff610-0xff69c
+    g = v[n - 1];
+    axGap = idm_acc(e, a.idm, nullptr, 0, g, a.x, a.v, a.l, vd);
+  } else {                                                            // so:0xfee31-0xfefd4
+    gf = v[k]; g = v[k - 1]; if (k + 1 < n) gff = v[k + 1];
+    axGap = idm_acc(e, a.idm, &gf, 1, g, a.x, a.v, a.l, vd);
+  }
+  bool safe = rss_safe_relax(front_gap(e, a, gff), speed_of(e, gff), front_gap(e, a, gf), speed_of(e, gf),
+                             back_gap(e, a, g), speed_of(e, g), a.v, vd, a.rss, a.idm);
+  return merge_finish(e, a, c, tc, front, left, safe, axGap);
+}
+
 
 // Simulation::run  so:0x10e790-0x10f8ed
 bool run_rollout(Env& e, const mcs_sim_param& sp, mcs_status& st) {
@@ -798,8 +1092,6 @@ bool run_rollout(Env& e, const mcs_sim_param& sp, mcs_status& st) {
   return true;
 }
 
-Action customized_merging(Env& e, int, int, int) { e.error = true; return {0.0, 0.0}; }
-Action merging_closest_gap(Env& e, int, int) { e.error = true; return {0.0, 0.0}; }
 
 int one_rollout(const mcs_corridor* cs, int nc, const mcs_agent* as, int na, const mcs_candidate& cand,
                 const mcs_sim_param& sp, uint64_t key, mcs_status& st, double* states, int32_t* nStates) {
@@ -951,5 +1243,7 @@ int orc_decide_closest_gap(const mcs_corridor* cs, int nc, const mcs_agent* as, 
   out->ax = a.ax; out->vy = a.vy;
   return MCS_OK;
 }
+
+double orc_time_to_reach_gap(const double* p) { return time_to_reach_gap(p[0], p[1], p[2], p[3], p[4], p[5], p[6]); }
 
 }  // extern "C"

@@ -52,6 +52,9 @@ int orc_decide_fixed_gap(const mcs_corridor* corridors, int n_corridors, const m
 int orc_decide_closest_gap(const mcs_corridor* corridors, int n_corridors, const mcs_agent* agents, int n_agents,
                            int32_t agent_id, int32_t direction, uint64_t key, mcs_action* out);
 
+/* timeToReachGap(xBack, vBack, xFront, vFront, xEgo, vEgo, vTarget), p = the 7 arguments */
+double orc_time_to_reach_gap(const double* p);
+
 #ifdef __cplusplus
 }
 #endif

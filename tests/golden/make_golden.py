@@ -70,6 +70,49 @@ def decision_cases(tag, s, ids, key=99):
     return {"tag": tag, "kind": "decisions", "scene": scene_dict(s), "key": key, "calls": out}
 
 
+def merging_decision_cases(tag, s, d, gaps, key=5):
+    """fixedGapMergingBehavior / closestGapMergingBehavior for every vehicle that has a lane on that side."""
+    ref = RefHarness()
+    ref.load(s, 0.3, 40, 10)
+    out = []
+    for a in s.agents:
+        if not scenes.has_side_lane(s, a, d):
+            continue
+        for gap in [-2] + list(gaps):
+            cmd = "fixed_gap %d %s %d" % (a["id"], d, gap)
+            out.append({"cmd": cmd, "answer": ref.decide(key, cmd)})
+        cmd = "closest_gap %d %s" % (a["id"], d)
+        out.append({"cmd": cmd, "answer": ref.decide(key, cmd)})
+    ref.close()
+    return {"tag": tag, "kind": "decisions", "scene": scene_dict(s), "key": key, "calls": out}
+
+
+def ttrg_case():
+    """timeToReachGap on a fixed list of argument tuples (regimes: gap ahead / behind / alongside, and boundaries)."""
+    rng = random.Random(77)
+    ref = RefHarness()
+    rows = []
+    for i in range(300):
+        xE, vE = rng.uniform(0, 300), rng.uniform(0, 35)
+        m = i % 3
+        if m == 0:
+            xB = xE + rng.uniform(-5, 100); xF = xB + rng.uniform(0, 60)
+        elif m == 1:
+            xF = xE - rng.uniform(-5, 100); xB = xF - rng.uniform(0, 60)
+        else:
+            xB = xE - rng.uniform(0, 30); xF = xE + rng.uniform(0, 30)
+        if i % 17 == 0: xB = xE
+        if i % 19 == 0: xF = xE
+        vB, vF, vT = rng.uniform(0, 35), rng.uniform(0, 35), rng.uniform(5, 40)
+        if i % 11 == 0: xB, vB = -1e10, 0.0
+        if i % 13 == 0: xF, vF = 1e10, 100.0
+        p = [xB, vB, xF, vF, xE, vE, vT]
+        line, _ = ref.raw("ttrg " + " ".join(repr(x) for x in p))
+        rows.append({"args": p, "result": line.split()[1]})
+    ref.close()
+    return {"tag": "time_to_reach_gap", "kind": "ttrg", "rows": rows}
+
+
 def known_answer_libc():
     """probe scene, glibc srand(1) before agent construction and before each action, runMTimes M=20,
     platform libm — the reference's stock configuration."""
@@ -94,7 +137,13 @@ def main():
     for tag, s, ego, dt, steps, min_steps, seed in scenes.lane_change_cases(6, sizes=(5, 9, 14, 20, 31, 33)):
         cases.append(order_case(tag + "_order", s))
         for act in scenes.ACTIONS:
-            cases.append(rollout_case("%s_%s" % (tag, act), s, ego, act, -2, dt, steps, min_steps, seed, 0, 4, n_hist=1))
+            cases.append(rollout_case("%s_%s" % (tag, act), s, ego, act, -2, dt, steps, min_steps, seed, 0, 4,
+                                      n_hist=1 if act in ("keep_lane", "left") else 0))
+    for tag, s, ego, d, gaps, seed in scenes.merge_exit_cases(8, sizes=(4, 7, 12, 20)):
+        for gi, gap in enumerate(gaps):
+            cases.append(rollout_case("%s_gap%d" % (tag, gi), s, ego, d, gap, 0.3, 40, 10, seed, 0, 4, n_hist=1 if gi == 0 else 0))
+        cases.append(merging_decision_cases(tag + "_decisions", s, d, gaps))
+    cases.append(ttrg_case())
     cases.append(known_answer_libc())
     extra = os.path.join(HERE, "extra_cases.py")
     if os.path.exists(extra):

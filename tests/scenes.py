@@ -25,9 +25,11 @@ def probe_scene():
 
 
 def random_scene(rng, n_lanes=3, n_agents=12, trucks=0.3, lane_w=3.5, lane_types=None, ids_shuffled=True,
-                 ego_behavior="idm", others=("idm_lc", "idm_lc", "idm_lc", "idm"), ego_lane=None):
+                 ego_behavior="idm", others=("idm_lc", "idm_lc", "idm_lc", "idm"), ego_lane=None, spacing=(3, 60)):
     """Random straight-lane scene.  lane_types: list of corridor types bottom (right-most) to top, default all main.
-    Vehicles on a `merging` lane get behaviour `merging`, vehicles that should leave via an `exit` lane `exit`."""
+    Vehicles on a `merging` lane get behaviour `merging`.  Only the ego may have behaviour `exit`: for any other
+    vehicle the reference pushes no action and then reads past its action vector (so:0x10ed15), and mcs_wrapper.py
+    never builds such a scene."""
     s = SceneSpec()
     lane_types = lane_types or ["main"] * n_lanes
     n_lanes = len(lane_types)
@@ -47,7 +49,7 @@ def random_scene(rng, n_lanes=3, n_agents=12, trucks=0.3, lane_w=3.5, lane_types
             k = rng.choice([j for j in range(n_lanes) if lane_types[j] == "main"])
         truck = rng.random() < trucks
         l = rng.uniform(8, 14) if truck else rng.uniform(4, 5.5)
-        x = per_lane_x[k] + l + rng.uniform(3, 60)
+        x = per_lane_x[k] + l + rng.uniform(*spacing)
         per_lane_x[k] = x
         v = rng.uniform(12, 34)
         idm = (rng.uniform(0.8, 2.0), rng.uniform(1.5, 3), rng.uniform(-4, -2), rng.uniform(-2.5, -1.5), -8.0,
@@ -59,8 +61,6 @@ def random_scene(rng, n_lanes=3, n_agents=12, trucks=0.3, lane_w=3.5, lane_types
             beh = ego_behavior
         elif lane_types[k] == "merging":
             beh = "merging"
-        elif "exit" in lane_types and lane_types[k] == "main" and rng.random() < 0.3:
-            beh = "exit"
         else:
             beh = rng.choice(others)
         s.add_agent(ids[i], x, (k + 0.5) * lane_w + rng.gauss(0, 0.25), v, v + rng.uniform(-3, 6), beh,
@@ -86,3 +86,33 @@ STATUS_KEYS = ("ok", "finish", "fallBack", "finishStep", "utility", "comfort", "
 
 def same(a, b):
     return a == b or (isinstance(a, float) and isinstance(b, float) and a != a and b != b)
+
+
+def merge_exit_cases(n_scenes, seed0=900, sizes=(4, 7, 12, 20, 30)):
+    """(tag, scene, ego, direction, gap ids) — ego `merging` on a merging lane (direction left) or ego `exit` next to an
+    exit lane (direction right); main-lane vehicles beside the merging lane exercise the yielding model, vehicles on
+    the merging lane run mergingBehaviorClosestGap."""
+    out = []
+    for sc in range(n_scenes):
+        rng = random.Random(seed0 + sc)
+        kind = rng.choice(["merge", "exit"])
+        na = rng.choice(list(sizes))
+        spacing = rng.choice([(3, 60), (2, 25), (10, 90)])
+        if kind == "merge":
+            lt = ["merging", "main"] + ["main"] * rng.choice([0, 1, 2])
+            s, ego = random_scene(rng, n_agents=na, lane_types=lt, ego_behavior="merging", ego_lane=0, spacing=spacing)
+            d = "left"
+        else:
+            lt = ["exit", "main"] + ["main"] * rng.choice([0, 1])
+            s, ego = random_scene(rng, n_agents=na, lane_types=lt, ego_behavior="exit", ego_lane=1, spacing=spacing)
+            d = "right"
+        ids = [a["id"] for a in s.agents]
+        gaps = [-1] + rng.sample(ids, min(2, len(ids)))
+        out.append(("%s%d_n%d_L%d" % (kind, sc, na, len(lt)), s, ego, d, gaps, 40 + sc))
+    return out
+
+
+def has_side_lane(scene, agent, direction, lane_w=3.5):
+    k = int(agent["y"] // lane_w)
+    n = len(scene.corridors)
+    return 0 <= k < n and ((direction == "left" and k + 1 < n) or (direction == "right" and k - 1 >= 0))

@@ -59,9 +59,32 @@ def test_single_decisions_match_reference_binary(oracle, case):
             assert (out.ax, out.vy) == (float(ans["ax"]), float(ans["vy"])), call
             assert abi.COMMIT_NAMES[out.commit] == ans["commit"] and out.commit_keep_lane_step == int(ans["keep"])
             assert out.target_lane_id == int(ans["target"])
+        elif t[0] == "fixed_gap":
+            out = abi.Action()
+            rc = oracle.lib.orc_decide_fixed_gap(cs, len(cs), as_, len(as_), int(t[1]), abi.ACTIONS[t[2]], int(t[3]),
+                                                 case["key"], C.byref(out))
+            assert rc == 0
+            assert (out.ax, out.vy) == (float(ans["ax"]), float(ans["vy"])), call
+        elif t[0] == "closest_gap":
+            out = abi.Action()
+            rc = oracle.lib.orc_decide_closest_gap(cs, len(cs), as_, len(as_), int(t[1]), abi.ACTIONS[t[2]], case["key"],
+                                                   C.byref(out))
+            assert rc == 0
+            assert (out.ax, out.vy) == (float(ans["ax"]), float(ans["vy"])), call
         else:
             out = abi.Action()
             rc = oracle.lib.orc_decide_fixed_direction(cs, len(cs), as_, len(as_), int(t[1]), abi.ACTIONS[t[2]], case["key"],
                                                        C.byref(out))
             assert rc == 0
             assert (out.ax, out.vy) == (float(ans["ax"]), float(ans["vy"])), call
+
+
+def test_time_to_reach_gap_matches_reference_binary(oracle):
+    import math
+    oracle.lib.orc_time_to_reach_gap.restype = C.c_double
+    oracle.lib.orc_time_to_reach_gap.argtypes = [C.POINTER(C.c_double)]
+    (case,) = golden_io.load_all("ttrg")
+    for row in case["rows"]:
+        g = oracle.lib.orc_time_to_reach_gap((C.c_double * 7)(*row["args"]))
+        r = float(row["result"])
+        assert g == r or (math.isnan(g) and math.isnan(r)), row
