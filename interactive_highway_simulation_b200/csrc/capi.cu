@@ -140,20 +140,38 @@ int ensure_capacity(mcs_scene* sc, int n_cand, size_t n_status) {
   return MCS_OK;
 }
 
-int stage_candidates(mcs_scene* sc, const mcs_candidate* cands, int n_cand) {
+// resolves every candidate on the host (Environment::setEgoAgentIdAndDrivingBehavior) and decides which kernel
+// instantiation the launch needs; *merge_out = 1 when the merging / yielding code must be compiled in
+int stage_candidates(mcs_scene* sc, const mcs_candidate* cands, int n_cand, int* merge_out) {
+  int merge = sc->host.needs_merge_path ? 1 : 0;
   for (int c = 0; c < n_cand; ++c) {
     mcs::CandHost h = mcs::resolve_candidate(sc->host, cands[c]);
+    if (h.ok && h.gap_id >= 0 && h.gap_slot < 0)
+      return fail(MCS_ERR_SCENE, "gap id names no vehicle of the scene (the reference dereferences a null agent here)");
+    if (h.ok && h.bad_behavior)
+      return fail(MCS_ERR_SCENE, "a non-ego vehicle has a behaviour the reference pushes no action for (only idm, idm_lc, merging)");
+    if (h.gap_slot >= 0) merge = 1;
     mcs::CandDev d{};
     d.ego_slot = h.ego_slot; d.action = h.action; d.gap_id = h.gap_id; d.target_lane_id = h.target_lane_id; d.ok = h.ok;
+    d.gap_slot = h.gap_slot;
     sc->h_cand[c] = d;
   }
   CUDA_TRY(cudaMemcpyAsync(sc->d_cand, sc->h_cand, sizeof(mcs::CandDev) * n_cand, cudaMemcpyHostToDevice, sc->stream));
+  *merge_out = merge;
+  return MCS_OK;
+}
+
+template <bool kTraj, bool kMerge>
+int launch_one(mcs_scene* sc, dim3 grid, dim3 block, size_t smem, const mcs::LaunchParams& lp) {
+  CUDA_TRY(cudaFuncSetAttribute(mcs::rollout_kernel<kTraj, kMerge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mcs::rollout_kernel<kTraj, kMerge><<<grid, block, smem, sc->stream>>>(sc->dev, sc->d_cand, lp);
+  CUDA_TRY(cudaGetLastError());
   return MCS_OK;
 }
 
 // launch the rollout kernel for rollouts [first, first+count) of every candidate; statuses → d_status (device)
 int launch_rollouts(mcs_scene* sc, int n_cand, const mcs_sim_param* sp, uint64_t seed, int64_t first, int64_t count,
-                    mcs_status* d_status, double* d_traj, int32_t* d_traj_n, unsigned long long* d_counter) {
+                    mcs_status* d_status, double* d_traj, int32_t* d_traj_n, unsigned long long* d_counter, int merge) {
   if (sp->steps < 0 || sp->steps > 4096 || !(sp->dt > 0.0)) return fail(MCS_ERR_ARG, "bad SimParameter");
   if (count <= 0 || count > 0x7fffffffLL) return fail(MCS_ERR_ARG, "bad rollout count");
   mcs::LaunchParams lp{};
@@ -162,21 +180,18 @@ int launch_rollouts(mcs_scene* sc, int n_cand, const mcs_sim_param* sp, uint64_t
   lp.status = d_status; lp.traj = d_traj; lp.traj_n = d_traj_n; lp.vehicle_steps = d_counter;
   const size_t smem = rollout_smem_bytes(sc->dev.n_pad, sp->steps);
   dim3 grid((unsigned)count, (unsigned)n_cand), block((unsigned)sc->dev.n_pad);
-  if (d_traj) {
-    CUDA_TRY(cudaFuncSetAttribute(mcs::rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mcs::rollout_kernel<true><<<grid, block, smem, sc->stream>>>(sc->dev, sc->d_cand, lp);
-  } else {
-    CUDA_TRY(cudaFuncSetAttribute(mcs::rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mcs::rollout_kernel<false><<<grid, block, smem, sc->stream>>>(sc->dev, sc->d_cand, lp);
-  }
-  CUDA_TRY(cudaGetLastError());
-  return MCS_OK;
+  if (d_traj) return merge ? launch_one<true, true>(sc, grid, block, smem, lp) : launch_one<true, false>(sc, grid, block, smem, lp);
+  return merge ? launch_one<false, true>(sc, grid, block, smem, lp) : launch_one<false, false>(sc, grid, block, smem, lp);
 }
 
 int check_unsupported(const mcs_status* st, size_t n) {
-  for (size_t i = 0; i < n; ++i)
+  for (size_t i = 0; i < n; ++i) {
     if (st[i].overflow == 2)
-      return fail(MCS_ERR_SCENE, "scene uses a behaviour not implemented on the device path (merging/exit ego or yielding candidates)");
+      return fail(MCS_ERR_SCENE, "the reference's behaviour is undefined for this scene (vehicle without a usable behaviour, or a "
+                                 "merging command without a lane on that side)");
+    if (st[i].overflow == 1)
+      return fail(MCS_ERR_CAPACITY, "a vehicle met more distinct yielding candidates than the device table holds");
+  }
   return MCS_OK;
 }
 
@@ -222,7 +237,7 @@ int mcs_scene_create(const mcs_corridor* corridors, int n_corridors, const mcs_a
   for (int j = 0; j <= h.n_lanes; ++j) d.lane_start[j] = h.lane_start[j];
   for (int j = 0; j < h.n_lanes; ++j) {
     const mcs::LaneHost& L = h.lanes[j];
-    d.lanes[j] = mcs::LaneDev{L.leftY, L.rightY, L.centerY, L.vLimit, L.endX, L.id, L.type, L.leftIdx, L.rightIdx, L.leftmost, 0};
+    d.lanes[j] = mcs::LaneDev{L.leftY, L.rightY, L.centerY, L.vLimit, L.endX, L.startX, L.id, L.type, L.leftIdx, L.rightIdx, L.leftmost, 0};
   }
   if ((e = cudaStreamSynchronize(sc->stream)) != cudaSuccess) return bail("sync", e);
   *out = sc;
@@ -267,8 +282,9 @@ int mcs_rollouts(mcs_scene* sc, const mcs_candidate* cands, int n_cand, const mc
   const size_t n_status = (size_t)n_cand * count;
   int rc = ensure_capacity(sc, n_cand, n_status);
   if (rc != MCS_OK) return rc;
-  if ((rc = stage_candidates(sc, cands, n_cand)) != MCS_OK) return rc;
-  if ((rc = launch_rollouts(sc, n_cand, sp, seed, 0, count, sc->d_status, nullptr, nullptr, nullptr)) != MCS_OK) return rc;
+  int merge = 0;
+  if ((rc = stage_candidates(sc, cands, n_cand, &merge)) != MCS_OK) return rc;
+  if ((rc = launch_rollouts(sc, n_cand, sp, seed, 0, count, sc->d_status, nullptr, nullptr, nullptr, merge)) != MCS_OK) return rc;
   reduce_features_kernel<<<n_cand, 32, 0, sc->stream>>>(sc->d_status, MCS_GROUPS, n_per_group, sp->steps, sc->d_feat);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(sc->h_feat, sc->d_feat, sizeof(mcs_feature) * n_cand, cudaMemcpyDeviceToHost, sc->stream));
@@ -293,8 +309,9 @@ int mcs_rollouts_range(mcs_scene* sc, const mcs_candidate* cands, int n_cand, co
   const size_t n_status = (size_t)n_cand * count;
   int rc = ensure_capacity(sc, n_cand, n_status);
   if (rc != MCS_OK) return rc;
-  if ((rc = stage_candidates(sc, cands, n_cand)) != MCS_OK) return rc;
-  if ((rc = launch_rollouts(sc, n_cand, sp, seed, first, count, sc->d_status, nullptr, nullptr, nullptr)) != MCS_OK) return rc;
+  int merge = 0;
+  if ((rc = stage_candidates(sc, cands, n_cand, &merge)) != MCS_OK) return rc;
+  if ((rc = launch_rollouts(sc, n_cand, sp, seed, first, count, sc->d_status, nullptr, nullptr, nullptr, merge)) != MCS_OK) return rc;
   CUDA_TRY(cudaMemcpyAsync(status_out, sc->d_status, sizeof(mcs_status) * n_status, cudaMemcpyDeviceToHost, sc->stream));
   CUDA_TRY(cudaStreamSynchronize(sc->stream));
   return check_unsupported(status_out, n_status);
@@ -310,11 +327,12 @@ int mcs_rollouts_device(mcs_scene* sc, const mcs_candidate* cands, int n_cand, c
   const size_t n_status = (size_t)n_cand * count;
   int rc = ensure_capacity(sc, n_cand, d_status_out ? 0 : n_status);
   if (rc != MCS_OK) return rc;
-  if ((rc = stage_candidates(sc, cands, n_cand)) != MCS_OK) return rc;
+  int merge = 0;
+  if ((rc = stage_candidates(sc, cands, n_cand, &merge)) != MCS_OK) return rc;
   CUDA_TRY(cudaMemsetAsync(sc->d_counter, 0, sizeof(unsigned long long), sc->stream));
   mcs_status* dst = d_status_out ? (mcs_status*)d_status_out : sc->d_status;
   CUDA_TRY(cudaEventRecord(sc->ev0, sc->stream));
-  if ((rc = launch_rollouts(sc, n_cand, sp, seed, first, count, dst, nullptr, nullptr, sc->d_counter)) != MCS_OK) return rc;
+  if ((rc = launch_rollouts(sc, n_cand, sp, seed, first, count, dst, nullptr, nullptr, sc->d_counter, merge)) != MCS_OK) return rc;
   CUDA_TRY(cudaEventRecord(sc->ev1, sc->stream));
   unsigned long long steps = 0;
   CUDA_TRY(cudaMemcpyAsync(&steps, sc->d_counter, sizeof steps, cudaMemcpyDeviceToHost, sc->stream));
@@ -333,14 +351,15 @@ int mcs_trajectories(mcs_scene* sc, const mcs_candidate* cand, const mcs_sim_par
   CUDA_TRY(cudaSetDevice(sc->device));
   int rc = ensure_capacity(sc, 1, 1);
   if (rc != MCS_OK) return rc;
-  if ((rc = stage_candidates(sc, cand, 1)) != MCS_OK) return rc;
+  int merge = 0;
+  if ((rc = stage_candidates(sc, cand, 1, &merge)) != MCS_OK) return rc;
   const size_t n_d = (size_t)sc->host.n * (sp->steps + 1) * 4;
   double* d_traj = nullptr; int32_t* d_n = nullptr;
   CUDA_TRY(cudaMalloc(&d_traj, n_d * sizeof(double)));
   CUDA_TRY(cudaMalloc(&d_n, sizeof(int32_t)));
   cudaMemsetAsync(d_traj, 0, n_d * sizeof(double), sc->stream);
   cudaMemsetAsync(d_n, 0, sizeof(int32_t), sc->stream);
-  rc = launch_rollouts(sc, 1, sp, seed, rollout, 1, sc->d_status, d_traj, d_n, nullptr);
+  rc = launch_rollouts(sc, 1, sp, seed, rollout, 1, sc->d_status, d_traj, d_n, nullptr, merge);
   mcs_status st{};
   int32_t ns = 0;
   if (rc == MCS_OK) {

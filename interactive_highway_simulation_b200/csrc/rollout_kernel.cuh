@@ -29,7 +29,7 @@
 namespace mcs {
 
 struct LaneDev {
-  double leftY, rightY, centerY, vLimit, endX;
+  double leftY, rightY, centerY, vLimit, endX, startX;
   int id, type, leftIdx, rightIdx, leftmost, pad;
 };
 
@@ -42,7 +42,7 @@ struct SceneDev {
   LaneDev lanes[MCS_MAX_LANES];
 };
 
-struct CandDev { int ego_slot, action, gap_id, target_lane_id, ok, pad[3]; };
+struct CandDev { int ego_slot, action, gap_id, target_lane_id, ok, gap_slot /* slot of gap_id, -1 = last gap */, pad[2]; };
 
 struct LaunchParams {
   double dt;
@@ -327,7 +327,13 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int& to
   return base + inc - v;
 }
 
-template <bool kTraj>
+}  // namespace mcs
+#include "merge_behaviors.cuh"
+namespace mcs {
+
+// kMerge: the scene has a merging/exit lane or vehicle, or a candidate names a gap — yielding intentions and the gap
+// behaviours are compiled in.  The plain lane-change instantiation carries none of their registers.
+template <bool kTraj, bool kMerge>
 __global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int np = sc.n_pad, n = sc.n, k = threadIdx.x;
@@ -406,6 +412,7 @@ __global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, cons
   if (k < 8) s.flags[k] = 0;
   __syncthreads();
   if (k < laneStart[sc.n_lanes]) s.pos[s.vec[k]] = (uint8_t)k;
+  if (isEgo) s.flags[2] = beh;          // the ego's current behaviour: `exit` vehicles are yielding candidates (0x104c90)
   __syncthreads();
   myPos = s.pos[k];
 
@@ -430,38 +437,58 @@ __global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, cons
   int finishStep = lp.steps;
   bool finish = false;
   int step = 0;
-  bool unsupported = false;
+  bool unsupported = false;   // the reference's behaviour is undefined for this scene (no action pushed / missing corridor)
+  bool tableFull = false;     // yielding-intention table overflow
+  int gapSlot = cd.gap_slot;  // ego only: Agent::targetGapId as a slot; < 0 = last gap
+  YieldTable yt;
+  yt.n = 0; yt.yielding = 0u;
 
   while (lp.steps > step) {
     // ================= plan, part A: own-lane search, IDM, draw counts =================
     double ax = 0.0, avy = 0.0;
     int front = -1, back = -1;
-    bool needMobil = false, noise = false, egoCustom = false;
+    bool needMobil = false, noise = false;
+    int mode = 0;   // 1 idmBehaviorAndYielding, 2 customizedLaneChange (ego), 3 customizedMerging (ego), 4 closest gap
     int nDraw = 0;
     const bool hasLane = live && lane >= 0;
-    double pwOwn = 0.0, centerY = 0.0, vLimit = 0.0;
+    double centerY = 0.0, vLimit = 0.0;
+    int ycand[5];
+    int nY = 0;
     if (hasLane) {
       const LaneDev& L = sc.lanes[lane];
       centerY = L.centerY; vLimit = L.vLimit;
       const int lo = laneStart[lane], cnt = laneStart[lane + 1] - lo;
       const int fpos = lane_upper(s, lo, cnt, x);
       front = fpos < cnt ? s.vec[lo + fpos] : -1;
-      // yielding candidates (right lane of type merging, exit agents on the left main lane) are not handled yet
-      if ((L.rightIdx >= 0 && sc.lanes[L.rightIdx].type == MCS_LANE_MERGING) ||
-          (sc.has_exit_lanes && L.leftIdx >= 0 && sc.lanes[L.leftIdx].type == MCS_LANE_MAIN)) unsupported = true;
       if (isEgo) {
         const bool lr = cd.action == MCS_ACT_LEFT || cd.action == MCS_ACT_RIGHT;
-        if ((beh == MCS_BEH_IDM || beh == MCS_BEH_IDM_LC) && !(lr && reached)) egoCustom = true;
-        else if (beh == MCS_BEH_MERGING || beh == MCS_BEH_EXIT) { if (!reached) unsupported = true; }
+        if (beh == MCS_BEH_IDM || beh == MCS_BEH_IDM_LC) mode = (lr && reached) ? 1 : 2;
+        else if (beh == MCS_BEH_MERGING || beh == MCS_BEH_EXIT) mode = reached ? 1 : 3;
+        else unsupported = true;
       } else if (beh == MCS_BEH_IDM_LC) {
-        noise = true;
+        mode = 1; noise = true;
         const bool canL = L.leftIdx >= 0 && sc.lanes[L.leftIdx].type == MCS_LANE_MAIN;
         const bool canR = L.rightIdx >= 0 && sc.lanes[L.rightIdx].type == MCS_LANE_MAIN;
         needMobil = !(commit == MCS_COMMIT_KEEP_LANE && keepStep <= 9) && (canL || canR);
       } else if (beh == MCS_BEH_IDM) {
-        noise = true;
+        mode = 1; noise = true;
+      } else if (beh == MCS_BEH_MERGING) {
+        mode = 4;
       } else {
-        unsupported = true;
+        unsupported = true;   // the binary pushes no action for such a vehicle and then reads past its action vector (0x10ed15)
+      }
+      if (kMerge) {
+        if (mode == 1) {
+          // yielding candidates: neighbours on a merging lane to the right (0x104469), `exit` vehicles on the main lane to
+          // the left (0x1044df) — inside a rollout only the ego can still be an `exit` vehicle
+          if (L.rightIdx >= 0 && sc.lanes[L.rightIdx].type == MCS_LANE_MERGING) nY = side_vector(s, laneStart, L.rightIdx, x, ycand);
+          if (sc.has_exit_lanes && L.leftIdx >= 0 && sc.lanes[L.leftIdx].type == MCS_LANE_MAIN) {
+            const int eg = cd.ego_slot;
+            if (eg != k && s.lane[eg] == L.leftIdx && s.flags[2] == MCS_BEH_EXIT) ycand[nY++] = eg;
+          }
+        }
+      } else if (mode == 3 || mode == 4) {
+        unsupported = true;     // cannot happen: the host selects kMerge for such scenes
       }
       if (needMobil) {
         const int bpos = lane_reverse(s, lo, cnt, x);
@@ -493,7 +520,7 @@ __global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, cons
       const bool contR = commit == MCS_COMMIT_RIGHT && targetLane != laneId && (mf & MF_RELAX_R);
       mobilDraw = !(contL || contR);
     }
-    nDraw = (noise ? 1 : 0) + (mobilDraw ? 1 : 0);
+    nDraw = nY + (noise ? 1 : 0) + (mobilDraw ? 1 : 0);
     int totalDraws;
     const uint64_t drawBase = drawCtr + (uint64_t)block_exclusive_scan(nDraw, s.scan, totalDraws);
     drawCtr += (uint64_t)totalDraws;
@@ -507,7 +534,7 @@ __global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, cons
       else thwPush = 1.0;
       pushThw = true;
       avy = centering_vy(y, centerY);
-      if (egoCustom) {
+      if (mode == 2) {
         // customizedLaneChangeBehavior 0xf5e30
         const double vdCap = MCS_MINSD(evd, 1.1 * vLimit);
         const int cmd = cd.action;
@@ -536,17 +563,76 @@ __global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, cons
             ax = emergency ? aMin : 0.0;
           }
         }
-      } else {
-        // idmBehaviorAndYieldingToMergingAgents 0x104200 (no yielding candidates in supported scenes)
+      } else if (kMerge && (mode == 3 || mode == 4)) {
+        MergeSelf me;
+        me.k = k; me.lane = lane; me.front = front; me.x = x; me.y = y; me.v = v; me.l = el;
+        me.w = F[(size_t)F_W * np + k];
+        me.rss.rTOther = F[(size_t)F_RSS_RTOTHER * np + k]; me.rss.rTEgo = rTEgo; me.rss.aMin = aMin; me.rss.aMax = aMax;
+        me.rss.dSoft = F[(size_t)F_RSS_DSOFT * np + k];
+        me.idm = pe;
+        bool okSide;
+        if (mode == 3) okSide = customized_merging(s, sc, laneStart, me, evd, cd.action == MCS_ACT_LEFT, gapSlot, ax, avy);
+        else okSide = merging_closest_gap(s, sc, laneStart, me, evd, false, true, ax, avy);
+        if (!okSide) { unsupported = true; ax = 0.0; avy = 0.0; }
+      } else if (mode == 1) {
+        // idmBehaviorAndYieldingToMergingAgents 0x104200
         double vdd = evd;
         if (isEgo) vdd = MCS_MINSD(evd, 1.1 * vLimit);
         const double pw = mcs_pow4(v / vdd);
         const double axFront = idm_acc(s, pe, front, -1, -1, x, v, el, pw);
         IdmP py = pe;
         py.accMax = F[(size_t)F_IDMY_ACCMAX * np + k]; py.accMin = F[(size_t)F_IDMY_ACCMIN * np + k];
-        const double axY = idm_acc(s, py, -1, -1, -1, x, v, el, pw);
+        double axY;
+        if (kMerge && nY > 0) {
+          // intention per candidate: logistic of (thw, relative speed, own initial acceleration), one draw each, hysteresis 0.625
+          const double ypBias = F[(size_t)F_YP_BIAS * np + k], ypA = F[(size_t)F_YP_A * np + k], ypB = F[(size_t)F_YP_B * np + k],
+                       ypC = F[(size_t)F_YP_C * np + k];
+          int ylist[5];
+          int ny = 0;
+          for (int q = 0; q < nY; ++q) {
+            const int j = ycand[q];
+            double p = 0.0;
+            const double half = (el + s.l[j]) * 0.5;
+            const double dx = s.x[j] - x;
+            if (!(0.0 > dx + half)) {
+              const double thw = (dx - half) / MCS_MAXSD(1e-10, v);
+              const double rel = (v - s.v[j]) / MCS_MAXSD(v, 0.001);
+              double r = thw * ypA + ypBias;
+              r = r + rel * ypB;
+              r = r + a0 * ypC;
+              double arg;
+              if (100.0 > r) arg = (-100.0 > r) ? 100.0 : -r;
+              else arg = -100.0;
+              p = 1.0 / (mcs_exp(arg) + 1.0);
+            }
+            const int rnd = mcs_rand31(key, drawBase + (uint64_t)q);
+            const bool y0 = (100.0 * p) >= (double)(rnd % 100);
+            int e = -1;
+            for (int t = 0; t < yt.n; ++t) if (yt.key[t] == (uint8_t)j) { e = t; break; }
+            if (e < 0) {
+              if (yt.n < MCS_YCAP) {
+                e = yt.n++;
+                yt.key[e] = (uint8_t)j; yt.p0[e] = p;
+                if (y0) yt.yielding |= 1u << e; else yt.yielding &= ~(1u << e);
+              } else {
+                tableFull = true;
+              }
+            }
+            if (e >= 0) {
+              bool yl = (yt.yielding >> e) & 1u;
+              const double p0 = yt.p0[e];
+              if (!yl) { if ((1.0 - p0) * 0.625 >= 1.0 - p) yl = true; }
+              else { if (0.625 * p0 >= p) yl = false; }
+              if (yl) yt.yielding |= 1u << e; else yt.yielding &= ~(1u << e);
+              if (yl) ylist[ny++] = j;
+            }
+          }
+          axY = idm_acc_list(s, py, ylist, ny, -1, x, v, el, pw);
+        } else {
+          axY = idm_acc(s, py, -1, -1, -1, x, v, el, pw);
+        }
         ax = MCS_MINSD(axY, axFront);
-        if (noise) ax = ax + ((double)mcs_rand31(key, drawBase) / 2147483647.0 - 0.5);
+        if (noise) ax = ax + ((double)mcs_rand31(key, drawBase + (uint64_t)nY) / 2147483647.0 - 0.5);
         if (front >= 0 && rss_emergency(s, front, x, v, el, rTEgo, aMin, aMax)) ax = aMin;
         if (beh == MCS_BEH_IDM_LC && !isEgo) {
           // laneChangeBehaviorMOBIL 0xf42d0, decision part
@@ -598,7 +684,7 @@ __global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, cons
                 const double S = (k2 + pL) + r2;
                 p[1] = k2 / S; p[2] = r2 / S;
               }
-              const double u = (double)mcs_rand31(key, drawBase + 1) / 2147483647.0;
+              const double u = (double)mcs_rand31(key, drawBase + (uint64_t)nY + 1) / 2147483647.0;
               if (pL > u && canL) { commit = MCS_COMMIT_LEFT; targetLane = sc.lanes[L.leftIdx].id; ax = axLeft; avy = vyLeft; }
               else if (pL + p[2] > u && canR) { commit = MCS_COMMIT_RIGHT; targetLane = sc.lanes[L.rightIdx].id; ax = axRight; avy = vyRight; }
               else { commit = MCS_COMMIT_KEEP_LANE; targetLane = -1; }
@@ -739,8 +825,29 @@ __global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, cons
       oldLane = newLane == 0xff ? -1 : newLane;
     }
     // ================= termination (0x10edd0-0x10ee10) =================
-    if (isEgo) s.flags[0] = reached ? 1 : 0;
+    if (isEgo) { s.flags[0] = reached ? 1 : 0; s.flags[2] = beh; }
     __syncthreads();
+    if (kMerge && isEgo && gapSlot >= 0) {
+      // the gap's rear vehicle left the target lane: re-target to the last vehicle of that lane behind it, else the
+      // last gap (matchAgentsOnCorridor 0x10c320-0x10c39d)
+      const int gl = s.lane[gapSlot];
+      if (gl == 0xff) unsupported = true;
+      else if (sc.lanes[gl].id != targetLane) {
+        int tl = -1;
+        for (int j = 0; j < sc.n_lanes; ++j) if (sc.lanes[j].id == targetLane) tl = j;
+        if (tl < 0) unsupported = true;
+        else {
+          const int lo = laneStart[tl], cnt = laneStart[tl + 1] - lo;
+          const double gx = s.x[gapSlot];
+          int found = -1;
+          for (int q = cnt - 1; q >= 0; --q) {
+            const int o = s.vec[lo + q];
+            if (gx > s.x[o]) { found = o; break; }
+          }
+          gapSlot = found;
+        }
+      }
+    }
     const bool egoReached = s.flags[0] != 0;
     if (egoReached) {
       finish = true;
@@ -804,9 +911,8 @@ __global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, cons
     if (kTraj && lp.traj_n) lp.traj_n[(size_t)cand * lp.count + ridx] = nStates;
     if (lp.vehicle_steps) atomicAdd(lp.vehicle_steps, (unsigned long long)executed * (unsigned long long)n);
   }
-  if (__syncthreads_or(unsupported ? 1 : 0)) {
-    if (isEgo) st_out->overflow = 2;   // scene uses a behaviour this build does not implement: caller must fail loudly
-  }
+  const int bad = __syncthreads_or((unsupported ? 2 : 0) | (tableFull ? 1 : 0));
+  if (bad && isEgo) st_out->overflow = (uint8_t)((bad & 2) ? 2 : 1);   // the caller fails loudly (MCS_ERR_SCENE / MCS_ERR_CAPACITY)
 }
 
 }  // namespace mcs

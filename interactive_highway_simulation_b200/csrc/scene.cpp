@@ -40,12 +40,13 @@ int build_scene_host(const mcs_corridor* cs, int nc, const mcs_agent* as, int na
     const mcs_corridor& c = cs[order[k]];
     LaneHost& L = s.lanes[k];
     L.id = c.id; L.type = c.type;
-    L.leftY = c.left[1]; L.rightY = c.right[1]; L.centerY = c.center[1]; L.vLimit = c.v_limit; L.endX = c.center[2];
+    L.leftY = c.left[1]; L.rightY = c.right[1]; L.centerY = c.center[1]; L.vLimit = c.v_limit; L.endX = c.center[2]; L.startX = c.center[0];
     L.leftIdx = L.rightIdx = -1; L.leftmost = 0;
     for (int j : by_y) if (cs[j].center[1] > c.center[1]) { L.leftIdx = slot_of_lane_input[j]; break; }
     for (auto it = by_y.rbegin(); it != by_y.rend(); ++it)
       if (c.center[1] > cs[*it].center[1]) { L.rightIdx = slot_of_lane_input[*it]; break; }
     if (c.type == MCS_LANE_EXIT) s.has_exit_lanes = true;
+    if (c.type != MCS_LANE_MAIN) s.needs_merge_path = true;
     if (L.leftIdx < 0) leftmost_slot = k;   // last lane without a left neighbour in iteration order
   }
   if (leftmost_slot >= 0) s.lanes[leftmost_slot].leftmost = 1;
@@ -64,13 +65,14 @@ int build_scene_host(const mcs_corridor* cs, int nc, const mcs_agent* as, int na
     const mcs_agent& a = as[visit[k]];
     s.slot_of_input[visit[k]] = k;
     s.F(F_X, k) = a.x; s.F(F_Y, k) = a.y; s.F(F_V, k) = a.v; s.F(F_VY, k) = a.vy; s.F(F_A, k) = a.a;
-    s.F(F_L, k) = a.l; s.F(F_VD, k) = a.vd;
+    s.F(F_L, k) = a.l; s.F(F_W, k) = a.w; s.F(F_VD, k) = a.vd;
+    if (a.behavior == MCS_BEH_MERGING || a.behavior == MCS_BEH_EXIT) s.needs_merge_path = true;
     s.F(F_IDM_ACCMAX, k) = a.idm[0]; s.F(F_IDM_MINDIS, k) = a.idm[1]; s.F(F_IDM_ACCMIN, k) = a.idm[2];
     s.F(F_IDM_ACCCOM, k) = a.idm[3]; s.F(F_IDM_THW, k) = a.idm[5];
     // Agent ctor 0xf8941-0xf89db: softened copy for yielding, cars (l < 7) only
     s.F(F_IDMY_ACCMAX, k) = (7.0 > a.l) ? a.idm[0] - 0.8 : a.idm[0];
     s.F(F_IDMY_ACCMIN, k) = (7.0 > a.l) ? 1.0 + a.idm[2] : a.idm[2];
-    s.F(F_RSS_RTOTHER, k) = a.rss[0]; s.F(F_RSS_RTEGO, k) = a.rss[1]; s.F(F_RSS_AMIN, k) = a.rss[2]; s.F(F_RSS_AMAX, k) = a.rss[3];
+    s.F(F_RSS_RTOTHER, k) = a.rss[0]; s.F(F_RSS_RTEGO, k) = a.rss[1]; s.F(F_RSS_AMIN, k) = a.rss[2]; s.F(F_RSS_AMAX, k) = a.rss[3]; s.F(F_RSS_DSOFT, k) = a.rss[5];
     s.F(F_YP_BIAS, k) = a.yp[0]; s.F(F_YP_A, k) = a.yp[1]; s.F(F_YP_B, k) = a.yp[2]; s.F(F_YP_C, k) = a.yp[3];
     s.F(F_YP_PF, k) = a.yp[4]; s.F(F_YP_DA, k) = a.yp[5]; s.F(F_YP_BA, k) = a.yp[6];
     s.I(I_ID, k) = a.id; s.I(I_INPUT, k) = visit[k]; s.I(I_BEH, k) = a.behavior; s.I(I_BEH0, k) = a.behavior;
@@ -104,10 +106,18 @@ int build_scene_host(const mcs_corridor* cs, int nc, const mcs_agent* as, int na
 }
 
 CandHost resolve_candidate(const SceneHost& s, const mcs_candidate& c) {
-  CandHost r{-1, c.action, c.gap_id, -1, 0};
-  for (int k = 0; k < s.n; ++k)
-    if (s.i[(size_t)I_ID * s.n_pad + k] == c.ego_id) { r.ego_slot = k; break; }
+  CandHost r{-1, c.action, c.gap_id, -1, 0, -1, 0};
+  for (int k = 0; k < s.n; ++k) {
+    const int id = s.i[(size_t)I_ID * s.n_pad + k];
+    if (id == c.ego_id && r.ego_slot < 0) r.ego_slot = k;
+    if (c.gap_id >= 0 && id == c.gap_id && r.gap_slot < 0) r.gap_slot = k;
+  }
   if (r.ego_slot < 0) return r;                       // "No ego agent with id"
+  // Simulation::run 0x10ed15: a non-ego vehicle that is neither idm, idm_lc nor merging gets no action
+  for (int k = 0; k < s.n; ++k) {
+    const int b = s.i[(size_t)I_BEH * s.n_pad + k];
+    if (k != r.ego_slot && b != MCS_BEH_IDM && b != MCS_BEH_IDM_LC && b != MCS_BEH_MERGING) r.bad_behavior = 1;
+  }
   const int lane = s.i[(size_t)I_LANE * s.n_pad + r.ego_slot];
   if (lane < 0) return r;                             // "is not matched to any corridor"
   const LaneHost& L = s.lanes[lane];

@@ -17,10 +17,10 @@ namespace mcs {
 
 // per-agent double fields, one array of n_pad doubles each, slot order = reference visit order
 enum AgentField {
-  F_X = 0, F_Y, F_V, F_VY, F_A, F_L, F_VD,
+  F_X = 0, F_Y, F_V, F_VY, F_A, F_L, F_W, F_VD,
   F_IDM_ACCMAX, F_IDM_MINDIS, F_IDM_ACCMIN, F_IDM_ACCCOM, F_IDM_THW,
   F_IDMY_ACCMAX, F_IDMY_ACCMIN,
-  F_RSS_RTOTHER, F_RSS_RTEGO, F_RSS_AMIN, F_RSS_AMAX,
+  F_RSS_RTOTHER, F_RSS_RTEGO, F_RSS_AMIN, F_RSS_AMAX, F_RSS_DSOFT,
   F_YP_BIAS, F_YP_A, F_YP_B, F_YP_C, F_YP_PF, F_YP_DA, F_YP_BA,
   F_PRIOR_L, F_PRIOR_K, F_PRIOR_R,
   F_COUNT
@@ -30,7 +30,7 @@ enum AgentIntField { I_ID = 0, I_INPUT, I_BEH, I_BEH0, I_LANE, I_COMMIT, I_KEEPS
 
 struct LaneHost {
   int id, type;
-  double leftY, rightY, centerY, vLimit, endX;  // endX = center.p2.x
+  double leftY, rightY, centerY, vLimit, endX, startX;  // center.p2.x, center.p1.x
   int leftIdx, rightIdx;                        // slot of the neighbour lane or -1
   int leftmost;                                 // 1 if this is MapMultiLane's "leftmost" lane id (0x18)
 };
@@ -38,6 +38,7 @@ struct LaneHost {
 struct SceneHost {
   int n = 0, n_pad = 0, n_lanes = 0;
   bool has_exit_lanes = false;
+  bool needs_merge_path = false;  // a merging/exit lane or a merging/exit vehicle: yielding + gap behaviours are reachable
   std::vector<double> f;          // F_COUNT * n_pad
   std::vector<int32_t> i;         // I_COUNT * n_pad
   std::vector<LaneHost> lanes;    // hash iteration order
@@ -53,7 +54,7 @@ struct SceneHost {
 int build_scene_host(const mcs_corridor* corridors, int n_corridors, const mcs_agent* agents, int n_agents, SceneHost& out);
 
 // Environment::setEgoAgentIdAndDrivingBehavior 0xf3f20 evaluated on the host for one candidate
-struct CandHost { int ego_slot, action, gap_id, target_lane_id, ok; };
+struct CandHost { int ego_slot, action, gap_id, target_lane_id, ok, gap_slot /* -1 = last gap / unknown */, bad_behavior; };
 CandHost resolve_candidate(const SceneHost& s, const mcs_candidate& c);
 
 }  // namespace mcs

@@ -10,7 +10,7 @@ import pytest
 
 import golden_io
 from interactive_highway_simulation_b200 import _abi as abi
-from scenes import ACTIONS, STATUS_KEYS, lane_change_cases, probe_scene, same
+from scenes import ACTIONS, STATUS_KEYS, lane_change_cases, merge_exit_cases, probe_scene, random_scene, same
 
 pytestmark = pytest.mark.gpu
 
@@ -64,6 +64,37 @@ def test_probe_scene_against_oracle(gpu, oracle):
 def test_random_lane_change_scenes_against_oracle(gpu, oracle, case):
     tag, s, ego, dt, steps, min_steps, seed = case
     check_against_oracle(gpu, oracle, s, ego, dt, steps, min_steps, seed, 12, tag)
+
+
+@pytest.mark.parametrize("case", merge_exit_cases(24), ids=lambda c: c[0])
+def test_merging_and_exit_scenes_against_oracle(gpu, oracle, case):
+    """Ego `merging` / `exit` executing a gap (customizedMergingBehavior), non-ego `merging` vehicles choosing the closest
+    gap, main-lane vehicles yielding to them (intention draws), gap re-targeting, behaviour switches on lane entry."""
+    tag, s, ego, direction, gaps, seed = case
+    for gap in gaps:
+        check_against_oracle(gpu, oracle, s, ego, 0.3, 40, 10, seed, 8, tag, traj_rollouts=1, gap=gap, actions=(direction,))
+
+
+def test_scene_errors_where_the_reference_is_undefined(gpu):
+    """Unknown gap id / a non-ego vehicle without a usable behaviour: the reference reads invalid memory; we refuse."""
+    rng = random.Random(3)
+    s, ego = random_scene(rng, n_agents=8, lane_types=["merging", "main", "main"], ego_behavior="merging", ego_lane=0)
+    ds = gpu.DeviceScene(s.c_corridors(), s.c_agents())
+    try:
+        sp = abi.SimParam(0.3, 40, 10)
+        with pytest.raises(gpu.McsimError) as e:
+            ds.rollouts_range((abi.Candidate * 1)(abi.Candidate(ego, abi.ACTIONS["left"], 9999, 0)), sp, 1, 0, 2)
+        assert e.value.code == abi.MCS_ERR_SCENE
+    finally:
+        ds.close()
+    s.agents[1 if s.agents[0]["id"] == ego else 0]["behavior"] = "exit"      # a non-ego `exit` vehicle on a non-exit lane
+    ds = gpu.DeviceScene(s.c_corridors(), s.c_agents())
+    try:
+        with pytest.raises(gpu.McsimError) as e:
+            ds.rollouts_range((abi.Candidate * 1)(abi.Candidate(ego, abi.ACTIONS["left"], -1, 0)), sp, 1, 0, 2)
+        assert e.value.code == abi.MCS_ERR_SCENE
+    finally:
+        ds.close()
 
 
 @pytest.mark.parametrize("case", ROLLOUT_CASES, ids=golden_io.ids(ROLLOUT_CASES))
