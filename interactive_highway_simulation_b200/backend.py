@@ -138,6 +138,29 @@ class DeviceScene:
         return buf, ns.value, st
 
 
+    # ---- the reference's per-step Python-facing wrappers (behaviors.py:81,114,135,144,152,174)
+    def decide_mobil(self, agent_id, ax, vy, require_rss, seed):
+        out = abi.ActionWithType()
+        act = abi.Action(ax, vy)
+        check(lib().mcs_decide_mobil(self._h, agent_id, C.byref(act), 1 if require_rss else 0, seed, C.byref(out)))
+        return out
+
+    def decide_fixed_direction(self, agent_id, action):
+        out = abi.Action()
+        check(lib().mcs_decide_fixed_direction(self._h, agent_id, action, C.byref(out)))
+        return out
+
+    def decide_fixed_gap(self, agent_id, direction, gap_id):
+        out = abi.Action()
+        check(lib().mcs_decide_fixed_gap(self._h, agent_id, direction, gap_id, C.byref(out)))
+        return out
+
+    def decide_closest_gap(self, agent_id, direction):
+        out = abi.Action()
+        check(lib().mcs_decide_closest_gap(self._h, agent_id, direction, C.byref(out)))
+        return out
+
+
 def reduce_features(statuses, n_candidates, groups, n_per_group, steps):
     feats = (abi.Feature * n_candidates)()
     check(lib().mcs_reduce_features(statuses, n_candidates, groups, n_per_group, steps, feats))

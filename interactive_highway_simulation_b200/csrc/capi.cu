@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "rollout_kernel.cuh"
+#include "decide_kernel.cuh"
 #include "scene.hpp"
 
 namespace {
@@ -109,6 +110,7 @@ struct mcs_scene {
   mcs_status* d_status = nullptr; size_t status_cap = 0;
   mcs_feature* d_feat = nullptr; int feat_cap = 0;
   unsigned long long* d_counter = nullptr;
+  void* d_decide = nullptr;             // mcs::DecideOut
   mcs::CandDev* h_cand = nullptr;      // pinned
   mcs_feature* h_feat = nullptr;       // pinned
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -249,7 +251,7 @@ int mcs_scene_destroy(mcs_scene* sc) {
   cudaSetDevice(sc->device);
   if (sc->stream) cudaStreamSynchronize(sc->stream);
   cudaFree(sc->d_f); cudaFree(sc->d_i); cudaFree(sc->d_vec); cudaFree(sc->d_cand); cudaFree(sc->d_status);
-  cudaFree(sc->d_feat); cudaFree(sc->d_counter);
+  cudaFree(sc->d_feat); cudaFree(sc->d_counter); cudaFree(sc->d_decide);
   if (sc->h_cand) cudaFreeHost(sc->h_cand);
   if (sc->h_feat) cudaFreeHost(sc->h_feat);
   if (sc->ev0) cudaEventDestroy(sc->ev0);
@@ -376,9 +378,74 @@ int mcs_trajectories(mcs_scene* sc, const mcs_candidate* cand, const mcs_sim_par
   return check_unsupported(&st, 1);
 }
 
-int mcs_decide_mobil(mcs_scene*, int32_t, const mcs_action*, int, uint64_t, mcs_action_with_type*) { return fail(MCS_ERR_ARG, "mcs_decide_mobil: not implemented yet"); }
-int mcs_decide_fixed_direction(mcs_scene*, int32_t, int32_t, mcs_action*) { return fail(MCS_ERR_ARG, "mcs_decide_fixed_direction: not implemented yet"); }
-int mcs_decide_fixed_gap(mcs_scene*, int32_t, int32_t, int32_t, mcs_action*) { return fail(MCS_ERR_ARG, "mcs_decide_fixed_gap: not implemented yet"); }
-int mcs_decide_closest_gap(mcs_scene*, int32_t, int32_t, mcs_action*) { return fail(MCS_ERR_ARG, "mcs_decide_closest_gap: not implemented yet"); }
+static int run_decision(mcs_scene* sc, int32_t agent_id, mcs::DecideParams dp, int32_t gap_id, mcs::DecideOut* res) {
+  if (!sc) return fail(MCS_ERR_ARG, "scene is null");
+  std::lock_guard<std::mutex> lock(sc->mu);
+  CUDA_TRY(cudaSetDevice(sc->device));
+  const mcs::SceneHost& h = sc->host;
+  dp.slot = -1; dp.gap_slot = -1;
+  for (int k = 0; k < h.n; ++k) {
+    const int id = h.i[(size_t)mcs::I_ID * h.n_pad + k];
+    if (id == agent_id && dp.slot < 0) dp.slot = k;
+    if (gap_id >= 0 && id == gap_id && dp.gap_slot < 0) dp.gap_slot = k;
+  }
+  if (dp.slot < 0) return fail(MCS_ERR_ARG, "No agent with id: " + std::to_string(agent_id));   // the reference traps (ud2, 0xb9a37)
+  if (!sc->d_decide) CUDA_TRY(cudaMalloc(&sc->d_decide, sizeof(mcs::DecideOut)));
+  const size_t smem = rollout_smem_bytes(sc->dev.n_pad, 0);
+  CUDA_TRY(cudaFuncSetAttribute(mcs::decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mcs::decide_kernel<<<1, sc->dev.n_pad, smem, sc->stream>>>(sc->dev, dp, (mcs::DecideOut*)sc->d_decide);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(res, sc->d_decide, sizeof *res, cudaMemcpyDeviceToHost, sc->stream));
+  CUDA_TRY(cudaStreamSynchronize(sc->stream));
+  if (res->status != MCS_OK)
+    return fail(res->status, "the reference's behaviour is undefined here (vehicle not on a lane, or no lane on that side)");
+  return MCS_OK;
+}
+
+int mcs_decide_mobil(mcs_scene* sc, int32_t agent_id, const mcs_action* idm_action, int require_rss, uint64_t seed,
+                     mcs_action_with_type* out) {
+  if (!idm_action || !out) return fail(MCS_ERR_ARG, "bad arguments");
+  mcs::DecideParams dp{};
+  dp.kind = 0; dp.ax = idm_action->ax; dp.vy = idm_action->vy; dp.require_rss = require_rss ? 1 : 0; dp.key = seed;
+  mcs::DecideOut r{};
+  int rc = run_decision(sc, agent_id, dp, -2, &r);
+  if (rc != MCS_OK) return rc;
+  out->ax = r.ax; out->vy = r.vy; out->commit = r.commit; out->commit_keep_lane_step = r.keepStep;
+  out->target_lane_id = r.targetLane; out->reserved = 0;
+  return MCS_OK;
+}
+
+int mcs_decide_fixed_direction(mcs_scene* sc, int32_t agent_id, int32_t action, mcs_action* out) {
+  if (!out) return fail(MCS_ERR_ARG, "bad arguments");
+  mcs::DecideParams dp{};
+  dp.kind = 1; dp.action = action;
+  mcs::DecideOut r{};
+  int rc = run_decision(sc, agent_id, dp, -2, &r);
+  if (rc != MCS_OK) return rc;
+  out->ax = r.ax; out->vy = r.vy;
+  return MCS_OK;
+}
+
+int mcs_decide_fixed_gap(mcs_scene* sc, int32_t agent_id, int32_t direction, int32_t gap_id, mcs_action* out) {
+  if (!out) return fail(MCS_ERR_ARG, "bad arguments");
+  mcs::DecideParams dp{};
+  dp.kind = 2; dp.action = direction;
+  mcs::DecideOut r{};
+  int rc = run_decision(sc, agent_id, dp, gap_id, &r);
+  if (rc != MCS_OK) return rc;
+  out->ax = r.ax; out->vy = r.vy;
+  return MCS_OK;
+}
+
+int mcs_decide_closest_gap(mcs_scene* sc, int32_t agent_id, int32_t direction, mcs_action* out) {
+  if (!out) return fail(MCS_ERR_ARG, "bad arguments");
+  mcs::DecideParams dp{};
+  dp.kind = 3; dp.action = direction;
+  mcs::DecideOut r{};
+  int rc = run_decision(sc, agent_id, dp, -2, &r);
+  if (rc != MCS_OK) return rc;
+  out->ax = r.ax; out->vy = r.vy;
+  return MCS_OK;
+}
 
 }  // extern "C"

@@ -83,6 +83,27 @@ struct Smem {
   uint8_t* pos;    // [n_pad] position of each vehicle inside vec
 };
 
+// shared-memory layout of one rollout (host twin: rollout_smem_bytes in capi.cu)
+__device__ __forceinline__ void carve_smem(Smem& s, unsigned char* p, int np, int steps) {
+  s.x = (double*)p; p += sizeof(double) * np;
+  s.v = (double*)p; p += sizeof(double) * np;
+  s.l = (double*)p; p += sizeof(double) * np;
+  s.vd = (double*)p; p += sizeof(double) * np;
+  s.idm = (double*)p; p += sizeof(double) * 5 * np;
+  s.mob = (double*)p; p += sizeof(double) * 6 * np;
+  s.chist = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
+  s.csort = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
+  s.red = (double*)p; p += sizeof(double) * 16;
+  s.scan = (int*)p; p += sizeof(int) * 16;
+  s.cnt = (int*)p; p += sizeof(int) * 16;
+  s.flags = (int*)p; p += sizeof(int) * 8;
+  s.tasks = (int*)p; p += sizeof(int) * np;
+  s.lane = p; p += np;
+  s.vec = p; p += np;
+  s.mflag = p; p += 2 * np;
+  s.pos = p; p += np;
+}
+
 __device__ __forceinline__ IdmP load_idm(const Smem& s, int np, int k) {
   IdmP p;
   p.accMax = s.idm[k]; p.minDis = s.idm[np + k]; p.accMin = s.idm[2 * np + k]; p.accCom = s.idm[3 * np + k];
@@ -304,6 +325,102 @@ __device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc
   s.mflag[side * np + k] = (uint8_t)mf;
 }
 
+// Agent fields laneChangeBehaviorMOBIL writes back (commitToDecision 0x90, commitKeepLaneStep 0xb0, targetLaneId 0x68)
+struct MobilState { int commit, keepStep, targetLane; };
+
+// laneChangeBehaviorMOBIL 0xf42d0, decision part (0xf4f12-0xf5195), after mobil_geometry has filled s.mob / s.mflag for
+// vehicle k and the keep-lane counter test (0xf434c) has passed.  `u` = the uniform draw of 0xf510f (consumed only when
+// the vehicle does not continue a committed change).  mode: 0 = inside a rollout at the vehicle's first step (lateral-offset
+// prior blended in, 0xf58a0), 1 = inside a rollout later, 2 = Python-facing with requireRssSafety (0xf5858), 3 = without (0xf5053).
+__device__ __forceinline__ void mobil_decide(const Smem& s, const SceneDev& sc, int np, int k, int lane, double v, double el,
+                                             double aMin, double pf, double dA, double bA, int mode, bool aggressive,
+                                             double prior0, double prior1, double prior2, double u, MobilState& ms,
+                                             double& ax, double& avy) {
+  const int mf = s.mflag[k] | s.mflag[np + k];
+  const bool canL = mf & MF_CAN_L, canR = mf & MF_CAN_R;
+  const bool strictL = mf & MF_STRICT_L, relaxL = mf & MF_RELAX_L, strictR = mf & MF_STRICT_R, relaxR = mf & MF_RELAX_R;
+  const double accNewL = s.mob[k], accNewR = s.mob[np + k], dNewL = s.mob[2 * np + k], dNewR = s.mob[3 * np + k];
+  const double deltaOld = s.mob[4 * np + k];
+  const double axIdm = ax, vyIdm = avy;
+  double axLeft = axIdm, vyLeft = vyIdm, axRight = 0.0, vyRight = 0.0;
+  double incL = -10000000000.0, incR = -10000000000.0;
+  if (canL) {
+    axLeft = (axIdm == aMin) ? axIdm : accNewL;
+    vyLeft = MCS_MINSD(1.0, 0.17 * v);
+    incL = (((dNewL + deltaOld) * pf + (accNewL - axIdm)) - dA) - bA;
+  }
+  if (canR) {
+    axRight = accNewR;
+    vyRight = MCS_MAXSD(-1.0, -0.17 * v);
+    incR = (((dNewR + deltaOld) * pf + (accNewR - axIdm)) - dA) + bA;
+  }
+  const LaneDev& L = sc.lanes[lane];
+  if (ms.commit == MCS_COMMIT_LEFT && ms.targetLane != L.id && relaxL) { ax = axLeft; avy = vyLeft; return; }
+  if (ms.commit == MCS_COMMIT_RIGHT && ms.targetLane != L.id && relaxR) { ax = axRight; avy = vyRight; return; }
+  ms.keepStep = 0;
+  const double eL = mcs_exp(incL), eR = mcs_exp(incR);
+  const double denom = (1.0 + eL) + eR;
+  double p[3];
+  p[0] = eL / denom; p[2] = eR / denom; p[1] = (1.0 - p[0]) - p[2];
+  if (mode <= 1) {
+    if (ms.commit == MCS_COMMIT_NOT_DECIDED && mode == 0) {
+      if (aggressive) lane_change_probability(p, prior0, prior1, prior2, relaxL, relaxR);
+      else {
+        const bool r = strictR ? true : ((prior2 >= 0.5) && relaxR);
+        const bool l = strictL ? true : ((prior0 >= 0.5) && relaxL);
+        lane_change_probability(p, prior0, prior1, prior2, l, r);
+      }
+    } else if (aggressive) lane_change_probability(p, 0.0, 0.0, 0.0, relaxL, relaxR);
+    else lane_change_probability(p, 0.0, 0.0, 0.0, strictL, strictR);
+  } else if (mode == 2) lane_change_probability(p, 0.0, 0.0, 0.0, strictL, strictR);
+  else lane_change_probability(p, 0.0, 0.0, 0.0, relaxL, relaxR);
+  double pL = p[0];
+  if (el > 6.0) {
+    pL = pL * 0.5;
+    if (L.leftIdx >= 0 && sc.lanes[L.leftIdx].leftmost) pL = 0.0;
+    const double k2 = p[1] + p[1], r2 = p[2] + p[2];
+    const double S = (k2 + pL) + r2;
+    p[1] = k2 / S; p[2] = r2 / S;
+  }
+  if (pL > u && canL) { ms.commit = MCS_COMMIT_LEFT; ms.targetLane = sc.lanes[L.leftIdx].id; ax = axLeft; avy = vyLeft; }
+  else if (pL + p[2] > u && canR) { ms.commit = MCS_COMMIT_RIGHT; ms.targetLane = sc.lanes[L.rightIdx].id; ax = axRight; avy = vyRight; }
+  else { ms.commit = MCS_COMMIT_KEEP_LANE; ms.targetLane = -1; }
+}
+
+// customizedLaneChangeBehavior 0xf5e30 for vehicle k (avy enters as the lane-centring speed 0xf61af-0xf61fb)
+__device__ __forceinline__ void customized_lane_change(const Smem& s, const SceneDev& sc, const int* laneStart, int np, int k,
+                                                       int lane, int front, int cmd, double x, double v, double el, double evd,
+                                                       double rTOther, double rTEgo, double aMin, double aMax, double& ax,
+                                                       double& avy) {
+  const IdmP pe = load_idm(s, np, k);
+  const LaneDev& L = sc.lanes[lane];
+  const double vdCap = MCS_MINSD(evd, 1.1 * L.vLimit);
+  if (cmd == MCS_ACT_KEEP_LANE || cmd == MCS_ACT_ACC || cmd == MCS_ACT_DCC) {
+    IdmP p = pe;
+    double vdd = vdCap;
+    if (cmd == MCS_ACT_DCC) { p.thw = pe.thw + pe.thw; vdd = 0.8 * vdCap; }
+    if (cmd == MCS_ACT_ACC) { p.thw = 0.9; vdd = 1.1 * vdCap; }
+    ax = idm_acc(s, p, front, -1, -1, x, v, el, mcs_pow4(v / vdd));
+    if (front >= 0 && rss_emergency(s, front, x, v, el, rTEgo, aMin, aMax)) ax = aMin;
+    return;
+  }
+  // for left/right the binary's emergency select reads an uninitialised stack slot (0xf6263); only the aMin outcome is observable
+  const bool emergency = front >= 0 && rss_emergency(s, front, x, v, el, rTEgo, aMin, aMax);
+  const int sl = cmd == MCS_ACT_LEFT ? L.leftIdx : L.rightIdx;
+  if (sl >= 0 && sc.lanes[sl].type == MCS_LANE_MAIN) {
+    int leader, follower;
+    side_leader_follower(s, laneStart, sl, x, leader, follower);
+    ax = idm_acc(s, pe, leader, front, follower, x, v, el, mcs_pow4(v / vdCap));
+    if (emergency) ax = aMin;
+    if (rss_safe(s, leader, follower, x, v, el, rTOther, rTEgo, aMin, aMax)) {
+      const double m = MCS_MINSD(1.0, 0.17 * v);
+      avy = m * (cmd == MCS_ACT_LEFT ? 1.0 : -1.0);
+    }
+  } else {
+    ax = emergency ? aMin : 0.0;
+  }
+}
+
 // block-wide exclusive scan of one int per thread; blockDim.x multiple of 32, ≤ 256
 __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int& total) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -342,28 +459,8 @@ __global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, cons
   const CandDev cd = cands[cand];
   mcs_status* st_out = lp.status + ((size_t)cand * lp.count + ridx);
 
-  // ---- carve shared memory
   Smem s;
-  {
-    unsigned char* p = smem_raw;
-    s.x = (double*)p; p += sizeof(double) * np;
-    s.v = (double*)p; p += sizeof(double) * np;
-    s.l = (double*)p; p += sizeof(double) * np;
-    s.vd = (double*)p; p += sizeof(double) * np;
-    s.idm = (double*)p; p += sizeof(double) * 5 * np;
-    s.mob = (double*)p; p += sizeof(double) * 6 * np;
-    s.chist = (double*)p; p += sizeof(double) * ((lp.steps + 2) & ~1);
-    s.csort = (double*)p; p += sizeof(double) * ((lp.steps + 2) & ~1);
-    s.red = (double*)p; p += sizeof(double) * 16;
-    s.scan = (int*)p; p += sizeof(int) * 16;
-    s.cnt = (int*)p; p += sizeof(int) * 16;
-    s.flags = (int*)p; p += sizeof(int) * 8;
-    s.tasks = (int*)p; p += sizeof(int) * np;
-    s.lane = p; p += np;
-    s.vec = p; p += np;
-    s.mflag = p; p += 2 * np;
-    s.pos = p; p += np;
-  }
+  carve_smem(s, smem_raw, np, lp.steps);
   int* laneStart = s.cnt;  // [n_lanes + 1]
 
   if (!cd.ok) {           // setEgoAgentIdAndDrivingBehavior failed: the reference runs nothing (runMTimes 0xc2935)
@@ -535,34 +632,8 @@ __global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, cons
       pushThw = true;
       avy = centering_vy(y, centerY);
       if (mode == 2) {
-        // customizedLaneChangeBehavior 0xf5e30
-        const double vdCap = MCS_MINSD(evd, 1.1 * vLimit);
-        const int cmd = cd.action;
-        if (cmd == MCS_ACT_KEEP_LANE || cmd == MCS_ACT_ACC || cmd == MCS_ACT_DCC) {
-          IdmP p = pe;
-          double vdd = vdCap;
-          if (cmd == MCS_ACT_DCC) { p.thw = pe.thw + pe.thw; vdd = 0.8 * vdCap; }
-          if (cmd == MCS_ACT_ACC) { p.thw = 0.9; vdd = 1.1 * vdCap; }
-          ax = idm_acc(s, p, front, -1, -1, x, v, el, mcs_pow4(v / vdd));
-          if (front >= 0 && rss_emergency(s, front, x, v, el, rTEgo, aMin, aMax)) ax = aMin;
-        } else {
-          const bool emergency = front >= 0 && rss_emergency(s, front, x, v, el, rTEgo, aMin, aMax);
-          const LaneDev& L = sc.lanes[lane];
-          const int sl = cmd == MCS_ACT_LEFT ? L.leftIdx : L.rightIdx;
-          if (sl >= 0 && sc.lanes[sl].type == MCS_LANE_MAIN) {
-            int leader, follower;
-            side_leader_follower(s, laneStart, sl, x, leader, follower);
-            ax = idm_acc(s, pe, leader, front, follower, x, v, el, mcs_pow4(v / vdCap));
-            if (emergency) ax = aMin;
-            const double rTOther = F[(size_t)F_RSS_RTOTHER * np + k];
-            if (rss_safe(s, leader, follower, x, v, el, rTOther, rTEgo, aMin, aMax)) {
-              const double m = MCS_MINSD(1.0, 0.17 * v);
-              avy = m * (cmd == MCS_ACT_LEFT ? 1.0 : -1.0);
-            }
-          } else {
-            ax = emergency ? aMin : 0.0;
-          }
-        }
+        customized_lane_change(s, sc, laneStart, np, k, lane, front, cd.action, x, v, el, evd, F[(size_t)F_RSS_RTOTHER * np + k],
+                               rTEgo, aMin, aMax, ax, avy);
       } else if (kMerge && (mode == 3 || mode == 4)) {
         MergeSelf me;
         me.k = k; me.lane = lane; me.front = front; me.x = x; me.y = y; me.v = v; me.l = el;
@@ -639,56 +710,11 @@ __global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, cons
           if (commit == MCS_COMMIT_KEEP_LANE && keepStep <= 9) {
             keepStep = keepStep + 1;
           } else if (needMobil) {
-            const int mf = s.mflag[k] | s.mflag[np + k];
-            const bool canL = mf & MF_CAN_L, canR = mf & MF_CAN_R;
-            const bool strictL = mf & MF_STRICT_L, relaxL = mf & MF_RELAX_L, strictR = mf & MF_STRICT_R, relaxR = mf & MF_RELAX_R;
-            const double accNewL = s.mob[k], accNewR = s.mob[np + k], dNewL = s.mob[2 * np + k], dNewR = s.mob[3 * np + k];
-            const double deltaOld = s.mob[4 * np + k];
-            const double pf = F[(size_t)F_YP_PF * np + k], dA = F[(size_t)F_YP_DA * np + k], bA = F[(size_t)F_YP_BA * np + k];
-            const double axIdm = ax, vyIdm = avy;
-            double axLeft = axIdm, vyLeft = vyIdm, axRight = 0.0, vyRight = 0.0;
-            double incL = -10000000000.0, incR = -10000000000.0;
-            if (canL) {
-              axLeft = (axIdm == aMin) ? axIdm : accNewL;
-              vyLeft = MCS_MINSD(1.0, 0.17 * v);
-              incL = (((dNewL + deltaOld) * pf + (accNewL - axIdm)) - dA) - bA;
-            }
-            if (canR) {
-              axRight = accNewR;
-              vyRight = MCS_MAXSD(-1.0, -0.17 * v);
-              incR = (((dNewR + deltaOld) * pf + (accNewR - axIdm)) - dA) + bA;
-            }
-            const LaneDev& L = sc.lanes[lane];
-            if (commit == MCS_COMMIT_LEFT && targetLane != L.id && relaxL) { ax = axLeft; avy = vyLeft; }
-            else if (commit == MCS_COMMIT_RIGHT && targetLane != L.id && relaxR) { ax = axRight; avy = vyRight; }
-            else {
-              keepStep = 0;
-              const double eL = mcs_exp(incL), eR = mcs_exp(incR);
-              const double denom = (1.0 + eL) + eR;
-              double p[3];
-              p[0] = eL / denom; p[2] = eR / denom; p[1] = (1.0 - p[0]) - p[2];
-              if (commit == MCS_COMMIT_NOT_DECIDED && nStates <= 1) {
-                if (aggressive) lane_change_probability(p, prior0, prior1, prior2, relaxL, relaxR);
-                else {
-                  const bool r = strictR ? true : ((prior2 >= 0.5) && relaxR);
-                  const bool l = strictL ? true : ((prior0 >= 0.5) && relaxL);
-                  lane_change_probability(p, prior0, prior1, prior2, l, r);
-                }
-              } else if (aggressive) lane_change_probability(p, 0.0, 0.0, 0.0, relaxL, relaxR);
-              else lane_change_probability(p, 0.0, 0.0, 0.0, strictL, strictR);
-              double pL = p[0];
-              if (el > 6.0) {
-                pL = pL * 0.5;
-                if (L.leftIdx >= 0 && sc.lanes[L.leftIdx].leftmost) pL = 0.0;
-                const double k2 = p[1] + p[1], r2 = p[2] + p[2];
-                const double S = (k2 + pL) + r2;
-                p[1] = k2 / S; p[2] = r2 / S;
-              }
-              const double u = (double)mcs_rand31(key, drawBase + (uint64_t)nY + 1) / 2147483647.0;
-              if (pL > u && canL) { commit = MCS_COMMIT_LEFT; targetLane = sc.lanes[L.leftIdx].id; ax = axLeft; avy = vyLeft; }
-              else if (pL + p[2] > u && canR) { commit = MCS_COMMIT_RIGHT; targetLane = sc.lanes[L.rightIdx].id; ax = axRight; avy = vyRight; }
-              else { commit = MCS_COMMIT_KEEP_LANE; targetLane = -1; }
-            }
+            const double u = (double)mcs_rand31(key, drawBase + (uint64_t)nY + 1) / 2147483647.0;
+            MobilState ms{commit, keepStep, targetLane};
+            mobil_decide(s, sc, np, k, lane, v, el, aMin, F[(size_t)F_YP_PF * np + k], F[(size_t)F_YP_DA * np + k],
+                         F[(size_t)F_YP_BA * np + k], /*mode=*/(nStates <= 1) ? 0 : 1, aggressive, prior0, prior1, prior2, u, ms, ax, avy);
+            commit = ms.commit; keepStep = ms.keepStep; targetLane = ms.targetLane;
           }
         }
       }

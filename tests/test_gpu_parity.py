@@ -211,3 +211,73 @@ def test_full_size_properties(gpu, oracle):
             assert bytes(a[1000 + i])[:48] == bytes(ost[i])[:48], i
     finally:
         ds.close()
+
+
+DECISION_CASES = golden_io.load_all("decisions")
+
+
+@pytest.mark.parametrize("case", DECISION_CASES, ids=golden_io.ids(DECISION_CASES))
+def test_single_decisions_against_reference_golden_vectors(gpu, case):
+    """mcs_decide_* (laneChangeMobilBehavior, fixedDirectionLaneChangeBehavior, fixedGapMergingBehavior,
+    closestGapMergingBehavior) against what the reference binary's wrappers returned."""
+    s = golden_io.scene_of(case)
+    ds = gpu.DeviceScene(s.c_corridors(), s.c_agents())
+    try:
+        for call in case["calls"]:
+            t = call["cmd"].split()
+            ans = call["answer"]
+            if t[0] == "mobil":
+                out = ds.decide_mobil(int(t[1]), float(t[2]), float(t[3]), int(t[4]), case["key"])
+                assert abi.COMMIT_NAMES[out.commit] == ans["commit"] and out.commit_keep_lane_step == int(ans["keep"]), call
+                assert out.target_lane_id == int(ans["target"]), call
+            elif t[0] == "fixed_dir":
+                out = ds.decide_fixed_direction(int(t[1]), abi.ACTIONS[t[2]])
+            elif t[0] == "fixed_gap":
+                out = ds.decide_fixed_gap(int(t[1]), abi.ACTIONS[t[2]], int(t[3]))
+            else:
+                out = ds.decide_closest_gap(int(t[1]), abi.ACTIONS[t[2]])
+            assert (out.ax, out.vy) == (float(ans["ax"]), float(ans["vy"])), call
+    finally:
+        ds.close()
+
+
+def test_mobil_decisions_against_oracle(gpu, oracle):
+    """laneChangeMobilBehavior with the commit state Python pokes into the agent (behaviors.py:75-80), both requireRss values."""
+    rng = random.Random(12)
+    commits = ["not_decided", "keep_lane", "left", "right"]
+    checked = 0
+    for sc in range(12):
+        s, ego = random_scene(rng, rng.choice([2, 3, 4]), rng.choice([6, 12, 25]))
+        for a in s.agents:
+            a["commit"] = rng.choice(commits); a["keep_step"] = rng.randrange(0, 14)
+            a["target_lane"] = rng.choice([-1, 1, 2, 3])
+        cs, as_ = s.c_corridors(), s.c_agents()
+        ds = gpu.DeviceScene(cs, as_)
+        try:
+            for a in rng.sample(s.agents, min(6, len(s.agents))):
+                for req in (0, 1):
+                    ax, vy = rng.uniform(-6, 1.5), rng.uniform(-0.3, 0.3)
+                    if rng.random() < 0.2:
+                        ax = a["rss"][2]
+                    want = abi.ActionWithType()
+                    act = abi.Action(ax, vy)
+                    rc = oracle.lib.orc_decide_mobil(cs, len(cs), as_, len(as_), a["id"], C.byref(act), req, 900 + sc, C.byref(want))
+                    assert rc == 0
+                    got = ds.decide_mobil(a["id"], ax, vy, req, 900 + sc)
+                    assert (got.ax, got.vy, got.commit, got.commit_keep_lane_step, got.target_lane_id) == \
+                        (want.ax, want.vy, want.commit, want.commit_keep_lane_step, want.target_lane_id), (sc, a["id"], req)
+                    checked += 1
+        finally:
+            ds.close()
+    assert checked > 100
+
+
+def test_decide_unknown_agent_is_an_error(gpu):
+    s = probe_scene()
+    ds = gpu.DeviceScene(s.c_corridors(), s.c_agents())
+    try:
+        with pytest.raises(gpu.McsimError) as e:
+            ds.decide_fixed_direction(4242, abi.ACTIONS["keep_lane"])
+        assert e.value.code == abi.MCS_ERR_ARG
+    finally:
+        ds.close()
