@@ -1,14 +1,19 @@
 #!/usr/bin/env python
-"""bench.py — MC rollout throughput (vehicle-steps/s) of the B200 rollout path, next to the reference's CPU path.
+"""bench.py — MC rollout throughput (vehicle-steps/s) and decision latency of the B200 rollout path, next to the
+reference's own CPU path.
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
     python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's own machine code on the host cores)
 
-A "step" is one launch of the rollout kernel over one batch of rollouts of BASELINE.json's throughput
-configuration (configs[4]): 256 vehicles x 100 steps, every non-ego vehicle `idm_lc`, ego `keep_lane`,
-minSteps = steps (no early exit); `--rollouts` rollouts per step per GPU (default 65536 = 1/16 of the 1M sweep,
-so the default run ends in minutes).  Rollouts are independent, so ranks shard the rollout index range with no
+Throughput (the JSON line's `value`): a "step" is one launch of the rollout kernel over one batch of rollouts of
+BASELINE.json's throughput configuration (configs[4]): 256 vehicles x 100 steps, every non-ego vehicle `idm_lc`, ego
+`keep_lane`, minSteps = steps (no early exit); `--rollouts` rollouts per step per GPU (default 65536 = 1/16 of the 1M
+sweep, so the default run ends in minutes).  Rollouts are independent, so ranks shard the rollout index range with no
 data-path collective (weak scaling: per-GPU batch fixed).
+
+Decision latency (`decision`): BASELINE.json configs[1] — merging lane + 3 main lanes, 40 vehicles, 512 rollouts per
+candidate gap, 4 candidates, SimParameter(0.3, 40, 10) — through the public API: scene upload, one launch for all
+candidates, (N>1: NCCL all-gather of the 64-byte group partials), fixed-order combine, learned model, final gap action.
 """
 import argparse
 import ctypes as C
@@ -27,6 +32,8 @@ UNIT = "vehicle-steps/s"
 FLOP_PER_VEHICLE_STEP = 100.0     # 63 base + 380 per MOBIL evaluation at ~1/10 duty
 SIM_DT, SIM_STEPS = 0.3, 100
 N_VEHICLES, N_LANES = 256, 4
+DEC_VEHICLES, DEC_N_PER_GROUP, DEC_STEPS, DEC_MIN_STEPS = 40, 64, 40, 10
+N_SM = 148
 
 
 def workload_config(args):
@@ -95,20 +102,13 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def dist_setup(n_gpus):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def reference_rollouts_per_s(args, sample_m, threads_mode):
-    """Time the reference's own machine code (oracle/_ref) on this box's host cores: runMultiThreads (its own
-    8-thread fan-out) or runMTimes (one thread) over a bounded sample of the same scene."""
-    from oracle.pyoracle import RefHarness, SceneSpec
-    from interactive_highway_simulation_b200 import synthetic
-    corridors, agents, ego = synthetic.lane_change_scene(N_VEHICLES, N_LANES, seed=args.scene_seed)
+def scene_spec(corridors, agents):
+    from oracle.pyoracle import SceneSpec
     spec = SceneSpec()
     lane_names = {0: "main", 1: "merging", 2: "exit"}
     for c in corridors:
@@ -118,37 +118,64 @@ def reference_rollouts_per_s(args, sample_m, threads_mode):
     for a in agents:
         spec.add_agent(a.id, a.x, a.y, a.v, a.vd, beh[a.behavior], vy=a.vy, a=a.a, l=a.l, w=a.w, idm=tuple(a.idm),
                        rss=tuple(a.rss), yp=tuple(a.yp))
+    return spec
+
+
+def reference_time(spec, dt, steps, min_steps, mode, m, ego, action, gap, reps=1):
+    """Wall time of the reference's own machine code (oracle/_ref): runMultiThreads (`mt`: its own 8 std::threads x m)
+    or runMTimes (`m`: one thread, m rollouts) on this box's host cores, platform libm, lock-free interposed rand()."""
+    from oracle.pyoracle import RefHarness
     ref = RefHarness(math="libm")     # stock path: the platform libm, as the reference ships
-    ref.load(spec, SIM_DT, SIM_STEPS, SIM_STEPS)
+    ref.load(spec, dt, steps, min_steps)
     ref._send("rng counter 12345")
-    line, _ = ref.raw("bench %s %d %d keep_lane -2 1" % (threads_mode, sample_m, ego), tag="bench")
+    line, _ = ref.raw("bench %s %d %d %s %d %d" % (mode, m, ego, action, gap, reps), tag="bench")
     ref.close()
     kv = dict(t.split("=", 1) for t in line.split()[1:] if "=" in t)
-    rollouts = int(kv["rollouts"]); secs = float(kv["best_s"])
-    return rollouts, secs
+    return int(kv["rollouts"]), float(kv["best_s"])
+
+
+def reference_throughput(args, m, mode):
+    from interactive_highway_simulation_b200 import synthetic
+    corridors, agents, ego = synthetic.lane_change_scene(N_VEHICLES, N_LANES, seed=args.scene_seed)
+    return reference_time(scene_spec(corridors, agents), SIM_DT, SIM_STEPS, SIM_STEPS, mode, m, ego, "keep_lane", -2)
+
+
+def reference_decision_ms(args):
+    """The reference's decision on the configs[1] scene: one runMultiThreads call per candidate gap, sequentially
+    (behaviors.py:125-126), 8 x DEC_N_PER_GROUP rollouts each."""
+    from interactive_highway_simulation_b200 import synthetic
+    corridors, agents, ego, gaps = synthetic.merging_scene(DEC_VEHICLES, args.scene_seed)
+    spec = scene_spec(corridors, agents)
+    total = 0.0
+    for g in gaps:
+        _, secs = reference_time(spec, 0.3, DEC_STEPS, DEC_MIN_STEPS, "mt", DEC_N_PER_GROUP, ego, "left", g)
+        total += secs
+    return 1e3 * total, len(gaps)
 
 
 def run_reference(args):
-    rank, world, local = dist_setup(args.gpus)
+    rank, world, local = dist_env()
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
     m = max(1, args.ref_rollouts // 8)
     times, units = [], 0
     for i in range(args.warmup + args.steps):
-        rollouts, secs = reference_rollouts_per_s(args, m, "mt")
+        rollouts, secs = reference_throughput(args, m, "mt")
         if i >= args.warmup:
             times.append(secs); units += rollouts * N_VEHICLES * SIM_STEPS
     total = sum(times)
     value = units / total
-    cfg = workload_config(args)
     sample = "%d rollouts per step through the reference's runMultiThreads (8 std::threads x %d), platform libm, " \
              "lock-free interposed rand()" % (8 * m, m)
+    dec_ms, n_gaps = reference_decision_ms(args)
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(8, cores), "kind": "reference", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "decision": {"latency_ms": dec_ms, "candidates": n_gaps, "rollouts_per_candidate": 8 * DEC_N_PER_GROUP,
+                        "vehicles": DEC_VEHICLES, "note": "sum of one runMultiThreads call per candidate gap"},
            "gpu_launches": 0}
     print(json.dumps(out))
     return 0
@@ -156,7 +183,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ FP64 peak probe
 def fp64_peak_tflops(torch, device):
-    """Measured FP64 FMA rate of this GPU via a torch DGEMM (cuBLAS); the denominator of the FP64 view of the roofline."""
+    """Measured FP64 rate of this GPU via a torch DGEMM (cuBLAS); the denominator of the FP64 view of the roofline."""
     n = 4096
     a = torch.randn(n, n, dtype=torch.float64, device=device)
     b = torch.randn(n, n, dtype=torch.float64, device=device)
@@ -170,16 +197,52 @@ def fp64_peak_tflops(torch, device):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
+# ------------------------------------------------------------------------------------------------ decision latency
+def decision_latency(torch, dist, world, device, args):
+    """p50 wall time of one full learned merging decision through the public API (host buffers in, action out)."""
+    from interactive_highway_simulation_b200 import backend, synthetic, sharding, learned_model, _abi as abi
+    corridors, agents, ego, gaps = synthetic.merging_scene(DEC_VEHICLES, args.scene_seed)
+    cands = (abi.Candidate * len(gaps))(*[abi.Candidate(ego, abi.ACTIONS["left"], g, 0) for g in gaps])
+    sp = abi.SimParam(0.3, DEC_STEPS, DEC_MIN_STEPS)
+    model = learned_model.LearnedMergingModel()
+    times = []
+    decision = None
+    for i in range(args.decisions + 5):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        scene = backend.DeviceScene(corridors, agents, device=device)                    # H2D: the marshalled scene
+        feats = sharding.simulation_multi_thread_sharded(scene, cands, sp, DEC_N_PER_GROUP, 1000 + i)
+        idx, _ = model.inference([learned_model.feature_vector(f) for f in feats])
+        decision = gaps[idx]
+        act = scene.decide_fixed_gap(ego, abi.ACTIONS["left"], decision)                 # D2H: the chosen action
+        t1 = time.perf_counter()
+        scene.close()
+        if i >= 5:
+            times.append(t1 - t0)
+    t = torch.tensor(times, dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ts = sorted(t.tolist())
+    return {"latency_ms_p50": 1e3 * ts[len(ts) // 2], "latency_ms_p90": 1e3 * ts[int(len(ts) * 0.9)], "decisions": len(ts),
+            "candidates": len(gaps), "rollouts_per_candidate": 8 * DEC_N_PER_GROUP, "vehicles": DEC_VEHICLES,
+            "horizon_steps": DEC_STEPS, "last_decision_gap_id": decision, "last_action": [act.ax, act.vy],
+            "h2d_bytes": C.sizeof(corridors) + C.sizeof(agents) + C.sizeof(cands), "d2h_bytes": 64 * 8 * len(gaps) + 16,
+            "exchange": "none (1 GPU)" if world == 1 else "NCCL all_gather_into_tensor of %d B per rank" % (64 * 8 // world * len(gaps))}
+
+
 # ------------------------------------------------------------------------------------------------ product arm
 def run_product(args):
     import torch
     from interactive_highway_simulation_b200 import backend, synthetic, _abi as abi
 
-    rank, world, local = dist_setup(args.gpus)
+    rank, world, local = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the rollout path has no CPU fallback")
     device = local if world > 1 else 0
     torch.cuda.set_device(device)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", device))
@@ -201,7 +264,7 @@ def run_product(args):
         flush.zero_()
         torch.cuda.synchronize(device)
         first = (i * world + rank) * R        # disjoint rollout index ranges per rank and step
-        return scene.rollouts_device(cand, sp, seed, first, R)
+        return scene.rollouts_device(cand, sp, seed, first, R)     # CUDA events on the kernel's own stream
 
     for i in range(args.warmup):
         one_step(i)
@@ -218,14 +281,16 @@ def run_product(args):
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end-to-end through the reference-facing call (simulationMultiThread semantics): host buffers in,
-    # scene upload + launch + fixed-order reduction + feature read-back inside the timed region
+    # ---- end-to-end through the reference-facing call (simulationMultiThread semantics): host buffers in, every step
+    # uploads the scene (mcs_scene_create), launches, reduces in fixed order and reads the features back
     e2e_R = max(8, (R // 8) * 8)
     h2d = C.sizeof(corridors) + C.sizeof(agents) + C.sizeof(cand)
     d2h = C.sizeof(abi.Feature)
+    e2e_steps = max(1, min(args.steps, 3))
+    sc2 = backend.DeviceScene(corridors, agents, device=device); sc2.rollouts(cand, sp, 8, seed); sc2.close()   # warm-up
+    barrier()
     e2e_t0 = time.perf_counter()
     e2e_units = 0
-    e2e_steps = max(1, min(args.steps, 3))
     for i in range(e2e_steps):
         sc2 = backend.DeviceScene(corridors, agents, device=device)
         feats, _ = sc2.rollouts(cand, sp, e2e_R // 8, seed + 17 + i)
@@ -233,6 +298,8 @@ def run_product(args):
         sc2.close()
     torch.cuda.synchronize(device)
     e2e_s = time.perf_counter() - e2e_t0
+
+    decision = decision_latency(torch, dist, world, device, args) if args.decisions > 0 else None
 
     # ---- max over ranks, whole-job aggregate
     t = torch.tensor([kernel_ms, float(vsteps), e2e_s, float(e2e_units)], dtype=torch.float64, device=device)
@@ -252,21 +319,30 @@ def run_product(args):
     # roofline of the rollout kernel (one launch = one step)
     peak_gbs, peak_src = read_peaks()
     launch_s = kernel_ms / args.steps * 1e-3
-    scene_bytes = C.sizeof(corridors) + 28 * 8 * 256 + 8 * 4 * 256 + 256     # SoA scene read once (L2-shared)
+    scene_bytes = C.sizeof(corridors) + 30 * 8 * 256 + 8 * 4 * 256 + 256     # SoA scene read once (L2-shared)
     alg_bytes = R * 64 + scene_bytes
     achieved_gbs = alg_bytes / launch_s / 1e9
-    fp64_peak = fp64_peak_tflops(torch, device)
-    fp64_achieved = (vsteps / args.steps) * FLOP_PER_VEHICLE_STEP / launch_s / 1e12
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs,
                 "traffic": None, "peak_source": peak_src,
-                "note": "algorithmic HBM traffic is 64 B per rollout + one scene read: the kernel is FP64 issue/latency "
-                        "bound, see fp64"}
+                "note": "algorithmic HBM traffic is 64 B per rollout + one scene read (state lives in registers/shared "
+                        "memory for the whole rollout): by design the kernel is nowhere near the HBM roof; its limiter is "
+                        "FP64/control instruction issue and barrier latency, see `issue` and `fp64`"}
+    issue = None
     prof = os.path.join(HERE, "profiles", "r01_rollout_kernel_dram.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            pj = json.load(open(prof))
+            roofline["traffic"] = pj.get("dram_bytes_per_rollout", 0) * R or None
+            ipv = pj.get("warp_inst_per_vehicle_step")
+            if ipv and clocks and clocks.get("sm_mhz"):
+                per_gpu = value / world
+                issue = {"achieved_warp_inst_per_s": per_gpu * ipv, "peak_warp_inst_per_s": N_SM * 4 * clocks["sm_mhz"] * 1e6,
+                         "frac": per_gpu * ipv / (N_SM * 4 * clocks["sm_mhz"] * 1e6), "warp_inst_per_vehicle_step": ipv,
+                         "source": "instruction count per vehicle-step from the committed ncu capture (%s), rate from this run" % pj.get("source")}
         except Exception:
             pass
+    fp64_peak = fp64_peak_tflops(torch, device)
+    fp64_achieved = (vsteps / args.steps) * FLOP_PER_VEHICLE_STEP / launch_s / 1e12
     fp64 = {"achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak,
             "flop_per_vehicle_step": FLOP_PER_VEHICLE_STEP, "peak_source": "cuBLAS DGEMM 4096^3 measured in this run"}
 
@@ -275,23 +351,27 @@ def run_product(args):
     if world == 1 and not args.no_cpu_baseline:
         try:
             m = max(1, args.ref_rollouts // 8)
-            rollouts, secs = reference_rollouts_per_s(args, m, "mt")
-            r1, s1 = reference_rollouts_per_s(args, max(1, m), "m")
+            rollouts, secs = reference_throughput(args, m, "mt")
+            r1, s1 = reference_throughput(args, max(1, m), "m")
             cpu = {"value": rollouts * N_VEHICLES * SIM_STEPS / secs, "unit": UNIT, "cores": min(8, os.cpu_count() or 1),
                    "kind": "reference",
                    "sample": "%d rollouts of the same scene through the reference's runMultiThreads (8 threads), platform "
                              "libm; single-thread runMTimes on %d rollouts: %.3g vehicle-steps/s"
                              % (rollouts, r1, r1 * N_VEHICLES * SIM_STEPS / s1)}
+            if decision is not None:
+                dec_ms, _ = reference_decision_ms(args)
+                decision["cpu_reference_latency_ms"] = dec_ms
         except Exception as e:    # oracle/_ref is built only where /root/reference exists
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-           "roofline": roofline, "fp64": fp64, "cpu_baseline": cpu, "clocks": clocks,
+           "roofline": roofline, "issue": issue, "fp64": fp64, "cpu_baseline": cpu, "clocks": clocks,
            "e2e": {"value": e2e_units_total / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h,
                    "note": "mcs_scene_create + mcs_rollouts (8 groups x %d) + feature read-back per step, host buffers" % (e2e_R // 8)},
+           "decision": decision,
            "gpu_launches": args.steps, "wall_s_timed_region": wall,
            "rollouts_per_s": units_total / (N_VEHICLES * SIM_STEPS) / (kernel_ms_max * 1e-3)}
     print(json.dumps(out))
@@ -308,6 +388,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rollouts", type=int, default=65536, help="rollouts per step per GPU")
     ap.add_argument("--ref-rollouts", type=int, default=192, help="rollouts per CPU-reference sample")
+    ap.add_argument("--decisions", type=int, default=40, help="timed decisions for the latency figure (0 = skip)")
     ap.add_argument("--scene-seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -98,6 +98,12 @@ typedef struct mcs_status { /* StatusOneSim of one rollout + bookkeeping; 64 byt
   int32_t reserved[4];
 } mcs_status;
 
+typedef struct mcs_group_partial { /* one runMTimes group = one thread's BehaviorFeature inside runMultiThreads; 64 bytes */
+  double f[7];       /* group means: fallBackRate successRate utility comfort expectedStepRatio utilityObjects comfortObjects */
+  int32_t fromNSims; /* n_per_group, or 0 when setEgoAgentIdAndDrivingBehavior failed (group skipped by the mean) */
+  int32_t reserved;
+} mcs_group_partial;
+
 typedef struct mcs_action { double ax, vy; } mcs_action;
 
 typedef struct mcs_action_with_type { /* ActionWithType */
@@ -138,6 +144,25 @@ int mcs_rollouts_range(mcs_scene* scene, const mcs_candidate* candidates, int n_
 /* Fixed-order two-level mean (host, pure function): statuses = n_candidates × (groups*n_per_group). */
 int mcs_reduce_features(const mcs_status* statuses, int n_candidates, int groups, int n_per_group, int steps,
                         mcs_feature* features_out);
+
+/* Multi-GPU form of simulationMultiThread: the 8 groups of runMultiThreads are the shard unit.  A rank simulates groups
+ * [first_group, first_group+n_groups) of every candidate (rollouts first_group*n_per_group ...) and gets one partial
+ * per (candidate, group): partials_out[c*n_groups + g].  The ranks all-gather their partials (64 B each — the only
+ * data that crosses NVLink) and every rank calls mcs_combine_groups, which adds them in group order exactly like
+ * runMultiThreads 0xbca08-0xbca92: the result is bit-identical to the single-GPU mcs_rollouts.
+ * mcs_rollouts_groups_device leaves the partials in device memory (d_partials_out, e.g. a torch tensor handed to NCCL)
+ * and only enqueues work on the scene's stream; mcs_scene_sync waits for it. */
+int mcs_rollouts_groups(mcs_scene* scene, const mcs_candidate* candidates, int n_candidates, const mcs_sim_param* param,
+                        int n_per_group, uint64_t seed, int first_group, int n_groups, mcs_group_partial* partials_out);
+int mcs_rollouts_groups_device(mcs_scene* scene, const mcs_candidate* candidates, int n_candidates,
+                               const mcs_sim_param* param, int n_per_group, uint64_t seed, int first_group, int n_groups,
+                               void* d_partials_out);
+int mcs_scene_sync(mcs_scene* scene);
+/* host, pure: statuses[n_candidates][groups*n_per_group] -> partials[n_candidates][groups] (runMTimes 0xc2a6e-0xc2b1f) */
+int mcs_group_partials(const mcs_status* statuses, int n_candidates, int groups, int n_per_group, int steps,
+                       mcs_group_partial* partials_out);
+/* host, pure: partials[n_candidates][groups] -> features (runMultiThreads 0xbca08-0xbca92, fixed group order) */
+int mcs_combine_groups(const mcs_group_partial* partials, int n_candidates, int groups, mcs_feature* features_out);
 
 /* Device-resident variant used by the throughput benchmark: results stay in HBM
  * (d_status_out = device pointer or NULL to keep only the per-block vehicle-step counters).

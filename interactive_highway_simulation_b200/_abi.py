@@ -56,6 +56,10 @@ class Status(C.Structure):
                 ("overflow", C.c_uint8), ("reserved", C.c_int32 * 4)]
 
 
+class GroupPartial(C.Structure):
+    _fields_ = [("f", C.c_double * 7), ("fromNSims", C.c_int32), ("reserved", C.c_int32)]
+
+
 class Action(C.Structure):
     _fields_ = [("ax", C.c_double), ("vy", C.c_double)]
 
@@ -66,4 +70,5 @@ class ActionWithType(C.Structure):
 
 
 
+assert C.sizeof(GroupPartial) == 64
 assert C.sizeof(Status) == 64 and C.sizeof(Feature) == 64 and C.sizeof(Agent) == 240 and C.sizeof(Corridor) == 112

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libmcsim_b200.so")
 EXPORTS = [
     "mcs_device_count", "mcs_last_error", "mcs_version", "mcs_scene_create", "mcs_scene_destroy",
     "mcs_scene_visit_order", "mcs_rollouts", "mcs_rollouts_range", "mcs_reduce_features", "mcs_rollouts_device",
+    "mcs_rollouts_groups", "mcs_rollouts_groups_device", "mcs_scene_sync", "mcs_group_partials", "mcs_combine_groups",
     "mcs_trajectories", "mcs_decide_mobil", "mcs_decide_fixed_direction", "mcs_decide_fixed_gap",
     "mcs_decide_closest_gap",
 ]
@@ -59,6 +60,18 @@ def lib():
     L.mcs_rollouts_device.restype = C.c_int
     L.mcs_rollouts_device.argtypes = [C.c_void_p, P(abi.Candidate), C.c_int, P(abi.SimParam), C.c_uint64, C.c_int64,
                                       C.c_int64, C.c_void_p, C.c_void_p, P(C.c_float), P(C.c_uint64)]
+    L.mcs_rollouts_groups.restype = C.c_int
+    L.mcs_rollouts_groups.argtypes = [C.c_void_p, P(abi.Candidate), C.c_int, P(abi.SimParam), C.c_int, C.c_uint64, C.c_int,
+                                      C.c_int, P(abi.GroupPartial)]
+    L.mcs_rollouts_groups_device.restype = C.c_int
+    L.mcs_rollouts_groups_device.argtypes = [C.c_void_p, P(abi.Candidate), C.c_int, P(abi.SimParam), C.c_int, C.c_uint64,
+                                             C.c_int, C.c_int, C.c_void_p]
+    L.mcs_scene_sync.restype = C.c_int
+    L.mcs_scene_sync.argtypes = [C.c_void_p]
+    L.mcs_group_partials.restype = C.c_int
+    L.mcs_group_partials.argtypes = [P(abi.Status), C.c_int, C.c_int, C.c_int, C.c_int, P(abi.GroupPartial)]
+    L.mcs_combine_groups.restype = C.c_int
+    L.mcs_combine_groups.argtypes = [P(abi.GroupPartial), C.c_int, C.c_int, P(abi.Feature)]
     L.mcs_trajectories.restype = C.c_int
     L.mcs_trajectories.argtypes = [C.c_void_p, P(abi.Candidate), P(abi.SimParam), C.c_uint64, C.c_int64,
                                    P(C.c_double), P(C.c_int32), P(abi.Status)]
@@ -121,6 +134,18 @@ class DeviceScene:
         check(lib().mcs_rollouts_range(self._h, candidates, nc, C.byref(sim_param), seed, first, count, st))
         return st
 
+    def rollouts_groups(self, candidates, sim_param, n_per_group, seed, first_group, n_groups, d_partials_ptr=None):
+        """Groups [first_group, first_group+n_groups) of every candidate -> one GroupPartial per (candidate, group); with
+        d_partials_ptr (a device pointer, e.g. tensor.data_ptr()) the partials stay on the GPU for the NCCL exchange."""
+        nc = len(candidates)
+        if d_partials_ptr is not None:
+            check(lib().mcs_rollouts_groups_device(self._h, candidates, nc, C.byref(sim_param), n_per_group, seed, first_group,
+                                                   n_groups, d_partials_ptr))
+            return None
+        out = (abi.GroupPartial * (nc * n_groups))()
+        check(lib().mcs_rollouts_groups(self._h, candidates, nc, C.byref(sim_param), n_per_group, seed, first_group, n_groups, out))
+        return out
+
     def rollouts_device(self, candidates, sim_param, seed, first, count, d_status_ptr=None):
         ms = C.c_float()
         steps = C.c_uint64()
@@ -159,6 +184,18 @@ class DeviceScene:
         out = abi.Action()
         check(lib().mcs_decide_closest_gap(self._h, agent_id, direction, C.byref(out)))
         return out
+
+
+def group_partials(statuses, n_candidates, groups, n_per_group, steps):
+    out = (abi.GroupPartial * (n_candidates * groups))()
+    check(lib().mcs_group_partials(statuses, n_candidates, groups, n_per_group, steps, out))
+    return out
+
+
+def combine_groups(partials, n_candidates, groups):
+    feats = (abi.Feature * n_candidates)()
+    check(lib().mcs_combine_groups(partials, n_candidates, groups, feats))
+    return feats
 
 
 def reduce_features(statuses, n_candidates, groups, n_per_group, steps):

@@ -27,13 +27,12 @@ size_t rollout_smem_bytes(int n_pad, int steps) {
   return doubles * 8 + ints * 4 + 5 * (size_t)n_pad;
 }
 
-// per-candidate two-level mean, fixed order: runMTimes 0xc2a6e-0xc2b1f per group, runMultiThreads 0xbca08-0xbca92
-__host__ __device__ inline void reduce_one(const mcs_status* s, int groups, int m, int steps, mcs_feature* out) {
-  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-  int nOk = 0;
-  for (int g = 0; g < groups; ++g) {
-    const mcs_status* p = s + (size_t)g * m;
-    if (m <= 0 || !p[0].ok) continue;
+// runMTimes 0xc2a6e-0xc2b1f: the means of one group of m rollouts (p[0].ok == 0: setEgo failed, fromNSims = 0)
+__host__ __device__ inline void group_partial(const mcs_status* p, int m, int steps, mcs_group_partial* out) {
+  mcs_group_partial g;
+  for (int t = 0; t < 7; ++t) g.f[t] = 0.0;
+  g.fromNSims = 0; g.reserved = 0;
+  if (m > 0 && p[0].ok) {
     int nFall = 0, nFin = 0, sumStep = 0;
     double u = 0.0, c = 0.0, uo = 0.0, co = 0.0;
     for (int i = 0; i < m; ++i) {
@@ -42,102 +41,120 @@ __host__ __device__ inline void reduce_one(const mcs_status* s, int groups, int 
       u = u + p[i].utility; c = c + p[i].comfort; uo = uo + p[i].utilityObjects; co = co + p[i].comfortObjects;
     }
     const double M = (double)m;
-    acc[0] = acc[0] + (double)nFall / M;
-    acc[1] = acc[1] + (double)nFin / M;
-    acc[2] = acc[2] + u / M;
-    acc[3] = acc[3] + c / M;
-    acc[4] = acc[4] + (double)(sumStep <= 0 ? 1 : sumStep) / (double)(nFin * steps <= 0 ? 1 : nFin * steps);
-    acc[5] = acc[5] + uo / M;
-    acc[6] = acc[6] + co / M;
-    nOk++;
+    g.f[0] = (double)nFall / M; g.f[1] = (double)nFin / M; g.f[2] = u / M; g.f[3] = c / M;
+    g.f[4] = (double)(sumStep <= 0 ? 1 : sumStep) / (double)(nFin * steps <= 0 ? 1 : nFin * steps);
+    g.f[5] = uo / M; g.f[6] = co / M;
+    g.fromNSims = m;
   }
+  *out = g;
+}
+
+// runMultiThreads 0xbca08-0xbca92: plain mean, in group order, of the groups whose fromNSims > 0
+__host__ __device__ inline void combine_groups(const mcs_group_partial* g, int groups, mcs_feature* out) {
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  int nOk = 0, m = 0;
+  for (int q = 0; q < groups; ++q)
+    if (g[q].fromNSims > 0) { for (int t = 0; t < 7; ++t) acc[t] = acc[t] + g[q].f[t]; nOk++; m = g[q].fromNSims; }
   const double d = (double)nOk;
   out->fallBackRate = acc[0] / d; out->successRate = acc[1] / d; out->utility = acc[2] / d; out->comfort = acc[3] / d;
   out->expectedStepRatio = acc[4] / d; out->utilityObjects = acc[5] / d; out->comfortObjects = acc[6] / d;
   out->fromNSims = nOk * m; out->reserved = 0;
 }
 
-// one thread per (candidate, group) computes the group's means; thread 0 of the candidate combines them in group order
-__global__ void reduce_features_kernel(const mcs_status* __restrict__ st, int groups, int m, int steps, mcs_feature* out) {
-  __shared__ double part[MCS_GROUPS][7];
-  __shared__ int okf[MCS_GROUPS];
-  const int c = blockIdx.x, g = threadIdx.x;
-  const mcs_status* p = st + ((size_t)c * groups + g) * m;
-  if (g < groups) {
-    int ok = (m > 0 && p[0].ok) ? 1 : 0;
-    if (ok) {
-      int nFall = 0, nFin = 0, sumStep = 0;
-      double u = 0.0, cf = 0.0, uo = 0.0, co = 0.0;
-      for (int i = 0; i < m; ++i) {
-        nFall += p[i].fallBack != 0;
-        if (p[i].finish) { nFin++; sumStep += p[i].finishStep; }
-        u = u + p[i].utility; cf = cf + p[i].comfort; uo = uo + p[i].utilityObjects; co = co + p[i].comfortObjects;
-      }
-      const double M = (double)m;
-      part[g][0] = (double)nFall / M; part[g][1] = (double)nFin / M; part[g][2] = u / M; part[g][3] = cf / M;
-      part[g][4] = (double)(sumStep <= 0 ? 1 : sumStep) / (double)(nFin * steps <= 0 ? 1 : nFin * steps);
-      part[g][5] = uo / M; part[g][6] = co / M;
-    }
-    okf[g] = ok;
-  }
-  __syncthreads();
-  if (g == 0) {
-    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    int nOk = 0;
-    for (int q = 0; q < groups; ++q)
-      if (okf[q]) { for (int t = 0; t < 7; ++t) acc[t] = acc[t] + part[q][t]; nOk++; }
-    const double d = (double)nOk;
-    mcs_feature f;
-    f.fallBackRate = acc[0] / d; f.successRate = acc[1] / d; f.utility = acc[2] / d; f.comfort = acc[3] / d;
-    f.expectedStepRatio = acc[4] / d; f.utilityObjects = acc[5] / d; f.comfortObjects = acc[6] / d;
-    f.fromNSims = nOk * m; f.reserved = 0;
-    out[c] = f;
-  }
+// one thread per (candidate, group): statuses [n_cand][groups*m] -> partials [n_cand][groups]
+__global__ void group_partials_kernel(const mcs_status* __restrict__ st, int n_cand, int groups, int m, int steps,
+                                      mcs_group_partial* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cand * groups) return;
+  group_partial(st + (size_t)i * m, m, steps, out + i);
+}
+
+// one thread per candidate: partials [n_cand][groups] -> features
+__global__ void combine_groups_kernel(const mcs_group_partial* __restrict__ g, int n_cand, int groups, mcs_feature* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cand) return;
+  combine_groups(g + (size_t)c * groups, groups, out + c);
 }
 
 }  // namespace
 
+// Everything a call needs besides the scene itself lives in one grow-only context per device: creating and destroying
+// scenes (one per decision in the reference's call pattern) then costs one stream-ordered allocation and one H2D copy.
+struct DeviceCtx {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  mcs::CandDev* d_cand = nullptr; int cand_cap = 0;
+  mcs_feature* d_feat = nullptr;
+  mcs_group_partial* d_part = nullptr;   // [cand_cap][MCS_GROUPS]
+  mcs::CandDev* h_cand = nullptr;        // pinned
+  mcs_feature* h_feat = nullptr;         // pinned
+  mcs_status* d_status = nullptr; size_t status_cap = 0;
+  unsigned long long* d_counter = nullptr;
+  void* d_decide = nullptr;              // mcs::DecideOut
+  unsigned char* h_stage = nullptr; size_t stage_cap = 0;   // pinned staging of the scene blob
+  std::mutex mu;
+};
+
 struct mcs_scene {
   int device = 0;
+  DeviceCtx* ctx = nullptr;
   mcs::SceneHost host;
   mcs::SceneDev dev{};
-  double* d_f = nullptr;
-  int32_t* d_i = nullptr;
-  uint8_t* d_vec = nullptr;
-  cudaStream_t stream = nullptr;
-  // reusable device / pinned staging
-  mcs::CandDev* d_cand = nullptr; int cand_cap = 0;
-  mcs_status* d_status = nullptr; size_t status_cap = 0;
-  mcs_feature* d_feat = nullptr; int feat_cap = 0;
-  unsigned long long* d_counter = nullptr;
-  void* d_decide = nullptr;             // mcs::DecideOut
-  mcs::CandDev* h_cand = nullptr;      // pinned
-  mcs_feature* h_feat = nullptr;       // pinned
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  std::mutex mu;
+  unsigned char* d_blob = nullptr;   // f | i | lane_vec in one allocation
 };
 
 namespace {
 
-int ensure_capacity(mcs_scene* sc, int n_cand, size_t n_status) {
-  if (n_cand > sc->cand_cap) {
-    if (sc->d_cand) cudaFree(sc->d_cand);
-    if (sc->d_feat) cudaFree(sc->d_feat);
-    if (sc->h_cand) cudaFreeHost(sc->h_cand);
-    if (sc->h_feat) cudaFreeHost(sc->h_feat);
-    sc->cand_cap = sc->feat_cap = 0;
-    int cap = n_cand < 8 ? 8 : n_cand;
-    CUDA_TRY(cudaMalloc(&sc->d_cand, sizeof(mcs::CandDev) * cap));
-    CUDA_TRY(cudaMalloc(&sc->d_feat, sizeof(mcs_feature) * cap));
-    CUDA_TRY(cudaMallocHost(&sc->h_cand, sizeof(mcs::CandDev) * cap));
-    CUDA_TRY(cudaMallocHost(&sc->h_feat, sizeof(mcs_feature) * cap));
-    sc->cand_cap = sc->feat_cap = cap;
+std::mutex g_ctx_mu;
+DeviceCtx* g_ctx[64] = {nullptr};
+
+int get_ctx(int device, DeviceCtx** out) {
+  if (device < 0 || device >= 64) return fail(MCS_ERR_CUDA, "no such CUDA device");
+  std::lock_guard<std::mutex> lock(g_ctx_mu);
+  if (!g_ctx[device]) {
+    CUDA_TRY(cudaSetDevice(device));
+    DeviceCtx* c = new DeviceCtx();
+    c->device = device;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_counter, sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_decide, sizeof(mcs::DecideOut))) != cudaSuccess) {
+      delete c;
+      return fail(MCS_ERR_CUDA, cudaGetErrorString(e));
+    }
+    g_ctx[device] = c;
   }
-  if (n_status > sc->status_cap) {
-    if (sc->d_status) cudaFree(sc->d_status);
-    sc->status_cap = 0;
-    CUDA_TRY(cudaMalloc(&sc->d_status, sizeof(mcs_status) * n_status));
-    sc->status_cap = n_status;
+  *out = g_ctx[device];
+  return MCS_OK;
+}
+
+int ensure_capacity(mcs_scene* sc, int n_cand, size_t n_status) {
+  DeviceCtx* c = sc->ctx;
+  if (n_cand > c->cand_cap) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->d_cand) cudaFree(c->d_cand);
+    if (c->d_feat) cudaFree(c->d_feat);
+    if (c->d_part) cudaFree(c->d_part);
+    if (c->h_cand) cudaFreeHost(c->h_cand);
+    if (c->h_feat) cudaFreeHost(c->h_feat);
+    c->cand_cap = 0;
+    int cap = n_cand < 8 ? 8 : n_cand;
+    CUDA_TRY(cudaMalloc(&c->d_cand, sizeof(mcs::CandDev) * cap));
+    CUDA_TRY(cudaMalloc(&c->d_feat, sizeof(mcs_feature) * cap));
+    CUDA_TRY(cudaMalloc(&c->d_part, sizeof(mcs_group_partial) * cap * MCS_GROUPS));
+    CUDA_TRY(cudaMallocHost(&c->h_cand, sizeof(mcs::CandDev) * cap));
+    CUDA_TRY(cudaMallocHost(&c->h_feat, sizeof(mcs_feature) * cap));
+    c->cand_cap = cap;
+  }
+  if (n_status > c->status_cap) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->d_status) cudaFree(c->d_status);
+    c->status_cap = 0;
+    size_t cap = n_status < 4096 ? 4096 : n_status;
+    CUDA_TRY(cudaMalloc(&c->d_status, sizeof(mcs_status) * cap));
+    c->status_cap = cap;
   }
   return MCS_OK;
 }
@@ -156,9 +173,9 @@ int stage_candidates(mcs_scene* sc, const mcs_candidate* cands, int n_cand, int*
     mcs::CandDev d{};
     d.ego_slot = h.ego_slot; d.action = h.action; d.gap_id = h.gap_id; d.target_lane_id = h.target_lane_id; d.ok = h.ok;
     d.gap_slot = h.gap_slot;
-    sc->h_cand[c] = d;
+    sc->ctx->h_cand[c] = d;
   }
-  CUDA_TRY(cudaMemcpyAsync(sc->d_cand, sc->h_cand, sizeof(mcs::CandDev) * n_cand, cudaMemcpyHostToDevice, sc->stream));
+  CUDA_TRY(cudaMemcpyAsync(sc->ctx->d_cand, sc->ctx->h_cand, sizeof(mcs::CandDev) * n_cand, cudaMemcpyHostToDevice, sc->ctx->stream));
   *merge_out = merge;
   return MCS_OK;
 }
@@ -166,7 +183,7 @@ int stage_candidates(mcs_scene* sc, const mcs_candidate* cands, int n_cand, int*
 template <bool kTraj, bool kMerge>
 int launch_one(mcs_scene* sc, dim3 grid, dim3 block, size_t smem, const mcs::LaunchParams& lp) {
   CUDA_TRY(cudaFuncSetAttribute(mcs::rollout_kernel<kTraj, kMerge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mcs::rollout_kernel<kTraj, kMerge><<<grid, block, smem, sc->stream>>>(sc->dev, sc->d_cand, lp);
+  mcs::rollout_kernel<kTraj, kMerge><<<grid, block, smem, sc->ctx->stream>>>(sc->dev, sc->ctx->d_cand, lp);
   CUDA_TRY(cudaGetLastError());
   return MCS_OK;
 }
@@ -219,44 +236,50 @@ int mcs_scene_create(const mcs_corridor* corridors, int n_corridors, const mcs_a
   if (rc != MCS_OK) { std::string e = sc->host.error; delete sc; return fail(rc, e); }
   if (mcs_device_count() <= device || device < 0) { delete sc; return fail(MCS_ERR_CUDA, "no such CUDA device (libmcsim_b200 has no CPU fallback)"); }
   sc->device = device;
+  if ((rc = get_ctx(device, &sc->ctx)) != MCS_OK) { delete sc; return rc; }
+  DeviceCtx* c = sc->ctx;
+  std::lock_guard<std::mutex> lock(c->mu);
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) { delete sc; return fail(MCS_ERR_CUDA, cudaGetErrorString(e)); }
   const mcs::SceneHost& h = sc->host;
-  auto bail = [&](const char* what, cudaError_t err) { std::string m = std::string(what) + ": " + cudaGetErrorString(err); mcs_scene_destroy(sc); return fail(MCS_ERR_CUDA, m); };
-  if ((e = cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-  if ((e = cudaMalloc(&sc->d_f, h.f.size() * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMalloc(&sc->d_i, h.i.size() * sizeof(int32_t))) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMalloc(&sc->d_vec, h.lane_vec.size())) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMalloc(&sc->d_counter, sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMemcpyAsync(sc->d_f, h.f.data(), h.f.size() * sizeof(double), cudaMemcpyHostToDevice, sc->stream)) != cudaSuccess) return bail("H2D", e);
-  if ((e = cudaMemcpyAsync(sc->d_i, h.i.data(), h.i.size() * sizeof(int32_t), cudaMemcpyHostToDevice, sc->stream)) != cudaSuccess) return bail("H2D", e);
-  if ((e = cudaMemcpyAsync(sc->d_vec, h.lane_vec.data(), h.lane_vec.size(), cudaMemcpyHostToDevice, sc->stream)) != cudaSuccess) return bail("H2D", e);
-  if ((e = cudaEventCreate(&sc->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
-  if ((e = cudaEventCreate(&sc->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+  // one blob: doubles | ints | lane vector, staged through pinned memory, one stream-ordered allocation, one copy
+  const size_t bf = h.f.size() * sizeof(double), bi = h.i.size() * sizeof(int32_t), bv = h.lane_vec.size();
+  const size_t total = bf + bi + ((bv + 15) & ~(size_t)15);
+  auto bail = [&](const char* what, cudaError_t err) { std::string m = std::string(what) + ": " + cudaGetErrorString(err); if (sc->d_blob) cudaFreeAsync(sc->d_blob, c->stream); delete sc; return fail(MCS_ERR_CUDA, m); };
+  if (total > c->stage_cap) {
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return bail("sync", e);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->stage_cap = 0;
+    size_t cap = total < (1u << 18) ? (1u << 18) : total;
+    if ((e = cudaMallocHost(&c->h_stage, cap)) != cudaSuccess) return bail("cudaMallocHost", e);
+    c->stage_cap = cap;
+  } else if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {   // the staging buffer may still feed an earlier copy
+    return bail("sync", e);
+  }
+  memcpy(c->h_stage, h.f.data(), bf);
+  memcpy(c->h_stage + bf, h.i.data(), bi);
+  memcpy(c->h_stage + bf + bi, h.lane_vec.data(), bv);
+  if ((e = cudaMallocAsync(&sc->d_blob, total, c->stream)) != cudaSuccess) return bail("cudaMallocAsync", e);
+  if ((e = cudaMemcpyAsync(sc->d_blob, c->h_stage, total, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return bail("H2D", e);
   mcs::SceneDev& d = sc->dev;
   d.n = h.n; d.n_pad = h.n_pad; d.n_lanes = h.n_lanes; d.has_exit_lanes = h.has_exit_lanes ? 1 : 0;
-  d.f = sc->d_f; d.i = sc->d_i; d.lane_vec = sc->d_vec;
+  d.f = (const double*)sc->d_blob; d.i = (const int32_t*)(sc->d_blob + bf); d.lane_vec = sc->d_blob + bf + bi;
   for (int j = 0; j <= h.n_lanes; ++j) d.lane_start[j] = h.lane_start[j];
   for (int j = 0; j < h.n_lanes; ++j) {
     const mcs::LaneHost& L = h.lanes[j];
     d.lanes[j] = mcs::LaneDev{L.leftY, L.rightY, L.centerY, L.vLimit, L.endX, L.startX, L.id, L.type, L.leftIdx, L.rightIdx, L.leftmost, 0};
   }
-  if ((e = cudaStreamSynchronize(sc->stream)) != cudaSuccess) return bail("sync", e);
-  *out = sc;
+  *out = sc;     // the copy is ordered before every later launch on the context's stream
   return MCS_OK;
 }
 
 int mcs_scene_destroy(mcs_scene* sc) {
   if (!sc) return MCS_OK;
-  cudaSetDevice(sc->device);
-  if (sc->stream) cudaStreamSynchronize(sc->stream);
-  cudaFree(sc->d_f); cudaFree(sc->d_i); cudaFree(sc->d_vec); cudaFree(sc->d_cand); cudaFree(sc->d_status);
-  cudaFree(sc->d_feat); cudaFree(sc->d_counter); cudaFree(sc->d_decide);
-  if (sc->h_cand) cudaFreeHost(sc->h_cand);
-  if (sc->h_feat) cudaFreeHost(sc->h_feat);
-  if (sc->ev0) cudaEventDestroy(sc->ev0);
-  if (sc->ev1) cudaEventDestroy(sc->ev1);
-  if (sc->stream) cudaStreamDestroy(sc->stream);
+  if (sc->ctx) {
+    std::lock_guard<std::mutex> lock(sc->ctx->mu);
+    cudaSetDevice(sc->device);
+    if (sc->d_blob) cudaFreeAsync(sc->d_blob, sc->ctx->stream);
+  }
   delete sc;
   return MCS_OK;
 }
@@ -270,15 +293,87 @@ int mcs_scene_visit_order(const mcs_scene* sc, int32_t* order_out, int n) {
 int mcs_reduce_features(const mcs_status* statuses, int n_candidates, int groups, int n_per_group, int steps,
                         mcs_feature* features_out) {
   if (!statuses || !features_out || n_candidates < 0 || groups <= 0 || n_per_group <= 0) return fail(MCS_ERR_ARG, "bad arguments");
-  for (int c = 0; c < n_candidates; ++c)
-    reduce_one(statuses + (size_t)c * groups * n_per_group, groups, n_per_group, steps, features_out + c);
+  std::vector<mcs_group_partial> part(groups);
+  for (int c = 0; c < n_candidates; ++c) {
+    for (int g = 0; g < groups; ++g)
+      group_partial(statuses + ((size_t)c * groups + g) * n_per_group, n_per_group, steps, &part[g]);
+    combine_groups(part.data(), groups, features_out + c);
+  }
   return MCS_OK;
+}
+
+int mcs_group_partials(const mcs_status* statuses, int n_candidates, int groups, int n_per_group, int steps,
+                       mcs_group_partial* partials_out) {
+  if (!statuses || !partials_out || n_candidates < 0 || groups <= 0 || n_per_group <= 0) return fail(MCS_ERR_ARG, "bad arguments");
+  for (int i = 0; i < n_candidates * groups; ++i)
+    group_partial(statuses + (size_t)i * n_per_group, n_per_group, steps, partials_out + i);
+  return MCS_OK;
+}
+
+int mcs_combine_groups(const mcs_group_partial* partials, int n_candidates, int groups, mcs_feature* features_out) {
+  if (!partials || !features_out || n_candidates < 0 || groups <= 0) return fail(MCS_ERR_ARG, "bad arguments");
+  for (int c = 0; c < n_candidates; ++c) combine_groups(partials + (size_t)c * groups, groups, features_out + c);
+  return MCS_OK;
+}
+
+int mcs_scene_sync(mcs_scene* sc) {
+  if (!sc) return fail(MCS_ERR_ARG, "scene is null");
+  CUDA_TRY(cudaSetDevice(sc->device));
+  CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
+  return MCS_OK;
+}
+
+// shared by mcs_rollouts_groups{,_device}: rollouts of groups [first_group, first_group+n_groups) -> partials in `d_out`
+static int groups_on_device(mcs_scene* sc, const mcs_candidate* cands, int n_cand, const mcs_sim_param* sp, int n_per_group,
+                            uint64_t seed, int first_group, int n_groups, mcs_group_partial* d_out, mcs_status* probe) {
+  if (first_group < 0 || n_groups <= 0 || first_group + n_groups > MCS_GROUPS) return fail(MCS_ERR_ARG, "bad group range");
+  const int64_t count = (int64_t)n_groups * n_per_group;
+  const size_t n_status = (size_t)n_cand * count;
+  int rc = ensure_capacity(sc, n_cand, n_status);
+  if (rc != MCS_OK) return rc;
+  int merge = 0;
+  if ((rc = stage_candidates(sc, cands, n_cand, &merge)) != MCS_OK) return rc;
+  if ((rc = launch_rollouts(sc, n_cand, sp, seed, (int64_t)first_group * n_per_group, count, sc->ctx->d_status, nullptr, nullptr,
+                            nullptr, merge)) != MCS_OK) return rc;
+  const int total = n_cand * n_groups;
+  group_partials_kernel<<<(total + 63) / 64, 64, 0, sc->ctx->stream>>>(sc->ctx->d_status, n_cand, n_groups, n_per_group, sp->steps,
+                                                                   d_out ? d_out : sc->ctx->d_part);
+  CUDA_TRY(cudaGetLastError());
+  for (int c = 0; c < n_cand; ++c)   // the scene-error marker lives in the statuses: fetch the first rollout of each candidate
+    CUDA_TRY(cudaMemcpyAsync(probe + c, sc->ctx->d_status + (size_t)c * count, sizeof(mcs_status), cudaMemcpyDeviceToHost, sc->ctx->stream));
+  return MCS_OK;
+}
+
+int mcs_rollouts_groups(mcs_scene* sc, const mcs_candidate* cands, int n_cand, const mcs_sim_param* sp, int n_per_group,
+                        uint64_t seed, int first_group, int n_groups, mcs_group_partial* partials_out) {
+  if (!sc || !cands || !sp || !partials_out || n_cand <= 0 || n_per_group <= 0) return fail(MCS_ERR_ARG, "bad arguments");
+  std::lock_guard<std::mutex> lock(sc->ctx->mu);
+  CUDA_TRY(cudaSetDevice(sc->device));
+  std::vector<mcs_status> probe(n_cand);
+  int rc = groups_on_device(sc, cands, n_cand, sp, n_per_group, seed, first_group, n_groups, nullptr, probe.data());
+  if (rc != MCS_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(partials_out, sc->ctx->d_part, sizeof(mcs_group_partial) * n_cand * n_groups, cudaMemcpyDeviceToHost, sc->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
+  return check_unsupported(probe.data(), probe.size());
+}
+
+int mcs_rollouts_groups_device(mcs_scene* sc, const mcs_candidate* cands, int n_cand, const mcs_sim_param* sp, int n_per_group,
+                               uint64_t seed, int first_group, int n_groups, void* d_partials_out) {
+  if (!sc || !cands || !sp || !d_partials_out || n_cand <= 0 || n_per_group <= 0) return fail(MCS_ERR_ARG, "bad arguments");
+  std::lock_guard<std::mutex> lock(sc->ctx->mu);
+  CUDA_TRY(cudaSetDevice(sc->device));
+  std::vector<mcs_status> probe(n_cand);
+  int rc = groups_on_device(sc, cands, n_cand, sp, n_per_group, seed, first_group, n_groups, (mcs_group_partial*)d_partials_out,
+                            probe.data());
+  if (rc != MCS_OK) return rc;
+  CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
+  return check_unsupported(probe.data(), probe.size());
 }
 
 int mcs_rollouts(mcs_scene* sc, const mcs_candidate* cands, int n_cand, const mcs_sim_param* sp, int n_per_group,
                  uint64_t seed, mcs_feature* features_out, mcs_status* status_out) {
   if (!sc || !cands || !sp || !features_out || n_cand <= 0 || n_per_group <= 0) return fail(MCS_ERR_ARG, "bad arguments");
-  std::lock_guard<std::mutex> lock(sc->mu);
+  std::lock_guard<std::mutex> lock(sc->ctx->mu);
   CUDA_TRY(cudaSetDevice(sc->device));
   const int64_t count = (int64_t)MCS_GROUPS * n_per_group;
   const size_t n_status = (size_t)n_cand * count;
@@ -286,36 +381,38 @@ int mcs_rollouts(mcs_scene* sc, const mcs_candidate* cands, int n_cand, const mc
   if (rc != MCS_OK) return rc;
   int merge = 0;
   if ((rc = stage_candidates(sc, cands, n_cand, &merge)) != MCS_OK) return rc;
-  if ((rc = launch_rollouts(sc, n_cand, sp, seed, 0, count, sc->d_status, nullptr, nullptr, nullptr, merge)) != MCS_OK) return rc;
-  reduce_features_kernel<<<n_cand, 32, 0, sc->stream>>>(sc->d_status, MCS_GROUPS, n_per_group, sp->steps, sc->d_feat);
+  if ((rc = launch_rollouts(sc, n_cand, sp, seed, 0, count, sc->ctx->d_status, nullptr, nullptr, nullptr, merge)) != MCS_OK) return rc;
+  group_partials_kernel<<<(n_cand * MCS_GROUPS + 63) / 64, 64, 0, sc->ctx->stream>>>(sc->ctx->d_status, n_cand, MCS_GROUPS, n_per_group,
+                                                                                sp->steps, sc->ctx->d_part);
+  combine_groups_kernel<<<(n_cand + 31) / 32, 32, 0, sc->ctx->stream>>>(sc->ctx->d_part, n_cand, MCS_GROUPS, sc->ctx->d_feat);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(sc->h_feat, sc->d_feat, sizeof(mcs_feature) * n_cand, cudaMemcpyDeviceToHost, sc->stream));
+  CUDA_TRY(cudaMemcpyAsync(sc->ctx->h_feat, sc->ctx->d_feat, sizeof(mcs_feature) * n_cand, cudaMemcpyDeviceToHost, sc->ctx->stream));
   std::vector<mcs_status> first_status;
-  if (status_out) CUDA_TRY(cudaMemcpyAsync(status_out, sc->d_status, sizeof(mcs_status) * n_status, cudaMemcpyDeviceToHost, sc->stream));
+  if (status_out) CUDA_TRY(cudaMemcpyAsync(status_out, sc->ctx->d_status, sizeof(mcs_status) * n_status, cudaMemcpyDeviceToHost, sc->ctx->stream));
   else {
     // the "unsupported" marker lives in the statuses; fetch the first rollout of each candidate
     first_status.resize(n_cand);
     for (int c = 0; c < n_cand; ++c)
-      CUDA_TRY(cudaMemcpyAsync(&first_status[c], sc->d_status + (size_t)c * count, sizeof(mcs_status), cudaMemcpyDeviceToHost, sc->stream));
+      CUDA_TRY(cudaMemcpyAsync(&first_status[c], sc->ctx->d_status + (size_t)c * count, sizeof(mcs_status), cudaMemcpyDeviceToHost, sc->ctx->stream));
   }
-  CUDA_TRY(cudaStreamSynchronize(sc->stream));
-  memcpy(features_out, sc->h_feat, sizeof(mcs_feature) * n_cand);
+  CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
+  memcpy(features_out, sc->ctx->h_feat, sizeof(mcs_feature) * n_cand);
   return status_out ? check_unsupported(status_out, n_status) : check_unsupported(first_status.data(), first_status.size());
 }
 
 int mcs_rollouts_range(mcs_scene* sc, const mcs_candidate* cands, int n_cand, const mcs_sim_param* sp, uint64_t seed,
                        int64_t first, int64_t count, mcs_status* status_out) {
   if (!sc || !cands || !sp || !status_out || n_cand <= 0 || count <= 0) return fail(MCS_ERR_ARG, "bad arguments");
-  std::lock_guard<std::mutex> lock(sc->mu);
+  std::lock_guard<std::mutex> lock(sc->ctx->mu);
   CUDA_TRY(cudaSetDevice(sc->device));
   const size_t n_status = (size_t)n_cand * count;
   int rc = ensure_capacity(sc, n_cand, n_status);
   if (rc != MCS_OK) return rc;
   int merge = 0;
   if ((rc = stage_candidates(sc, cands, n_cand, &merge)) != MCS_OK) return rc;
-  if ((rc = launch_rollouts(sc, n_cand, sp, seed, first, count, sc->d_status, nullptr, nullptr, nullptr, merge)) != MCS_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(status_out, sc->d_status, sizeof(mcs_status) * n_status, cudaMemcpyDeviceToHost, sc->stream));
-  CUDA_TRY(cudaStreamSynchronize(sc->stream));
+  if ((rc = launch_rollouts(sc, n_cand, sp, seed, first, count, sc->ctx->d_status, nullptr, nullptr, nullptr, merge)) != MCS_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(status_out, sc->ctx->d_status, sizeof(mcs_status) * n_status, cudaMemcpyDeviceToHost, sc->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
   return check_unsupported(status_out, n_status);
 }
 
@@ -323,7 +420,7 @@ int mcs_rollouts_device(mcs_scene* sc, const mcs_candidate* cands, int n_cand, c
                         int64_t first, int64_t count, void* d_status_out, void* cuda_stream, float* kernel_ms_out,
                         uint64_t* vehicle_steps_out) {
   if (!sc || !cands || !sp || n_cand <= 0 || count <= 0) return fail(MCS_ERR_ARG, "bad arguments");
-  std::lock_guard<std::mutex> lock(sc->mu);
+  std::lock_guard<std::mutex> lock(sc->ctx->mu);
   CUDA_TRY(cudaSetDevice(sc->device));
   (void)cuda_stream;  // launches go to the scene's own stream; events below are recorded on that stream
   const size_t n_status = (size_t)n_cand * count;
@@ -331,17 +428,17 @@ int mcs_rollouts_device(mcs_scene* sc, const mcs_candidate* cands, int n_cand, c
   if (rc != MCS_OK) return rc;
   int merge = 0;
   if ((rc = stage_candidates(sc, cands, n_cand, &merge)) != MCS_OK) return rc;
-  CUDA_TRY(cudaMemsetAsync(sc->d_counter, 0, sizeof(unsigned long long), sc->stream));
-  mcs_status* dst = d_status_out ? (mcs_status*)d_status_out : sc->d_status;
-  CUDA_TRY(cudaEventRecord(sc->ev0, sc->stream));
-  if ((rc = launch_rollouts(sc, n_cand, sp, seed, first, count, dst, nullptr, nullptr, sc->d_counter, merge)) != MCS_OK) return rc;
-  CUDA_TRY(cudaEventRecord(sc->ev1, sc->stream));
+  CUDA_TRY(cudaMemsetAsync(sc->ctx->d_counter, 0, sizeof(unsigned long long), sc->ctx->stream));
+  mcs_status* dst = d_status_out ? (mcs_status*)d_status_out : sc->ctx->d_status;
+  CUDA_TRY(cudaEventRecord(sc->ctx->ev0, sc->ctx->stream));
+  if ((rc = launch_rollouts(sc, n_cand, sp, seed, first, count, dst, nullptr, nullptr, sc->ctx->d_counter, merge)) != MCS_OK) return rc;
+  CUDA_TRY(cudaEventRecord(sc->ctx->ev1, sc->ctx->stream));
   unsigned long long steps = 0;
-  CUDA_TRY(cudaMemcpyAsync(&steps, sc->d_counter, sizeof steps, cudaMemcpyDeviceToHost, sc->stream));
+  CUDA_TRY(cudaMemcpyAsync(&steps, sc->ctx->d_counter, sizeof steps, cudaMemcpyDeviceToHost, sc->ctx->stream));
   mcs_status probe;
-  CUDA_TRY(cudaMemcpyAsync(&probe, dst, sizeof probe, cudaMemcpyDeviceToHost, sc->stream));
-  CUDA_TRY(cudaStreamSynchronize(sc->stream));
-  if (kernel_ms_out) CUDA_TRY(cudaEventElapsedTime(kernel_ms_out, sc->ev0, sc->ev1));
+  CUDA_TRY(cudaMemcpyAsync(&probe, dst, sizeof probe, cudaMemcpyDeviceToHost, sc->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
+  if (kernel_ms_out) CUDA_TRY(cudaEventElapsedTime(kernel_ms_out, sc->ctx->ev0, sc->ctx->ev1));
   if (vehicle_steps_out) *vehicle_steps_out = steps;
   return check_unsupported(&probe, 1);
 }
@@ -349,7 +446,7 @@ int mcs_rollouts_device(mcs_scene* sc, const mcs_candidate* cands, int n_cand, c
 int mcs_trajectories(mcs_scene* sc, const mcs_candidate* cand, const mcs_sim_param* sp, uint64_t seed, int64_t rollout,
                      double* states_out, int32_t* n_states_out, mcs_status* status_out) {
   if (!sc || !cand || !sp || !states_out) return fail(MCS_ERR_ARG, "bad arguments");
-  std::lock_guard<std::mutex> lock(sc->mu);
+  std::lock_guard<std::mutex> lock(sc->ctx->mu);
   CUDA_TRY(cudaSetDevice(sc->device));
   int rc = ensure_capacity(sc, 1, 1);
   if (rc != MCS_OK) return rc;
@@ -359,17 +456,17 @@ int mcs_trajectories(mcs_scene* sc, const mcs_candidate* cand, const mcs_sim_par
   double* d_traj = nullptr; int32_t* d_n = nullptr;
   CUDA_TRY(cudaMalloc(&d_traj, n_d * sizeof(double)));
   CUDA_TRY(cudaMalloc(&d_n, sizeof(int32_t)));
-  cudaMemsetAsync(d_traj, 0, n_d * sizeof(double), sc->stream);
-  cudaMemsetAsync(d_n, 0, sizeof(int32_t), sc->stream);
-  rc = launch_rollouts(sc, 1, sp, seed, rollout, 1, sc->d_status, d_traj, d_n, nullptr, merge);
+  cudaMemsetAsync(d_traj, 0, n_d * sizeof(double), sc->ctx->stream);
+  cudaMemsetAsync(d_n, 0, sizeof(int32_t), sc->ctx->stream);
+  rc = launch_rollouts(sc, 1, sp, seed, rollout, 1, sc->ctx->d_status, d_traj, d_n, nullptr, merge);
   mcs_status st{};
   int32_t ns = 0;
   if (rc == MCS_OK) {
-    cudaMemcpyAsync(states_out, d_traj, n_d * sizeof(double), cudaMemcpyDeviceToHost, sc->stream);
-    cudaMemcpyAsync(&ns, d_n, sizeof ns, cudaMemcpyDeviceToHost, sc->stream);
-    cudaMemcpyAsync(&st, sc->d_status, sizeof st, cudaMemcpyDeviceToHost, sc->stream);
+    cudaMemcpyAsync(states_out, d_traj, n_d * sizeof(double), cudaMemcpyDeviceToHost, sc->ctx->stream);
+    cudaMemcpyAsync(&ns, d_n, sizeof ns, cudaMemcpyDeviceToHost, sc->ctx->stream);
+    cudaMemcpyAsync(&st, sc->ctx->d_status, sizeof st, cudaMemcpyDeviceToHost, sc->ctx->stream);
   }
-  cudaError_t e = cudaStreamSynchronize(sc->stream);
+  cudaError_t e = cudaStreamSynchronize(sc->ctx->stream);
   cudaFree(d_traj); cudaFree(d_n);
   if (rc != MCS_OK) return rc;
   if (e != cudaSuccess) return fail(MCS_ERR_CUDA, cudaGetErrorString(e));
@@ -380,7 +477,7 @@ int mcs_trajectories(mcs_scene* sc, const mcs_candidate* cand, const mcs_sim_par
 
 static int run_decision(mcs_scene* sc, int32_t agent_id, mcs::DecideParams dp, int32_t gap_id, mcs::DecideOut* res) {
   if (!sc) return fail(MCS_ERR_ARG, "scene is null");
-  std::lock_guard<std::mutex> lock(sc->mu);
+  std::lock_guard<std::mutex> lock(sc->ctx->mu);
   CUDA_TRY(cudaSetDevice(sc->device));
   const mcs::SceneHost& h = sc->host;
   dp.slot = -1; dp.gap_slot = -1;
@@ -390,13 +487,12 @@ static int run_decision(mcs_scene* sc, int32_t agent_id, mcs::DecideParams dp, i
     if (gap_id >= 0 && id == gap_id && dp.gap_slot < 0) dp.gap_slot = k;
   }
   if (dp.slot < 0) return fail(MCS_ERR_ARG, "No agent with id: " + std::to_string(agent_id));   // the reference traps (ud2, 0xb9a37)
-  if (!sc->d_decide) CUDA_TRY(cudaMalloc(&sc->d_decide, sizeof(mcs::DecideOut)));
   const size_t smem = rollout_smem_bytes(sc->dev.n_pad, 0);
   CUDA_TRY(cudaFuncSetAttribute(mcs::decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mcs::decide_kernel<<<1, sc->dev.n_pad, smem, sc->stream>>>(sc->dev, dp, (mcs::DecideOut*)sc->d_decide);
+  mcs::decide_kernel<<<1, sc->dev.n_pad, smem, sc->ctx->stream>>>(sc->dev, dp, (mcs::DecideOut*)sc->ctx->d_decide);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(res, sc->d_decide, sizeof *res, cudaMemcpyDeviceToHost, sc->stream));
-  CUDA_TRY(cudaStreamSynchronize(sc->stream));
+  CUDA_TRY(cudaMemcpyAsync(res, sc->ctx->d_decide, sizeof *res, cudaMemcpyDeviceToHost, sc->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
   if (res->status != MCS_OK)
     return fail(res->status, "the reference's behaviour is undefined here (vehicle not on a lane, or no lane on that side)");
   return MCS_OK;

@@ -99,3 +99,30 @@ def lane_change_scene(n_vehicles, n_lanes=4, seed=0, truck_ratio=0.4, thw_mean=1
             o.yp[:] = GENERIC_YP
         o.commit = abi.COMMITS["not_decided"]; o.commit_keep_lane_step = 0; o.target_lane_id = -1
     return corridors, agents, ego_rec
+
+
+def merging_scene(n_vehicles=40, seed=0, n_main=3):
+    """BASELINE.json configs[1] shape: a merging lane (id 0) + n_main main lanes, ego `merging` on the merging lane, the
+    other merging-lane vehicles `merging`, main-lane vehicles `idm_lc` with the generic parameters and rss_param(True)
+    (mcs_wrapper.py:24-75).  Returns (corridors, agents, ego_id, gap_ids) with gap_ids = [-1] + up to three vehicles of
+    the adjacent main lane around the ego (the reference's `possible_actions`, mcs_wrapper.py:40,57-59)."""
+    corridors, agents, _ = lane_change_scene(n_vehicles, n_main + 1, seed=seed, merging_lane=True)
+    on_merge = [a for a in agents if 0.0 <= a.y < LANE_WIDTH]
+    if not on_merge:
+        raise ValueError("no vehicle on the merging lane")
+    ego = on_merge[len(on_merge) // 2]
+    rs = np.random.RandomState(seed + 1000)
+    for a in agents:
+        if a.id == ego.id:
+            a.behavior = abi.BEHAVIORS["merging"]
+            a.idm[:] = [rs.uniform(1.8, 2.2), max(2.0, rs.normal(4, 1)), rs.uniform(-4.0, -2.0), rs.normal(-2.0, 0.1), -8.0,
+                        max(1.0, rs.normal(1.5, 0.1))]
+            a.rss[:] = EGO_RSS
+            a.yp[:] = [1.70968573, 0.00582201, 0.40742229, 1.02390871, rs.uniform(0, 1), 0.5, 0.6]
+        else:
+            a.idm[:] = generic_idm(a.l)
+            a.yp[:] = GENERIC_YP
+            a.rss[:] = EGO_RSS if a.behavior == abi.BEHAVIORS["merging"] else GENERIC_RSS
+    left = sorted((a for a in agents if LANE_WIDTH <= a.y < 2 * LANE_WIDTH), key=lambda a: abs(a.x - ego.x))[:3]
+    gaps = [-1] + [a.id for a in sorted(left, key=lambda a: -a.x)]
+    return corridors, agents, ego.id, gaps

@@ -281,3 +281,33 @@ def test_decide_unknown_agent_is_an_error(gpu):
         assert e.value.code == abi.MCS_ERR_ARG
     finally:
         ds.close()
+
+
+def test_sharded_groups_equal_single_gpu(gpu):
+    """The multi-GPU exchange unit: per-group partials computed shard by shard (as 1, 2, 4, 8 ranks would) and combined
+    in group order give exactly mcs_rollouts' features; also through a device buffer (the NCCL hand-off path)."""
+    import torch
+    from interactive_highway_simulation_b200 import sharding
+    s = probe_scene()
+    ds = gpu.DeviceScene(s.c_corridors(), s.c_agents())
+    try:
+        cands = (abi.Candidate * 3)(*[abi.Candidate(0, abi.ACTIONS[a], -2, 0) for a in ("keep_lane", "left", "acc")])
+        sp = abi.SimParam(0.3, 40, 30)
+        n = 16
+        want, _ = ds.rollouts(cands, sp, n, 31)
+        for world in (1, 2, 4, 8):
+            per = 8 // world
+            chunks = []
+            for rank in range(world):
+                first, cnt = sharding.group_range(rank, world)
+                t = torch.empty((3 * per, 8), dtype=torch.float64, device="cuda")
+                ds.rollouts_groups(cands, sp, n, 31, first, cnt, d_partials_ptr=t.data_ptr())
+                host = ds.rollouts_groups(cands, sp, n, 31, first, cnt)
+                assert bytes(host) == t.cpu().numpy().tobytes()
+                chunks.append(t)
+            gathered = torch.cat(chunks, 0)
+            feats = sharding.features_from_gathered(sharding.interleave_gathered(gathered, 3, world).cpu(), 3)
+            for c in range(3):
+                assert bytes(feats[c]) == bytes(want[c]), (world, c)
+    finally:
+        ds.close()
