@@ -260,6 +260,7 @@ __device__ __forceinline__ void prior_from_offset(double y, double vy, double ce
 }
 
 // MOBIL flag bits (Smem::mflag)
+enum { MOBIL_PARTS = 5 };
 enum { MF_STRICT_L = 1, MF_RELAX_L = 2, MF_STRICT_R = 4, MF_RELAX_R = 8, MF_CAN_L = 16, MF_CAN_R = 32 };
 
 // side neighbours of vehicle at x in lane `ln`: leader = first with x_elem >= x, follower = last with x_elem < x
@@ -273,9 +274,9 @@ __device__ __forceinline__ void side_leader_follower(const Smem& s, const int* l
 }
 
 // The part of laneChangeBehaviorMOBIL (0xf44c9-0xf4dde, 0xf5259-0xf584e) that does not depend on the vehicle's own
-// IDM action: accelerations in the neighbour lanes, follower deltas, RSS gates.  A vehicle's evaluation is three
-// independent sub-tasks (part 0: old follower, part 1: left lane, part 2: right lane) executed by whichever
-// threads picked them from the queue; results go to shared memory.
+// IDM action: accelerations in the neighbour lanes, follower deltas, RSS gates.  A vehicle's evaluation is five
+// independent sub-tasks of similar cost (part 0: old follower; 1/2: left lane A/B; 3/4: right lane A/B) executed by
+// whichever threads picked them from the queue; results go to shared memory.
 __device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc, const int* laneStart, int np, int k,
                                                int front, int back, int part) {
   const int ln = s.lane[k];
@@ -293,22 +294,32 @@ __device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc
     s.mob[4 * np + k] = deltaOld;
     return;
   }
-  const int side = part - 1;
+  // parts 1..4: (left, right) x (A: own acceleration in that lane + RSS gates, B: the would-be follower's loss)
+  const int side = (part - 1) >> 1, sub = (part - 1) & 1;
   const int sl = side == 0 ? L.leftIdx : L.rightIdx;
   const bool can = sl >= 0 && sc.lanes[sl].type == MCS_LANE_MAIN;
-  int mf = 0;
-  double accNew = 0.0, dNew = 0.0;
-  if (can) {
-    const double ex = s.x[k], ev = s.v[k], el = s.l[k], evd = s.vd[k];
+  if (!can) {
+    if (sub == 0) { s.mob[side * np + k] = 0.0; s.mflag[side * np + k] = 0; }
+    else s.mob[(2 + side) * np + k] = 0.0;
+    return;
+  }
+  const double ex = s.x[k];
+  int leader, follower;
+  side_leader_follower(s, laneStart, sl, ex, leader, follower);
+  if (sub == 0) {
+    const double ev = s.v[k], el = s.l[k], evd = s.vd[k];
     const IdmP pe = load_idm(s, np, k);
     const double rTOther = sc.f[(size_t)F_RSS_RTOTHER * np + k], rTEgo = sc.f[(size_t)F_RSS_RTEGO * np + k];
     const double aMin = sc.f[(size_t)F_RSS_AMIN * np + k], aMax = sc.f[(size_t)F_RSS_AMAX * np + k];
-    int leader, follower;
-    side_leader_follower(s, laneStart, sl, ex, leader, follower);
     const double vdCap = MCS_MINSD(evd, 1.1 * sc.lanes[sl].vLimit);
-    accNew = idm_acc(s, pe, leader, -1, follower, ex, ev, el, mcs_pow4(ev / vdCap));
+    const double accNew = idm_acc(s, pe, leader, -1, follower, ex, ev, el, mcs_pow4(ev / vdCap));
     const bool strict = rss_safe(s, leader, follower, ex, ev, el, rTOther, rTEgo, aMin, aMax);
     const bool relax = rss_safe(s, leader, follower, ex, ev, el, rTOther, rTEgo, -10.0, -1.0);
+    s.mob[side * np + k] = accNew;
+    s.mflag[side * np + k] = (uint8_t)(side == 0 ? (MF_CAN_L | (strict ? MF_STRICT_L : 0) | (relax ? MF_RELAX_L : 0))
+                                                 : (MF_CAN_R | (strict ? MF_STRICT_R : 0) | (relax ? MF_RELAX_R : 0)));
+  } else {
+    double dNew = 0.0;
     if (follower >= 0) {
       const IdmP pn = load_idm(s, np, follower);
       const double nx = s.x[follower], nv = s.v[follower], nl = s.l[follower];
@@ -317,12 +328,8 @@ __device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc
       const double withEgo = idm_acc(s, pn, leader, k, -1, nx, nv, nl, pw);
       dNew = withEgo - without;
     }
-    mf = side == 0 ? (MF_CAN_L | (strict ? MF_STRICT_L : 0) | (relax ? MF_RELAX_L : 0))
-                   : (MF_CAN_R | (strict ? MF_STRICT_R : 0) | (relax ? MF_RELAX_R : 0));
+    s.mob[(2 + side) * np + k] = dNew;
   }
-  s.mob[side * np + k] = accNew;
-  s.mob[(2 + side) * np + k] = dNew;
-  s.mflag[side * np + k] = (uint8_t)mf;
 }
 
 // Agent fields laneChangeBehaviorMOBIL writes back (commitToDecision 0x90, commitKeepLaneStep 0xb0, targetLaneId 0x68)
@@ -451,7 +458,10 @@ namespace mcs {
 // kMerge: the scene has a merging/exit lane or vehicle, or a candidate names a gap — yielding intentions and the gap
 // behaviours are compiled in.  The plain lane-change instantiation carries none of their registers.
 template <bool kTraj, bool kMerge>
-__global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp) {
+#ifndef MCS_MIN_BLOCKS
+#define MCS_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, MCS_MIN_BLOCKS) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int np = sc.n_pad, n = sc.n, k = threadIdx.x;
   const int cand = blockIdx.y;
@@ -599,9 +609,13 @@ __global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, cons
       if (needMobil) s.tasks[pos] = k | (front & 0xff) << 8 | (back & 0xff) << 16 | ((front < 0) ? 1 << 24 : 0) | ((back < 0) ? 1 << 25 : 0);
     }
     __syncthreads();
-    for (int t = k; t < 3 * nTasks; t += blockDim.x) {
-      const int part = t / nTasks;                 // neighbouring threads run the same part: less divergence
-      const int rec = s.tasks[t - part * nTasks];
+    // sub-task slot = part * ceil32(nTasks) + i: every warp runs one part only, and the five parts run on five warps
+    // side by side instead of queueing up on the first ones
+    const int nT32 = (nTasks + 31) & ~31;
+    for (int t = k; t < MOBIL_PARTS * nT32; t += blockDim.x) {
+      const int part = t / nT32, ti = t - part * nT32;
+      if (ti >= nTasks) continue;
+      const int rec = s.tasks[ti];
       const int vk = rec & 0xff;
       const int vf = (rec >> 24 & 1) ? -1 : (rec >> 8 & 0xff);
       const int vb = (rec >> 25 & 1) ? -1 : (rec >> 16 & 0xff);
@@ -700,7 +714,9 @@ __global__ void __launch_bounds__(256, 2) rollout_kernel(const SceneDev sc, cons
           }
           axY = idm_acc_list(s, py, ylist, ny, -1, x, v, el, pw);
         } else {
-          axY = idm_acc(s, py, -1, -1, -1, x, v, el, pw);
+          // no yielding candidate: idmAccFrontBack over an empty list is the clamped free-road term
+          const double r = MCS_MINSD(0.0 + (1.0 - pw) * py.accMax, py.accMax);
+          axY = MCS_MAXSD(py.accMin, r);
         }
         ax = MCS_MINSD(axY, axFront);
         if (noise) ax = ax + ((double)mcs_rand31(key, drawBase + (uint64_t)nY) / 2147483647.0 - 0.5);

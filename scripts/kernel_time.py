@@ -1,0 +1,31 @@
+"""Kernel time of the two headline configurations (diagnostic; bench.py is the measurement of record).
+usage: kernel_time.py [path/to/libmcsim_b200.so]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from interactive_highway_simulation_b200 import backend, synthetic, _abi as abi
+if len(sys.argv) > 1:
+    backend.LIB_PATH = os.path.abspath(sys.argv[1])
+corridors, agents, ego = synthetic.lane_change_scene(256, 4, seed=0)
+sc = backend.DeviceScene(corridors, agents)
+cand = (abi.Candidate * 1)(abi.Candidate(ego, abi.ACTIONS["keep_lane"], -2, 0))
+sp = abi.SimParam(0.3, 100, 100)
+R = 16384
+best = 1e9
+for i in range(4):
+    ms, vs = sc.rollouts_device(cand, sp, 5, 0, R); best = min(best, ms)
+print("throughput config: %d rollouts %.2f ms -> %.3e vehicle-steps/s" % (R, best, vs / best * 1e3))
+chk = sc.rollouts_range(cand, sp, 5, 0, 64)
+import hashlib
+print("  checksum", hashlib.md5(bytes(chk)).hexdigest())
+sc.close()
+corridors, agents, ego, gaps = synthetic.merging_scene(40, 0)
+sc = backend.DeviceScene(corridors, agents)
+cands = (abi.Candidate * len(gaps))(*[abi.Candidate(ego, abi.ACTIONS["left"], g, 0) for g in gaps])
+sp = abi.SimParam(0.3, 40, 10)
+best = 1e9
+for i in range(4):
+    ms, vs = sc.rollouts_device(cands, sp, 1000, 0, 512); best = min(best, ms)
+print("decision config: 4 x 512 rollouts x 40 vehicles %.3f ms (%d vehicle-steps)" % (best, vs))
+chk = sc.rollouts_range(cands, sp, 1000, 0, 64)
+print("  checksum", hashlib.md5(bytes(chk)).hexdigest())
+sc.close()
