@@ -22,7 +22,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
   } while (0)
 
 size_t rollout_smem_bytes(int n_pad, int steps) {
-  size_t doubles = (size_t)n_pad * (4 + 5 + 6) + 2 * (size_t)((steps + 2) & ~1) + 16;
+  size_t doubles = (size_t)n_pad * (4 + 6 + 6) + 2 * (size_t)((steps + 2) & ~1) + 16;
   size_t ints = 16 + 16 + 8 + (size_t)n_pad;
   return doubles * 8 + ints * 4 + 5 * (size_t)n_pad;
 }
@@ -180,12 +180,23 @@ int stage_candidates(mcs_scene* sc, const mcs_candidate* cands, int n_cand, int*
   return MCS_OK;
 }
 
-template <bool kTraj, bool kMerge>
-int launch_one(mcs_scene* sc, dim3 grid, dim3 block, size_t smem, const mcs::LaunchParams& lp) {
-  CUDA_TRY(cudaFuncSetAttribute(mcs::rollout_kernel<kTraj, kMerge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mcs::rollout_kernel<kTraj, kMerge><<<grid, block, smem, sc->ctx->stream>>>(sc->dev, sc->ctx->d_cand, lp);
+template <bool kTraj, bool kMerge, int NPS>
+int launch_np(mcs_scene* sc, dim3 grid, size_t smem, const mcs::LaunchParams& lp) {
+  CUDA_TRY(cudaFuncSetAttribute(mcs::rollout_kernel<kTraj, kMerge, NPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mcs::rollout_kernel<kTraj, kMerge, NPS><<<grid, dim3(NPS), smem, sc->ctx->stream>>>(sc->dev, sc->ctx->d_cand, lp);
   CUDA_TRY(cudaGetLastError());
   return MCS_OK;
+}
+
+template <bool kTraj, bool kMerge>
+int launch_one(mcs_scene* sc, dim3 grid, size_t smem, const mcs::LaunchParams& lp) {
+  switch (sc->dev.n_pad) {
+    case 32: return launch_np<kTraj, kMerge, 32>(sc, grid, smem, lp);
+    case 64: return launch_np<kTraj, kMerge, 64>(sc, grid, smem, lp);
+    case 128: return launch_np<kTraj, kMerge, 128>(sc, grid, smem, lp);
+    case 256: return launch_np<kTraj, kMerge, 256>(sc, grid, smem, lp);
+    default: return fail(MCS_ERR_CAPACITY, "unsupported block size");
+  }
 }
 
 // launch the rollout kernel for rollouts [first, first+count) of every candidate; statuses → d_status (device)
@@ -198,9 +209,10 @@ int launch_rollouts(mcs_scene* sc, int n_cand, const mcs_sim_param* sp, uint64_t
   lp.seed = seed; lp.first = first; lp.count = count; lp.n_cand = n_cand;
   lp.status = d_status; lp.traj = d_traj; lp.traj_n = d_traj_n; lp.vehicle_steps = d_counter;
   const size_t smem = rollout_smem_bytes(sc->dev.n_pad, sp->steps);
-  dim3 grid((unsigned)count, (unsigned)n_cand), block((unsigned)sc->dev.n_pad);
-  if (d_traj) return merge ? launch_one<true, true>(sc, grid, block, smem, lp) : launch_one<true, false>(sc, grid, block, smem, lp);
-  return merge ? launch_one<false, true>(sc, grid, block, smem, lp) : launch_one<false, false>(sc, grid, block, smem, lp);
+  dim3 grid((unsigned)count, (unsigned)n_cand);
+  // the trajectory-writing variant is a test / Simulation.run() path: one instantiation (the merging superset) serves it
+  if (d_traj) return launch_one<true, true>(sc, grid, smem, lp);
+  return merge ? launch_one<false, true>(sc, grid, smem, lp) : launch_one<false, false>(sc, grid, smem, lp);
 }
 
 int check_unsupported(const mcs_status* st, size_t n) {

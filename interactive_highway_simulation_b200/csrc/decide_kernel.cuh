@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(256, 1) decide_kernel(const SceneDev sc, const
   s.idm[2 * np + k] = live ? F[(size_t)F_IDM_ACCMIN * np + k] : 0.0;
   s.idm[3 * np + k] = live ? F[(size_t)F_IDM_ACCCOM * np + k] : -1.0;
   s.idm[4 * np + k] = live ? F[(size_t)F_IDM_THW * np + k] : 0.0;
+  { const double sq = sqrt((-s.idm[k]) * s.idm[3 * np + k]); s.idm[5 * np + k] = sq + sq; }
   s.lane[k] = (uint8_t)(lane < 0 ? 0xff : lane);
   s.vec[k] = sc.lane_vec[k];
   if (k <= sc.n_lanes) laneStart[k] = sc.lane_start[k];
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256, 1) decide_kernel(const SceneDev sc, const
         for (int part = 0; part < MOBIL_PARTS; ++part) mobil_geometry(s, sc, laneStart, np, k, front, back, part);
         const double u = (double)mcs_rand31(dp.key, (uint64_t)n) / 2147483647.0;
         mobil_decide(s, sc, np, k, lane, v, el, aMin, F[(size_t)F_YP_PF * np + k], F[(size_t)F_YP_DA * np + k],
-                     F[(size_t)F_YP_BA * np + k], dp.require_rss ? 2 : 3, false, 0.0, 0.0, 0.0, u, ms, ax, avy);
+                     F[(size_t)F_YP_BA * np + k], dp.require_rss ? 2 : 3, false, F + (size_t)F_PRIOR_L * np, u, ms, ax, avy);
       }
     }
     o.ax = ax; o.vy = avy; o.commit = ms.commit; o.keepStep = ms.keepStep; o.targetLane = ms.targetLane;

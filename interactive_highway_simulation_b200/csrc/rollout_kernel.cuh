@@ -60,7 +60,7 @@ struct LaunchParams {
 #define MCS_MINSD(a, b) (((a) < (b)) ? (a) : (b))   /* x86 vminsd: second source when not less / unordered */
 #define MCS_MAXSD(a, b) (((a) > (b)) ? (a) : (b))
 
-struct IdmP { double accMax, minDis, accMin, accCom, thw; };
+struct IdmP { double accMax, minDis, accMin, accCom, thw, sq2 /* 2*sqrt(-accMax*accCom), static per vehicle */; };
 
 // shared-memory view of one rollout
 struct Smem {
@@ -68,7 +68,7 @@ struct Smem {
   double* v;       // [n_pad]
   double* l;       // [n_pad] static
   double* vd;      // [n_pad] static
-  double* idm;     // [5][n_pad] static: accMax minDis accMin accCom thw
+  double* idm;     // [6][n_pad] static: accMax minDis accMin accCom thw 2*sqrt(-accMax*accCom)
   double* mob;     // [6][n_pad] MOBIL geometry results per vehicle: accNewL accNewR dNewL dNewR deltaOld (+1 spare)
   double* chist;   // [steps+2] ego comfort samples
   double* csort;   // [steps+2] the same, sorted descending
@@ -89,7 +89,7 @@ __device__ __forceinline__ void carve_smem(Smem& s, unsigned char* p, int np, in
   s.v = (double*)p; p += sizeof(double) * np;
   s.l = (double*)p; p += sizeof(double) * np;
   s.vd = (double*)p; p += sizeof(double) * np;
-  s.idm = (double*)p; p += sizeof(double) * 5 * np;
+  s.idm = (double*)p; p += sizeof(double) * 6 * np;
   s.mob = (double*)p; p += sizeof(double) * 6 * np;
   s.chist = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
   s.csort = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
@@ -107,7 +107,7 @@ __device__ __forceinline__ void carve_smem(Smem& s, unsigned char* p, int np, in
 __device__ __forceinline__ IdmP load_idm(const Smem& s, int np, int k) {
   IdmP p;
   p.accMax = s.idm[k]; p.minDis = s.idm[np + k]; p.accMin = s.idm[2 * np + k]; p.accCom = s.idm[3 * np + k];
-  p.thw = s.idm[4 * np + k];
+  p.thw = s.idm[4 * np + k]; p.sq2 = s.idm[5 * np + k];
   return p;
 }
 
@@ -116,8 +116,7 @@ __device__ __forceinline__ double idm_acc(const Smem& s, const IdmP& p, int f0, 
                                           double egoV, double egoL, double pw) {
   const double freeAcc = (1.0 - pw) * p.accMax;
   const double na = -p.accMax;
-  const double sq = sqrt(na * p.accCom);
-  const double sq2 = sq + sq;
+  const double sq2 = p.sq2;
   const double dDes = (egoV * p.thw + p.minDis) * 0.7;
   bool any = false;
   double d = 0.0;
@@ -242,23 +241,6 @@ __device__ __forceinline__ bool rss_emergency(const Smem& s, int front, double e
   return gap < d;
 }
 
-// lane-change prior, first match of an agent that had no lane at scene creation (0x10bb97-0x10bd8a)
-__device__ __forceinline__ void prior_from_offset(double y, double vy, double centerY, double out[3]) {
-  const double d = ((y - centerY) * 0.333 + 0.6805 * vy) - 0.01;
-  double t;
-  t = d - 1.04; const double e1 = mcs_exp(((-t) * t) / 0.055);
-  t = d - 0.35; const double e2 = mcs_exp(((-t) * t) / 0.055);
-  t = d - 0.7; const double e3 = mcs_exp(((-t) * t) / 0.07);
-  const double a = (0.8 * e1 + 0.8 * e2) + e3 * 0.65;
-  t = 1.04 + d; const double e4 = mcs_exp(((-t) * t) / 0.055);
-  t = 0.35 + d; const double e5 = mcs_exp(((-t) * t) / 0.055);
-  t = 0.7 + d; const double e6 = mcs_exp(((-t) * t) / 0.07);
-  const double c = (0.75 * e4 + 0.75 * e5) + e6 * 0.6;
-  const double b = mcs_exp(((-d) * d) / 0.055) * 2.5;
-  const double sum = (a + b) + c;
-  out[0] = a / sum; out[1] = b / sum; out[2] = c / sum;
-}
-
 // MOBIL flag bits (Smem::mflag)
 enum { MOBIL_PARTS = 5 };
 enum { MF_STRICT_L = 1, MF_RELAX_L = 2, MF_STRICT_R = 4, MF_RELAX_R = 8, MF_CAN_L = 16, MF_CAN_R = 32 };
@@ -341,7 +323,7 @@ struct MobilState { int commit, keepStep, targetLane; };
 // prior blended in, 0xf58a0), 1 = inside a rollout later, 2 = Python-facing with requireRssSafety (0xf5858), 3 = without (0xf5053).
 __device__ __forceinline__ void mobil_decide(const Smem& s, const SceneDev& sc, int np, int k, int lane, double v, double el,
                                              double aMin, double pf, double dA, double bA, int mode, bool aggressive,
-                                             double prior0, double prior1, double prior2, double u, MobilState& ms,
+                                             const double* __restrict__ priors /* F_PRIOR_L row, stride np */, double u, MobilState& ms,
                                              double& ax, double& avy) {
   const int mf = s.mflag[k] | s.mflag[np + k];
   const bool canL = mf & MF_CAN_L, canR = mf & MF_CAN_R;
@@ -371,6 +353,9 @@ __device__ __forceinline__ void mobil_decide(const Smem& s, const SceneDev& sc, 
   p[0] = eL / denom; p[2] = eR / denom; p[1] = (1.0 - p[0]) - p[2];
   if (mode <= 1) {
     if (ms.commit == MCS_COMMIT_NOT_DECIDED && mode == 0) {
+      // lateral-offset prior of the first lane match (computed on the host, scene.cpp).  A vehicle first matched later
+      // never uses its prior: this branch needs a history of one state.
+      const double prior0 = priors[k], prior1 = priors[np + k], prior2 = priors[2 * np + k];
       if (aggressive) lane_change_probability(p, prior0, prior1, prior2, relaxL, relaxR);
       else {
         const bool r = strictR ? true : ((prior2 >= 0.5) && relaxR);
@@ -457,13 +442,16 @@ namespace mcs {
 
 // kMerge: the scene has a merging/exit lane or vehicle, or a candidate names a gap — yielding intentions and the gap
 // behaviours are compiled in.  The plain lane-change instantiation carries none of their registers.
-template <bool kTraj, bool kMerge>
+template <bool kTraj, bool kMerge, int NPS>
 #ifndef MCS_MIN_BLOCKS
 #define MCS_MIN_BLOCKS 2
 #endif
-__global__ void __launch_bounds__(256, MCS_MIN_BLOCKS) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp) {
+__global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int np = sc.n_pad, n = sc.n, k = threadIdx.x;
+  // NPS = sc.n_pad = blockDim.x as a compile-time constant: every shared-memory array address and row stride folds into
+  // the instruction's immediate offset instead of living in registers
+  constexpr int np = NPS;
+  const int n = sc.n, k = threadIdx.x;
   const int cand = blockIdx.y;
   const int64_t ridx = (int64_t)blockIdx.x;           // rollout within this launch
   const CandDev cd = cands[cand];
@@ -502,8 +490,6 @@ __global__ void __launch_bounds__(256, MCS_MIN_BLOCKS) rollout_kernel(const Scen
     if (isEgo) targetLane = cd.target_lane_id;
   }
   const int beh0 = live ? I[(size_t)I_BEH0 * np + k] : 0;
-  double prior0 = live ? F[(size_t)F_PRIOR_L * np + k] : 0, prior1 = live ? F[(size_t)F_PRIOR_K * np + k] : 0,
-         prior2 = live ? F[(size_t)F_PRIOR_R * np + k] : 0;
   // stage what neighbours gather
   s.x[k] = x; s.v[k] = v; s.l[k] = el; s.vd[k] = evd;
   s.idm[k] = live ? F[(size_t)F_IDM_ACCMAX * np + k] : 1.0;
@@ -511,6 +497,7 @@ __global__ void __launch_bounds__(256, MCS_MIN_BLOCKS) rollout_kernel(const Scen
   s.idm[2 * np + k] = live ? F[(size_t)F_IDM_ACCMIN * np + k] : 0.0;
   s.idm[3 * np + k] = live ? F[(size_t)F_IDM_ACCCOM * np + k] : -1.0;
   s.idm[4 * np + k] = live ? F[(size_t)F_IDM_THW * np + k] : 0.0;
+  { const double sq = sqrt((-s.idm[k]) * s.idm[3 * np + k]); s.idm[5 * np + k] = sq + sq; }   // idmAccFrontBack 0xebd2b, hoisted
   s.lane[k] = (uint8_t)(lane < 0 ? 0xff : lane);
   s.vec[k] = sc.lane_vec[k];
   int oldLane = lane;           // lane whose vector currently holds this vehicle
@@ -554,7 +541,7 @@ __global__ void __launch_bounds__(256, MCS_MIN_BLOCKS) rollout_kernel(const Scen
     // ================= plan, part A: own-lane search, IDM, draw counts =================
     double ax = 0.0, avy = 0.0;
     int front = -1, back = -1;
-    bool needMobil = false, noise = false;
+    bool needMobil = false, noise = false, inversion = false;
     int mode = 0;   // 1 idmBehaviorAndYielding, 2 customizedLaneChange (ego), 3 customizedMerging (ego), 4 closest gap
     int nDraw = 0;
     const bool hasLane = live && lane >= 0;
@@ -564,9 +551,9 @@ __global__ void __launch_bounds__(256, MCS_MIN_BLOCKS) rollout_kernel(const Scen
     if (hasLane) {
       const LaneDev& L = sc.lanes[lane];
       centerY = L.centerY; vLimit = L.vLimit;
-      const int lo = laneStart[lane], cnt = laneStart[lane + 1] - lo;
-      const int fpos = lane_upper(s, lo, cnt, x);
-      front = fpos < cnt ? s.vec[lo + fpos] : -1;
+      // own-lane leader / follower: while every lane vector is strictly ordered by x (checked pairwise, OR-ed through the
+      // scan below) upper_bound / the reverse search of frontAgent / followingAgent land on the neighbours in the vector
+      if (myPos > laneStart[lane]) inversion = !(s.x[s.vec[myPos - 1]] < x);
       if (isEgo) {
         const bool lr = cd.action == MCS_ACT_LEFT || cd.action == MCS_ACT_RIGHT;
         if (beh == MCS_BEH_IDM || beh == MCS_BEH_IDM_LC) mode = (lr && reached) ? 1 : 2;
@@ -597,15 +584,24 @@ __global__ void __launch_bounds__(256, MCS_MIN_BLOCKS) rollout_kernel(const Scen
       } else if (mode == 3 || mode == 4) {
         unsupported = true;     // cannot happen: the host selects kMerge for such scenes
       }
-      if (needMobil) {
-        const int bpos = lane_reverse(s, lo, cnt, x);
-        back = bpos > 0 ? s.vec[lo + bpos - 1] : -1;
-      }
     }
     // compaction: queue MOBIL tasks
     int nTasks;
     {
-      const int pos = block_exclusive_scan(needMobil ? 1 : 0, s.scan, nTasks);
+      int total;
+      const int pos = block_exclusive_scan((needMobil ? 1 : 0) | (inversion ? 1 << 16 : 0), s.scan, total) & 0xffff;
+      nTasks = total & 0xffff;
+      if (hasLane) {
+        const int lo = laneStart[lane], cnt = laneStart[lane + 1] - lo;
+        if (total >> 16) {          // some lane vector is stale-ordered: search it the way the reference does
+          const int fpos = lane_upper(s, lo, cnt, x);
+          front = fpos < cnt ? s.vec[lo + fpos] : -1;
+          if (needMobil) { const int bpos = lane_reverse(s, lo, cnt, x); back = bpos > 0 ? s.vec[lo + bpos - 1] : -1; }
+        } else {
+          front = myPos + 1 < lo + cnt ? s.vec[myPos + 1] : -1;
+          if (needMobil) back = myPos > lo ? s.vec[myPos - 1] : -1;
+        }
+      }
       if (needMobil) s.tasks[pos] = k | (front & 0xff) << 8 | (back & 0xff) << 16 | ((front < 0) ? 1 << 24 : 0) | ((back < 0) ? 1 << 25 : 0);
     }
     __syncthreads();
@@ -641,9 +637,11 @@ __global__ void __launch_bounds__(256, MCS_MIN_BLOCKS) rollout_kernel(const Scen
     bool pushThw = false;
     if (hasLane) {
       const IdmP pe = load_idm(s, np, k);
-      if (front >= 0) thwPush = (((s.x[front] - x) - (s.l[front] + el) * 0.5) / v) / pe.thw;
-      else thwPush = 1.0;
-      pushThw = true;
+      if (isEgo) {    // Agent::thwRatioHistory is read for the ego only (0x10f14b)
+        if (front >= 0) thwPush = (((s.x[front] - x) - (s.l[front] + el) * 0.5) / v) / pe.thw;
+        else thwPush = 1.0;
+        pushThw = true;
+      }
       avy = centering_vy(y, centerY);
       if (mode == 2) {
         customized_lane_change(s, sc, laneStart, np, k, lane, front, cd.action, x, v, el, evd, F[(size_t)F_RSS_RTOTHER * np + k],
@@ -729,7 +727,7 @@ __global__ void __launch_bounds__(256, MCS_MIN_BLOCKS) rollout_kernel(const Scen
             const double u = (double)mcs_rand31(key, drawBase + (uint64_t)nY + 1) / 2147483647.0;
             MobilState ms{commit, keepStep, targetLane};
             mobil_decide(s, sc, np, k, lane, v, el, aMin, F[(size_t)F_YP_PF * np + k], F[(size_t)F_YP_DA * np + k],
-                         F[(size_t)F_YP_BA * np + k], /*mode=*/(nStates <= 1) ? 0 : 1, aggressive, prior0, prior1, prior2, u, ms, ax, avy);
+                         F[(size_t)F_YP_BA * np + k], /*mode=*/(nStates <= 1) ? 0 : 1, aggressive, F + (size_t)F_PRIOR_L * np, u, ms, ax, avy);
             commit = ms.commit; keepStep = ms.keepStep; targetLane = ms.targetLane;
           }
         }
@@ -775,11 +773,9 @@ __global__ void __launch_bounds__(256, MCS_MIN_BLOCKS) rollout_kernel(const Scen
         for (int j = 0; j < sc.n_lanes; ++j) {
           const LaneDev& L = sc.lanes[j];
           if (!(L.leftY >= y && y >= L.rightY)) continue;
-          const bool first = lane < 0;
           lane = j;
           if (L.type == MCS_LANE_MAIN && beh == MCS_BEH_MERGING) beh = MCS_BEH_IDM_LC;
           if (L.type == MCS_LANE_EXIT && beh == MCS_BEH_EXIT) beh = MCS_BEH_IDM;
-          if (first) { double p[3]; prior_from_offset(y, vy, L.centerY, p); prior0 = p[0]; prior1 = p[1]; prior2 = p[2]; }
           break;
         }
         s.lane[k] = (uint8_t)(lane < 0 ? 0xff : lane);

@@ -57,7 +57,7 @@ int build_scene_host(const mcs_corridor* cs, int nc, const mcs_agent* as, int na
   std::vector<int> visit;
   for (auto& kv : agent_order) visit.push_back(kv.second);
   s.n = na;
-  s.n_pad = (na + 31) / 32 * 32;
+  s.n_pad = na <= 32 ? 32 : na <= 64 ? 64 : na <= 128 ? 128 : 256;   // one kernel instantiation per block size
   s.f.assign((size_t)F_COUNT * s.n_pad, 0.0);
   s.i.assign((size_t)I_COUNT * s.n_pad, -1);
   s.slot_of_input.assign(na, -1);
