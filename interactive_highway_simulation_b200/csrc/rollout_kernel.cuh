@@ -70,11 +70,13 @@ struct Smem {
   double* vd;      // [n_pad] static
   double* idm;     // [6][n_pad] static: accMax minDis accMin accCom thw 2*sqrt(-accMax*accCom)
   double* mob;     // [6][n_pad] MOBIL geometry results per vehicle: accNewL accNewR dNewL dNewR deltaOld (+1 spare)
-  double* chist;   // [steps+2] ego comfort samples
-  double* csort;   // [steps+2] the same, sorted descending
+  double* chist;   // [steps+2] ego acceleration history, turned into comfort samples at the end
+  double* csort;   // [steps+2] the comfort samples sorted descending
+  double* vhist;   // [steps+2] ego speed history, turned into per-state utilities at the end
+  double* thist;   // [steps+2] ego thwRatioHistory
   double* red;     // [16] reduction scratch
-  int* scan;       // [n_pad/32 + 1]
-  int* cnt;        // [MCS_MAX_LANES + 1] lane counts / starts
+  int* scan;       // [32] warp totals of the two per-step scans (8 + 8), lane counters of the re-ranking (16..)
+  int* cnt;        // [2][16] lane starts, double-buffered across rebuilds
   int* flags;      // [8] block flags
   int* tasks;      // [n_pad] MOBIL task queue
   uint8_t* lane;   // [n_pad] lane slot of each vehicle (0xff = none)
@@ -93,9 +95,11 @@ __device__ __forceinline__ void carve_smem(Smem& s, unsigned char* p, int np, in
   s.mob = (double*)p; p += sizeof(double) * 6 * np;
   s.chist = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
   s.csort = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
+  s.vhist = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
+  s.thist = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
   s.red = (double*)p; p += sizeof(double) * 16;
-  s.scan = (int*)p; p += sizeof(int) * 16;
-  s.cnt = (int*)p; p += sizeof(int) * 16;
+  s.scan = (int*)p; p += sizeof(int) * 32;
+  s.cnt = (int*)p; p += sizeof(int) * 32;
   s.flags = (int*)p; p += sizeof(int) * 8;
   s.tasks = (int*)p; p += sizeof(int) * np;
   s.lane = p; p += np;
@@ -112,7 +116,10 @@ __device__ __forceinline__ IdmP load_idm(const Smem& s, int np, int k) {
 }
 
 // idmAccFrontBack 0xebc30: fronts (slots, -1 = null), back slot or -1.  pw = pow(egoV/vd, 4) supplied by the caller.
-__device__ __forceinline__ double idm_acc(const Smem& s, const IdmP& p, int f0, int f1, int back, double egoX,
+#ifndef MCS_HEAVY_INLINE
+#define MCS_HEAVY_INLINE __forceinline__
+#endif
+__device__ MCS_HEAVY_INLINE double idm_acc(const Smem& s, const IdmP& p, int f0, int f1, int back, double egoX,
                                           double egoV, double egoL, double pw) {
   const double freeAcc = (1.0 - pw) * p.accMax;
   const double na = -p.accMax;
@@ -189,7 +196,7 @@ __device__ __forceinline__ int lane_reverse(const Smem& s, int lo, int n, double
 }
 
 // rssSafe 0xb8950 with optionals given as slots (-1 = nullopt); rTOther/rTEgo/aMin/aMax of the evaluating vehicle
-__device__ __forceinline__ bool rss_safe(const Smem& s, int leader, int follower, double ex, double ev, double el,
+__device__ MCS_HEAVY_INLINE bool rss_safe(const Smem& s, int leader, int follower, double ex, double ev, double el,
                                          double rTOther, double rTEgo, double aMin, double aMax) {
   if (leader < 0 && follower < 0) return true;
   if (leader >= 0) {
@@ -414,6 +421,7 @@ __device__ __forceinline__ void customized_lane_change(const Smem& s, const Scen
 }
 
 // block-wide exclusive scan of one int per thread; blockDim.x multiple of 32, ≤ 256
+template <int NW>
 __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int& total) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int inc = v;
@@ -424,16 +432,15 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int& to
   }
   if (lane == 31) scratch[w] = inc;
   __syncthreads();
-  const int nw = blockDim.x >> 5;
   int base = 0, tot = 0;
-  for (int q = 0; q < nw; ++q) {
+#pragma unroll
+  for (int q = 0; q < NW; ++q) {
     const int c = scratch[q];
     if (q < w) base += c;
     tot += c;
   }
   total = tot;
-  __syncthreads();
-  return base + inc - v;
+  return base + inc - v;     // no trailing barrier: the two scans of a step use different scratch rows
 }
 
 }  // namespace mcs
@@ -443,10 +450,13 @@ namespace mcs {
 // kMerge: the scene has a merging/exit lane or vehicle, or a candidate names a gap — yielding intentions and the gap
 // behaviours are compiled in.  The plain lane-change instantiation carries none of their registers.
 template <bool kTraj, bool kMerge, int NPS>
+// resident 256-thread-equivalents per SM the register allocation aims at: 3 (80 registers) for the lane-change path —
+// the kernel is latency-bound, the third block hides more than its few spills cost (measured 6.26e9 -> 7.06e9
+// vehicle-steps/s) — and 2 (128 registers) for the much larger merging instantiation
 #ifndef MCS_MIN_BLOCKS
-#define MCS_MIN_BLOCKS 2
+#define MCS_MIN_BLOCKS 3
 #endif
-__global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp) {
+__global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCKS)) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // NPS = sc.n_pad = blockDim.x as a compile-time constant: every shared-memory array address and row stride folds into
   // the instruction's immediate offset instead of living in registers
@@ -459,7 +469,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
 
   Smem s;
   carve_smem(s, smem_raw, np, lp.steps);
-  int* laneStart = s.cnt;  // [n_lanes + 1]
+  int* laneStart = s.cnt;  // [n_lanes + 1]; flips between s.cnt and s.cnt + 16 at every rebuild
 
   if (!cd.ok) {           // setEgoAgentIdAndDrivingBehavior failed: the reference runs nothing (runMTimes 0xc2935)
     if (k == 0) { mcs_status z; memset(&z, 0, sizeof z); *st_out = z; }
@@ -472,7 +482,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
   const double* F = sc.f;
   const int32_t* I = sc.i;
   double x = 0, y = 0, v = 0, vy = 0;
-  double el = 0, evd = 1, a0 = 0;
+  double el = 0, evd = 1;
   double rTEgo = 0, aMin = -1, aMax = -1;
   int lane = -1, beh = MCS_BEH_OTHER, commit = 0, keepStep = 0, targetLane = -1, inputIdx = 0;
   bool aggressive = false;
@@ -480,7 +490,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
   bool reached = false;
   if (live) {
     x = F[(size_t)F_X * np + k]; y = F[(size_t)F_Y * np + k]; v = F[(size_t)F_V * np + k]; vy = F[(size_t)F_VY * np + k];
-    a0 = F[(size_t)F_A * np + k]; el = F[(size_t)F_L * np + k]; evd = F[(size_t)F_VD * np + k];
+    el = F[(size_t)F_L * np + k]; evd = F[(size_t)F_VD * np + k];
     rTEgo = F[(size_t)F_RSS_RTEGO * np + k]; aMin = F[(size_t)F_RSS_AMIN * np + k]; aMax = F[(size_t)F_RSS_AMAX * np + k];
     lane = I[(size_t)I_LANE * np + k]; beh = I[(size_t)I_BEH * np + k]; commit = I[(size_t)I_COMMIT * np + k];
     keepStep = I[(size_t)I_KEEPSTEP * np + k]; targetLane = I[(size_t)I_TARGETLANE * np + k];
@@ -489,7 +499,6 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
     aggressive = ((double)mcs_rand31(key, (uint64_t)inputIdx) / 2147483647.0) > 0.8;
     if (isEgo) targetLane = cd.target_lane_id;
   }
-  const int beh0 = live ? I[(size_t)I_BEH0 * np + k] : 0;
   // stage what neighbours gather
   s.x[k] = x; s.v[k] = v; s.l[k] = el; s.vd[k] = evd;
   s.idm[k] = live ? F[(size_t)F_IDM_ACCMAX * np + k] : 1.0;
@@ -511,21 +520,18 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
   myPos = s.pos[k];
 
   // statistics (Simulation::run 0x10ee71-0x10f49a) accumulated on the fly in history order
-  double sumAbsA = fabs(a0), sumV = v;
-  double prevA = a0;
-  bool fallBack = false;
-  double sumU = 0.0, thwAcc = 0.0;
-  int thwCnt = 0, nStates = 1;
-  if (isEgo) {
-    const double r = v / evd;
-    double u = r;
-    if (!(evd >= v)) u = MCS_MAXSD(0.9, 1.0 - (r - 1.0));
-    sumU = u;
-    s.chist[0] = a0 > 0.0 ? fabs(a0) * 0.5 : fabs(a0);
+  // statistics (Simulation::run 0x10ee71-0x10f49a): per-object sums accumulated on the fly in history order; the ego's own
+  // history (acceleration, speed, thw ratio) is kept in shared memory and reduced in the same order after the loop
+  double sumAbsA, sumV = v;
+  int nStates = 1;
+  {
+    const double a0 = live ? F[(size_t)F_A * np + k] : 0.0;
+    sumAbsA = fabs(a0);
+    if (isEgo) { s.chist[0] = a0; s.vhist[0] = v; }
   }
   if (kTraj && live) {
     double* t = lp.traj + ((((size_t)cand * lp.count + ridx) * n + inputIdx) * (size_t)(lp.steps + 1)) * 4;
-    t[0] = x; t[1] = y; t[2] = v; t[3] = a0;
+    t[0] = x; t[1] = y; t[2] = v; t[3] = F[(size_t)F_A * np + k];
   }
   uint64_t drawCtr = (uint64_t)n;   // draws 0..n-1 were the ctor flags
   int finishStep = lp.steps;
@@ -589,7 +595,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
     int nTasks;
     {
       int total;
-      const int pos = block_exclusive_scan((needMobil ? 1 : 0) | (inversion ? 1 << 16 : 0), s.scan, total) & 0xffff;
+      const int pos = block_exclusive_scan<NPS / 32>((needMobil ? 1 : 0) | (inversion ? 1 << 16 : 0), s.scan, total) & 0xffff;
       nTasks = total & 0xffff;
       if (hasLane) {
         const int lo = laneStart[lane], cnt = laneStart[lane + 1] - lo;
@@ -608,7 +614,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
     // sub-task slot = part * ceil32(nTasks) + i: every warp runs one part only, and the five parts run on five warps
     // side by side instead of queueing up on the first ones
     const int nT32 = (nTasks + 31) & ~31;
-    for (int t = k; t < MOBIL_PARTS * nT32; t += blockDim.x) {
+    for (int t = k; t < MOBIL_PARTS * nT32; t += NPS) {
       const int part = t / nT32, ti = t - part * nT32;
       if (ti >= nTasks) continue;
       const int rec = s.tasks[ti];
@@ -629,18 +635,16 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
     }
     nDraw = nY + (noise ? 1 : 0) + (mobilDraw ? 1 : 0);
     int totalDraws;
-    const uint64_t drawBase = drawCtr + (uint64_t)block_exclusive_scan(nDraw, s.scan, totalDraws);
+    const uint64_t drawBase = drawCtr + (uint64_t)block_exclusive_scan<NPS / 32>(nDraw, s.scan + 8, totalDraws);
     drawCtr += (uint64_t)totalDraws;
 
     // ================= plan, part B: actions =================
-    double thwPush = 0.0;
-    bool pushThw = false;
     if (hasLane) {
       const IdmP pe = load_idm(s, np, k);
       if (isEgo) {    // Agent::thwRatioHistory is read for the ego only (0x10f14b)
+        double thwPush = 1.0;
         if (front >= 0) thwPush = (((s.x[front] - x) - (s.l[front] + el) * 0.5) / v) / pe.thw;
-        else thwPush = 1.0;
-        pushThw = true;
+        s.thist[s.flags[3]++] = thwPush;
       }
       avy = centering_vy(y, centerY);
       if (mode == 2) {
@@ -682,7 +686,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
               const double rel = (v - s.v[j]) / MCS_MAXSD(v, 0.001);
               double r = thw * ypA + ypBias;
               r = r + rel * ypB;
-              r = r + a0 * ypC;
+              r = r + F[(size_t)F_A * np + k] * ypC;     // Agent::statesHistory[0].a
               double arg;
               if (100.0 > r) arg = (-100.0 > r) ? 100.0 : -r;
               else arg = -100.0;
@@ -746,16 +750,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
       }
       s.x[k] = x; s.v[k] = v;
       sumAbsA = sumAbsA + fabs(acc); sumV = sumV + v;
-      if (isEgo) {
-        if (aMin == prevA && aMin == acc) fallBack = true;
-        const double r = v / evd;
-        double u = r;
-        if (!(evd >= v)) u = MCS_MAXSD(0.9, 1.0 - (r - 1.0));
-        sumU = sumU + u;
-        s.chist[nStates] = acc > 0.0 ? fabs(acc) * 0.5 : fabs(acc);
-        if (pushThw) { if (0.9 > thwPush && thwPush > 0.0) thwAcc = (thwPush + thwAcc) - 0.9; thwCnt++; }
-      }
-      prevA = acc;
+      if (isEgo) { s.chist[nStates] = acc; s.vhist[nStates] = v; }
       if (kTraj) {
         double* t = lp.traj + ((((size_t)cand * lp.count + ridx) * n + inputIdx) * (size_t)(lp.steps + 1) + nStates) * 4;
         t[0] = x; t[1] = y; t[2] = v; t[3] = acc;
@@ -782,7 +777,10 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
       }
       if (isEgo && !reached && lane >= 0) reached = sc.lanes[lane].id == targetLane;
     }
-    const int anyChanged = __syncthreads_or(changed ? 1 : 0);   // also publishes the new x / v / lane
+    if (isEgo) { s.flags[0] = reached ? 1 : 0; if (kMerge) s.flags[2] = beh; }
+    // one barrier publishes the new x / v / lane and the ego's arrival, and tells whether any membership changed
+    const int anyChanged = __syncthreads_or(changed ? 1 : 0);
+    const bool egoReached = s.flags[0] != 0;
     if (anyChanged) {
       // The reference rebuilds every lane vector (members in visit order) and std::sorts it by x (0x10be30-0x10c1a5):
       // the result is "members ordered by (x, slot)".  Vehicles that kept their lane are already in that order unless
@@ -800,7 +798,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
         inversion = xp > x || (xp == x && pj > k);
       }
       if (k == 0) s.flags[1] = 0;
-      if (k < MCS_MAX_LANES + 1) s.scan[k] = 0;
+      if (k < MCS_MAX_LANES + 1) s.scan[16 + k] = 0;
       const int anyInv = __syncthreads_or(inversion ? 1 : 0);
       int rank = 0;
       if (anyInv) {
@@ -809,7 +807,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
             const double xj = s.x[j];
             rank += (s.lane[j] == newLane && (xj < x || (xj == x && j < k))) ? 1 : 0;
           }
-          atomicAdd(&s.scan[newLane], 1);
+          atomicAdd(&s.scan[16 + newLane], 1);
         }
       } else {
         if (mover) {
@@ -845,26 +843,29 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
             if (mnew == newLane && mk != k) { const double xm = s.x[mk]; rank += (xm < x || (xm == x && mk < k)) ? 1 : 0; }
           }
         }
-        if (newLane != 0xff && (mover || !inVec)) atomicAdd(&s.scan[newLane], 1);      // arrivals
-        if (mover && inVec) atomicSub(&s.scan[oldL], 1);                               // leavers
+        if (newLane != 0xff && (mover || !inVec)) atomicAdd(&s.scan[16 + newLane], 1);      // arrivals
+        if (mover && inVec) atomicSub(&s.scan[16 + oldL], 1);                               // leavers
       }
       __syncthreads();
-      if (k == 0) {
-        int run = 0;
+      // every thread derives the new lane starts itself (≤ 8 lanes) and places its vehicle; the shared copy goes to the
+      // other buffer, so one barrier publishes the vectors and the starts together
+      int* nextStart = laneStart == s.cnt ? s.cnt + 16 : s.cnt;
+      {
+        int run = 0, myStart = 0;
         for (int j = 0; j < sc.n_lanes; ++j) {
-          const int c = anyInv ? s.scan[j] : (laneStart[j + 1] - laneStart[j]) + s.scan[j];
-          s.scan[j] = c;
+          const int c = anyInv ? s.scan[16 + j] : (laneStart[j + 1] - laneStart[j]) + s.scan[16 + j];
+          if (j == newLane) myStart = run;
+          if (k == 0) nextStart[j] = run;
+          run += c;
         }
-        for (int j = 0; j < sc.n_lanes; ++j) { laneStart[j] = run; run += s.scan[j]; }
-        laneStart[sc.n_lanes] = run;
+        if (k == 0) nextStart[sc.n_lanes] = run;
+        if (newLane != 0xff) { myPos = myStart + rank; s.vec[myPos] = (uint8_t)k; }
       }
-      __syncthreads();
-      if (newLane != 0xff) { myPos = laneStart[newLane] + rank; s.vec[myPos] = (uint8_t)k; }
+      laneStart = nextStart;
       oldLane = newLane == 0xff ? -1 : newLane;
+      __syncthreads();
     }
     // ================= termination (0x10edd0-0x10ee10) =================
-    if (isEgo) { s.flags[0] = reached ? 1 : 0; s.flags[2] = beh; }
-    __syncthreads();
     if (kMerge && isEgo && gapSlot >= 0) {
       // the gap's rear vehicle left the target lane: re-target to the last vehicle of that lane behind it, else the
       // last gap (matchAgentsOnCorridor 0x10c320-0x10c39d)
@@ -886,7 +887,6 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
         }
       }
     }
-    const bool egoReached = s.flags[0] != 0;
     if (egoReached) {
       finish = true;
       finishStep = min(finishStep, step);
@@ -911,12 +911,32 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
     utilO = MCS_MINSD(u2, utilO); comfO = MCS_MINSD(c2, comfO);
   }
   if ((k & 31) == 0) { s.red[(k >> 5) * 2] = utilO; s.red[(k >> 5) * 2 + 1] = comfO; }
-  // ego comfort: mean over the k largest samples of 1 + c/aMin, summed in descending order (0x10f1c3-0x10f49a)
   __syncthreads();
+  // ego history -> per-state terms, one state per thread: fall-back = two consecutive states at rss.aMin (0x10f797),
+  // utility term u(v/vd) (0x10f0c4), comfort sample (0x10f1c3)
+  const int egoSlot = cd.ego_slot;
+  const double egoAMin = F[(size_t)F_RSS_AMIN * np + egoSlot], egoVd = s.vd[egoSlot];
+  bool fb = false;
+  for (int t = k; t < nStates; t += NPS) {
+    const double a = s.chist[t];
+    if (t + 1 < nStates && egoAMin == a && egoAMin == s.chist[t + 1]) fb = true;
+  }
+  const int anyFallBack = __syncthreads_or(fb ? 1 : 0);
+  for (int t = k; t < nStates; t += NPS) {
+    const double a = s.chist[t];
+    s.chist[t] = a > 0.0 ? fabs(a) * 0.5 : fabs(a);
+    const double ve = s.vhist[t];
+    const double r = ve / egoVd;
+    double u = r;
+    if (!(egoVd >= ve)) u = MCS_MAXSD(0.9, 1.0 - (r - 1.0));
+    s.vhist[t] = u;
+  }
+  __syncthreads();
+  // ego comfort: mean over the k largest samples of 1 + c/aMin, summed in descending order (0x10f1c3-0x10f49a)
   {
     const int ns = nStates;
     double* sorted = s.csort;
-    for (int t = k; t < ns; t += blockDim.x) {
+    for (int t = k; t < ns; t += NPS) {
       const double c = s.chist[t];
       int rank = 0;
       for (int j = 0; j < ns; ++j) { const double cj = s.chist[j]; rank += (cj > c || (cj == c && j < t)) ? 1 : 0; }
@@ -925,14 +945,19 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
   }
   __syncthreads();
   if (isEgo) {
-    const int nw = blockDim.x >> 5;
+    constexpr int nw = NPS >> 5;
     double uo = s.red[0], co = s.red[1];
     for (int q = 1; q < nw; ++q) { uo = MCS_MINSD(s.red[2 * q], uo); co = MCS_MINSD(s.red[2 * q + 1], co); }
     if (n <= 1) { uo = 1.0; co = 1.0; }
     mcs_status st;
     memset(&st, 0, sizeof st);
     st.utilityObjects = uo; st.comfortObjects = co;
+    double sumU = 0.0;
+    for (int t = 0; t < nStates; ++t) sumU = sumU + s.vhist[t];
     const double util = sumU / (double)nStates;
+    const int thwCnt = s.flags[3];
+    double thwAcc = 0.0;                                  // 0x10f14b-0x10f19f
+    for (int t = 0; t < thwCnt; ++t) { const double e = s.thist[t]; if (0.9 > e && e > 0.0) thwAcc = (e + thwAcc) - 0.9; }
     const double thwTerm = thwCnt > 0 ? thwAcc / (double)thwCnt : 0.0;
     st.utility = util + thwTerm;
     const int kk = (int)((double)nStates * 0.2);
@@ -941,8 +966,9 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * MCS_MIN_BLOCKS) rollout_ker
     st.comfort = sumC / (double)kk;
     st.finishStep = fs; st.executedSteps = executed; st.draws = (uint32_t)drawCtr;
     st.finish = finish ? 1 : 0;
+    const int beh0 = I[(size_t)I_BEH0 * np + k];
     if (beh0 == MCS_BEH_MERGING || beh0 == MCS_BEH_EXIT) st.fallBack = (2.0 > v) ? 1 : 0;
-    else st.fallBack = fallBack ? 1 : 0;
+    else st.fallBack = anyFallBack ? 1 : 0;
     st.ok = 1;
     st.overflow = 0;
     *st_out = st;
