@@ -98,13 +98,16 @@ __device__ __forceinline__ double idm_acc_match(const IdmP& p, int fid, double f
 struct RssP { double rTOther, rTEgo, aMin, aMax, dSoft; };
 
 // rssSafeRelax 0xb9210: entity 1 = leader of the gap's front vehicle, 3 = the gap's front vehicle, 5 = the gap's rear vehicle
-__device__ __forceinline__ bool rss_safe_relax(bool h1, double gap1, double v1, bool h3, double gap3, double v3, bool h5,
+// out of line on purpose: the merging instantiation is instruction-cache bound (ncu: 48 % of its stall samples were
+// `no instruction`), and these bodies are reached by a handful of threads per step
+__device__ __noinline__ bool rss_safe_relax(bool h1, double gap1, double v1, bool h3, double gap3, double v3, bool h5,
                                                double gapb, double vb, double egoV, double vd, const RssP& r, const IdmP& idm) {
   double v = egoV;
   const int id1 = h1 ? 1 : -1, id3 = h3 ? 1 : -1, idb = h5 ? 1 : -1;
   if (!h1) { gap1 = 0.0; v1 = 0.0; }
   if (!h3) { gap3 = 0.0; v3 = 0.0; }
   if (!h5) { gapb = 0.0; vb = 0.0; }
+#pragma unroll 1
   for (int it = 2;; it = 1) {
     const double aMaxHalf = r.aMax * 0.5;
     double a3 = aMaxHalf;
@@ -161,7 +164,7 @@ __device__ __forceinline__ bool rss_safe_relax(bool h1, double gap1, double v1, 
 }
 
 // timeToReachGap(xBack, vBack, xFront, vFront, xEgo, vEgo, vTarget) 0xe1630
-__device__ __forceinline__ double time_to_reach_gap(double xB, double vB, double xF, double vF, double xE, double vE, double vT) {
+__device__ __noinline__ double time_to_reach_gap(double xB, double vB, double xF, double vF, double xE, double vE, double vT) {
   const double a = (vT - vE) / 5.0;
   if (xB > xE) {
     const double acc = (a > 2.0) ? 2.0 : MCS_MAXSD(0.5, a);
@@ -321,18 +324,11 @@ __device__ __forceinline__ bool merging_closest_gap(const Smem& s, const SceneDe
     const double t = time_to_reach_gap((s.l[last] + a.l) * 0.5 + s.x[last], s.v[last], 10000000000.0, 100.0, a.x, a.v, vd);
     if (best > t) { best = t; kbest = n; }
   }
-  int gf = -1, gff = -1, g = -1;
-  double axGap;
-  if (kbest == 0) {
-    gf = v4[0]; if (n >= 2) gff = v4[1];
-    axGap = idm_acc(s, a.idm, gf, -1, -1, a.x, a.v, a.l, pw);
-  } else if (kbest == n) {
-    g = v4[n - 1];
-    axGap = idm_acc(s, a.idm, -1, -1, g, a.x, a.v, a.l, pw);
-  } else {
-    gf = v4[kbest]; g = v4[kbest - 1]; if (kbest + 1 < n) gff = v4[kbest + 1];
-    axGap = idm_acc(s, a.idm, gf, -1, g, a.x, a.v, a.l, pw);
-  }
+  // gap kbest: front vehicle v4[kbest] (none behind the last gap), its leader v4[kbest+1], rear vehicle v4[kbest-1]
+  const int gf = kbest < n ? v4[kbest] : -1;
+  const int gff = kbest + 1 < n ? v4[kbest + 1] : -1;
+  const int g = kbest > 0 ? v4[kbest - 1] : -1;
+  const double axGap = idm_acc(s, a.idm, gf, -1, g, a.x, a.v, a.l, pw);     // 0xff370 / 0xff610 / 0xfee31: one call shape
   const bool safe = gap_is_safe(s, a, gff, gf, g, vd);
   merge_finish(s, sc, a, side, left, safe, axGap, ax, vy);
   return true;

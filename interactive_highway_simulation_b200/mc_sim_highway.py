@@ -59,6 +59,11 @@ class Corridor:
         self.vLimit = float(vLimit)
         self.leftId = self.rightId = None
 
+    # the binding registers the three lines under the attribute names l / r / m (mcs_wrapper.py:114 reads `.m.p2.x`)
+    l = property(lambda self: self.left, lambda self, v: setattr(self, "left", v))
+    r = property(lambda self: self.right, lambda self, v: setattr(self, "right", v))
+    m = property(lambda self: self.center, lambda self, v: setattr(self, "center", v))
+
     def setLeftAndRightCorridorId(self, left_id, right_id):
         # MapMultiLane recomputes both from the lanes' centre offsets (0x10a780-0x10a839); kept for API parity
         self.leftId, self.rightId = left_id, right_id
@@ -79,6 +84,14 @@ class IdmParam:
     def _memory_order(self):
         return (self.accMax, self.minDis, self.accMin, self.accCom, self.aEmergency, self.thw)
 
+    # attribute names of the binding (constructor keywords are the long names above)
+    am = property(lambda self: self.accMax, lambda self, v: setattr(self, "accMax", float(v)))
+    amin = property(lambda self: self.accMin, lambda self, v: setattr(self, "accMin", float(v)))
+    minD = property(lambda self: self.minDis, lambda self, v: setattr(self, "minDis", float(v)))
+    aCom = property(lambda self: self.accCom, lambda self, v: setattr(self, "accCom", float(v)))
+    aE = property(lambda self: self.aEmergency, lambda self, v: setattr(self, "aEmergency", float(v)))
+    t = property(lambda self: self.thw, lambda self, v: setattr(self, "thw", float(v)))
+
 
 class RSSParam:
     def __init__(self, rTimeOther=0.7, rTimeEgo=0.4, aMinBrake=-6.0, aMaxBrake=-6.0, aSoft=1.8, dSoft=1.2):
@@ -88,6 +101,11 @@ class RSSParam:
 
     def _memory_order(self):
         return (self.rTimeOther, self.rTimeEgo, self.aMinBrake, self.aMaxBrake, self.aSoft, self.dSoft)
+
+    rTOther = property(lambda self: self.rTimeOther, lambda self, v: setattr(self, "rTimeOther", float(v)))
+    rTEgo = property(lambda self: self.rTimeEgo, lambda self, v: setattr(self, "rTimeEgo", float(v)))
+    aMin = property(lambda self: self.aMinBrake, lambda self, v: setattr(self, "aMinBrake", float(v)))
+    aMax = property(lambda self: self.aMaxBrake, lambda self, v: setattr(self, "aMaxBrake", float(v)))
 
 
 class YieldingParam:
@@ -99,6 +117,10 @@ class YieldingParam:
 
     def _memory_order(self):
         return (self.bias, self.a, self.b, self.c, self.politenessFactor, self.deltaA, self.biasA)
+
+    pf = property(lambda self: self.politenessFactor, lambda self, v: setattr(self, "politenessFactor", float(v)))
+    da = property(lambda self: self.deltaA, lambda self, v: setattr(self, "deltaA", float(v)))
+    ba = property(lambda self: self.biasA, lambda self, v: setattr(self, "biasA", float(v)))
 
 
 class State:
