@@ -268,57 +268,77 @@ __device__ __forceinline__ void side_leader_follower(const Smem& s, const int* l
 // whichever threads picked them from the queue; results go to shared memory.
 __device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc, const int* laneStart, int np, int k,
                                                int front, int back, int part) {
-  const int ln = s.lane[k];
-  const LaneDev& L = sc.lanes[ln];
-  if (part == 0) {
-    double deltaOld = 0.0;
-    if (back >= 0) {
-      const IdmP pb = load_idm(s, np, back);
-      const double bx = s.x[back], bv = s.v[back], bl = s.l[back];
-      const double pw = mcs_pow4(bv / s.vd[back]);
-      const double withEgo = idm_acc(s, pb, front, k, -1, bx, bv, bl, pw);
-      const double without = idm_acc(s, pb, front, -1, -1, bx, bv, bl, pw);
-      deltaOld = without - withEgo;
+  const LaneDev& L = sc.lanes[s.lane[k]];
+  // Which IDM evaluation is this sub-task?  Parts 0, 2, 4 are all "what does vehicle j lose when k drives between it
+  // and F" (j = old follower / would-be follower on the left / right); parts 1, 3 are k's own acceleration behind the
+  // side lane's leader plus the two RSS gates.  Branches only select the operands; each formula is instantiated once.
+  const int side = (part - 1) >> 1;
+  const bool partA = part == 1 || part == 3;
+  int leader = -1, follower = -1;
+  bool can = true;
+  if (part != 0) {
+    const int sl = side == 0 ? L.leftIdx : L.rightIdx;
+    can = sl >= 0 && sc.lanes[sl].type == MCS_LANE_MAIN;
+    if (can) side_leader_follower(s, laneStart, sl, s.x[k], leader, follower);
+  }
+  if (partA) {
+    double accNew = 0.0;
+    int mf = 0;
+    if (can) {
+      const int sl = side == 0 ? L.leftIdx : L.rightIdx;
+      const double ex = s.x[k], ev = s.v[k], el = s.l[k], evd = s.vd[k];
+      const IdmP pe = load_idm(s, np, k);
+      const double rTOther = sc.f[(size_t)F_RSS_RTOTHER * np + k], rTEgo = sc.f[(size_t)F_RSS_RTEGO * np + k];
+      const double aMin = sc.f[(size_t)F_RSS_AMIN * np + k], aMax = sc.f[(size_t)F_RSS_AMAX * np + k];
+      const double vdCap = MCS_MINSD(evd, 1.1 * sc.lanes[sl].vLimit);
+      accNew = idm_acc(s, pe, leader, -1, follower, ex, ev, el, mcs_pow4(ev / vdCap));
+      mf = side == 0 ? MF_CAN_L : MF_CAN_R;
+#pragma unroll 1
+      for (int relaxed = 0; relaxed < 2; ++relaxed) {     // strict (Agent+0x118) and relaxed (Agent+0x148: aMin -10, aMax -1) RSS
+        const bool ok = rss_safe(s, leader, follower, ex, ev, el, rTOther, rTEgo, relaxed ? -10.0 : aMin, relaxed ? -1.0 : aMax);
+        if (ok) mf |= (side == 0 ? MF_STRICT_L : MF_STRICT_R) << relaxed;
+      }
     }
-    s.mob[4 * np + k] = deltaOld;
-    return;
-  }
-  // parts 1..4: (left, right) x (A: own acceleration in that lane + RSS gates, B: the would-be follower's loss)
-  const int side = (part - 1) >> 1, sub = (part - 1) & 1;
-  const int sl = side == 0 ? L.leftIdx : L.rightIdx;
-  const bool can = sl >= 0 && sc.lanes[sl].type == MCS_LANE_MAIN;
-  if (!can) {
-    if (sub == 0) { s.mob[side * np + k] = 0.0; s.mflag[side * np + k] = 0; }
-    else s.mob[(2 + side) * np + k] = 0.0;
-    return;
-  }
-  const double ex = s.x[k];
-  int leader, follower;
-  side_leader_follower(s, laneStart, sl, ex, leader, follower);
-  if (sub == 0) {
-    const double ev = s.v[k], el = s.l[k], evd = s.vd[k];
-    const IdmP pe = load_idm(s, np, k);
-    const double rTOther = sc.f[(size_t)F_RSS_RTOTHER * np + k], rTEgo = sc.f[(size_t)F_RSS_RTEGO * np + k];
-    const double aMin = sc.f[(size_t)F_RSS_AMIN * np + k], aMax = sc.f[(size_t)F_RSS_AMAX * np + k];
-    const double vdCap = MCS_MINSD(evd, 1.1 * sc.lanes[sl].vLimit);
-    const double accNew = idm_acc(s, pe, leader, -1, follower, ex, ev, el, mcs_pow4(ev / vdCap));
-    const bool strict = rss_safe(s, leader, follower, ex, ev, el, rTOther, rTEgo, aMin, aMax);
-    const bool relax = rss_safe(s, leader, follower, ex, ev, el, rTOther, rTEgo, -10.0, -1.0);
     s.mob[side * np + k] = accNew;
-    s.mflag[side * np + k] = (uint8_t)(side == 0 ? (MF_CAN_L | (strict ? MF_STRICT_L : 0) | (relax ? MF_RELAX_L : 0))
-                                                 : (MF_CAN_R | (strict ? MF_STRICT_R : 0) | (relax ? MF_RELAX_R : 0)));
-  } else {
-    double dNew = 0.0;
-    if (follower >= 0) {
-      const IdmP pn = load_idm(s, np, follower);
-      const double nx = s.x[follower], nv = s.v[follower], nl = s.l[follower];
-      const double pw = mcs_pow4(nv / s.vd[follower]);
-      const double without = idm_acc(s, pn, leader, -1, -1, nx, nv, nl, pw);
-      const double withEgo = idm_acc(s, pn, leader, k, -1, nx, nv, nl, pw);
-      dNew = withEgo - without;
-    }
-    s.mob[(2 + side) * np + k] = dNew;
+    s.mflag[side * np + k] = (uint8_t)mf;
+    return;
   }
+  const int j = part == 0 ? back : follower;
+  const int F = part == 0 ? front : leader;
+  double delta = 0.0;
+  if (can && j >= 0) {
+    // idmAccFrontBack for j with fronts {F, k} and with {F}: the two calls share every term
+    const IdmP pj = load_idm(s, np, j);
+    const double xj = s.x[j], vj = s.v[j], lj = s.l[j];
+    const double freeAcc = (1.0 - mcs_pow4(vj / s.vd[j])) * pj.accMax;
+    const double na = -pj.accMax;
+    const double dDes = (vj * pj.thw + pj.minDis) * 0.7;
+    double termF = 0.0, termK = 0.0;
+#pragma unroll 1
+    for (int q = 0; q < 2; ++q) {
+      const int f = q == 0 ? F : k;
+      double t = -10000000000.0;
+      if (f >= 0) {
+        const double gap = (s.x[f] - xj) - (lj + s.l[f]) * 0.5;
+        if (gap > 0.0) {
+          const double dv = (vj - s.v[f]) * vj;
+          t = dv / pj.sq2 + dDes;
+          t = MCS_MAXSD(t, 0.0);
+          t = t / gap;
+          t = (t * t) * na;
+        }
+      }
+      if (q == 0) termF = t; else termK = t;
+    }
+    const double dWith = F >= 0 ? MCS_MINSD(termK, termF) : termK;
+    const double sumWithout = F >= 0 ? termF + 0.0 : 0.0;
+    double rw = MCS_MINSD((dWith + 0.0) + freeAcc, pj.accMax);
+    rw = MCS_MAXSD(pj.accMin, rw);
+    double ro = MCS_MINSD(sumWithout + freeAcc, pj.accMax);
+    ro = MCS_MAXSD(pj.accMin, ro);
+    delta = part == 0 ? ro - rw : rw - ro;       // old follower: without - with (0xf4583); new follower: with - without
+  }
+  s.mob[(part == 0 ? 4 : 2 + side) * np + k] = delta;
 }
 
 // Agent fields laneChangeBehaviorMOBIL writes back (commitToDecision 0x90, commitKeepLaneStep 0xb0, targetLaneId 0x68)
@@ -358,21 +378,24 @@ __device__ __forceinline__ void mobil_decide(const Smem& s, const SceneDev& sc, 
   const double denom = (1.0 + eL) + eR;
   double p[3];
   p[0] = eL / denom; p[2] = eR / denom; p[1] = (1.0 - p[0]) - p[2];
+  // which gates and which prior laneChangeProbability sees (0xf58a0-0xf595a, 0xf5858, 0xf5053); one call below
+  double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+  bool okL, okR;
   if (mode <= 1) {
     if (ms.commit == MCS_COMMIT_NOT_DECIDED && mode == 0) {
       // lateral-offset prior of the first lane match (computed on the host, scene.cpp).  A vehicle first matched later
       // never uses its prior: this branch needs a history of one state.
-      const double prior0 = priors[k], prior1 = priors[np + k], prior2 = priors[2 * np + k];
-      if (aggressive) lane_change_probability(p, prior0, prior1, prior2, relaxL, relaxR);
+      q0 = priors[k]; q1 = priors[np + k]; q2 = priors[2 * np + k];
+      if (aggressive) { okL = relaxL; okR = relaxR; }
       else {
-        const bool r = strictR ? true : ((prior2 >= 0.5) && relaxR);
-        const bool l = strictL ? true : ((prior0 >= 0.5) && relaxL);
-        lane_change_probability(p, prior0, prior1, prior2, l, r);
+        okR = strictR ? true : ((q2 >= 0.5) && relaxR);
+        okL = strictL ? true : ((q0 >= 0.5) && relaxL);
       }
-    } else if (aggressive) lane_change_probability(p, 0.0, 0.0, 0.0, relaxL, relaxR);
-    else lane_change_probability(p, 0.0, 0.0, 0.0, strictL, strictR);
-  } else if (mode == 2) lane_change_probability(p, 0.0, 0.0, 0.0, strictL, strictR);
-  else lane_change_probability(p, 0.0, 0.0, 0.0, relaxL, relaxR);
+    } else if (aggressive) { okL = relaxL; okR = relaxR; }
+    else { okL = strictL; okR = strictR; }
+  } else if (mode == 2) { okL = strictL; okR = strictR; }
+  else { okL = relaxL; okR = relaxR; }
+  lane_change_probability(p, q0, q1, q2, okL, okR);
   double pL = p[0];
   if (el > 6.0) {
     pL = pL * 0.5;
@@ -647,10 +670,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
         s.thist[s.flags[3]++] = thwPush;
       }
       avy = centering_vy(y, centerY);
-      if (mode == 2) {
-        customized_lane_change(s, sc, laneStart, np, k, lane, front, cd.action, x, v, el, evd, F[(size_t)F_RSS_RTOTHER * np + k],
-                               rTEgo, aMin, aMax, ax, avy);
-      } else if (kMerge && (mode == 3 || mode == 4)) {
+      if (kMerge && (mode == 3 || mode == 4)) {
         MergeSelf me;
         me.k = k; me.lane = lane; me.front = front; me.x = x; me.y = y; me.v = v; me.l = el;
         me.w = F[(size_t)F_W * np + k];
@@ -661,12 +681,47 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
         if (mode == 3) okSide = customized_merging(s, sc, laneStart, me, evd, cd.action == MCS_ACT_LEFT, gapSlot, ax, avy);
         else okSide = merging_closest_gap(s, sc, laneStart, me, evd, false, true, ax, avy);
         if (!okSide) { unsupported = true; ax = 0.0; avy = 0.0; }
-      } else if (mode == 1) {
-        // idmBehaviorAndYieldingToMergingAgents 0x104200
+      } else if (mode == 1 || mode == 2) {
+        // One idmAccFrontBack call per vehicle and step: the branches only choose its operands.
+        //   mode 1  idmBehaviorAndYieldingToMergingAgents 0x104200: own leader, vd (capped for the ego 0x104301)
+        //   mode 2  customizedLaneChangeBehavior 0xf5e30: keep / acc (thw 0.9, 1.1 vd) / dcc (2 thw, 0.8 vd) to the own
+        //           leader; left / right to {target-lane leader, own leader} with the target-lane follower behind
+        IdmP p = pe;
+        int f0 = front, f1 = -1, bk = -1;
         double vdd = evd;
-        if (isEgo) vdd = MCS_MINSD(evd, 1.1 * vLimit);
+        bool evalIdm = true, lateral = false;
+        const int cmd = cd.action;
+        if (mode == 1) {
+          if (isEgo) vdd = MCS_MINSD(evd, 1.1 * vLimit);
+        } else {
+          const double vdCap = MCS_MINSD(evd, 1.1 * vLimit);
+          vdd = vdCap;
+          if (cmd == MCS_ACT_DCC) { p.thw = pe.thw + pe.thw; vdd = 0.8 * vdCap; }
+          else if (cmd == MCS_ACT_ACC) { p.thw = 0.9; vdd = 1.1 * vdCap; }
+          else if (cmd != MCS_ACT_KEEP_LANE) {
+            const LaneDev& L = sc.lanes[lane];
+            const int sl = cmd == MCS_ACT_LEFT ? L.leftIdx : L.rightIdx;
+            if (sl >= 0 && sc.lanes[sl].type == MCS_LANE_MAIN) {
+              int leader, follower;
+              side_leader_follower(s, laneStart, sl, x, leader, follower);
+              f0 = leader; f1 = front; bk = follower; lateral = true;
+            } else {
+              evalIdm = false;      // no main lane on that side: ax = 0 unless the RSS emergency fires (0xf6976)
+            }
+          }
+        }
         const double pw = mcs_pow4(v / vdd);
-        const double axFront = idm_acc(s, pe, front, -1, -1, x, v, el, pw);
+        double axFront = 0.0;
+        if (evalIdm) axFront = idm_acc(s, p, f0, f1, bk, x, v, el, pw);
+        const bool emergency = front >= 0 && rss_emergency(s, front, x, v, el, rTEgo, aMin, aMax);
+        if (mode == 2) {
+          // for left/right the binary's emergency select reads an uninitialised stack slot (0xf6263); only the aMin outcome is observable
+          ax = emergency ? aMin : axFront;
+          if (lateral && rss_safe(s, f0, bk, x, v, el, F[(size_t)F_RSS_RTOTHER * np + k], rTEgo, aMin, aMax)) {
+            const double m = MCS_MINSD(1.0, 0.17 * v);
+            avy = m * (cmd == MCS_ACT_LEFT ? 1.0 : -1.0);
+          }
+        } else {
         IdmP py = pe;
         py.accMax = F[(size_t)F_IDMY_ACCMAX * np + k]; py.accMin = F[(size_t)F_IDMY_ACCMIN * np + k];
         double axY;
@@ -722,7 +777,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
         }
         ax = MCS_MINSD(axY, axFront);
         if (noise) ax = ax + ((double)mcs_rand31(key, drawBase + (uint64_t)nY) / 2147483647.0 - 0.5);
-        if (front >= 0 && rss_emergency(s, front, x, v, el, rTEgo, aMin, aMax)) ax = aMin;
+        if (emergency) ax = aMin;
         if (beh == MCS_BEH_IDM_LC && !isEgo) {
           // laneChangeBehaviorMOBIL 0xf42d0, decision part
           if (commit == MCS_COMMIT_KEEP_LANE && keepStep <= 9) {
@@ -734,6 +789,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
                          F[(size_t)F_YP_BA * np + k], /*mode=*/(nStates <= 1) ? 0 : 1, aggressive, F + (size_t)F_PRIOR_L * np, u, ms, ax, avy);
             commit = ms.commit; keepStep = ms.keepStep; targetLane = ms.targetLane;
           }
+        }
         }
       }
     }
