@@ -60,6 +60,14 @@ struct LaunchParams {
 #define MCS_MINSD(a, b) (((a) < (b)) ? (a) : (b))   /* x86 vminsd: second source when not less / unordered */
 #define MCS_MAXSD(a, b) (((a) > (b)) ? (a) : (b))
 
+// num / den, bit-identical to IEEE division.  A zero numerator over a positive denominator (ubiquitous here: clamped
+// IDM interaction terms, probabilities of gated-off lane changes) would take the division's out-of-line slow path
+// (~9 % of all executed instructions in the r01e profile); the quotient is the numerator itself.
+__device__ __forceinline__ double mcs_div(double num, double den) {
+  if (num == 0.0 && den > 0.0) return num;
+  return num / den;
+}
+
 struct IdmP { double accMax, minDis, accMin, accCom, thw, sq2 /* 2*sqrt(-accMax*accCom), static per vehicle */; };
 
 // shared-memory view of one rollout
@@ -137,7 +145,7 @@ __device__ MCS_HEAVY_INLINE double idm_acc(const Smem& s, const IdmP& p, int f0,
       const double dv = (egoV - s.v[f]) * egoV;
       double t = dv / sq2 + dDes;
       t = MCS_MAXSD(t, 0.0);
-      t = t / gap;
+      t = mcs_div(t, gap);
       term = (t * t) * na;
     } else {
       term = -10000000000.0;
@@ -225,7 +233,7 @@ __device__ __forceinline__ void lane_change_probability(double p[3], double q0, 
   const double K = wP * p[1] + wQ * q1;
   if (rightOk) R = p[2] * wP + q2 * wQ;
   const double S = (L + K) + R;
-  p[0] = L / S; p[1] = K / S; p[2] = R / S;
+  p[0] = mcs_div(L, S); p[1] = K / S; p[2] = mcs_div(R, S);
 }
 
 // lateral centring 0x10441b-0x10447f
@@ -249,49 +257,56 @@ __device__ __forceinline__ bool rss_emergency(const Smem& s, int front, double e
 }
 
 // MOBIL flag bits (Smem::mflag)
-enum { MOBIL_PARTS = 5 };
+enum { MOBIL_PARTS = 7 };
 enum { MF_STRICT_L = 1, MF_RELAX_L = 2, MF_STRICT_R = 4, MF_RELAX_R = 8, MF_CAN_L = 16, MF_CAN_R = 32 };
 
 // side neighbours of vehicle at x in lane `ln`: leader = first with x_elem >= x, follower = last with x_elem < x
-__device__ __forceinline__ void side_leader_follower(const Smem& s, const int* laneStart, int ln, double x, int& leader,
-                                                     int& follower) {
+__device__ __forceinline__ void side_leader_follower(const Smem& s, const int* laneStart, int ln, double x, bool ordered,
+                                                     int& leader, int& follower) {
   const int lo = laneStart[ln], n = laneStart[ln + 1] - lo;
   const int f = lane_lower(s, lo, n, x);
   leader = f < n ? s.vec[lo + f] : -1;
-  const int r = lane_reverse(s, lo, n, x);
+  // `ordered`: no lane vector is stale-ordered this step, so the reference's second (reverse) search ends right below f
+  const int r = ordered ? f : lane_reverse(s, lo, n, x);
   follower = r > 0 ? s.vec[lo + r - 1] : -1;
 }
 
 // The part of laneChangeBehaviorMOBIL (0xf44c9-0xf4dde, 0xf5259-0xf584e) that does not depend on the vehicle's own
-// IDM action: accelerations in the neighbour lanes, follower deltas, RSS gates.  A vehicle's evaluation is five
-// independent sub-tasks of similar cost (part 0: old follower; 1/2: left lane A/B; 3/4: right lane A/B) executed by
-// whichever threads picked them from the queue; results go to shared memory.
+// IDM action: accelerations in the neighbour lanes, follower deltas, RSS gates.  A vehicle's evaluation is seven
+// independent sub-tasks of similar cost (part 0: old follower delta; 1-3: left lane own IDM / RSS gates / follower
+// delta; 4-6: the same for the right lane) executed by whichever threads picked them from the queue; results go to
+// shared memory.
 __device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc, const int* laneStart, int np, int k,
-                                               int front, int back, int part) {
+                                               int front, int back, int part, bool ordered) {
   const LaneDev& L = sc.lanes[s.lane[k]];
-  // Which IDM evaluation is this sub-task?  Parts 0, 2, 4 are all "what does vehicle j lose when k drives between it
+  // Which IDM evaluation is this sub-task?  Parts 0, 3, 6 are all "what does vehicle j lose when k drives between it
   // and F" (j = old follower / would-be follower on the left / right); parts 1, 3 are k's own acceleration behind the
   // side lane's leader plus the two RSS gates.  Branches only select the operands; each formula is instantiated once.
-  const int side = (part - 1) >> 1;
-  const bool partA = part == 1 || part == 3;
+  const int side = part > 3 ? 1 : 0, sub = part == 0 ? 2 : (part - 1) - 3 * side;   // sub 0: own IDM, 1: RSS gates, 2: follower delta
   int leader = -1, follower = -1;
   bool can = true;
   if (part != 0) {
     const int sl = side == 0 ? L.leftIdx : L.rightIdx;
     can = sl >= 0 && sc.lanes[sl].type == MCS_LANE_MAIN;
-    if (can) side_leader_follower(s, laneStart, sl, s.x[k], leader, follower);
+    if (can) side_leader_follower(s, laneStart, sl, s.x[k], ordered, leader, follower);
   }
-  if (partA) {
+  if (sub == 0) {
     double accNew = 0.0;
-    int mf = 0;
     if (can) {
       const int sl = side == 0 ? L.leftIdx : L.rightIdx;
-      const double ex = s.x[k], ev = s.v[k], el = s.l[k], evd = s.vd[k];
-      const IdmP pe = load_idm(s, np, k);
+      const double ev = s.v[k];
+      const double vdCap = MCS_MINSD(s.vd[k], 1.1 * sc.lanes[sl].vLimit);
+      accNew = idm_acc(s, load_idm(s, np, k), leader, -1, follower, s.x[k], ev, s.l[k], mcs_pow4(ev / vdCap));
+    }
+    s.mob[side * np + k] = accNew;
+    return;
+  }
+  if (sub == 1) {
+    int mf = 0;
+    if (can) {
+      const double ex = s.x[k], ev = s.v[k], el = s.l[k];
       const double rTOther = sc.f[(size_t)F_RSS_RTOTHER * np + k], rTEgo = sc.f[(size_t)F_RSS_RTEGO * np + k];
       const double aMin = sc.f[(size_t)F_RSS_AMIN * np + k], aMax = sc.f[(size_t)F_RSS_AMAX * np + k];
-      const double vdCap = MCS_MINSD(evd, 1.1 * sc.lanes[sl].vLimit);
-      accNew = idm_acc(s, pe, leader, -1, follower, ex, ev, el, mcs_pow4(ev / vdCap));
       mf = side == 0 ? MF_CAN_L : MF_CAN_R;
 #pragma unroll 1
       for (int relaxed = 0; relaxed < 2; ++relaxed) {     // strict (Agent+0x118) and relaxed (Agent+0x148: aMin -10, aMax -1) RSS
@@ -299,7 +314,6 @@ __device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc
         if (ok) mf |= (side == 0 ? MF_STRICT_L : MF_STRICT_R) << relaxed;
       }
     }
-    s.mob[side * np + k] = accNew;
     s.mflag[side * np + k] = (uint8_t)mf;
     return;
   }
@@ -324,7 +338,7 @@ __device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc
           const double dv = (vj - s.v[f]) * vj;
           t = dv / pj.sq2 + dDes;
           t = MCS_MAXSD(t, 0.0);
-          t = t / gap;
+          t = mcs_div(t, gap);
           t = (t * t) * na;
         }
       }
@@ -377,7 +391,7 @@ __device__ __forceinline__ void mobil_decide(const Smem& s, const SceneDev& sc, 
   const double eL = mcs_exp(incL), eR = mcs_exp(incR);
   const double denom = (1.0 + eL) + eR;
   double p[3];
-  p[0] = eL / denom; p[2] = eR / denom; p[1] = (1.0 - p[0]) - p[2];
+  p[0] = mcs_div(eL, denom); p[2] = mcs_div(eR, denom); p[1] = (1.0 - p[0]) - p[2];
   // which gates and which prior laneChangeProbability sees (0xf58a0-0xf595a, 0xf5858, 0xf5053); one call below
   double q0 = 0.0, q1 = 0.0, q2 = 0.0;
   bool okL, okR;
@@ -431,7 +445,7 @@ __device__ __forceinline__ void customized_lane_change(const Smem& s, const Scen
   const int sl = cmd == MCS_ACT_LEFT ? L.leftIdx : L.rightIdx;
   if (sl >= 0 && sc.lanes[sl].type == MCS_LANE_MAIN) {
     int leader, follower;
-    side_leader_follower(s, laneStart, sl, x, leader, follower);
+    side_leader_follower(s, laneStart, sl, x, false, leader, follower);
     ax = idm_acc(s, pe, leader, front, follower, x, v, el, mcs_pow4(v / vdCap));
     if (emergency) ax = aMin;
     if (rss_safe(s, leader, follower, x, v, el, rTOther, rTEgo, aMin, aMax)) {
@@ -570,7 +584,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
     // ================= plan, part A: own-lane search, IDM, draw counts =================
     double ax = 0.0, avy = 0.0;
     int front = -1, back = -1;
-    bool needMobil = false, noise = false, inversion = false;
+    bool needMobil = false, noise = false, inversion = false, ordered = false;
     int mode = 0;   // 1 idmBehaviorAndYielding, 2 customizedLaneChange (ego), 3 customizedMerging (ego), 4 closest gap
     int nDraw = 0;
     const bool hasLane = live && lane >= 0;
@@ -620,6 +634,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
       int total;
       const int pos = block_exclusive_scan<NPS / 32>((needMobil ? 1 : 0) | (inversion ? 1 << 16 : 0), s.scan, total) & 0xffff;
       nTasks = total & 0xffff;
+      ordered = (total >> 16) == 0;
       if (hasLane) {
         const int lo = laneStart[lane], cnt = laneStart[lane + 1] - lo;
         if (total >> 16) {          // some lane vector is stale-ordered: search it the way the reference does
@@ -644,7 +659,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
       const int vk = rec & 0xff;
       const int vf = (rec >> 24 & 1) ? -1 : (rec >> 8 & 0xff);
       const int vb = (rec >> 25 & 1) ? -1 : (rec >> 16 & 0xff);
-      mobil_geometry(s, sc, laneStart, np, vk, vf, vb, part);
+      mobil_geometry(s, sc, laneStart, np, vk, vf, vb, part, ordered);
     }
     __syncthreads();
     // draw counts: [noise][MOBIL decision draw]
@@ -703,7 +718,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
             const int sl = cmd == MCS_ACT_LEFT ? L.leftIdx : L.rightIdx;
             if (sl >= 0 && sc.lanes[sl].type == MCS_LANE_MAIN) {
               int leader, follower;
-              side_leader_follower(s, laneStart, sl, x, leader, follower);
+              side_leader_follower(s, laneStart, sl, x, ordered, leader, follower);
               f0 = leader; f1 = front; bk = follower; lateral = true;
             } else {
               evalIdm = false;      // no main lane on that side: ax = 0 unless the RSS emergency fires (0xf6976)
