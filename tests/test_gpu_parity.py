@@ -311,3 +311,44 @@ def test_sharded_groups_equal_single_gpu(gpu):
                 assert bytes(feats[c]) == bytes(want[c]), (world, c)
     finally:
         ds.close()
+
+
+@pytest.mark.parametrize("n_agents", [1, 2, 31, 32, 33, 64, 65, 128, 129, 200, 256])
+def test_block_size_boundaries_against_oracle(gpu, oracle, n_agents):
+    """Every kernel instantiation (32 / 64 / 128 / 256 threads) at and around its capacity, incl. an ego without objects."""
+    rng = random.Random(4000 + n_agents)
+    s, ego = random_scene(rng, rng.choice([2, 3, 4]), n_agents, spacing=(3, 40))
+    check_against_oracle(gpu, oracle, s, ego, 0.3, 30, 10, 900 + n_agents, 4, "n%d" % n_agents, traj_rollouts=1,
+                         actions=("keep_lane", "left", "dcc"))
+
+
+def test_eight_lanes_and_zero_steps(gpu, oracle):
+    rng = random.Random(77)
+    s, ego = random_scene(rng, 8, 120, spacing=(3, 50))                       # MCS_MAX_LANES corridors
+    check_against_oracle(gpu, oracle, s, ego, 0.2, 25, 25, 5, 4, "8lanes", traj_rollouts=1, actions=("keep_lane", "right"))
+    s, ego = random_scene(rng, 3, 12)
+    check_against_oracle(gpu, oracle, s, ego, 0.3, 0, 0, 6, 2, "0steps", traj_rollouts=1, actions=("keep_lane",))   # comfort = 0/0
+    check_against_oracle(gpu, oracle, s, ego, 0.3, 1, 1, 6, 2, "1step", traj_rollouts=1, actions=("acc",))
+
+
+@pytest.mark.parametrize("block", range(6))
+def test_many_random_scenes_against_oracle(gpu, oracle, block):
+    """Breadth: 60 more random scenes (lane change, merging, exit; sparse to dense) — statuses only."""
+    for sc in range(10):
+        rng = random.Random(50000 + 10 * block + sc)
+        kind = rng.choice(["lc", "lc", "merge", "exit"])
+        na = rng.choice([6, 11, 18, 27, 40, 70])
+        spacing = rng.choice([(3, 60), (2, 20), (8, 100)])
+        if kind == "lc":
+            s, ego = random_scene(rng, rng.choice([2, 3, 4, 5]), na, spacing=spacing)
+            actions, gap = (rng.choice(ACTIONS), rng.choice(ACTIONS)), -2
+        elif kind == "merge":
+            s, ego = random_scene(rng, n_agents=na, lane_types=["merging", "main"] + ["main"] * rng.choice([0, 1, 2]),
+                                  ego_behavior="merging", ego_lane=0, spacing=spacing)
+            actions, gap = ("left",), rng.choice([-1] + [a["id"] for a in s.agents])
+        else:
+            s, ego = random_scene(rng, n_agents=na, lane_types=["exit", "main"] + ["main"] * rng.choice([0, 1]),
+                                  ego_behavior="exit", ego_lane=1, spacing=spacing)
+            actions, gap = ("right",), rng.choice([-1] + [a["id"] for a in s.agents])
+        check_against_oracle(gpu, oracle, s, ego, rng.choice([0.2, 0.3]), rng.choice([20, 40, 50]), rng.choice([5, 10, 30]),
+                             7 + sc, 6, "%s_b%d_%d" % (kind, block, sc), traj_rollouts=0, gap=gap, actions=actions)
