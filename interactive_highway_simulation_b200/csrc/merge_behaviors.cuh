@@ -13,7 +13,7 @@
 namespace mcs {
 
 // idmAccFrontBack 0xebc30 with an arbitrary list of fronts (slots, -1 = null)
-__device__ __forceinline__ double idm_acc_list(const Smem& s, const IdmP& p, const int* fronts, int nf, int back,
+__device__ __noinline__ double idm_acc_list(const Smem& s, const IdmP& p, const int* fronts, int nf, int back,
                                                double egoX, double egoV, double egoL, double pw) {
   const double freeAcc = (1.0 - pw) * p.accMax;
   const double na = -p.accMax;
@@ -261,77 +261,83 @@ __device__ __forceinline__ bool gap_is_safe(const Smem& s, const MergeSelf& a, i
   return rss_safe_relax(h1, g1, h1 ? s.v[gff] : 0.0, h3, g3, h3 ? s.v[gf] : 0.0, h5, g5, h5 ? s.v[g] : 0.0, a.v, vd, a.rss, a.idm);
 }
 
-// customizedMergingBehavior 0xf6ba0.  gapSlot: slot of the gap's rear vehicle, or < 0 = "last gap".  Returns false when
+// customizedMergingBehavior 0xf6ba0 (fixedGap = true; gapSlot: slot of the gap's rear vehicle, < 0 = "last gap") and
+// mergingBehaviorClosestGap 0xfe660 (fixedGap = false) share everything after the choice of the gap — its front vehicle
+// gf, that one's leader gff and its rear vehicle g: rssSafeRelax on the three, one idmAccFrontBack, and the common tail.
+// One body, so that the merging instantiation (instruction-cache bound) carries each formula once.  Returns false when
 // the reference would dereference a missing corridor (no lane on that side).
-__device__ __forceinline__ bool customized_merging(const Smem& s, const SceneDev& sc, const int* laneStart, const MergeSelf& a,
-                                                   double evd, bool left, int gapSlot, double& ax, double& vy) {
+__device__ __forceinline__ bool merging_behavior(const Smem& s, const SceneDev& sc, const int* laneStart, const MergeSelf& a,
+                                                 double evd, bool fixedGap, bool isEgo, bool left, int gapSlot, double& ax,
+                                                 double& vy) {
   const LaneDev& c = sc.lanes[a.lane];
   const int side = left ? c.leftIdx : c.rightIdx;
   if (side < 0) return false;
+  // customizedMerging caps vd for everybody (0xf6f90), closest-gap only for the ego (0xfe757)
+  const double vd = (fixedGap || isEgo) ? MCS_MINSD(evd, 1.1 * c.vLimit) : evd;
+  const double pw = mcs_pow4(a.v / vd);
   int g = -1, gf = -1, gff = -1;
-  if (gapSlot >= 0) {
+  int fronts[3];
+  int nf;
+  bool execute = true;
+  if (fixedGap && gapSlot >= 0) {
     g = gapSlot;
     gf = front_of(s, laneStart, g);
     if (gf >= 0) gff = front_of(s, laneStart, gf);
   } else {
     int v4[4];
     const int n = side_vector(s, laneStart, side, a.x, v4);
-    if (n >= 1) gf = v4[0];
-    if (n >= 2) gff = v4[1];
+    if (fixedGap) {                         // "go to last gap": behind the rearmost neighbour (0xf7488)
+      if (n >= 1) gf = v4[0];
+      if (n >= 2) gff = v4[1];
+    } else if (n == 0) {
+      execute = false;                      // nobody on the target lane: plain IDM to the own leader (0xff2bf)
+    } else {
+      // std::map<int,double> of time-to-reach per gap; gap j lies behind v4[j], gap n in front of the last neighbour;
+      // strict > keeps the smallest key on ties (0xfed88-0xfedaf)
+      double best = 0.0;
+      int kbest = 0;
+#pragma unroll 1
+      for (int j = 0; j <= n; ++j) {
+        const int B = j > 0 ? v4[j - 1] : -1, F = j < n ? v4[j] : -1;
+        const double xB = B >= 0 ? (a.l + s.l[B]) * 0.5 + s.x[B] : -10000000000.0;
+        const double vB = B >= 0 ? s.v[B] : 0.0;
+        const double xF = F >= 0 ? s.x[F] - (a.l + s.l[F]) * 0.5 : 10000000000.0;
+        const double vF = F >= 0 ? s.v[F] : 100.0;
+        const double t = time_to_reach_gap(xB, vB, xF, vF, a.x, a.v, vd);
+        if (j == 0 || best > t) { best = t; kbest = j; }
+      }
+      gf = kbest < n ? v4[kbest] : -1;
+      gff = kbest + 1 < n ? v4[kbest + 1] : -1;
+      g = kbest > 0 ? v4[kbest - 1] : -1;
+    }
   }
-  const double vdCap = MCS_MINSD(evd, 1.1 * c.vLimit);
-  const bool safe = gap_is_safe(s, a, gff, gf, g, vdCap);
-  const int f3[3] = {gf, gff, a.front};
-  const double axGap = idm_acc_list(s, a.idm, f3, 3, g, a.x, a.v, a.l, mcs_pow4(a.v / vdCap));
-  merge_finish(s, sc, a, side, left, safe, axGap, ax, vy);
-  return true;
-}
-
-// mergingBehaviorClosestGap 0xfe660
-__device__ __forceinline__ bool merging_closest_gap(const Smem& s, const SceneDev& sc, const int* laneStart, const MergeSelf& a,
-                                                    double evd, bool isEgo, bool left, double& ax, double& vy) {
-  const LaneDev& c = sc.lanes[a.lane];
-  double vd = evd;
-  if (isEgo) vd = MCS_MINSD(vd, 1.1 * c.vLimit);
-  const double pw = mcs_pow4(a.v / vd);
-  const double axFront = idm_acc(s, a.idm, a.front, -1, -1, a.x, a.v, a.l, pw);
-  const int side = left ? c.leftIdx : c.rightIdx;
-  if (side < 0) return false;
-  int v4[4];
-  const int n = side_vector(s, laneStart, side, a.x, v4);
-  if (n == 0) {
+  if (fixedGap) { fronts[0] = gf; fronts[1] = gff; fronts[2] = a.front; nf = 3; }      // 0xf707a-0xf70d9
+  else if (execute) { fronts[0] = gf; nf = 1; }                                        // 0xff370 / 0xff610 / 0xfee31
+  else { fronts[0] = a.front; nf = 1; }
+  const double axI = idm_acc_list(s, a.idm, fronts, nf, execute ? g : -1, a.x, a.v, a.l, pw);
+  if (!execute) {
     const bool far = left ? (-0.5 > (a.w * 0.5 + a.y) - c.leftY) : ((a.y - a.w * 0.5) - c.rightY > 0.5);
-    ax = axFront;
+    ax = axI;
+    vy = 0.0;
     if (a.x >= sc.lanes[side].startX || far) {
       const double sign = left ? 1.0 : -1.0;
       const double m = a.v * 0.17;
       vy = (m > 1.0) ? sign : m * sign;
-    } else {
-      vy = 0.0;
     }
     return true;
   }
-  // std::map<int,double>: gap j lies behind v4[j]; strict > keeps the smallest key on ties (0xfed88-0xfedaf)
-  const int first = v4[0], last = v4[n - 1];
-  double best = time_to_reach_gap(-10000000000.0, 0.0, s.x[first] - (s.l[first] + a.l) * 0.5, s.v[first], a.x, a.v, vd);
-  int kbest = 0;
-  for (int i = 0; i + 1 < n; ++i) {
-    const int B = v4[i], F = v4[i + 1];
-    const double t = time_to_reach_gap((a.l + s.l[B]) * 0.5 + s.x[B], s.v[B], s.x[F] - (a.l + s.l[F]) * 0.5, s.v[F], a.x, a.v, vd);
-    if (best > t) { best = t; kbest = i + 1; }
-  }
-  {
-    const double t = time_to_reach_gap((s.l[last] + a.l) * 0.5 + s.x[last], s.v[last], 10000000000.0, 100.0, a.x, a.v, vd);
-    if (best > t) { best = t; kbest = n; }
-  }
-  // gap kbest: front vehicle v4[kbest] (none behind the last gap), its leader v4[kbest+1], rear vehicle v4[kbest-1]
-  const int gf = kbest < n ? v4[kbest] : -1;
-  const int gff = kbest + 1 < n ? v4[kbest + 1] : -1;
-  const int g = kbest > 0 ? v4[kbest - 1] : -1;
-  const double axGap = idm_acc(s, a.idm, gf, -1, g, a.x, a.v, a.l, pw);     // 0xff370 / 0xff610 / 0xfee31: one call shape
   const bool safe = gap_is_safe(s, a, gff, gf, g, vd);
-  merge_finish(s, sc, a, side, left, safe, axGap, ax, vy);
+  merge_finish(s, sc, a, side, left, safe, axI, ax, vy);
   return true;
+}
+
+__device__ __forceinline__ bool customized_merging(const Smem& s, const SceneDev& sc, const int* laneStart, const MergeSelf& a,
+                                                   double evd, bool left, int gapSlot, double& ax, double& vy) {
+  return merging_behavior(s, sc, laneStart, a, evd, true, false, left, gapSlot, ax, vy);
+}
+__device__ __forceinline__ bool merging_closest_gap(const Smem& s, const SceneDev& sc, const int* laneStart, const MergeSelf& a,
+                                                    double evd, bool isEgo, bool left, double& ax, double& vy) {
+  return merging_behavior(s, sc, laneStart, a, evd, false, isEgo, left, -1, ax, vy);
 }
 
 // ---- yielding intentions (Agent+0x238: unordered_map<int, YieldingIntention>) as a small per-thread table ----

@@ -692,9 +692,9 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
         me.rss.rTOther = F[(size_t)F_RSS_RTOTHER * np + k]; me.rss.rTEgo = rTEgo; me.rss.aMin = aMin; me.rss.aMax = aMax;
         me.rss.dSoft = F[(size_t)F_RSS_DSOFT * np + k];
         me.idm = pe;
-        bool okSide;
-        if (mode == 3) okSide = customized_merging(s, sc, laneStart, me, evd, cd.action == MCS_ACT_LEFT, gapSlot, ax, avy);
-        else okSide = merging_closest_gap(s, sc, laneStart, me, evd, false, true, ax, avy);
+        // mode 3: the ego executes its gap (customizedMerging); mode 4: a non-ego `merging` vehicle picks the closest gap to the left
+        const bool okSide = merging_behavior(s, sc, laneStart, me, evd, mode == 3, false, mode == 3 ? cd.action == MCS_ACT_LEFT : true,
+                                             gapSlot, ax, avy);
         if (!okSide) { unsupported = true; ax = 0.0; avy = 0.0; }
       } else if (mode == 1 || mode == 2) {
         // One idmAccFrontBack call per vehicle and step: the branches only choose its operands.
@@ -1010,6 +1010,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
     for (int t = k; t < ns; t += NPS) {
       const double c = s.chist[t];
       int rank = 0;
+#pragma unroll 1
       for (int j = 0; j < ns; ++j) { const double cj = s.chist[j]; rank += (cj > c || (cj == c && j < t)) ? 1 : 0; }
       sorted[rank] = c;
     }
@@ -1024,15 +1025,18 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
     memset(&st, 0, sizeof st);
     st.utilityObjects = uo; st.comfortObjects = co;
     double sumU = 0.0;
+#pragma unroll 1
     for (int t = 0; t < nStates; ++t) sumU = sumU + s.vhist[t];
     const double util = sumU / (double)nStates;
     const int thwCnt = s.flags[3];
     double thwAcc = 0.0;                                  // 0x10f14b-0x10f19f
+#pragma unroll 1
     for (int t = 0; t < thwCnt; ++t) { const double e = s.thist[t]; if (0.9 > e && e > 0.0) thwAcc = (e + thwAcc) - 0.9; }
     const double thwTerm = thwCnt > 0 ? thwAcc / (double)thwCnt : 0.0;
     st.utility = util + thwTerm;
     const int kk = (int)((double)nStates * 0.2);
     double sumC = 0.0;
+#pragma unroll 1
     for (int t = 0; t < kk; ++t) sumC = sumC + (s.csort[t] / aMin + 1.0);
     st.comfort = sumC / (double)kk;
     st.finishStep = fs; st.executedSteps = executed; st.draws = (uint32_t)drawCtr;
