@@ -22,7 +22,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
   } while (0)
 
 size_t rollout_smem_bytes(int n_pad, int steps) {
-  size_t doubles = (size_t)n_pad * (4 + 6 + 6) + 4 * (size_t)((steps + 2) & ~1) + 16;
+  size_t doubles = (size_t)n_pad * (4 + 6 + 6 + 3 + 2) + 4 * (size_t)((steps + 2) & ~1) + 16;
   size_t ints = 32 + 32 + 8 + (size_t)n_pad;
   return doubles * 8 + ints * 4 + 5 * (size_t)n_pad;
 }

@@ -78,6 +78,8 @@ struct Smem {
   double* vd;      // [n_pad] static
   double* idm;     // [6][n_pad] static: accMax minDis accMin accCom thw 2*sqrt(-accMax*accCom)
   double* mob;     // [6][n_pad] MOBIL geometry results per vehicle: accNewL accNewR dNewL dNewR deltaOld (+1 spare)
+  double* rss;     // [3][n_pad] static: rTEgo aMin aMax (read once per step by the RSS emergency test)
+  double* acc;     // [2][n_pad] per-object statistics: sum |a_t|, sum v_t
   double* chist;   // [steps+2] ego acceleration history, turned into comfort samples at the end
   double* csort;   // [steps+2] the comfort samples sorted descending
   double* vhist;   // [steps+2] ego speed history, turned into per-state utilities at the end
@@ -101,6 +103,8 @@ __device__ __forceinline__ void carve_smem(Smem& s, unsigned char* p, int np, in
   s.vd = (double*)p; p += sizeof(double) * np;
   s.idm = (double*)p; p += sizeof(double) * 6 * np;
   s.mob = (double*)p; p += sizeof(double) * 6 * np;
+  s.rss = (double*)p; p += sizeof(double) * 3 * np;
+  s.acc = (double*)p; p += sizeof(double) * 2 * np;
   s.chist = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
   s.csort = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
   s.vhist = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
@@ -519,16 +523,12 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
   const double* F = sc.f;
   const int32_t* I = sc.i;
   double x = 0, y = 0, v = 0, vy = 0;
-  double el = 0, evd = 1;
-  double rTEgo = 0, aMin = -1, aMax = -1;
   int lane = -1, beh = MCS_BEH_OTHER, commit = 0, keepStep = 0, targetLane = -1, inputIdx = 0;
   bool aggressive = false;
   const bool isEgo = live && k == cd.ego_slot;
   bool reached = false;
   if (live) {
     x = F[(size_t)F_X * np + k]; y = F[(size_t)F_Y * np + k]; v = F[(size_t)F_V * np + k]; vy = F[(size_t)F_VY * np + k];
-    el = F[(size_t)F_L * np + k]; evd = F[(size_t)F_VD * np + k];
-    rTEgo = F[(size_t)F_RSS_RTEGO * np + k]; aMin = F[(size_t)F_RSS_AMIN * np + k]; aMax = F[(size_t)F_RSS_AMAX * np + k];
     lane = I[(size_t)I_LANE * np + k]; beh = I[(size_t)I_BEH * np + k]; commit = I[(size_t)I_COMMIT * np + k];
     keepStep = I[(size_t)I_KEEPSTEP * np + k]; targetLane = I[(size_t)I_TARGETLANE * np + k];
     inputIdx = I[(size_t)I_INPUT * np + k];
@@ -537,7 +537,12 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
     if (isEgo) targetLane = cd.target_lane_id;
   }
   // stage what neighbours gather
-  s.x[k] = x; s.v[k] = v; s.l[k] = el; s.vd[k] = evd;
+  // static per-vehicle values live in shared memory only (registers are what limits the resident blocks per SM)
+  s.x[k] = x; s.v[k] = v;
+  s.l[k] = live ? F[(size_t)F_L * np + k] : 0.0; s.vd[k] = live ? F[(size_t)F_VD * np + k] : 1.0;
+  s.rss[k] = live ? F[(size_t)F_RSS_RTEGO * np + k] : 0.0;
+  s.rss[np + k] = live ? F[(size_t)F_RSS_AMIN * np + k] : -1.0;
+  s.rss[2 * np + k] = live ? F[(size_t)F_RSS_AMAX * np + k] : -1.0;
   s.idm[k] = live ? F[(size_t)F_IDM_ACCMAX * np + k] : 1.0;
   s.idm[np + k] = live ? F[(size_t)F_IDM_MINDIS * np + k] : 0.0;
   s.idm[2 * np + k] = live ? F[(size_t)F_IDM_ACCMIN * np + k] : 0.0;
@@ -559,11 +564,10 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
   // statistics (Simulation::run 0x10ee71-0x10f49a) accumulated on the fly in history order
   // statistics (Simulation::run 0x10ee71-0x10f49a): per-object sums accumulated on the fly in history order; the ego's own
   // history (acceleration, speed, thw ratio) is kept in shared memory and reduced in the same order after the loop
-  double sumAbsA, sumV = v;
   int nStates = 1;
   {
     const double a0 = live ? F[(size_t)F_A * np + k] : 0.0;
-    sumAbsA = fabs(a0);
+    s.acc[k] = fabs(a0); s.acc[np + k] = v;
     if (isEgo) { s.chist[0] = a0; s.vhist[0] = v; }
   }
   if (kTraj && live) {
@@ -679,6 +683,8 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
     // ================= plan, part B: actions =================
     if (hasLane) {
       const IdmP pe = load_idm(s, np, k);
+      const double el = s.l[k], evd = s.vd[k];
+      const double rTEgo = s.rss[k], aMin = s.rss[np + k], aMax = s.rss[2 * np + k];
       if (isEgo) {    // Agent::thwRatioHistory is read for the ego only (0x10f14b)
         double thwPush = 1.0;
         if (front >= 0) thwPush = (((s.x[front] - x) - (s.l[front] + el) * 0.5) / v) / pe.thw;
@@ -820,7 +826,7 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
         v = v1; x = v1 * lp.dt + x; vy = avy; y = avy * lp.dt + y; acc = (v1 == 0.0) ? 0.0 : ax;
       }
       s.x[k] = x; s.v[k] = v;
-      sumAbsA = sumAbsA + fabs(acc); sumV = sumV + v;
+      s.acc[k] = s.acc[k] + fabs(acc); s.acc[np + k] = s.acc[np + k] + v;
       if (isEgo) { s.chist[nStates] = acc; s.vhist[nStates] = v; }
       if (kTraj) {
         double* t = lp.traj + ((((size_t)cand * lp.count + ridx) * n + inputIdx) * (size_t)(lp.steps + 1) + nStates) * 4;
@@ -970,10 +976,11 @@ __global__ void __launch_bounds__(NPS, (256 / NPS) * (kMerge ? 2 : MCS_MIN_BLOCK
   const int executed = nStates - 1;
   const int fs = max(finishStep, (int)(1.0 / lp.dt));
   double utilO = 1e300, comfO = 1e300;   // min identity; replaced by 1.0 when the rollout has no objects
+  const double aMin = s.rss[np + k];
   if (live && !isEgo) {
-    const double cnt = (double)nStates;
-    const double meanV = sumV / cnt;
-    comfO = (sumAbsA / cnt) / aMin + 1.0;
+    const double cnt = (double)nStates, evd = s.vd[k];
+    const double meanV = s.acc[np + k] / cnt;
+    comfO = (s.acc[k] / cnt) / aMin + 1.0;
     utilO = (meanV >= evd) ? 1.0 : meanV / evd;
   }
 #pragma unroll
