@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -181,9 +182,12 @@ int stage_candidates(mcs_scene* sc, const mcs_candidate* cands, int n_cand, int*
 }
 
 template <bool kTraj, bool kMerge, int NPS>
-int launch_np(mcs_scene* sc, dim3 grid, size_t smem, const mcs::LaunchParams& lp) {
+int launch_np(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& lp) {
+  constexpr int G = 256 / NPS;      // rollouts per 256-thread block
+  const size_t smem = region * G;
+  grid.x = (grid.x + G - 1) / G;
   CUDA_TRY(cudaFuncSetAttribute(mcs::rollout_kernel<kTraj, kMerge, NPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mcs::rollout_kernel<kTraj, kMerge, NPS><<<grid, dim3(NPS), smem, sc->ctx->stream>>>(sc->dev, sc->ctx->d_cand, lp);
+  mcs::rollout_kernel<kTraj, kMerge, NPS><<<grid, dim3(256), smem, sc->ctx->stream>>>(sc->dev, sc->ctx->d_cand, lp, (int)region);
   CUDA_TRY(cudaGetLastError());
   return MCS_OK;
 }
@@ -208,7 +212,8 @@ int launch_rollouts(mcs_scene* sc, int n_cand, const mcs_sim_param* sp, uint64_t
   lp.dt = sp->dt; lp.steps = sp->steps; lp.min_steps = sp->min_steps;
   lp.seed = seed; lp.first = first; lp.count = count; lp.n_cand = n_cand;
   lp.status = d_status; lp.traj = d_traj; lp.traj_n = d_traj_n; lp.vehicle_steps = d_counter;
-  const size_t smem = rollout_smem_bytes(sc->dev.n_pad, sp->steps);
+  size_t smem = (rollout_smem_bytes(sc->dev.n_pad, sp->steps) + 15) & ~(size_t)15;   // one rollout's region
+  if (const char* e = getenv("MCS_EXTRA_SMEM")) smem += (size_t)atoi(e) & ~(size_t)15;   // diagnostic: caps the resident blocks per SM
   dim3 grid((unsigned)count, (unsigned)n_cand);
   // the trajectory-writing variant is a test / Simulation.run() path: one instantiation (the merging superset) serves it
   if (d_traj) return launch_one<true, true>(sc, grid, smem, lp);
