@@ -181,13 +181,22 @@ int stage_candidates(mcs_scene* sc, const mcs_candidate* cands, int n_cand, int*
   return MCS_OK;
 }
 
+// Threads per block.  A 256-vehicle rollout owns a 256-thread block.  Smaller rollouts share a block and start every
+// step together (rollout_kernel.cuh): 4-8 per block.  The merging instantiation is the instruction-fetch-bound one and
+// gets 512 threads (measured, 4 x 512 rollouts x 40 vehicles: 128 threads 3.42 ms, 256: 2.73 ms, 512: 2.48 ms); named
+// barriers limit a block to 15 rollouts.
+template <bool kMerge, int NPS>
+struct BlockThreads { static constexpr int value = NPS == 256 ? 256 : (kMerge && NPS >= 64 ? 512 : 256); };
+
 template <bool kTraj, bool kMerge, int NPS>
 int launch_np(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& lp) {
-  constexpr int G = 256 / NPS;      // rollouts per 256-thread block
+  constexpr int BT = BlockThreads<kMerge, NPS>::value;
+  constexpr int G = BT / NPS;       // rollouts per thread block
+  static_assert(G >= 1 && G <= 15, "one named barrier per rollout of a block");
   const size_t smem = region * G;
   grid.x = (grid.x + G - 1) / G;
-  CUDA_TRY(cudaFuncSetAttribute(mcs::rollout_kernel<kTraj, kMerge, NPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mcs::rollout_kernel<kTraj, kMerge, NPS><<<grid, dim3(256), smem, sc->ctx->stream>>>(sc->dev, sc->ctx->d_cand, lp, (int)region);
+  CUDA_TRY(cudaFuncSetAttribute(mcs::rollout_kernel<kTraj, kMerge, NPS, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mcs::rollout_kernel<kTraj, kMerge, NPS, BT><<<grid, dim3(BT), smem, sc->ctx->stream>>>(sc->dev, sc->ctx->d_cand, lp, (int)region);
   CUDA_TRY(cudaGetLastError());
   return MCS_OK;
 }

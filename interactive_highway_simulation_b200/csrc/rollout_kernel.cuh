@@ -465,14 +465,14 @@ __device__ __forceinline__ void customized_lane_change(const Smem& s, const Scen
 // (256 / NPS rollouts side by side, each on its own named barrier and its own slice of shared memory), so that the
 // warps of several rollouts fetch the same instructions at about the same time: the small-block instantiations are
 // instruction-fetch bound (ncu r01g: 35-48 % `no instruction` stalls with 8 independent 64-thread blocks per SM).
-template <int NPS>
+template <int NPS, bool kWholeBlock = (NPS == 256)>
 __device__ __forceinline__ void sub_sync(int sub) {
-  if (NPS == 256) __syncthreads();
+  if (kWholeBlock) __syncthreads();
   else asm volatile("bar.sync %0, %1;" ::"r"(sub + 1), "n"(NPS) : "memory");
 }
-template <int NPS>
+template <int NPS, bool kWholeBlock = (NPS == 256)>
 __device__ __forceinline__ int sub_sync_or(int sub, int pred) {
-  if (NPS == 256) return __syncthreads_or(pred);
+  if (kWholeBlock) return __syncthreads_or(pred);
   int r;
   asm volatile(
       "{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbar.red.or.pred q, %2, %3, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
@@ -483,7 +483,7 @@ __device__ __forceinline__ int sub_sync_or(int sub, int pred) {
 }
 
 // exclusive scan of one int per thread over the NPS threads of one rollout
-template <int NPS>
+template <int NPS, bool kWholeBlock>
 __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int& total, int k, int sub) {
   constexpr int NW = NPS / 32;
   const int lane = k & 31, w = k >> 5;
@@ -494,7 +494,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int& to
     if (lane >= o) inc += t;
   }
   if (lane == 31) scratch[w] = inc;
-  sub_sync<NPS>(sub);
+  sub_sync<NPS, kWholeBlock>(sub);
   int base = 0, tot = 0;
 #pragma unroll
   for (int q = 0; q < NW; ++q) {
@@ -512,19 +512,19 @@ namespace mcs {
 
 // kMerge: the scene has a merging/exit lane or vehicle, or a candidate names a gap — yielding intentions and the gap
 // behaviours are compiled in.  The plain lane-change instantiation carries none of their registers.
-template <bool kTraj, bool kMerge, int NPS>
+template <bool kTraj, bool kMerge, int NPS, int BT>
 // resident 256-thread-equivalents per SM the register allocation aims at: 3 (80 registers) for the lane-change path —
 // the kernel is latency-bound, the third block hides more than its few spills cost (measured 6.26e9 -> 7.06e9
 // vehicle-steps/s) — and 2 (128 registers) for the much larger merging instantiation
 #ifndef MCS_MIN_BLOCKS
 #define MCS_MIN_BLOCKS 3
 #endif
-__global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp, const int region_bytes) {
+__global__ void __launch_bounds__(BT, (kMerge ? 2 : MCS_MIN_BLOCKS) * 256 / BT) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp, const int region_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // NPS = sc.n_pad = blockDim.x as a compile-time constant: every shared-memory array address and row stride folds into
   // the instruction's immediate offset instead of living in registers
   constexpr int np = NPS;
-  constexpr int G = 256 / NPS;                         // rollouts per thread block
+  constexpr int G = BT / NPS;                          // rollouts per thread block
   const int sub = threadIdx.x / NPS;                   // which of them this warp belongs to
   const int n = sc.n, k = threadIdx.x - sub * NPS;
   const int cand = blockIdx.y;
@@ -582,10 +582,10 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
   int myPos = 0;                // its position in s.vec
   if (k <= sc.n_lanes) laneStart[k] = sc.lane_start[k];
   if (k < 8) s.flags[k] = 0;
-  sub_sync<NPS>(sub);
+  sub_sync<NPS, G == 1>(sub);
   if (k < laneStart[sc.n_lanes]) s.pos[s.vec[k]] = (uint8_t)k;
   if (isEgo) s.flags[2] = beh;          // the ego's current behaviour: `exit` vehicles are yielding candidates (0x104c90)
-  sub_sync<NPS>(sub);
+  sub_sync<NPS, G == 1>(sub);
   myPos = s.pos[k];
 
   // statistics (Simulation::run 0x10ee71-0x10f49a) accumulated on the fly in history order
@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
     int nTasks;
     {
       int total;
-      const int pos = block_exclusive_scan<NPS>((needMobil ? 1 : 0) | (inversion ? 1 << 16 : 0), s.scan, total, k, sub) & 0xffff;
+      const int pos = block_exclusive_scan<NPS, G == 1>((needMobil ? 1 : 0) | (inversion ? 1 << 16 : 0), s.scan, total, k, sub) & 0xffff;
       nTasks = total & 0xffff;
       ordered = (total >> 16) == 0;
       if (hasLane) {
@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
       }
       if (needMobil) s.tasks[pos] = k | (front & 0xff) << 8 | (back & 0xff) << 16 | ((front < 0) ? 1 << 24 : 0) | ((back < 0) ? 1 << 25 : 0);
     }
-    sub_sync<NPS>(sub);
+    sub_sync<NPS, G == 1>(sub);
     // sub-task slot = part * ceil32(nTasks) + i: every warp runs one part only, and the five parts run on five warps
     // side by side instead of queueing up on the first ones
     const int nT32 = (nTasks + 31) & ~31;
@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
       const int vb = (rec >> 25 & 1) ? -1 : (rec >> 16 & 0xff);
       mobil_geometry(s, sc, laneStart, np, vk, vf, vb, part, ordered);
     }
-    sub_sync<NPS>(sub);
+    sub_sync<NPS, G == 1>(sub);
     // draw counts: [noise][MOBIL decision draw]
     bool mobilDraw = false;
     if (needMobil) {
@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
     }
     nDraw = nY + (noise ? 1 : 0) + (mobilDraw ? 1 : 0);
     int totalDraws;
-    const uint64_t drawBase = drawCtr + (uint64_t)block_exclusive_scan<NPS>(nDraw, s.scan + 8, totalDraws, k, sub);
+    const uint64_t drawBase = drawCtr + (uint64_t)block_exclusive_scan<NPS, G == 1>(nDraw, s.scan + 8, totalDraws, k, sub);
     drawCtr += (uint64_t)totalDraws;
 
     // ================= plan, part B: actions =================
@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
         }
       }
     }
-    sub_sync<NPS>(sub);   // every read of the pre-step x / v is done
+    sub_sync<NPS, G == 1>(sub);   // every read of the pre-step x / v is done
 
     // ================= integrate (0x10ea36-0x10eb80) =================
     double acc = 0.0;
@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
     }
     if (isEgo) { s.flags[0] = reached ? 1 : 0; if (kMerge) s.flags[2] = beh; }
     // one barrier publishes the new x / v / lane and the ego's arrival, and tells whether any membership changed
-    const int anyChanged = sub_sync_or<NPS>(sub, changed ? 1 : 0);
+    const int anyChanged = sub_sync_or<NPS, G == 1>(sub, changed ? 1 : 0);
     const bool egoReached = s.flags[0] != 0;
     if (anyChanged) {
       // The reference rebuilds every lane vector (members in visit order) and std::sorts it by x (0x10be30-0x10c1a5):
@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
       }
       if (k == 0) s.flags[1] = 0;
       if (k < MCS_MAX_LANES + 1) s.scan[16 + k] = 0;
-      const int anyInv = sub_sync_or<NPS>(sub, inversion ? 1 : 0);
+      const int anyInv = sub_sync_or<NPS, G == 1>(sub, inversion ? 1 : 0);
       int rank = 0;
       if (anyInv) {
         if (newLane != 0xff) {
@@ -927,7 +927,7 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
           const int slot = atomicAdd(&s.flags[1], 1);
           s.tasks[slot] = k | (inVec ? myPos : 0) << 8 | oldL << 16 | newLane << 24;
         }
-        sub_sync<NPS>(sub);
+        sub_sync<NPS, G == 1>(sub);
         const int nm = s.flags[1];
         if (!mover && inVec) {
           rank = myPos - laneStart[oldL];
@@ -959,7 +959,7 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
         if (newLane != 0xff && (mover || !inVec)) atomicAdd(&s.scan[16 + newLane], 1);      // arrivals
         if (mover && inVec) atomicSub(&s.scan[16 + oldL], 1);                               // leavers
       }
-      sub_sync<NPS>(sub);
+      sub_sync<NPS, G == 1>(sub);
       // every thread derives the new lane starts itself (≤ 8 lanes) and places its vehicle; the shared copy goes to the
       // other buffer, so one barrier publishes the vectors and the starts together
       int* nextStart = laneStart == s.cnt ? s.cnt + 16 : s.cnt;
@@ -976,7 +976,7 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
       }
       laneStart = nextStart;
       oldLane = newLane == 0xff ? -1 : newLane;
-      sub_sync<NPS>(sub);
+      sub_sync<NPS, G == 1>(sub);
     }
     // ================= termination (0x10edd0-0x10ee10) =================
     if (kMerge && isEgo && gapSlot >= 0) {
@@ -1025,7 +1025,7 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
     utilO = MCS_MINSD(u2, utilO); comfO = MCS_MINSD(c2, comfO);
   }
   if ((k & 31) == 0) { s.red[(k >> 5) * 2] = utilO; s.red[(k >> 5) * 2 + 1] = comfO; }
-  sub_sync<NPS>(sub);
+  sub_sync<NPS, G == 1>(sub);
   // ego history -> per-state terms, one state per thread: fall-back = two consecutive states at rss.aMin (0x10f797),
   // utility term u(v/vd) (0x10f0c4), comfort sample (0x10f1c3)
   const int egoSlot = cd.ego_slot;
@@ -1035,7 +1035,7 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
     const double a = s.chist[t];
     if (t + 1 < nStates && egoAMin == a && egoAMin == s.chist[t + 1]) fb = true;
   }
-  const int anyFallBack = sub_sync_or<NPS>(sub, fb ? 1 : 0);
+  const int anyFallBack = sub_sync_or<NPS, G == 1>(sub, fb ? 1 : 0);
   for (int t = k; t < nStates; t += NPS) {
     const double a = s.chist[t];
     s.chist[t] = a > 0.0 ? fabs(a) * 0.5 : fabs(a);
@@ -1045,7 +1045,7 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
     if (!(egoVd >= ve)) u = MCS_MAXSD(0.9, 1.0 - (r - 1.0));
     s.vhist[t] = u;
   }
-  sub_sync<NPS>(sub);
+  sub_sync<NPS, G == 1>(sub);
   // ego comfort: mean over the k largest samples of 1 + c/aMin, summed in descending order (0x10f1c3-0x10f49a)
   {
     const int ns = nStates;
@@ -1058,7 +1058,7 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
       sorted[rank] = c;
     }
   }
-  sub_sync<NPS>(sub);
+  sub_sync<NPS, G == 1>(sub);
   if (isEgo) {
     constexpr int nw = NPS >> 5;
     double uo = s.red[0], co = s.red[1];
@@ -1093,7 +1093,7 @@ __global__ void __launch_bounds__(256, kMerge ? 2 : MCS_MIN_BLOCKS) rollout_kern
     if (kTraj && lp.traj_n) lp.traj_n[(size_t)cand * lp.count + ridx] = nStates;
     if (lp.vehicle_steps) atomicAdd(lp.vehicle_steps, (unsigned long long)executed * (unsigned long long)n);
   }
-  const int anyUnsupported = sub_sync_or<NPS>(sub, unsupported ? 1 : 0), anyFull = sub_sync_or<NPS>(sub, tableFull ? 1 : 0);
+  const int anyUnsupported = sub_sync_or<NPS, G == 1>(sub, unsupported ? 1 : 0), anyFull = sub_sync_or<NPS, G == 1>(sub, tableFull ? 1 : 0);
   if ((anyUnsupported || anyFull) && isEgo) st_out->overflow = (uint8_t)(anyUnsupported ? 2 : 1);   // the caller fails loudly (MCS_ERR_SCENE / MCS_ERR_CAPACITY)
 }
 

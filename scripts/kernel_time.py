@@ -29,3 +29,17 @@ print("decision config: 4 x 512 rollouts x 40 vehicles %.3f ms (%d vehicle-steps
 chk = sc.rollouts_range(cands, sp, 1000, 0, 64)
 print("  checksum", hashlib.md5(bytes(chk)).hexdigest())
 sc.close()
+corridors, agents, ego = synthetic.lane_change_scene(24, 4, seed=3)
+sc = backend.DeviceScene(corridors, agents)
+acts = ["keep_lane", "dcc", "acc", "left", "right"]
+cands = (abi.Candidate * 5)(*[abi.Candidate(ego, abi.ACTIONS[a], -2, 0) for a in acts])
+sp = abi.SimParam(0.3, 40, 30)
+best = 1e9
+for i in range(4):
+    ms, vs = sc.rollouts_device(cands, sp, 77, 0, 160); best = min(best, ms)
+print("reference-size lane-change decision: 5 x 160 rollouts x 24 vehicles %.3f ms (%d vehicle-steps)" % (best, vs))
+best = 1e9
+for i in range(4):
+    ms, vs = sc.rollouts_device(cands, sp, 77, 0, 4096); best = min(best, ms)
+print("lane-change decision x 4096 rollouts: 5 x 4096 x 24 vehicles %.3f ms (%d vehicle-steps)" % (best, vs))
+sc.close()

@@ -3,4 +3,4 @@ import sys, os, subprocess
 here = os.path.dirname(os.path.abspath(__file__))
 for lib in sys.argv[1:]:
     out = subprocess.run([sys.executable, os.path.join(here, "kernel_time.py"), lib], capture_output=True, text=True).stdout
-    print(lib, "|", " | ".join(l.strip() for l in out.splitlines() if "config" in l or "checksum" in l))
+    print(lib, "|", " | ".join(l.strip() for l in out.splitlines() if "config" in l or "decision" in l))
