@@ -186,7 +186,10 @@ int stage_candidates(mcs_scene* sc, const mcs_candidate* cands, int n_cand, int*
 // gets 512 threads (measured, 4 x 512 rollouts x 40 vehicles: 128 threads 3.42 ms, 256: 2.73 ms, 512: 2.48 ms); named
 // barriers limit a block to 15 rollouts.
 template <bool kMerge, int NPS>
-struct BlockThreads { static constexpr int value = NPS == 256 ? 256 : (kMerge && NPS >= 64 ? 512 : 256); };
+#ifndef MCS_BT_256
+#define MCS_BT_256 256
+#endif
+struct BlockThreads { static constexpr int value = NPS == 256 ? MCS_BT_256 : (kMerge && NPS >= 64 ? 512 : 256); };
 
 template <bool kTraj, bool kMerge, int NPS>
 int launch_np(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& lp) {

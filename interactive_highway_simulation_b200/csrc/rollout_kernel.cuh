@@ -519,7 +519,10 @@ template <bool kTraj, bool kMerge, int NPS, int BT>
 #ifndef MCS_MIN_BLOCKS
 #define MCS_MIN_BLOCKS 3
 #endif
-__global__ void __launch_bounds__(BT, (kMerge ? 2 : MCS_MIN_BLOCKS) * 256 / BT) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp, const int region_bytes) {
+#ifndef MCS_MIN_BLOCKS_MERGE
+#define MCS_MIN_BLOCKS_MERGE 2
+#endif
+__global__ void __launch_bounds__(BT, (kMerge ? MCS_MIN_BLOCKS_MERGE : MCS_MIN_BLOCKS) * 256 / BT) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp, const int region_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // NPS = sc.n_pad = blockDim.x as a compile-time constant: every shared-memory array address and row stride folds into
   // the instruction's immediate offset instead of living in registers

@@ -134,3 +134,46 @@ def test_mobil_wrapper_like_behaviors_py(oracle, backend_lib):
     assert oracle.lib.orc_decide_mobil(cs, len(cs), as_, len(as_), 1, C.byref(act), 1, 77, C.byref(want)) == 0
     assert (out.ax, out.vy, out.commitToDecision, out.commitKeepLaneStep, out.targetLaneId) == \
         (want.ax, want.vy, abi.COMMIT_NAMES[want.commit], want.commit_keep_lane_step, want.target_lane_id)
+
+
+@pytest.mark.gpu
+def test_decision_helpers_follow_behaviors_py(oracle, backend_lib):
+    """decisions.lane_change_decision / gap_decision = behaviors.py:89-115 / :118-137 with one launch per decision: features,
+    q-values, the discrete decision and the final action equal what the per-candidate reference flow gives (oracle)."""
+    import random
+    from interactive_highway_simulation_b200 import decisions, learned_model
+    from scenes import random_scene
+    m = module()
+    s = probe_scene()
+    mcs_map, mcs_agents = build(m, s)
+    actions = ["keep_lane", "dcc", "acc", "left", "right"]
+    m.seed(500)
+    act, decision, q_values, features = decisions.lane_change_decision(mcs_map, mcs_agents, 0, actions, "keep_lane")
+    want_features = []
+    for c, a in enumerate(actions):
+        _, ost = oracle.rollouts(s, 0, a, -2, 0.3, 40, 30, 500 + c, 0, 160)
+        want_features.append(learned_model.feature_vector(oracle.reduce(ost, 8, 20, 40)))
+    assert features == want_features
+    wq, wd = learned_model.LearnedLaneChangeModel().inference(want_features, actions, "keep_lane")
+    assert decision == wd and [[c, float(v)] for c, v in q_values] == [[c, float(v)] for c, v in wq]
+    want = abi.Action()
+    cs, as_ = s.c_corridors(), s.c_agents()
+    assert oracle.lib.orc_decide_fixed_direction(cs, len(cs), as_, len(as_), 0, abi.ACTIONS[decision], 0, C.byref(want)) == 0
+    assert (act.ax, act.vy) == (want.ax, want.vy)
+    # merging: ego on the merging lane chooses among gaps
+    rng = random.Random(3)
+    s2, ego = random_scene(rng, n_agents=14, lane_types=["merging", "main", "main"], ego_behavior="merging", ego_lane=0)
+    mcs_map, mcs_agents = build(m, s2)
+    gaps = [-1] + [a["id"] for a in s2.agents if 3.5 <= a["y"] < 7.0][:3]
+    m.seed(900)
+    act, chosen, q_values, features = decisions.gap_decision(mcs_map, mcs_agents, ego, gaps, "left", n_per_group=30)
+    want_features = []
+    for c, g in enumerate(gaps):
+        _, ost = oracle.rollouts(s2, ego, "left", g, 0.3, 40, 10, 900 + c, 0, 240)
+        want_features.append(learned_model.feature_vector(oracle.reduce(ost, 8, 30, 40)))
+    assert features == want_features
+    idx, _ = learned_model.LearnedMergingModel().inference(want_features)
+    assert chosen == gaps[idx]
+    cs, as_ = s2.c_corridors(), s2.c_agents()
+    assert oracle.lib.orc_decide_fixed_gap(cs, len(cs), as_, len(as_), ego, abi.ACTIONS["left"], chosen, 0, C.byref(want)) == 0
+    assert (act.ax, act.vy) == (want.ax, want.vy)
