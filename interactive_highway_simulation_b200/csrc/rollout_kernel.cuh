@@ -1,19 +1,25 @@
-// Rollout kernel for sm_100a: one thread block per Monte-Carlo rollout, one thread per vehicle.
+// Rollout kernel for sm_100a: one thread per vehicle, NPS = 32 / 64 / 128 / 256 threads per Monte-Carlo rollout
+// (a template constant).  A 256-vehicle rollout owns its thread block; smaller rollouts share a 256- or 512-thread block,
+// each on its own named barrier and shared-memory slice, and start every step together so their warps share instruction
+// fetches (the kernel body is ~5 K instructions, far beyond the 32 KB L1.5 instruction cache).
 //
 // Replaces the reference's Simulation::run (mc_sim_highway.so 0x10e790) and everything it calls:
 //   idmAccFrontBack 0xebc30, idmBehaviorAndYieldingToMergingAgents 0x104200, laneChangeBehaviorMOBIL 0xf42d0,
 //   laneChangeProbability 0xe19f0, rssSafe 0xb8950, customizedLaneChangeBehavior 0xf5e30,
-//   Environment::{matchAgentsOnCorridor 0x10b810, frontAgent 0xe2670, followingAgent 0xe2920, neighborAgents 0xe8240}.
+//   Environment::{matchAgentsOnCorridor 0x10b810, frontAgent 0xe2670, followingAgent 0xe2920, neighborAgents 0xe8240};
+//   with kMerge also customizedMergingBehavior 0xf6ba0, mergingBehaviorClosestGap 0xfe660, rssSafeRelax 0xb9210,
+//   timeToReachGap 0xe1630 and the yielding intentions (merge_behaviors.cuh).
 //
-// Design (B200): the path is FP64-latency/issue bound, not HBM bound — a rollout reads the scene once
-// (L2-resident, shared by every block) and writes one 64-byte record.  Vehicle state lives in registers;
-// only what neighbours gather (x, v, plus static l / vd / IDM parameters) is staged in shared memory.
-// The reference's per-lane std::vector<AgentPtr> (sorted only when lane membership changes, searched by
-// binary search every step) is a byte array of slots per lane in shared memory with exactly those
-// semantics.  MOBIL (≈90 % of the arithmetic, needed by ≈1 vehicle in 11 per step) is compacted: vehicles
-// that need it queue in shared memory and the first nTasks threads of the block evaluate them, so whole
-// warps skip it.  Random draws come from the counter stream of include/mcsim_rng.h at the index the
-// reference's sequential loop would have consumed them (block-wide exclusive scan of per-vehicle counts).
+// Design (B200): the path is FP64-latency / instruction-issue bound, not HBM bound — a rollout reads the scene once
+// (L2-resident, shared by every block) and writes one 64-byte record.  Dynamic vehicle state (x y v vy, commit state)
+// lives in registers; what neighbours gather (x, v) and everything static per vehicle (l, vd, IDM and RSS parameters)
+// lives in shared memory — registers, not shared memory, limit the resident rollouts per SM.  The reference's per-lane
+// std::vector<AgentPtr> (sorted only when lane membership changes, searched by binary search every step) is a byte
+// array of slots per lane in shared memory with exactly those semantics, including stale order; while every vector is
+// strictly ordered the searches collapse to neighbour lookups.  MOBIL (most of the arithmetic, needed by ≈ 1 vehicle in
+// 11 per step) is compacted: vehicles that need it queue in shared memory and their evaluation runs as seven independent
+// sub-tasks on seven warps side by side.  Random draws come from the counter stream of include/mcsim_rng.h at the index
+// the reference's sequential loop would have consumed them (exclusive scan of per-vehicle draw counts).
 //
 // Arithmetic is written in the operation order of the reference machine code and compiled with
 // -fmad=false: results are bit-identical to the reference binary given the same exp/pow (mcsim_math.h).
