@@ -66,12 +66,18 @@ struct LaunchParams {
 #define MCS_MINSD(a, b) (((a) < (b)) ? (a) : (b))   /* x86 vminsd: second source when not less / unordered */
 #define MCS_MAXSD(a, b) (((a) > (b)) ? (a) : (b))
 
-// num / den, bit-identical to IEEE division.  A zero numerator over a positive denominator (ubiquitous here: clamped
-// IDM interaction terms, probabilities of gated-off lane changes) would take the division's out-of-line slow path
-// (~9 % of all executed instructions in the r01e profile); the quotient is the numerator itself.
+// num / den, bit-identical to IEEE division.  A zero numerator (ubiquitous here: clamped IDM interaction terms,
+// probabilities of gated-off lane changes) sends the hardware division sequence into its out-of-line slow path — 9 % of all
+// executed instructions in the r01h profile.  A plain `if (num == 0) return num` does not help: the compiler evaluates the
+// division speculatively.  Instead the division itself never sees a zero numerator, and the exact quotient of a zero
+// numerator is selected afterwards: +-0 with the sign of num for den > 0, the opposite sign for den < 0, NaN for 0 / NaN.
 __device__ __forceinline__ double mcs_div(double num, double den) {
-  if (num == 0.0 && den > 0.0) return num;
-  return num / den;
+  const bool zero = num == 0.0;
+  const double q = (zero ? 1.0 : num) / den;
+  if (!zero) return q;
+  if (den > 0.0) return num;
+  if (den < 0.0) return -num;
+  return q * 0.0;       // den is 0 or NaN: 1/den is inf or NaN, times zero is the NaN that 0/den would be
 }
 
 struct IdmP { double accMax, minDis, accMin, accCom, thw, sq2 /* 2*sqrt(-accMax*accCom), static per vehicle */; };
@@ -172,7 +178,7 @@ __device__ MCS_HEAVY_INLINE double idm_acc(const Smem& s, const IdmP& p, int f0,
       const double dv = (bv - egoV) * egoV;
       double t = dv / sq2 + dDesB;
       t = MCS_MAXSD(t, 0.0);
-      t = t / gap;
+      t = mcs_div(t, gap);
       sum = sum + (t * t) * p.accMax;
     } else {
       sum = sum + 10000000000.0;
@@ -426,7 +432,7 @@ __device__ __forceinline__ void mobil_decide(const Smem& s, const SceneDev& sc, 
     if (L.leftIdx >= 0 && sc.lanes[L.leftIdx].leftmost) pL = 0.0;
     const double k2 = p[1] + p[1], r2 = p[2] + p[2];
     const double S = (k2 + pL) + r2;
-    p[1] = k2 / S; p[2] = r2 / S;
+    p[1] = k2 / S; p[2] = mcs_div(r2, S);
   }
   if (pL > u && canL) { ms.commit = MCS_COMMIT_LEFT; ms.targetLane = sc.lanes[L.leftIdx].id; ax = axLeft; avy = vyLeft; }
   else if (pL + p[2] > u && canR) { ms.commit = MCS_COMMIT_RIGHT; ms.targetLane = sc.lanes[L.rightIdx].id; ax = axRight; avy = vyRight; }
