@@ -341,7 +341,7 @@ __device__ __forceinline__ bool merging_closest_gap(const Smem& s, const SceneDe
 }
 
 // ---- yielding intentions (Agent+0x238: unordered_map<int, YieldingIntention>) as a small per-thread table ----
-#define MCS_YCAP 24
+#define MCS_YCAP 32
 struct YieldTable {
   uint8_t key[MCS_YCAP];
   double p0[MCS_YCAP];
