@@ -181,19 +181,19 @@ int stage_candidates(mcs_scene* sc, const mcs_candidate* cands, int n_cand, int*
   return MCS_OK;
 }
 
-// Threads per block.  A 256-vehicle rollout owns a 256-thread block.  Smaller rollouts share a block and start every
-// step together (rollout_kernel.cuh): 4-8 per block.  The merging instantiation is the instruction-fetch-bound one and
-// gets 512 threads (measured, 4 x 512 rollouts x 40 vehicles: 128 threads 3.42 ms, 256: 2.73 ms, 512: 2.48 ms); named
-// barriers limit a block to 15 rollouts.
-template <bool kMerge, int NPS>
-#ifndef MCS_BT_256
-#define MCS_BT_256 256
+// Threads per block.  A 256-vehicle rollout owns a 256-thread block.  Smaller rollouts either own a block too (small
+// launches: every rollout gets an SM to itself, nothing to share) or share one and start every step together
+// (rollout_kernel.cuh) — 8 per block; the merging instantiation, the instruction-fetch-bound one, in 512-thread blocks
+// (measured, 4 x 512 rollouts x 40 vehicles: 128 threads 3.42 ms, 256: 2.73 ms, 512: 2.48 ms).  Named barriers limit a
+// block to 15 rollouts.
+#ifndef MCS_SHARE_MIN_PER_SM
+#define MCS_SHARE_MIN_PER_SM 4   // rollouts per SM from which sharing a block wins (scripts/kernel_time.py sweep)
 #endif
-struct BlockThreads { static constexpr int value = NPS == 256 ? MCS_BT_256 : (kMerge && NPS >= 64 ? 512 : 256); };
+template <bool kMerge, int NPS>
+struct BlockThreads { static constexpr int value = NPS == 256 ? 256 : (kMerge && NPS >= 64 ? 512 : 256); };
 
-template <bool kTraj, bool kMerge, int NPS>
-int launch_np(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& lp) {
-  constexpr int BT = BlockThreads<kMerge, NPS>::value;
+template <bool kTraj, bool kMerge, int NPS, int BT>
+int launch_bt(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& lp) {
   constexpr int G = BT / NPS;       // rollouts per thread block
   static_assert(G >= 1 && G <= 15, "one named barrier per rollout of a block");
   const size_t smem = region * G;
@@ -202,6 +202,18 @@ int launch_np(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& 
   mcs::rollout_kernel<kTraj, kMerge, NPS, BT><<<grid, dim3(BT), smem, sc->ctx->stream>>>(sc->dev, sc->ctx->d_cand, lp, (int)region);
   CUDA_TRY(cudaGetLastError());
   return MCS_OK;
+}
+
+template <bool kTraj, bool kMerge, int NPS>
+int launch_np(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& lp) {
+  constexpr int BT = BlockThreads<kMerge, NPS>::value;
+  if (NPS == BT || kTraj) return launch_bt<kTraj, kMerge, NPS, NPS>(sc, grid, region, lp);
+  // shared blocks pay off once the launch puts several rollouts on every SM
+  const long long rollouts = (long long)grid.x * grid.y;
+  long long threshold = 148LL * MCS_SHARE_MIN_PER_SM;
+  if (const char* e = getenv("MCS_SHARE_MIN_PER_SM")) threshold = 148LL * atoi(e);   // diagnostic
+  if (rollouts < threshold) return launch_bt<kTraj, kMerge, NPS, NPS>(sc, grid, region, lp);
+  return launch_bt<kTraj, kMerge, NPS, BT>(sc, grid, region, lp);
 }
 
 template <bool kTraj, bool kMerge>

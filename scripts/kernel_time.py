@@ -43,3 +43,25 @@ for i in range(4):
     ms, vs = sc.rollouts_device(cands, sp, 77, 0, 4096); best = min(best, ms)
 print("lane-change decision x 4096 rollouts: 5 x 4096 x 24 vehicles %.3f ms (%d vehicle-steps)" % (best, vs))
 sc.close()
+print("sweep of decision sizes (merging scene, 4 candidates):")
+corridors, agents, ego, gaps = synthetic.merging_scene(40, 0)
+sc = backend.DeviceScene(corridors, agents)
+cands = (abi.Candidate * len(gaps))(*[abi.Candidate(ego, abi.ACTIONS["left"], g, 0) for g in gaps])
+sp = abi.SimParam(0.3, 40, 10)
+for R in (32, 64, 128, 256, 512, 1024):
+    best = 1e9
+    for i in range(4):
+        ms, vs = sc.rollouts_device(cands, sp, 1000, 0, R); best = min(best, ms)
+    print("  4 x %4d rollouts: %.3f ms" % (R, best))
+sc.close()
+print("sweep of decision sizes (24-vehicle lane change, 5 candidates):")
+corridors, agents, ego = synthetic.lane_change_scene(24, 4, seed=3)
+sc = backend.DeviceScene(corridors, agents)
+cands = (abi.Candidate * 5)(*[abi.Candidate(ego, abi.ACTIONS[a], -2, 0) for a in acts])
+sp = abi.SimParam(0.3, 40, 30)
+for R in (32, 64, 160, 320, 640, 1280):
+    best = 1e9
+    for i in range(4):
+        ms, vs = sc.rollouts_device(cands, sp, 77, 0, R); best = min(best, ms)
+    print("  5 x %4d rollouts: %.3f ms" % (R, best))
+sc.close()
