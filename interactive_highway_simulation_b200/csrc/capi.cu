@@ -83,6 +83,7 @@ __global__ void combine_groups_kernel(const mcs_group_partial* __restrict__ g, i
 // scenes (one per decision in the reference's call pattern) then costs one stream-ordered allocation and one H2D copy.
 struct DeviceCtx {
   int device = -1;
+  int n_sm = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   mcs::CandDev* d_cand = nullptr; int cand_cap = 0;
@@ -117,6 +118,7 @@ int get_ctx(int device, DeviceCtx** out) {
     CUDA_TRY(cudaSetDevice(device));
     DeviceCtx* c = new DeviceCtx();
     c->device = device;
+    cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device);
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
@@ -210,8 +212,8 @@ int launch_np(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& 
   if (NPS == BT || kTraj) return launch_bt<kTraj, kMerge, NPS, NPS>(sc, grid, region, lp);
   // shared blocks pay off once the launch puts several rollouts on every SM
   const long long rollouts = (long long)grid.x * grid.y;
-  long long threshold = 148LL * MCS_SHARE_MIN_PER_SM;
-  if (const char* e = getenv("MCS_SHARE_MIN_PER_SM")) threshold = 148LL * atoi(e);   // diagnostic
+  long long threshold = (long long)sc->ctx->n_sm * MCS_SHARE_MIN_PER_SM;
+  if (const char* e = getenv("MCS_SHARE_MIN_PER_SM")) threshold = (long long)sc->ctx->n_sm * atoi(e);   // tuning override
   if (rollouts < threshold) return launch_bt<kTraj, kMerge, NPS, NPS>(sc, grid, region, lp);
   return launch_bt<kTraj, kMerge, NPS, BT>(sc, grid, region, lp);
 }
@@ -237,7 +239,6 @@ int launch_rollouts(mcs_scene* sc, int n_cand, const mcs_sim_param* sp, uint64_t
   lp.seed = seed; lp.first = first; lp.count = count; lp.n_cand = n_cand;
   lp.status = d_status; lp.traj = d_traj; lp.traj_n = d_traj_n; lp.vehicle_steps = d_counter;
   size_t smem = (rollout_smem_bytes(sc->dev.n_pad, sp->steps) + 15) & ~(size_t)15;   // one rollout's region
-  if (const char* e = getenv("MCS_EXTRA_SMEM")) smem += (size_t)atoi(e) & ~(size_t)15;   // diagnostic: caps the resident blocks per SM
   dim3 grid((unsigned)count, (unsigned)n_cand);
   // the trajectory-writing variant is a test / Simulation.run() path: one instantiation (the merging superset) serves it
   if (d_traj) return launch_one<true, true>(sc, grid, smem, lp);
