@@ -352,3 +352,22 @@ def test_many_random_scenes_against_oracle(gpu, oracle, block):
             actions, gap = ("right",), rng.choice([-1] + [a["id"] for a in s.agents])
         check_against_oracle(gpu, oracle, s, ego, rng.choice([0.2, 0.3]), rng.choice([20, 40, 50]), rng.choice([5, 10, 30]),
                              7 + sc, 6, "%s_b%d_%d" % (kind, block, sc), traj_rollouts=0, gap=gap, actions=actions)
+
+
+def test_sharded_entry_point_single_rank(gpu):
+    """sharding.simulation_multi_thread_sharded without a process group (world 1): the device-tensor hand-off path that
+    bench.py runs over NCCL gives mcs_rollouts' features."""
+    import torch
+    from interactive_highway_simulation_b200 import sharding, synthetic
+    corridors, agents, ego, gaps = synthetic.merging_scene(40, 1)
+    ds = gpu.DeviceScene(corridors, agents)
+    try:
+        torch.cuda.set_device(0)
+        cands = (abi.Candidate * len(gaps))(*[abi.Candidate(ego, abi.ACTIONS["left"], g, 0) for g in gaps])
+        sp = abi.SimParam(0.3, 40, 10)
+        got = sharding.simulation_multi_thread_sharded(ds, cands, sp, 8, 123)
+        want, _ = ds.rollouts(cands, sp, 8, 123)
+        for c in range(len(gaps)):
+            assert bytes(got[c]) == bytes(want[c])
+    finally:
+        ds.close()
