@@ -115,7 +115,7 @@ def evaluation_env(kind, seed):
 
 
 def main():
-    steps = int(os.environ.get("SCENARIO_STEPS", "12"))
+    steps = int(os.environ.get("SCENARIO_STEPS", "100"))      # configs[0]: dt 0.2, 100 steps
     # configs[0]: the shipped scene as is (idm / idm_mobil_lane_change_safe / merging_closest_gap_policy agents)
     run_scene("test_scene", steps)
     # learned behaviours on the same scene: find suitable vehicles by their lane type
@@ -125,21 +125,21 @@ def main():
     env = sim.environment
     main_ids = [a.id for a in env.agents.values() if env.corridor_for_agent(a.id).type == "main"]
     merging_ids = [a.id for a in env.agents.values() if env.corridor_for_agent(a.id).type == "merging"]
-    run_scene("lane_change_learned", 4, {main_ids[len(main_ids) // 2]: "lane_change_learned", main_ids[1]: "lane_change_learned"}, seed=1)
-    run_scene("merging_learned", 4, {merging_ids[0]: "merging_learned"}, seed=2)
+    run_scene("lane_change_learned", 10, {main_ids[len(main_ids) // 2]: "lane_change_learned", main_ids[1]: "lane_change_learned"}, seed=1)
+    run_scene("merging_learned", 10, {merging_ids[0]: "merging_learned"}, seed=2)
     # configs[1..3]: one epoch of each evaluation script's random scene, egos chosen as the scripts choose them
     env = evaluation_env("merging", 3)                                      # evaluation_merging.py:56-62: every merging agent
     egos = {a.id: "merging_learned" for a in env.agents.values() if "merging" in a.behavior_model}
-    record_env("eval_merging_learned", env, 5, egos, 3)
+    record_env("eval_merging_learned", env, 12, egos, 3)
     env = evaluation_env("lane_change", 4)                                  # evaluation_lane_change.py: 2nd..4th vehicle of a lane
     lane2 = [a for _, a in env.matched_agents_sorted_by_arc_length[2][2:4] if a.l <= 7]
-    record_env("eval_lane_change_learned", env, 4, {lane2[0].id: "lane_change_learned"}, 4)
+    record_env("eval_lane_change_learned", env, 12, {lane2[0].id: "lane_change_learned"}, 4)
     env = evaluation_env("exit", 5)                                         # evaluation_exit.py:123-128
     lane2 = [a for _, a in env.matched_agents_sorted_by_arc_length[2][2:4] if a.l <= 7]
-    record_env("eval_exit_learned", env, 5, {lane2[0].id: "exit_learned"}, 5, fall_back=0.2)
+    record_env("eval_exit_learned", env, 12, {lane2[0].id: "exit_learned"}, 5, fall_back=0.2)
     env = evaluation_env("exit", 6)
     lane1 = [a for _, a in env.matched_agents_sorted_by_arc_length[1][2:4] if a.l <= 7]
-    record_env("eval_exit_closest_gap", env, 6, {lane1[0].id: "exit"}, 6)
+    record_env("eval_exit_closest_gap", env, 20, {lane1[0].id: "exit"}, 6)
 
 
 if __name__ == "__main__":
