@@ -126,3 +126,29 @@ def merging_scene(n_vehicles=40, seed=0, n_main=3):
     left = sorted((a for a in agents if LANE_WIDTH <= a.y < 2 * LANE_WIDTH), key=lambda a: abs(a.x - ego.x))[:3]
     gaps = [-1] + [a.id for a in sorted(left, key=lambda a: -a.x)]
     return corridors, agents, ego.id, gaps
+
+
+def exit_scene(n_vehicles=200, seed=0, n_main=3):
+    """BASELINE.json configs[3] shape: an exit lane (id 0) + n_main main lanes, ego `exit` on the main lane next to it,
+    every other vehicle `idm_lc` with the generic parameters (mcs_wrapper.py:78-190).  Returns (corridors, agents, ego_id,
+    gap_ids) with gap_ids = [-1] + up to three vehicles of the exit lane around the ego (mcs_wrapper.py:155-157)."""
+    corridors, agents, _ = lane_change_scene(n_vehicles, n_main + 1, seed=seed)
+    corridors[0].type = abi.LANE_TYPES["exit"]
+    on_main = sorted((a for a in agents if LANE_WIDTH <= a.y < 2 * LANE_WIDTH), key=lambda a: a.x)
+    ego = on_main[len(on_main) // 2]
+    rs = np.random.RandomState(seed + 2000)
+    for a in agents:
+        if a.id == ego.id:
+            a.behavior = abi.BEHAVIORS["exit"]
+            a.idm[:] = [rs.uniform(1.8, 2.2), max(2.0, rs.normal(4, 1)), rs.uniform(-4.0, -2.0), rs.normal(-2.0, 0.1), -8.0,
+                        max(1.0, rs.normal(1.5, 0.1))]
+            a.rss[:] = EGO_RSS
+            a.yp[:] = [1.70968573, 0.00582201, 0.40742229, 1.02390871, rs.uniform(0, 1), 0.5, 0.6]
+        else:
+            a.behavior = abi.BEHAVIORS["idm_lc"]
+            a.idm[:] = generic_idm(a.l)
+            a.yp[:] = GENERIC_YP
+            a.rss[:] = GENERIC_RSS
+    right = sorted((a for a in agents if 0.0 <= a.y < LANE_WIDTH), key=lambda a: abs(a.x - ego.x))[:3]
+    gaps = [-1] + [a.id for a in sorted(right, key=lambda a: -a.x)]
+    return corridors, agents, ego.id, gaps

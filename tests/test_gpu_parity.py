@@ -371,3 +371,35 @@ def test_sharded_entry_point_single_rank(gpu):
             assert bytes(got[c]) == bytes(want[c])
     finally:
         ds.close()
+
+
+def test_full_size_exit_configuration(gpu, oracle):
+    """BASELINE.json configs[3] shape: 200 vehicles with an exit lane, 4096 rollouts x 50-step horizon per candidate gap —
+    determinism, shard independence, the two-level mean over the sharded statuses, and a spot check against the oracle."""
+    from interactive_highway_simulation_b200 import synthetic
+    corridors, agents, ego, gaps = synthetic.exit_scene(200, 0)
+    ds = gpu.DeviceScene(corridors, agents)
+    try:
+        cands = (abi.Candidate * len(gaps))(*[abi.Candidate(ego, abi.ACTIONS["right"], g, 0) for g in gaps])
+        sp = abi.SimParam(0.3, 50, 10)
+        n = 512                                                    # 8 groups x 512 = 4096 rollouts per candidate
+        feats, st = ds.rollouts(cands, sp, n, 31, want_status=True)
+        feats2, _ = ds.rollouts(cands, sp, n, 31)
+        for c in range(len(gaps)):
+            assert bytes(feats[c]) == bytes(feats2[c]) and feats[c].fromNSims == 4096
+            assert 0.0 <= feats[c].successRate <= 1.0 and 0.0 <= feats[c].fallBackRate <= 1.0
+        shard = ds.rollouts_range(cands, sp, 31, 3000, 200)         # rollouts 3000..3199 of every candidate again
+        for c in range(len(gaps)):
+            for i in range(200):
+                assert bytes(shard[c * 200 + i]) == bytes(st[c * 4096 + 3000 + i])
+        red = gpu.reduce_features(st, len(gaps), 8, n, sp.steps)
+        for c in range(len(gaps)):
+            assert bytes(red[c]) == bytes(feats[c])
+        for c in (0, len(gaps) - 1):
+            ost = (abi.Status * 2)()
+            assert oracle.lib.orc_rollouts(corridors, len(corridors), agents, len(agents), C.byref(cands[c]), C.byref(sp), 31 + c,
+                                           4000, 2, ost, None, None) == 0
+            for i in range(2):
+                assert bytes(st[c * 4096 + 4000 + i])[:48] == bytes(ost[i])[:48], (c, i)
+    finally:
+        ds.close()
