@@ -403,3 +403,24 @@ def test_full_size_exit_configuration(gpu, oracle):
                 assert bytes(st[c * 4096 + 4000 + i])[:48] == bytes(ost[i])[:48], (c, i)
     finally:
         ds.close()
+
+
+def test_scene_lifecycle_does_not_leak(gpu):
+    """One scene per decision is the reference's call pattern: create / launch / destroy 600 times, device memory stays flat."""
+    import torch
+    s = probe_scene()
+    cs, as_ = s.c_corridors(), s.c_agents()
+    cand = (abi.Candidate * 1)(abi.Candidate(0, abi.ACTIONS["keep_lane"], -2, 0))
+    sp = abi.SimParam(0.3, 10, 10)
+    def cycle(n):
+        for i in range(n):
+            ds = gpu.DeviceScene(cs, as_)
+            ds.rollouts(cand, sp, 1, i)
+            ds.close()
+    cycle(50)
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    cycle(600)
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert abs(free0 - free1) < 64 << 20, (free0, free1)
