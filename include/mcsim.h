@@ -94,7 +94,7 @@ typedef struct mcs_status { /* StatusOneSim of one rollout + bookkeeping; 64 byt
   int32_t finishStep;
   int32_t executedSteps;  /* steps actually simulated (≤ steps) */
   uint32_t draws;         /* random draws consumed, incl. the N aggressive-flag draws */
-  uint8_t finish, fallBack, ok, overflow;
+  uint8_t finish, fallBack, ok, overflow;  /* overflow: 0 fine, 1 yielding table full, 2 reference undefined here (→ error codes) */
   int32_t reserved[4];
 } mcs_status;
 
@@ -150,8 +150,8 @@ int mcs_reduce_features(const mcs_status* statuses, int n_candidates, int groups
  * per (candidate, group): partials_out[c*n_groups + g].  The ranks all-gather their partials (64 B each — the only
  * data that crosses NVLink) and every rank calls mcs_combine_groups, which adds them in group order exactly like
  * runMultiThreads 0xbca08-0xbca92: the result is bit-identical to the single-GPU mcs_rollouts.
- * mcs_rollouts_groups_device leaves the partials in device memory (d_partials_out, e.g. a torch tensor handed to NCCL)
- * and only enqueues work on the scene's stream; mcs_scene_sync waits for it. */
+ * mcs_rollouts_groups_device leaves the partials in device memory (d_partials_out, e.g. a torch tensor that is then
+ * handed to NCCL); it returns after the device work has finished, so the buffer may be used from any stream. */
 int mcs_rollouts_groups(mcs_scene* scene, const mcs_candidate* candidates, int n_candidates, const mcs_sim_param* param,
                         int n_per_group, uint64_t seed, int first_group, int n_groups, mcs_group_partial* partials_out);
 int mcs_rollouts_groups_device(mcs_scene* scene, const mcs_candidate* candidates, int n_candidates,
@@ -166,7 +166,9 @@ int mcs_combine_groups(const mcs_group_partial* partials, int n_candidates, int 
 
 /* Device-resident variant used by the throughput benchmark: results stay in HBM
  * (d_status_out = device pointer or NULL to keep only the per-block vehicle-step counters).
- * Returns total executed vehicle-steps through *vehicle_steps_out after synchronising. */
+ * Returns total executed vehicle-steps through *vehicle_steps_out after synchronising; *kernel_ms_out = the rollout
+ * kernel's duration from CUDA events on the stream it was launched on.  `cuda_stream` is reserved (pass NULL): all work
+ * of a device goes to the library's own stream. */
 int mcs_rollouts_device(mcs_scene* scene, const mcs_candidate* candidates, int n_candidates, const mcs_sim_param* param,
                         uint64_t seed, int64_t first, int64_t count, void* d_status_out, void* cuda_stream,
                         float* kernel_ms_out, uint64_t* vehicle_steps_out);
