@@ -424,3 +424,19 @@ def test_scene_lifecycle_does_not_leak(gpu):
     torch.cuda.synchronize()
     free1, _ = torch.cuda.mem_get_info()
     assert abs(free0 - free1) < 64 << 20, (free0, free1)
+
+
+ORDER_CASES = golden_io.load_all("order")
+
+
+@pytest.mark.parametrize("case", ORDER_CASES, ids=golden_io.ids(ORDER_CASES))
+def test_visit_order_matches_reference_binary(gpu, case):
+    """The plan / random-draw order of the vehicles (iteration order of the reference's std::unordered_map<int, AgentPtr>),
+    as recorded from the reference binary."""
+    s = golden_io.scene_of(case)
+    ds = gpu.DeviceScene(s.c_corridors(), s.c_agents())
+    try:
+        order = ds.visit_order()                                  # input indices in visit order
+        assert [s.agents[i]["id"] for i in order] == case["agents"]
+    finally:
+        ds.close()
