@@ -127,6 +127,13 @@ int mcs_scene_create(const mcs_corridor* corridors, int n_corridors, const mcs_a
 int mcs_scene_destroy(mcs_scene* scene);
 /* agent visit order (std::unordered_map iteration order the reference walks) and neighbour lane ids, for tests */
 int mcs_scene_visit_order(const mcs_scene* scene, int32_t* order_out, int n);
+/* Host-side half of mcs_scene_create alone (no device needed): what the reference derives once per call —
+ * agent visit order (input indices), corridor iteration order (input indices), per input corridor the id of its left /
+ * right neighbour (INT32_MIN = none; MapMultiLane ctor 0x109f00), per input agent the id of the lane of its first match
+ * (INT32_MIN = none; matchAgentsOnCorridor 0x10b810) and its lane-change prior {left, keep, right} (0x10bb97). */
+int mcs_scene_prepare_host(const mcs_corridor* corridors, int n_corridors, const mcs_agent* agents, int n_agents,
+                           int32_t* agent_order_out, int32_t* corridor_order_out, int32_t* left_ids_out,
+                           int32_t* right_ids_out, int32_t* first_lane_ids_out, double* priors_out /* [n_agents][3] */);
 
 /* ---- simulationMultiThread, batched over candidates ----
  * For each candidate c: MCS_GROUPS groups × n_per_group rollouts; rollout r (0-based over the

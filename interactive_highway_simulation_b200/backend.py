@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmcsim_b200.so")
 
 EXPORTS = [
     "mcs_device_count", "mcs_last_error", "mcs_version", "mcs_scene_create", "mcs_scene_destroy",
-    "mcs_scene_visit_order", "mcs_rollouts", "mcs_rollouts_range", "mcs_reduce_features", "mcs_rollouts_device",
+    "mcs_scene_visit_order", "mcs_scene_prepare_host", "mcs_rollouts", "mcs_rollouts_range", "mcs_reduce_features", "mcs_rollouts_device",
     "mcs_rollouts_groups", "mcs_rollouts_groups_device", "mcs_scene_sync", "mcs_group_partials", "mcs_combine_groups",
     "mcs_trajectories", "mcs_decide_mobil", "mcs_decide_fixed_direction", "mcs_decide_fixed_gap",
     "mcs_decide_closest_gap",
@@ -49,6 +49,8 @@ def lib():
     L.mcs_scene_destroy.argtypes = [C.c_void_p]
     L.mcs_scene_visit_order.restype = C.c_int
     L.mcs_scene_visit_order.argtypes = [C.c_void_p, P(C.c_int32), C.c_int]
+    L.mcs_scene_prepare_host.restype = C.c_int
+    L.mcs_scene_prepare_host.argtypes = [P(abi.Corridor), C.c_int, P(abi.Agent), C.c_int] + [P(C.c_int32)] * 5 + [P(C.c_double)]
     L.mcs_rollouts.restype = C.c_int
     L.mcs_rollouts.argtypes = [C.c_void_p, P(abi.Candidate), C.c_int, P(abi.SimParam), C.c_int, C.c_uint64,
                                P(abi.Feature), P(abi.Status)]
@@ -184,6 +186,18 @@ class DeviceScene:
         out = abi.Action()
         check(lib().mcs_decide_closest_gap(self._h, agent_id, direction, C.byref(out)))
         return out
+
+
+def prepare_host(corridors, agents):
+    """Host-side scene preparation only (no device): visit order, corridor order, neighbour lane ids, first lane match and
+    lane-change prior of every agent."""
+    nc, na = len(corridors), len(agents)
+    ao, co = (C.c_int32 * na)(), (C.c_int32 * nc)()
+    li, ri, fl = (C.c_int32 * nc)(), (C.c_int32 * nc)(), (C.c_int32 * na)()
+    pr = (C.c_double * (3 * na))()
+    check(lib().mcs_scene_prepare_host(corridors, nc, agents, na, ao, co, li, ri, fl, pr))
+    return dict(agent_order=list(ao), corridor_order=list(co), left_ids=list(li), right_ids=list(ri), first_lane_ids=list(fl),
+                priors=[tuple(pr[3 * i:3 * i + 3]) for i in range(na)])
 
 
 def group_partials(statuses, n_candidates, groups, n_per_group, steps):

@@ -1,6 +1,7 @@
 // C ABI of libmcsim_b200.so (include/mcsim.h).  CUDA runtime only — no torch types cross this boundary.
 #include <cuda_runtime.h>
 
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -329,6 +330,30 @@ int mcs_scene_destroy(mcs_scene* sc) {
 int mcs_scene_visit_order(const mcs_scene* sc, int32_t* order_out, int n) {
   if (!sc || !order_out || n < sc->host.n) return fail(MCS_ERR_ARG, "bad arguments");
   for (int k = 0; k < sc->host.n; ++k) order_out[k] = sc->host.i[(size_t)mcs::I_INPUT * sc->host.n_pad + k];
+  return MCS_OK;
+}
+
+int mcs_scene_prepare_host(const mcs_corridor* corridors, int n_corridors, const mcs_agent* agents, int n_agents,
+                           int32_t* agent_order_out, int32_t* corridor_order_out, int32_t* left_ids_out,
+                           int32_t* right_ids_out, int32_t* first_lane_ids_out, double* priors_out) {
+  mcs::SceneHost h;
+  int rc = mcs::build_scene_host(corridors, n_corridors, agents, n_agents, h);
+  if (rc != MCS_OK) return fail(rc, h.error);
+  for (int k = 0; k < h.n; ++k) {
+    const int input = h.i[(size_t)mcs::I_INPUT * h.n_pad + k];
+    if (agent_order_out) agent_order_out[k] = input;
+    const int lane = h.i[(size_t)mcs::I_LANE * h.n_pad + k];
+    if (first_lane_ids_out) first_lane_ids_out[input] = lane >= 0 ? h.lanes[lane].id : INT32_MIN;
+    if (priors_out)
+      for (int q = 0; q < 3; ++q) priors_out[3 * input + q] = h.f[(size_t)(mcs::F_PRIOR_L + q) * h.n_pad + k];
+  }
+  for (int j = 0; j < h.n_lanes; ++j) {
+    int input = -1;
+    for (int c = 0; c < n_corridors; ++c) if (corridors[c].id == h.lanes[j].id) { input = c; break; }
+    if (corridor_order_out) corridor_order_out[j] = input;
+    if (left_ids_out && input >= 0) left_ids_out[input] = h.lanes[j].leftIdx >= 0 ? h.lanes[h.lanes[j].leftIdx].id : INT32_MIN;
+    if (right_ids_out && input >= 0) right_ids_out[input] = h.lanes[j].rightIdx >= 0 ? h.lanes[h.lanes[j].rightIdx].id : INT32_MIN;
+  }
   return MCS_OK;
 }
 

@@ -51,3 +51,68 @@ def test_reduce_features_rejects_bad_arguments(backend_lib):
     feats = (abi.Feature * 1)()
     assert backend_lib.lib().mcs_reduce_features(st, 1, 0, 1, 40, feats) == abi.MCS_ERR_ARG
     assert backend_lib.lib().mcs_reduce_features(None, 1, 8, 1, 40, feats) == abi.MCS_ERR_ARG
+
+
+# ---- scene preparation on the host (MapMultiLane ctor so:0x109f00, matchAgentsOnCorridor so:0x10b810) ----
+import math
+
+import pytest
+
+import golden_io
+import scenes
+
+ORDER_CASES = golden_io.load_all("order")
+NONE = -2 ** 31
+
+
+@pytest.mark.parametrize("case", ORDER_CASES, ids=golden_io.ids(ORDER_CASES))
+def test_prepare_host_orders_match_reference_binary(backend_lib, case):
+    """Vehicle visit order and corridor iteration order, as recorded from the reference binary's unordered_maps."""
+    s = golden_io.scene_of(case)
+    got = backend_lib.prepare_host(s.c_corridors(), s.c_agents())
+    assert [s.agents[i]["id"] for i in got["agent_order"]] == case["agents"]
+    assert [s.corridors[i]["id"] for i in got["corridor_order"]] == case["corridors"]
+
+
+def test_prepare_host_matches_oracle_on_random_scenes(oracle, backend_lib):
+    """Orders and neighbour lanes against the oracle (sizes cross several unordered_map rehash thresholds, ids shuffled and
+    sparse); first lane match and lane-change prior against their definition."""
+    rng = random.Random(77)
+    for n_agents in (1, 2, 5, 11, 12, 13, 14, 29, 30, 31, 59, 60, 61, 62, 97, 127, 128, 200, 256):
+        n_lanes = rng.choice([1, 2, 3, 4, 6, 8])
+        s, _ = scenes.random_scene(rng, n_lanes=n_lanes, n_agents=n_agents)
+        for a in s.agents:                                   # sparse / large ids exercise the bucket arithmetic
+            a["id"] = a["id"] * rng.choice([1, 7, 13]) + rng.choice([0, 1000, 100003])
+        if len({a["id"] for a in s.agents}) != n_agents:
+            continue
+        got = backend_lib.prepare_host(s.c_corridors(), s.c_agents())
+        ao, co, li, ri = oracle.orders(s)
+        assert [s.agents[i]["id"] for i in got["agent_order"]] == ao
+        assert [s.corridors[i]["id"] for i in got["corridor_order"]] == co
+        assert got["left_ids"] == li and got["right_ids"] == ri
+        cs = s.c_corridors()
+        box = {c.id: (max(c.left[1], c.left[3]), min(c.right[1], c.right[3]), c.center[1]) for c in cs}
+        for i, a in enumerate(s.agents):
+            first = next((cid for cid in co if box[cid][0] >= a["y"] >= box[cid][1]), NONE)
+            assert got["first_lane_ids"][i] == first, (n_agents, i)
+            if first == NONE:
+                continue
+            d = ((a["y"] - box[first][2]) * 0.333 + 0.6805 * a.get("vy", 0.0)) - 0.01
+            g = lambda t, w: math.exp(-t * t / w)
+            pl = 0.8 * g(d - 1.04, 0.055) + 0.8 * g(d - 0.35, 0.055) + g(d - 0.7, 0.07) * 0.65
+            pr = 0.75 * g(1.04 + d, 0.055) + 0.75 * g(0.35 + d, 0.055) + g(0.7 + d, 0.07) * 0.6
+            pk = g(d, 0.055) * 2.5
+            want = [pl / (pl + pk + pr), pk / (pl + pk + pr), pr / (pl + pk + pr)]
+            assert got["priors"][i] == pytest.approx(want, rel=1e-12, abs=1e-300)
+            assert sum(got["priors"][i]) == pytest.approx(1.0, abs=1e-15)
+
+
+def test_prepare_host_rejects_capacity(backend_lib):
+    rng = random.Random(3)
+    s, _ = scenes.random_scene(rng, n_lanes=2, n_agents=4)
+    cs, ag = s.c_corridors(), s.c_agents()
+    big = (abi.Agent * 257)(*[ag[0]] * 257)
+    for k in range(257):
+        big[k].id = k
+    with pytest.raises(Exception):
+        backend_lib.prepare_host(cs, big)
