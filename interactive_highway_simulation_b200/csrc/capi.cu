@@ -104,7 +104,8 @@ struct mcs_scene {
   DeviceCtx* ctx = nullptr;
   mcs::SceneHost host;
   mcs::SceneDev dev{};
-  unsigned char* d_blob = nullptr;   // f | i | lane_vec in one allocation
+  unsigned char* d_blob = nullptr;   // f | i | lane_vec in one allocation, rows dev.n_pad long (0 = not uploaded yet)
+  size_t blob_cap = 0;
 };
 
 namespace {
@@ -184,6 +185,74 @@ int stage_candidates(mcs_scene* sc, const mcs_candidate* cands, int n_cand, int*
   return MCS_OK;
 }
 
+// Copy the scene to the device with rows `pad` slots long (pad >= host.n_pad; the kernels index rows with their block
+// size as a compile-time stride).  The upload happens at the first use and again only if a later launch wants another
+// row length: one blob (doubles | ints | lane vector), staged through pinned memory, one stream-ordered allocation,
+// one copy.  Caller holds the context lock and has selected the device.
+int upload_scene(mcs_scene* sc, int pad) {
+  if (sc->dev.n_pad == pad) return MCS_OK;
+  DeviceCtx* c = sc->ctx;
+  const mcs::SceneHost& h = sc->host;
+  if (pad < h.n_pad) return fail(MCS_ERR_ARG, "row length below the scene's");
+  const size_t bf = (size_t)mcs::F_COUNT * pad * sizeof(double), bi = (size_t)mcs::I_COUNT * pad * sizeof(int32_t), bv = (size_t)pad;
+  const size_t total = bf + bi + ((bv + 15) & ~(size_t)15);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));     // the staging buffer may still feed an earlier copy
+  if (total > c->stage_cap) {
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr; c->stage_cap = 0;
+    const size_t cap = total < (1u << 18) ? (1u << 18) : total;
+    CUDA_TRY(cudaMallocHost(&c->h_stage, cap));
+    c->stage_cap = cap;
+  }
+  if (pad == h.n_pad) {
+    memcpy(c->h_stage, h.f.data(), bf);
+    memcpy(c->h_stage + bf, h.i.data(), bi);
+    memcpy(c->h_stage + bf + bi, h.lane_vec.data(), bv);
+  } else {
+    memset(c->h_stage, 0, bf);                    // padding slots: 0.0 / -1 / 0, as build_scene_host fills its own
+    memset(c->h_stage + bf, 0xff, bi);
+    memset(c->h_stage + bf + bi, 0, bv);
+    for (int q = 0; q < mcs::F_COUNT; ++q)
+      memcpy(c->h_stage + (size_t)q * pad * sizeof(double), h.f.data() + (size_t)q * h.n_pad, (size_t)h.n_pad * sizeof(double));
+    for (int q = 0; q < mcs::I_COUNT; ++q)
+      memcpy(c->h_stage + bf + (size_t)q * pad * sizeof(int32_t), h.i.data() + (size_t)q * h.n_pad, (size_t)h.n_pad * sizeof(int32_t));
+    memcpy(c->h_stage + bf + bi, h.lane_vec.data(), (size_t)h.n_pad);
+  }
+  if (total > sc->blob_cap) {
+    if (sc->d_blob) CUDA_TRY(cudaFreeAsync(sc->d_blob, c->stream));
+    sc->d_blob = nullptr; sc->blob_cap = 0; sc->dev.n_pad = 0;
+    CUDA_TRY(cudaMallocAsync(&sc->d_blob, total, c->stream));
+    sc->blob_cap = total;
+  }
+  sc->dev.n_pad = 0;
+  CUDA_TRY(cudaMemcpyAsync(sc->d_blob, c->h_stage, total, cudaMemcpyHostToDevice, c->stream));
+  mcs::SceneDev& d = sc->dev;
+  d.f = (const double*)sc->d_blob; d.i = (const int32_t*)(sc->d_blob + bf); d.lane_vec = sc->d_blob + bf + bi;
+  d.n_pad = pad;     // the copy is ordered before every later launch on the context's stream
+  return MCS_OK;
+}
+
+// Threads per rollout.  One per vehicle slot is the minimum; a small launch (few rollouts per SM) is latency-bound — each
+// rollout walks its barriers alone — and the phases that are task-parallel inside a rollout (the seven MOBIL sub-tasks
+// per undecided vehicle, the outcome statistics) finish sooner on more threads, so the row length doubles while the
+// launch stays under MCS_WIDE_WARPS_PER_SM resident warps per SM (scripts/kernel_time.py sweeps, 24 vehicles x 5
+// candidates x 160 rollouts: 32 threads 0.66 ms, 64: 0.50, 128: 0.44, 256: 0.55).  The result does not depend on it.
+#ifndef MCS_WIDE_WARPS_PER_SM
+#define MCS_WIDE_WARPS_PER_SM 24
+#endif
+int rollout_threads(const mcs_scene* sc, long long rollouts, bool traj) {
+  int t = sc->host.n_pad;
+  if (const char* e = getenv("MCS_ROLLOUT_THREADS")) {        // tuning / test override
+    const int want = atoi(e);
+    if ((want == 32 || want == 64 || want == 128 || want == 256) && want >= t) return want;
+    return t;
+  }
+  if (traj) return t;
+  const long long budget = (long long)MCS_WIDE_WARPS_PER_SM * sc->ctx->n_sm;
+  while (t < 256 && rollouts * (2 * t / 32) <= budget) t *= 2;
+  return t;
+}
+
 // Threads per block.  A 256-vehicle rollout owns a 256-thread block.  Smaller rollouts either own a block too (small
 // launches: every rollout gets an SM to itself, nothing to share) or share one and start every step together
 // (rollout_kernel.cuh) — 8 per block; the merging instantiation, the instruction-fetch-bound one, in 512-thread blocks
@@ -239,6 +308,8 @@ int launch_rollouts(mcs_scene* sc, int n_cand, const mcs_sim_param* sp, uint64_t
   lp.dt = sp->dt; lp.steps = sp->steps; lp.min_steps = sp->min_steps;
   lp.seed = seed; lp.first = first; lp.count = count; lp.n_cand = n_cand;
   lp.status = d_status; lp.traj = d_traj; lp.traj_n = d_traj_n; lp.vehicle_steps = d_counter;
+  int rc = upload_scene(sc, rollout_threads(sc, (long long)count * n_cand, d_traj != nullptr));
+  if (rc != MCS_OK) return rc;
   size_t smem = (rollout_smem_bytes(sc->dev.n_pad, sp->steps) + 15) & ~(size_t)15;   // one rollout's region
   dim3 grid((unsigned)count, (unsigned)n_cand);
   // the trajectory-writing variant is a test / Simulation.run() path: one instantiation (the merging superset) serves it
@@ -285,34 +356,14 @@ int mcs_scene_create(const mcs_corridor* corridors, int n_corridors, const mcs_a
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) { delete sc; return fail(MCS_ERR_CUDA, cudaGetErrorString(e)); }
   const mcs::SceneHost& h = sc->host;
-  // one blob: doubles | ints | lane vector, staged through pinned memory, one stream-ordered allocation, one copy
-  const size_t bf = h.f.size() * sizeof(double), bi = h.i.size() * sizeof(int32_t), bv = h.lane_vec.size();
-  const size_t total = bf + bi + ((bv + 15) & ~(size_t)15);
-  auto bail = [&](const char* what, cudaError_t err) { std::string m = std::string(what) + ": " + cudaGetErrorString(err); if (sc->d_blob) cudaFreeAsync(sc->d_blob, c->stream); delete sc; return fail(MCS_ERR_CUDA, m); };
-  if (total > c->stage_cap) {
-    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return bail("sync", e);
-    if (c->h_stage) cudaFreeHost(c->h_stage);
-    c->stage_cap = 0;
-    size_t cap = total < (1u << 18) ? (1u << 18) : total;
-    if ((e = cudaMallocHost(&c->h_stage, cap)) != cudaSuccess) return bail("cudaMallocHost", e);
-    c->stage_cap = cap;
-  } else if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {   // the staging buffer may still feed an earlier copy
-    return bail("sync", e);
-  }
-  memcpy(c->h_stage, h.f.data(), bf);
-  memcpy(c->h_stage + bf, h.i.data(), bi);
-  memcpy(c->h_stage + bf + bi, h.lane_vec.data(), bv);
-  if ((e = cudaMallocAsync(&sc->d_blob, total, c->stream)) != cudaSuccess) return bail("cudaMallocAsync", e);
-  if ((e = cudaMemcpyAsync(sc->d_blob, c->h_stage, total, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return bail("H2D", e);
   mcs::SceneDev& d = sc->dev;
-  d.n = h.n; d.n_pad = h.n_pad; d.n_lanes = h.n_lanes; d.has_exit_lanes = h.has_exit_lanes ? 1 : 0;
-  d.f = (const double*)sc->d_blob; d.i = (const int32_t*)(sc->d_blob + bf); d.lane_vec = sc->d_blob + bf + bi;
+  d.n = h.n; d.n_pad = 0; d.n_lanes = h.n_lanes; d.has_exit_lanes = h.has_exit_lanes ? 1 : 0;   // rows: upload_scene, at the first use
   for (int j = 0; j <= h.n_lanes; ++j) d.lane_start[j] = h.lane_start[j];
   for (int j = 0; j < h.n_lanes; ++j) {
     const mcs::LaneHost& L = h.lanes[j];
     d.lanes[j] = mcs::LaneDev{L.leftY, L.rightY, L.centerY, L.vLimit, L.endX, L.startX, L.id, L.type, L.leftIdx, L.rightIdx, L.leftmost, 0};
   }
-  *out = sc;     // the copy is ordered before every later launch on the context's stream
+  *out = sc;
   return MCS_OK;
 }
 
@@ -554,6 +605,7 @@ static int run_decision(mcs_scene* sc, int32_t agent_id, mcs::DecideParams dp, i
     if (gap_id >= 0 && id == gap_id && dp.gap_slot < 0) dp.gap_slot = k;
   }
   if (dp.slot < 0) return fail(MCS_ERR_ARG, "No agent with id: " + std::to_string(agent_id));   // the reference traps (ud2, 0xb9a37)
+  if (sc->dev.n_pad == 0) { const int rc = upload_scene(sc, h.n_pad); if (rc != MCS_OK) return rc; }   // any row length serves
   const size_t smem = rollout_smem_bytes(sc->dev.n_pad, 0);
   CUDA_TRY(cudaFuncSetAttribute(mcs::decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mcs::decide_kernel<<<1, sc->dev.n_pad, smem, sc->ctx->stream>>>(sc->dev, dp, (mcs::DecideOut*)sc->ctx->d_decide);

@@ -494,28 +494,33 @@ __device__ __forceinline__ int sub_sync_or(int sub, int pred) {
   return r;
 }
 
-// exclusive scan of one int per thread over the NPS threads of one rollout
-template <int NPS, bool kWholeBlock>
-__device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int& total, int k, int sub) {
+// exclusive scan over the NPS threads of one rollout of small per-thread counts (< 2^BITS): one warp vote per bit.
+// `flag` is OR-ed over the rollout and comes back in bit 16 of `total`.
+template <int NPS, bool kWholeBlock, int BITS>
+__device__ __forceinline__ int block_exclusive_scan_small(int v, bool flag, int* scratch, int& total, int k, int sub) {
   constexpr int NW = NPS / 32;
   const int lane = k & 31, w = k >> 5;
-  int inc = v;
+  const unsigned below = (1u << lane) - 1u;
+  int excl = 0, wtot = 0;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
+  for (int b = 0; b < BITS; ++b) {
+    const unsigned m = __ballot_sync(0xffffffffu, (v >> b) & 1);
+    excl += __popc(m & below) << b;
+    wtot += __popc(m) << b;
   }
-  if (lane == 31) scratch[w] = inc;
+  if (__any_sync(0xffffffffu, flag)) wtot |= 1 << 16;
+  if (lane == 0) scratch[w] = wtot;
   sub_sync<NPS, kWholeBlock>(sub);
   int base = 0, tot = 0;
 #pragma unroll
   for (int q = 0; q < NW; ++q) {
     const int c = scratch[q];
-    if (q < w) base += c;
-    tot += c;
+    if (q < w) base += c & 0xffff;
+    tot += c & 0xffff;
+    tot |= c & 0x10000;
   }
   total = tot;
-  return base + inc - v;     // no trailing barrier: the two scans of a step use different scratch rows
+  return base + excl;
 }
 
 }  // namespace mcs
@@ -687,7 +692,7 @@ __global__ void __launch_bounds__(BT, (kMerge ? MCS_MIN_BLOCKS_MERGE : MCS_MIN_B
     int nTasks;
     {
       int total;
-      const int pos = block_exclusive_scan<NPS, G == 1>((needMobil ? 1 : 0) | (inversion ? 1 << 16 : 0), s.scan, total, k, sub) & 0xffff;
+      const int pos = block_exclusive_scan_small<NPS, G == 1, 1>(needMobil ? 1 : 0, inversion, s.scan, total, k, sub);
       nTasks = total & 0xffff;
       ordered = (total >> 16) == 0;
       if (hasLane) {
@@ -728,7 +733,8 @@ __global__ void __launch_bounds__(BT, (kMerge ? MCS_MIN_BLOCKS_MERGE : MCS_MIN_B
     }
     nDraw = nY + (noise ? 1 : 0) + (mobilDraw ? 1 : 0);
     int totalDraws;
-    const uint64_t drawBase = drawCtr + (uint64_t)block_exclusive_scan<NPS, G == 1>(nDraw, s.scan + 8, totalDraws, k, sub);
+    // nDraw <= 5 yielding candidates + noise + MOBIL draw
+    const uint64_t drawBase = drawCtr + (uint64_t)block_exclusive_scan_small<NPS, G == 1, kMerge ? 3 : 2>(nDraw, false, s.scan + 8, totalDraws, k, sub);
     drawCtr += (uint64_t)totalDraws;
 
     // ================= plan, part B: actions =================

@@ -1,14 +1,15 @@
-"""Bucket an ncu report's samples / instructions by kernel phase (line ranges of rollout_kernel.cuh found by markers)."""
+"""Bucket an ncu report's samples / instructions by kernel phase (line ranges of rollout_kernel.cuh found by markers).
+usage: ncu_buckets.py report.ncu-rep [rollout_kernel.cuh as it was when the report was captured]"""
 import csv, subprocess, sys, io, re, os
 rep = sys.argv[1]
-src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "interactive_highway_simulation_b200/csrc/rollout_kernel.cuh")).read().splitlines()
+src = open(sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "interactive_highway_simulation_b200/csrc/rollout_kernel.cuh")).read().splitlines()
 def find(pat, start=0):
     for i in range(start, len(src)):
         if pat in src[i]: return i + 1
     raise KeyError(pat)
 marks = [("helpers:idm_acc", find("double idm_acc(")), ("helpers:search", find("int lane_upper(")), ("helpers:rss/prob/center", find("bool rss_safe(")),
          ("mobil_geometry", find("void mobil_geometry(")), ("mobil_decide", find("void mobil_decide(")), ("customized_lane_change", find("void customized_lane_change(")),
-         ("scan", find("int block_exclusive_scan(")), ("kernel:init", find("rollout_kernel(const SceneDev")), ("partA", find("plan, part A")),
+         ("scan", find("int block_exclusive_scan")), ("kernel:init", find("rollout_kernel(const SceneDev")), ("partA", find("plan, part A")),
          ("tasks", find("compaction: queue MOBIL tasks")), ("draws", find("// draw counts")), ("partB", find("plan, part B")),
          ("integrate", find("================= integrate")), ("match", find("================= matchAgentsOnCorridor")),
          ("termination", find("================= termination")), ("stats", find("================= outcome statistics")), ("end", len(src) + 1)]

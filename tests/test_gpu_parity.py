@@ -23,6 +23,18 @@ def gpu(backend_lib):
     return backend_lib
 
 
+@pytest.fixture(autouse=True, params=["one_thread_per_slot", "launch_sized"])
+def threads_per_rollout(request, monkeypatch):
+    """Every test runs twice: with the minimum block size of its scene (32 / 64 / 128 / 256 threads per rollout, so each
+    kernel instantiation and the shared-block path are exercised by the small scenes too) and with the library's own
+    choice, which widens the rollouts of a small launch (capi.cu rollout_threads).  Results must not depend on it."""
+    if request.param == "one_thread_per_slot":
+        monkeypatch.setenv("MCS_ROLLOUT_THREADS", "32")      # below every scene's minimum = the minimum
+    else:
+        monkeypatch.delenv("MCS_ROLLOUT_THREADS", raising=False)
+    return request.param
+
+
 def status_dict(g):
     return dict(ok=g.ok, finish=g.finish, fallBack=g.fallBack, finishStep=g.finishStep, utility=g.utility, comfort=g.comfort,
                 utilityObjects=g.utilityObjects, comfortObjects=g.comfortObjects, draws=g.draws, executedSteps=g.executedSteps)
@@ -438,5 +450,37 @@ def test_visit_order_matches_reference_binary(gpu, case):
     try:
         order = ds.visit_order()                                  # input indices in visit order
         assert [s.agents[i]["id"] for i in order] == case["agents"]
+    finally:
+        ds.close()
+
+
+@pytest.mark.parametrize("kind", ["lane_change", "merging"])
+def test_result_is_independent_of_threads_per_rollout(gpu, monkeypatch, kind):
+    """The same rollouts on 32 / 64 / 128 / 256 threads each, own and shared blocks: byte-identical outcome records."""
+    rng = random.Random(31337)
+    if kind == "lane_change":
+        s, ego = random_scene(rng, 4, 24, spacing=(3, 40))
+        cands = [(ego, a, -2) for a in ("keep_lane", "left", "right")]
+    else:
+        s, ego = random_scene(rng, n_agents=30, lane_types=["merging", "main", "main"], ego_behavior="merging", ego_lane=0,
+                              spacing=(3, 40))
+        cands = [(ego, "left", -1)]
+    cand = (abi.Candidate * len(cands))(*[abi.Candidate(e, abi.ACTIONS[a], g, 0) for e, a, g in cands])
+    sp = abi.SimParam(0.3, 30, 10)
+    ds = gpu.DeviceScene(s.c_corridors(), s.c_agents())
+    try:
+        ref = None
+        for threads in (32, 64, 128, 256, 64, None):
+            for count in (3, 700):                      # 700 x candidates: enough rollouts for the shared-block path
+                if threads is None:
+                    monkeypatch.delenv("MCS_ROLLOUT_THREADS", raising=False)
+                else:
+                    monkeypatch.setenv("MCS_ROLLOUT_THREADS", str(threads))
+                st = ds.rollouts_range(cand, sp, 99, 0, count)
+                got = [bytes(st)[(c * count + i) * 64:(c * count + i + 1) * 64] for c in range(len(cands)) for i in range(3)]
+                if ref is None:
+                    ref = got
+                    assert any(x != bytes(64) for x in ref)
+                assert got == ref, (kind, threads, count)
     finally:
         ds.close()
