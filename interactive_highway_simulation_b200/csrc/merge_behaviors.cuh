@@ -13,7 +13,7 @@
 namespace mcs {
 
 // idmAccFrontBack 0xebc30 with an arbitrary list of fronts (slots, -1 = null)
-__device__ __noinline__ double idm_acc_list(const Smem& s, const IdmP& p, const int* fronts, int nf, int back,
+__device__ __forceinline__ double idm_acc_list(const Smem& s, const IdmP& p, const int* fronts, int nf, int back,
                                                double egoX, double egoV, double egoL, double pw) {
   const double freeAcc = (1.0 - pw) * p.accMax;
   const double na = -p.accMax;
@@ -98,9 +98,11 @@ __device__ __forceinline__ double idm_acc_match(const IdmP& p, int fid, double f
 struct RssP { double rTOther, rTEgo, aMin, aMax, dSoft; };
 
 // rssSafeRelax 0xb9210: entity 1 = leader of the gap's front vehicle, 3 = the gap's front vehicle, 5 = the gap's rear vehicle
-// out of line on purpose: the merging instantiation is instruction-cache bound (ncu: 48 % of its stall samples were
-// `no instruction`), and these bodies are reached by a handful of threads per step
-__device__ __noinline__ bool rss_safe_relax(bool h1, double gap1, double v1, bool h3, double gap3, double v3, bool h5,
+// Inlined like every helper here, each at its single call site: a call that takes `s` (or any struct) by reference forces
+// the Smem pointer table into local memory, and then EVERY shared-memory access of the kernel becomes a generic load
+// through a pointer re-read from the stack (SASS of the merging instantiation: 3 LDS / 145 LD / 83 LDL before,
+// 450 LDS / 0 LD after; 4 x 512 x 40-vehicle decision 2.43 -> 2.03 ms).
+__device__ __forceinline__ bool rss_safe_relax(bool h1, double gap1, double v1, bool h3, double gap3, double v3, bool h5,
                                                double gapb, double vb, double egoV, double vd, const RssP& r, const IdmP& idm) {
   double v = egoV;
   const int id1 = h1 ? 1 : -1, id3 = h3 ? 1 : -1, idb = h5 ? 1 : -1;
@@ -164,7 +166,7 @@ __device__ __noinline__ bool rss_safe_relax(bool h1, double gap1, double v1, boo
 }
 
 // timeToReachGap(xBack, vBack, xFront, vFront, xEgo, vEgo, vTarget) 0xe1630
-__device__ __noinline__ double time_to_reach_gap(double xB, double vB, double xF, double vF, double xE, double vE, double vT) {
+__device__ __forceinline__ double time_to_reach_gap(double xB, double vB, double xF, double vF, double xE, double vE, double vT) {
   const double a = (vT - vE) / 5.0;
   if (xB > xE) {
     const double acc = (a > 2.0) ? 2.0 : MCS_MAXSD(0.5, a);
