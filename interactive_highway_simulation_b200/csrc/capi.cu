@@ -285,6 +285,15 @@ int launch_np(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& 
   long long threshold = (long long)sc->ctx->n_sm * MCS_SHARE_MIN_PER_SM;
   if (const char* e = getenv("MCS_SHARE_MIN_PER_SM")) threshold = (long long)sc->ctx->n_sm * atoi(e);   // tuning override
   if (rollouts < threshold) return launch_bt<kTraj, kMerge, NPS, NPS>(sc, grid, region, lp);
+  if constexpr (kMerge && NPS == 64) {
+    // The merging instantiation is latency-bound per step: a wave of 512-thread blocks (8 rollouts, 128 registers) takes
+    // about as long whether the SM holds one rollout or eight, so a launch that needs a second wave is better off in
+    // 896-thread blocks (14 rollouts, 72 registers, ~1.7x the time per wave — measured 4 x 512 rollouts x 40 vehicles:
+    // 2.03 -> 1.86 ms; 4 x 1024: 3.90 -> 3.42; but 4 x 256, one wave either way: 1.07 vs 1.74).
+    const long long sm = sc->ctx->n_sm;
+    const long long waves8 = ((rollouts + 7) / 8 + sm - 1) / sm, waves14 = ((rollouts + 13) / 14 + sm - 1) / sm;
+    if (waves14 * 17 < waves8 * 10) return launch_bt<kTraj, kMerge, NPS, 896>(sc, grid, region, lp);
+  }
   return launch_bt<kTraj, kMerge, NPS, BT>(sc, grid, region, lp);
 }
 

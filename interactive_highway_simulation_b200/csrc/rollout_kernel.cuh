@@ -539,7 +539,9 @@ template <bool kTraj, bool kMerge, int NPS, int BT>
 #ifndef MCS_MIN_BLOCKS_MERGE
 #define MCS_MIN_BLOCKS_MERGE 2
 #endif
-__global__ void __launch_bounds__(BT, (kMerge ? MCS_MIN_BLOCKS_MERGE : MCS_MIN_BLOCKS) * 256 / BT) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp, const int region_bytes) {
+// (a block of more than 512 threads is alone on its SM and gets what the register file allows: 896 threads -> 72)
+#define MCS_RESIDENT_BLOCKS(BT, kMerge) (((kMerge) ? MCS_MIN_BLOCKS_MERGE : MCS_MIN_BLOCKS) * 256 / (BT) > 0 ? ((kMerge) ? MCS_MIN_BLOCKS_MERGE : MCS_MIN_BLOCKS) * 256 / (BT) : 1)
+__global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp, const int region_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // NPS = sc.n_pad = blockDim.x as a compile-time constant: every shared-memory array address and row stride folds into
   // the instruction's immediate offset instead of living in registers

@@ -462,7 +462,7 @@ def test_result_is_independent_of_threads_per_rollout(gpu, monkeypatch, kind):
         s, ego = random_scene(rng, 4, 24, spacing=(3, 40))
         cands = [(ego, a, -2) for a in ("keep_lane", "left", "right")]
     else:
-        s, ego = random_scene(rng, n_agents=30, lane_types=["merging", "main", "main"], ego_behavior="merging", ego_lane=0,
+        s, ego = random_scene(rng, n_agents=40, lane_types=["merging", "main", "main"], ego_behavior="merging", ego_lane=0,
                               spacing=(3, 40))
         cands = [(ego, "left", -1)]
     cand = (abi.Candidate * len(cands))(*[abi.Candidate(e, abi.ACTIONS[a], g, 0) for e, a, g in cands])
@@ -471,7 +471,8 @@ def test_result_is_independent_of_threads_per_rollout(gpu, monkeypatch, kind):
     try:
         ref = None
         for threads in (32, 64, 128, 256, 64, None):
-            for count in (3, 700):                      # 700 x candidates: enough rollouts for the shared-block path
+            # 700 x candidates: enough rollouts for the shared-block path; 2000 merging rollouts: the 896-thread blocks
+            for count in (3, 700) + ((2000,) if kind == "merging" and threads in (64, None) else ()):
                 if threads is None:
                     monkeypatch.delenv("MCS_ROLLOUT_THREADS", raising=False)
                 else:
