@@ -99,7 +99,8 @@ struct Smem {
   double* red;     // [16] reduction scratch
   int* scan;       // [32] warp totals of the two per-step scans (8 + 8), lane counters of the re-ranking (16..)
   int* cnt;        // [2][16] lane starts, double-buffered across rebuilds
-  int* flags;      // [8] block flags
+  int* flags;      // [8] per-rollout scalars: 0 ego reached its target lane, 1 movers queued, 2 ego behaviour, 3 thw samples,
+                   //     4 ego's gap slot, 5 finish step, 6 scene unsupported, 7 yield table full
   int* tasks;      // [n_pad] MOBIL task queue
   uint8_t* lane;   // [n_pad] lane slot of each vehicle (0xff = none)
   uint8_t* vec;    // [n_pad] concatenated per-lane vectors
@@ -575,7 +576,6 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
   int lane = -1, beh = MCS_BEH_OTHER, commit = 0, keepStep = 0, targetLane = -1, inputIdx = 0;
   bool aggressive = false;
   const bool isEgo = live && k == cd.ego_slot;
-  bool reached = false;
   if (live) {
     x = F[(size_t)F_X * np + k]; y = F[(size_t)F_Y * np + k]; v = F[(size_t)F_V * np + k]; vy = F[(size_t)F_VY * np + k];
     lane = I[(size_t)I_LANE * np + k]; beh = I[(size_t)I_BEH * np + k]; commit = I[(size_t)I_COMMIT * np + k];
@@ -600,20 +600,23 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
   { const double sq = sqrt((-s.idm[k]) * s.idm[3 * np + k]); s.idm[5 * np + k] = sq + sq; }   // idmAccFrontBack 0xebd2b, hoisted
   s.lane[k] = (uint8_t)(lane < 0 ? 0xff : lane);
   s.vec[k] = sc.lane_vec[k];
-  int oldLane = lane;           // lane whose vector currently holds this vehicle
   int myPos = 0;                // its position in s.vec
   if (k <= sc.n_lanes) laneStart[k] = sc.lane_start[k];
   if (k < 8) s.flags[k] = 0;
   sub_sync<NPS, G == 1>(sub);
   if (k < laneStart[sc.n_lanes]) s.pos[s.vec[k]] = (uint8_t)k;
-  if (isEgo) s.flags[2] = beh;          // the ego's current behaviour: `exit` vehicles are yielding candidates (0x104c90)
+  if (isEgo) {
+    s.flags[2] = beh;                   // the ego's current behaviour: `exit` vehicles are yielding candidates (0x104c90)
+    s.flags[4] = cd.gap_slot;           // Agent::targetGapId as a slot; < 0 = last gap
+    s.flags[5] = lp.steps;              // < lp.steps once the ego has reached its target lane (StatusOneSim::finish)
+  }
   sub_sync<NPS, G == 1>(sub);
   myPos = s.pos[k];
 
   // statistics (Simulation::run 0x10ee71-0x10f49a) accumulated on the fly in history order
   // statistics (Simulation::run 0x10ee71-0x10f49a): per-object sums accumulated on the fly in history order; the ego's own
   // history (acceleration, speed, thw ratio) is kept in shared memory and reduced in the same order after the loop
-  int nStates = 1;
+  // states recorded so far = step + 1 (every executed step appends one)
   {
     const double a0 = live ? F[(size_t)F_A * np + k] : 0.0;
     s.acc[k] = fabs(a0); s.acc[np + k] = v;
@@ -623,13 +626,10 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
     double* t = lp.traj + ((((size_t)cand * lp.count + ridx) * n + inputIdx) * (size_t)(lp.steps + 1)) * 4;
     t[0] = x; t[1] = y; t[2] = v; t[3] = F[(size_t)F_A * np + k];
   }
-  uint64_t drawCtr = (uint64_t)n;   // draws 0..n-1 were the ctor flags
-  int finishStep = lp.steps;
-  bool finish = false;
+  uint32_t drawCtr = (uint32_t)n;   // draws 0..n-1 were the ctor flags
   int step = 0;
-  bool unsupported = false;   // the reference's behaviour is undefined for this scene (no action pushed / missing corridor)
-  bool tableFull = false;     // yielding-intention table overflow
-  int gapSlot = cd.gap_slot;  // ego only: Agent::targetGapId as a slot; < 0 = last gap
+  // scalars only the ego thread touches (arrival, gap slot, finish step) and the two sticky error marks live in s.flags:
+  // registers are what limits the resident rollouts per SM
   YieldTable yt;
   yt.n = 0; yt.yielding = 0u;
 
@@ -661,9 +661,10 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
       if (myPos > laneStart[lane]) inversion = !(s.x[s.vec[myPos - 1]] < x);
       if (isEgo) {
         const bool lr = cd.action == MCS_ACT_LEFT || cd.action == MCS_ACT_RIGHT;
+        const bool reached = s.flags[0] != 0;
         if (beh == MCS_BEH_IDM || beh == MCS_BEH_IDM_LC) mode = (lr && reached) ? 1 : 2;
         else if (beh == MCS_BEH_MERGING || beh == MCS_BEH_EXIT) mode = reached ? 1 : 3;
-        else unsupported = true;
+        else s.flags[6] = 1;
       } else if (beh == MCS_BEH_IDM_LC) {
         mode = 1; noise = true;
         const bool canL = L.leftIdx >= 0 && sc.lanes[L.leftIdx].type == MCS_LANE_MAIN;
@@ -674,7 +675,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
       } else if (beh == MCS_BEH_MERGING) {
         mode = 4;
       } else {
-        unsupported = true;   // the binary pushes no action for such a vehicle and then reads past its action vector (0x10ed15)
+        s.flags[6] = 1;       // the binary pushes no action for such a vehicle and then reads past its action vector (0x10ed15)
       }
       if (kMerge) {
         if (mode == 1) {
@@ -687,7 +688,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
           }
         }
       } else if (mode == 3 || mode == 4) {
-        unsupported = true;     // cannot happen: the host selects kMerge for such scenes
+        s.flags[6] = 1;         // cannot happen: the host selects kMerge for such scenes
       }
     }
     // compaction: queue MOBIL tasks
@@ -736,8 +737,8 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
     nDraw = nY + (noise ? 1 : 0) + (mobilDraw ? 1 : 0);
     int totalDraws;
     // nDraw <= 5 yielding candidates + noise + MOBIL draw
-    const uint64_t drawBase = drawCtr + (uint64_t)block_exclusive_scan_small<NPS, G == 1, kMerge ? 3 : 2>(nDraw, false, s.scan + 8, totalDraws, k, sub);
-    drawCtr += (uint64_t)totalDraws;
+    const uint64_t drawBase = (uint64_t)drawCtr + (uint64_t)block_exclusive_scan_small<NPS, G == 1, kMerge ? 3 : 2>(nDraw, false, s.scan + 8, totalDraws, k, sub);
+    drawCtr += (uint32_t)totalDraws;
 
     // ================= plan, part B: actions =================
     if (hasLane) {
@@ -759,8 +760,8 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
         me.idm = pe;
         // mode 3: the ego executes its gap (customizedMerging); mode 4: a non-ego `merging` vehicle picks the closest gap to the left
         const bool okSide = merging_behavior(s, sc, laneStart, me, evd, mode == 3, false, mode == 3 ? cd.action == MCS_ACT_LEFT : true,
-                                             gapSlot, ax, avy);
-        if (!okSide) { unsupported = true; ax = 0.0; avy = 0.0; }
+                                             mode == 3 ? s.flags[4] : -1, ax, avy);
+        if (!okSide) { s.flags[6] = 1; ax = 0.0; avy = 0.0; }
       } else if (mode == 1 || mode == 2) {
         // One idmAccFrontBack call per vehicle and step: the branches only choose its operands.
         //   mode 1  idmBehaviorAndYieldingToMergingAgents 0x104200: own leader, vd (capped for the ego 0x104301)
@@ -837,7 +838,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
                 yt.key[e] = (uint8_t)j; yt.p0[e] = p;
                 if (y0) yt.yielding |= 1u << e; else yt.yielding &= ~(1u << e);
               } else {
-                tableFull = true;
+                s.flags[7] = 1;
               }
             }
             if (e >= 0) {
@@ -866,7 +867,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
             const double u = (double)mcs_rand31(key, drawBase + (uint64_t)nY + 1) / 2147483647.0;
             MobilState ms{commit, keepStep, targetLane};
             mobil_decide(s, sc, np, k, lane, v, el, aMin, F[(size_t)F_YP_PF * np + k], F[(size_t)F_YP_DA * np + k],
-                         F[(size_t)F_YP_BA * np + k], /*mode=*/(nStates <= 1) ? 0 : 1, aggressive, F + (size_t)F_PRIOR_L * np, u, ms, ax, avy);
+                         F[(size_t)F_YP_BA * np + k], /*mode=*/(step == 0) ? 0 : 1, aggressive, F + (size_t)F_PRIOR_L * np, u, ms, ax, avy);
             commit = ms.commit; keepStep = ms.keepStep; targetLane = ms.targetLane;
           }
         }
@@ -886,16 +887,16 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
       }
       s.x[k] = x; s.v[k] = v;
       s.acc[k] = s.acc[k] + fabs(acc); s.acc[np + k] = s.acc[np + k] + v;
-      if (isEgo) { s.chist[nStates] = acc; s.vhist[nStates] = v; }
+      if (isEgo) { s.chist[step + 1] = acc; s.vhist[step + 1] = v; }
       if (kTraj) {
-        double* t = lp.traj + ((((size_t)cand * lp.count + ridx) * n + inputIdx) * (size_t)(lp.steps + 1) + nStates) * 4;
+        double* t = lp.traj + ((((size_t)cand * lp.count + ridx) * n + inputIdx) * (size_t)(lp.steps + 1) + step + 1) * 4;
         t[0] = x; t[1] = y; t[2] = v; t[3] = acc;
       }
     }
-    nStates++;
 
     // ================= matchAgentsOnCorridor (0x10b810) =================
     bool changed = false;
+    const int laneBefore = lane;      // the lane whose vector holds this vehicle (vectors are rebuilt whenever a lane changes)
     if (live) {
       bool stay = false;
       if (lane >= 0) { const LaneDev& L = sc.lanes[lane]; stay = L.leftY >= y && y >= L.rightY; }
@@ -911,9 +912,9 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
         }
         s.lane[k] = (uint8_t)(lane < 0 ? 0xff : lane);
       }
-      if (isEgo && !reached && lane >= 0) reached = sc.lanes[lane].id == targetLane;
+      if (isEgo && lane >= 0 && s.flags[0] == 0) s.flags[0] = sc.lanes[lane].id == targetLane ? 1 : 0;
     }
-    if (isEgo) { s.flags[0] = reached ? 1 : 0; if (kMerge) s.flags[2] = beh; }
+    if (kMerge && isEgo) s.flags[2] = beh;
     // one barrier publishes the new x / v / lane and the ego's arrival, and tells whether any membership changed
     const int anyChanged = sub_sync_or<NPS, G == 1>(sub, changed ? 1 : 0);
     const bool egoReached = s.flags[0] != 0;
@@ -924,7 +925,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
       // movers in: rank = old rank - leavers ahead + arrivals ahead.  An order inversion anywhere falls back to ranking
       // every vehicle against every other one.
       const int newLane = live ? (int)s.lane[k] : 0xff;
-      const int oldL = oldLane < 0 ? 0xff : oldLane;
+      const int oldL = laneBefore < 0 ? 0xff : laneBefore;
       const bool inVec = live && oldL != 0xff;
       const bool mover = live && newLane != oldL;
       bool inversion = false;
@@ -998,19 +999,19 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
         if (newLane != 0xff) { myPos = myStart + rank; s.vec[myPos] = (uint8_t)k; }
       }
       laneStart = nextStart;
-      oldLane = newLane == 0xff ? -1 : newLane;
       sub_sync<NPS, G == 1>(sub);
     }
     // ================= termination (0x10edd0-0x10ee10) =================
+    const int gapSlot = (kMerge && isEgo) ? s.flags[4] : -1;
     if (kMerge && isEgo && gapSlot >= 0) {
       // the gap's rear vehicle left the target lane: re-target to the last vehicle of that lane behind it, else the
       // last gap (matchAgentsOnCorridor 0x10c320-0x10c39d)
       const int gl = s.lane[gapSlot];
-      if (gl == 0xff) unsupported = true;
+      if (gl == 0xff) s.flags[6] = 1;
       else if (sc.lanes[gl].id != targetLane) {
         int tl = -1;
         for (int j = 0; j < sc.n_lanes; ++j) if (sc.lanes[j].id == targetLane) tl = j;
-        if (tl < 0) unsupported = true;
+        if (tl < 0) s.flags[6] = 1;
         else {
           const int lo = laneStart[tl], cnt = laneStart[tl + 1] - lo;
           const double gx = s.x[gapSlot];
@@ -1019,21 +1020,19 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
             const int o = s.vec[lo + q];
             if (gx > s.x[o]) { found = o; break; }
           }
-          gapSlot = found;
+          s.flags[4] = found;
         }
       }
     }
-    if (egoReached) {
-      finish = true;
-      finishStep = min(finishStep, step);
-      if (lp.min_steps <= step) { if (G > 1) { running = false; continue; } else break; }
-    }
     step++;
+    if (egoReached) {
+      if (isEgo) s.flags[5] = min(s.flags[5], step - 1);
+      if (lp.min_steps <= step - 1) { if (G > 1) { running = false; continue; } else break; }
+    }
   }
 
   // ================= outcome statistics (0x10ee20-0x10f64d) =================
-  const int executed = nStates - 1;
-  const int fs = max(finishStep, (int)(1.0 / lp.dt));
+  const int executed = step, nStates = step + 1;
   double utilO = 1e300, comfO = 1e300;   // min identity; replaced by 1.0 when the rollout has no objects
   const double aMin = s.rss[np + k];
   if (live && !isEgo) {
@@ -1105,8 +1104,8 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
 #pragma unroll 1
     for (int t = 0; t < kk; ++t) sumC = sumC + (s.csort[t] / aMin + 1.0);
     st.comfort = sumC / (double)kk;
-    st.finishStep = fs; st.executedSteps = executed; st.draws = (uint32_t)drawCtr;
-    st.finish = finish ? 1 : 0;
+    st.finishStep = max(s.flags[5], (int)(1.0 / lp.dt)); st.executedSteps = executed; st.draws = (uint32_t)drawCtr;
+    st.finish = s.flags[5] < lp.steps ? 1 : 0;
     const int beh0 = I[(size_t)I_BEH0 * np + k];
     if (beh0 == MCS_BEH_MERGING || beh0 == MCS_BEH_EXIT) st.fallBack = (2.0 > v) ? 1 : 0;
     else st.fallBack = anyFallBack ? 1 : 0;
@@ -1116,7 +1115,8 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
     if (kTraj && lp.traj_n) lp.traj_n[(size_t)cand * lp.count + ridx] = nStates;
     if (lp.vehicle_steps) atomicAdd(lp.vehicle_steps, (unsigned long long)executed * (unsigned long long)n);
   }
-  const int anyUnsupported = sub_sync_or<NPS, G == 1>(sub, unsupported ? 1 : 0), anyFull = sub_sync_or<NPS, G == 1>(sub, tableFull ? 1 : 0);
+  sub_sync<NPS, G == 1>(sub);
+  const int anyUnsupported = s.flags[6], anyFull = s.flags[7];
   if ((anyUnsupported || anyFull) && isEgo) st_out->overflow = (uint8_t)(anyUnsupported ? 2 : 1);   // the caller fails loudly (MCS_ERR_SCENE / MCS_ERR_CAPACITY)
 }
 
