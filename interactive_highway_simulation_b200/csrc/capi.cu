@@ -129,6 +129,14 @@ int get_ctx(int device, DeviceCtx** out) {
       delete c;
       return fail(MCS_ERR_CUDA, cudaGetErrorString(e));
     }
+    // scene blobs come from the stream-ordered pool: keep freed blocks in it (the default threshold 0 hands them back to
+    // the driver at every synchronisation, and the next decision's cudaMallocAsync then costs milliseconds)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ULL;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     g_ctx[device] = c;
   }
   *out = g_ctx[device];
