@@ -73,7 +73,11 @@ struct LaunchParams {
 // numerator is selected afterwards: +-0 with the sign of num for den > 0, the opposite sign for den < 0, NaN for 0 / NaN.
 __device__ __forceinline__ double mcs_div(double num, double den) {
   const bool zero = num == 0.0;
-  const double q = (zero ? 1.0 : num) / den;
+  double safe = zero ? 1.0 : num;
+  // opaque to the optimiser: otherwise it may move the select across the division (it did at four call sites — the
+  // stand-in 1.0 ended up in the denominator and 6 % of all executed instructions were still the slow path, r01n)
+  asm volatile("" : "+d"(safe));
+  const double q = safe / den;
   if (!zero) return q;
   if (den > 0.0) return num;
   if (den < 0.0) return -num;
