@@ -31,7 +31,7 @@ __device__ __forceinline__ double idm_acc_list(const Smem& s, const IdmP& p, con
       const double dv = (egoV - s.v[f]) * egoV;
       double t = dv / sq2 + dDes;
       t = MCS_MAXSD(t, 0.0);
-      t = t / gap;
+      t = mcs_div(t, gap);          // t is clamped at 0: keep the zero off the division's slow path
       term = (t * t) * na;
     } else {
       term = -10000000000.0;
@@ -48,7 +48,7 @@ __device__ __forceinline__ double idm_acc_list(const Smem& s, const IdmP& p, con
       const double dv = (bv - egoV) * egoV;
       double t = dv / sq2 + dDesB;
       t = MCS_MAXSD(t, 0.0);
-      t = t / gap;
+      t = mcs_div(t, gap);
       sum = sum + (t * t) * p.accMax;
     } else {
       sum = sum + 10000000000.0;
@@ -71,7 +71,7 @@ __device__ __forceinline__ double idm_acc_match(const IdmP& p, int fid, double f
       const double sq = sqrt(p.accMin * p.accCom);
       double t = dv / (sq + sq) + dDes;
       t = MCS_MAXSD(t, 0.0);
-      t = t / fdis;
+      t = mcs_div(t, fdis);
       term = (t * t) * p.accMin;
     } else {
       term = -10000000000.0;
@@ -85,7 +85,7 @@ __device__ __forceinline__ double idm_acc_match(const IdmP& p, int fid, double f
       const double sq = sqrt(p.accMin * p.accCom);
       double t = dv / (sq + sq) + dDes;
       t = MCS_MAXSD(t, 0.0);
-      t = t / bdis;
+      t = mcs_div(t, bdis);
       sum = sum + (t * t) * p.accMax;
     } else {
       sum = sum + 10000000000.0;
@@ -125,7 +125,7 @@ __device__ __forceinline__ bool rss_safe_relax(bool h1, double gap1, double v1, 
     }
     double aEgo = aMaxHalf;
     if (id3 != -1) {
-      const double q = (v3 * v3) / (a3 + a3);
+      const double q = mcs_div(v3 * v3, a3 + a3);
       const double vr = v * r.rTEgo;
       double d = (v * v) / (-2.0 * r.aMin);
       d = d + vr;
