@@ -122,10 +122,6 @@ __device__ __forceinline__ void carve_smem(Smem& s, unsigned char* p, int np, in
   s.mob = (double*)p; p += sizeof(double) * 6 * np;
   s.rss = (double*)p; p += sizeof(double) * 3 * np;
   s.acc = (double*)p; p += sizeof(double) * 2 * np;
-  s.chist = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
-  s.csort = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
-  s.vhist = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
-  s.thist = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
   s.red = (double*)p; p += sizeof(double) * 16;
   s.scan = (int*)p; p += sizeof(int) * 32;
   s.cnt = (int*)p; p += sizeof(int) * 32;
@@ -134,7 +130,13 @@ __device__ __forceinline__ void carve_smem(Smem& s, unsigned char* p, int np, in
   s.lane = p; p += np;
   s.vec = p; p += np;
   s.mflag = p; p += 2 * np;
-  s.pos = p; p += np;
+  s.pos = p; p += np;      // 5 * np bytes so far, np a multiple of 32: still 8-byte aligned
+  // the arrays whose size depends on the horizon come last: everything above sits at a compile-time offset (np is the
+  // block-size template constant), so the per-step accesses need no address arithmetic
+  s.chist = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
+  s.csort = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
+  s.vhist = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
+  s.thist = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
 }
 
 __device__ __forceinline__ IdmP load_idm(const Smem& s, int np, int k) {
@@ -719,8 +721,12 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
     // sub-task slot = part * ceil32(nTasks) + i: every warp runs one part only, and the five parts run on five warps
     // side by side instead of queueing up on the first ones
     const int nT32 = (nTasks + 31) & ~31;
+    // part = t / nT32 without the integer-division sequence: nT32 = 32 m with m <= 8, t / 32 < 64, and
+    // (u * ceil(2^16 / m)) >> 16 == u / m for u < 64 (error < 64 / 2^16 < 1 / m)
+    const unsigned magic = (nT32 == 32 ? 65536u : nT32 == 64 ? 32768u : nT32 == 96 ? 21846u : nT32 == 128 ? 16384u
+                            : nT32 == 160 ? 13108u : nT32 == 192 ? 10923u : nT32 == 224 ? 9363u : 8192u);
     for (int t = k; t < MOBIL_PARTS * nT32; t += NPS) {
-      const int part = t / nT32, ti = t - part * nT32;
+      const int part = (int)(((unsigned)t >> 5) * magic >> 16), ti = t - part * nT32;
       if (ti >= nTasks) continue;
       const int rec = s.tasks[ti];
       const int vk = rec & 0xff;
