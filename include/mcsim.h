@@ -121,7 +121,9 @@ int mcs_device_count(void);
 const char* mcs_last_error(void);
 const char* mcs_version(void);
 
-/* MapMultiLane(corridors) + list[Agent] → device-resident scene (structure-of-arrays).  `device` = CUDA ordinal. */
+/* MapMultiLane(corridors) + list[Agent] → scene bound to CUDA device `device` (structure-of-arrays).  Fails without a
+ * usable device (there is no CPU path).  The single host→device copy of the scene is made at its first use, when the
+ * launch has fixed the row length (threads per rollout); the scene then stays resident in HBM. */
 int mcs_scene_create(const mcs_corridor* corridors, int n_corridors, const mcs_agent* agents, int n_agents,
                      int device, mcs_scene** out);
 int mcs_scene_destroy(mcs_scene* scene);
