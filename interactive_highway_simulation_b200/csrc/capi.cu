@@ -193,6 +193,40 @@ int stage_candidates(mcs_scene* sc, const mcs_candidate* cands, int n_cand, int*
   return MCS_OK;
 }
 
+// Which vehicle slot each of the `pad` threads of a rollout handles (SceneDev::thread_slot).  Slots stay in the
+// reference's visit order and the live threads follow them in increasing order (so a scan over threads is a scan over
+// slots: the random-draw positions depend on it).  With spare warps (pad > slots) the table leaves gaps: the slot
+// sequence is cut where the initial lane changes — vehicles of one lane run the same behaviour code (merging vehicles
+// on the merging lane, yielding ones next to it, plain IDM / MOBIL elsewhere) — neighbouring pieces are merged,
+// smallest combined size first, until the pieces fit the warps, and every piece starts on a warp boundary.  Divergent
+// behaviour code then runs on different warps side by side instead of in series inside one warp.
+void thread_slots(const mcs::SceneHost& h, int pad, unsigned char* out) {
+  struct Piece { int first, count; };
+  std::vector<Piece> pieces;
+  for (int k = 0; k < h.n; ++k) {
+    const int lane = h.i[(size_t)mcs::I_LANE * h.n_pad + k];
+    const bool cut = pieces.empty() || lane != h.i[(size_t)mcs::I_LANE * h.n_pad + k - 1] || pieces.back().count == 32;
+    if (cut) pieces.push_back(Piece{k, 1}); else pieces.back().count++;
+  }
+  const int warps = pad / 32;
+  auto need = [&]() { int w = 0; for (const Piece& p : pieces) w += (p.count + 31) / 32; return w; };
+  while (pieces.size() > 1 && need() > warps) {
+    size_t best = 0;
+    for (size_t q = 1; q + 1 < pieces.size(); ++q)
+      if (pieces[q].count + pieces[q + 1].count < pieces[best].count + pieces[best + 1].count) best = q;
+    pieces[best].count += pieces[best + 1].count;
+    pieces.erase(pieces.begin() + (long)best + 1);
+  }
+  std::vector<int> slot_of(pad, -1);
+  int t = 0;
+  for (const Piece& p : pieces) {
+    t = (t + 31) & ~31;
+    for (int q = 0; q < p.count; ++q) slot_of[t++] = p.first + q;
+  }
+  int dead = h.n;                        // idle threads take the padding slots, any order
+  for (int q = 0; q < pad; ++q) out[q] = (unsigned char)(slot_of[q] >= 0 ? slot_of[q] : dead++);
+}
+
 // Copy the scene to the device with rows `pad` slots long (pad >= host.n_pad; the kernels index rows with their block
 // size as a compile-time stride).  The upload happens at the first use and again only if a later launch wants another
 // row length: one blob (doubles | ints | lane vector), staged through pinned memory, one stream-ordered allocation,
@@ -203,7 +237,7 @@ int upload_scene(mcs_scene* sc, int pad) {
   const mcs::SceneHost& h = sc->host;
   if (pad < h.n_pad) return fail(MCS_ERR_ARG, "row length below the scene's");
   const size_t bf = (size_t)mcs::F_COUNT * pad * sizeof(double), bi = (size_t)mcs::I_COUNT * pad * sizeof(int32_t), bv = (size_t)pad;
-  const size_t total = bf + bi + ((bv + 15) & ~(size_t)15);
+  const size_t total = bf + bi + 2 * ((bv + 15) & ~(size_t)15);        // doubles | ints | lane vector | thread -> slot table
   CUDA_TRY(cudaStreamSynchronize(c->stream));     // the staging buffer may still feed an earlier copy
   if (total > c->stage_cap) {
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -226,6 +260,7 @@ int upload_scene(mcs_scene* sc, int pad) {
       memcpy(c->h_stage + bf + (size_t)q * pad * sizeof(int32_t), h.i.data() + (size_t)q * h.n_pad, (size_t)h.n_pad * sizeof(int32_t));
     memcpy(c->h_stage + bf + bi, h.lane_vec.data(), (size_t)h.n_pad);
   }
+  thread_slots(h, pad, c->h_stage + bf + bi + ((bv + 15) & ~(size_t)15));
   if (total > sc->blob_cap) {
     if (sc->d_blob) CUDA_TRY(cudaFreeAsync(sc->d_blob, c->stream));
     sc->d_blob = nullptr; sc->blob_cap = 0; sc->dev.n_pad = 0;
@@ -236,6 +271,7 @@ int upload_scene(mcs_scene* sc, int pad) {
   CUDA_TRY(cudaMemcpyAsync(sc->d_blob, c->h_stage, total, cudaMemcpyHostToDevice, c->stream));
   mcs::SceneDev& d = sc->dev;
   d.f = (const double*)sc->d_blob; d.i = (const int32_t*)(sc->d_blob + bf); d.lane_vec = sc->d_blob + bf + bi;
+  d.thread_slot = d.lane_vec + ((bv + 15) & ~(size_t)15);
   d.n_pad = pad;     // the copy is ordered before every later launch on the context's stream
   return MCS_OK;
 }

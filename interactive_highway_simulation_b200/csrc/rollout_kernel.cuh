@@ -44,6 +44,7 @@ struct SceneDev {
   const double* f;          // F_COUNT * n_pad
   const int32_t* i;         // I_COUNT * n_pad
   const uint8_t* lane_vec;  // n_pad
+  const uint8_t* thread_slot;   // n_pad: vehicle slot handled by each thread of a rollout (capi.cu thread_slots)
   int lane_start[MCS_MAX_LANES + 1];
   LaneDev lanes[MCS_MAX_LANES];
 };
@@ -555,7 +556,12 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
   constexpr int np = NPS;
   constexpr int G = BT / NPS;                          // rollouts per thread block
   const int sub = threadIdx.x / NPS;                   // which of them this warp belongs to
-  const int n = sc.n, k = threadIdx.x - sub * NPS;
+  const int tid = threadIdx.x - sub * NPS;             // thread within the rollout: warp votes, task loops
+  // Vehicle slot of this thread.  Slots keep the reference's visit order and every shared array is indexed by slot; the
+  // threads follow the slots in increasing order, so scans over threads are scans over slots, but when a rollout has
+  // spare warps the host leaves gaps so that vehicles that start on different lanes — i.e. run different behaviour code
+  // (merging / yielding / plain) — sit in different warps and their code runs side by side instead of in series.
+  const int n = sc.n, k = sc.thread_slot[tid];
   const int cand = blockIdx.y;
   const int64_t ridx = (int64_t)blockIdx.x * G + sub;  // rollout within this launch
   const CandDev cd = cands[cand];
@@ -701,7 +707,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
     int nTasks;
     {
       int total;
-      const int pos = block_exclusive_scan_small<NPS, G == 1, 1>(needMobil ? 1 : 0, inversion, s.scan, total, k, sub);
+      const int pos = block_exclusive_scan_small<NPS, G == 1, 1>(needMobil ? 1 : 0, inversion, s.scan, total, tid, sub);
       nTasks = total & 0xffff;
       ordered = (total >> 16) == 0;
       if (hasLane) {
@@ -725,7 +731,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
     // (u * ceil(2^16 / m)) >> 16 == u / m for u < 64 (error < 64 / 2^16 < 1 / m)
     const unsigned magic = (nT32 == 32 ? 65536u : nT32 == 64 ? 32768u : nT32 == 96 ? 21846u : nT32 == 128 ? 16384u
                             : nT32 == 160 ? 13108u : nT32 == 192 ? 10923u : nT32 == 224 ? 9363u : 8192u);
-    for (int t = k; t < MOBIL_PARTS * nT32; t += NPS) {
+    for (int t = tid; t < MOBIL_PARTS * nT32; t += NPS) {
       const int part = (int)(((unsigned)t >> 5) * magic >> 16), ti = t - part * nT32;
       if (ti >= nTasks) continue;
       const int rec = s.tasks[ti];
@@ -747,7 +753,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
     nDraw = nY + (noise ? 1 : 0) + (mobilDraw ? 1 : 0);
     int totalDraws;
     // nDraw <= 5 yielding candidates + noise + MOBIL draw
-    const uint64_t drawBase = (uint64_t)drawCtr + (uint64_t)block_exclusive_scan_small<NPS, G == 1, kMerge ? 3 : 2>(nDraw, false, s.scan + 8, totalDraws, k, sub);
+    const uint64_t drawBase = (uint64_t)drawCtr + (uint64_t)block_exclusive_scan_small<NPS, G == 1, kMerge ? 3 : 2>(nDraw, false, s.scan + 8, totalDraws, tid, sub);
     drawCtr += (uint32_t)totalDraws;
 
     // ================= plan, part B: actions =================
@@ -1056,19 +1062,19 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
     const double u2 = __shfl_xor_sync(0xffffffffu, utilO, o), c2 = __shfl_xor_sync(0xffffffffu, comfO, o);
     utilO = MCS_MINSD(u2, utilO); comfO = MCS_MINSD(c2, comfO);
   }
-  if ((k & 31) == 0) { s.red[(k >> 5) * 2] = utilO; s.red[(k >> 5) * 2 + 1] = comfO; }
+  if ((tid & 31) == 0) { s.red[(tid >> 5) * 2] = utilO; s.red[(tid >> 5) * 2 + 1] = comfO; }
   sub_sync<NPS, G == 1>(sub);
   // ego history -> per-state terms, one state per thread: fall-back = two consecutive states at rss.aMin (0x10f797),
   // utility term u(v/vd) (0x10f0c4), comfort sample (0x10f1c3)
   const int egoSlot = cd.ego_slot;
   const double egoAMin = F[(size_t)F_RSS_AMIN * np + egoSlot], egoVd = s.vd[egoSlot];
   bool fb = false;
-  for (int t = k; t < nStates; t += NPS) {
+  for (int t = tid; t < nStates; t += NPS) {
     const double a = s.chist[t];
     if (t + 1 < nStates && egoAMin == a && egoAMin == s.chist[t + 1]) fb = true;
   }
   const int anyFallBack = sub_sync_or<NPS, G == 1>(sub, fb ? 1 : 0);
-  for (int t = k; t < nStates; t += NPS) {
+  for (int t = tid; t < nStates; t += NPS) {
     const double a = s.chist[t];
     s.chist[t] = a > 0.0 ? fabs(a) * 0.5 : fabs(a);
     const double ve = s.vhist[t];
@@ -1082,7 +1088,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_k
   {
     const int ns = nStates;
     double* sorted = s.csort;
-    for (int t = k; t < ns; t += NPS) {
+    for (int t = tid; t < ns; t += NPS) {
       const double c = s.chist[t];
       int rank = 0;
 #pragma unroll 1
