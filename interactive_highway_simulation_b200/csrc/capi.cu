@@ -85,6 +85,7 @@ __global__ void combine_groups_kernel(const mcs_group_partial* __restrict__ g, i
 struct DeviceCtx {
   int device = -1;
   int n_sm = 148;
+  size_t smem_per_block = 227 * 1024;     // opt-in dynamic shared memory limit of a block
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   mcs::CandDev* d_cand = nullptr; int cand_cap = 0;
@@ -121,6 +122,7 @@ int get_ctx(int device, DeviceCtx** out) {
     DeviceCtx* c = new DeviceCtx();
     c->device = device;
     cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device);
+    { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess && v > 0) c->smem_per_block = (size_t)v; }
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
@@ -313,6 +315,7 @@ int launch_bt(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& 
   constexpr int G = BT / NPS;       // rollouts per thread block
   static_assert(G >= 1 && G <= 15, "one named barrier per rollout of a block");
   const size_t smem = region * G;
+  if (smem > sc->ctx->smem_per_block) return fail(MCS_ERR_CAPACITY, "horizon too long: one rollout's histories do not fit shared memory");
   grid.x = (grid.x + G - 1) / G;
   CUDA_TRY(cudaFuncSetAttribute(mcs::rollout_kernel<kTraj, kMerge, NPS, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mcs::rollout_kernel<kTraj, kMerge, NPS, BT><<<grid, dim3(BT), smem, sc->ctx->stream>>>(sc->dev, sc->ctx->d_cand, lp, (int)region);
@@ -329,6 +332,10 @@ int launch_np(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& 
   long long threshold = (long long)sc->ctx->n_sm * MCS_SHARE_MIN_PER_SM;
   if (const char* e = getenv("MCS_SHARE_MIN_PER_SM")) threshold = (long long)sc->ctx->n_sm * atoi(e);   // tuning override
   if (rollouts < threshold) return launch_bt<kTraj, kMerge, NPS, NPS>(sc, grid, region, lp);
+  // a long horizon makes the per-rollout region large (four history arrays of steps + 2 doubles): share a block only
+  // while its rollouts fit the SM's shared memory
+  const size_t smem_limit = sc->ctx->smem_per_block;
+  if (region * (BT / NPS) > smem_limit) return launch_bt<kTraj, kMerge, NPS, NPS>(sc, grid, region, lp);
   if constexpr (kMerge && NPS == 64) {
     // The merging instantiation is latency-bound per step: a wave of 512-thread blocks (8 rollouts, 128 registers) takes
     // about as long whether the SM holds one rollout or eight, so a launch that needs a second wave is better off in
@@ -336,7 +343,7 @@ int launch_np(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& 
     // 2.03 -> 1.86 ms; 4 x 1024: 3.90 -> 3.42; but 4 x 256, one wave either way: 1.07 vs 1.74).
     const long long sm = sc->ctx->n_sm;
     const long long waves8 = ((rollouts + 7) / 8 + sm - 1) / sm, waves14 = ((rollouts + 13) / 14 + sm - 1) / sm;
-    if (waves14 * 17 < waves8 * 10) return launch_bt<kTraj, kMerge, NPS, 896>(sc, grid, region, lp);
+    if (waves14 * 17 < waves8 * 10 && region * 14 <= smem_limit) return launch_bt<kTraj, kMerge, NPS, 896>(sc, grid, region, lp);
   }
   return launch_bt<kTraj, kMerge, NPS, BT>(sc, grid, region, lp);
 }

@@ -485,3 +485,26 @@ def test_result_is_independent_of_threads_per_rollout(gpu, monkeypatch, kind):
                 assert got == ref, (kind, threads, count)
     finally:
         ds.close()
+
+
+@pytest.mark.parametrize("kind", ["lane_change", "merging"])
+def test_long_horizon_in_a_large_launch(gpu, kind):
+    """A long horizon makes the per-rollout shared-memory region large; a launch big enough to share thread blocks must
+    fall back to fewer rollouts per block instead of failing, with the same outcome records as a small launch."""
+    rng = random.Random(4242)
+    if kind == "lane_change":
+        s, ego = random_scene(rng, 3, 20, spacing=(3, 40))
+        cand = (abi.Candidate * 1)(abi.Candidate(ego, abi.ACTIONS["keep_lane"], -2, 0))
+    else:
+        s, ego = random_scene(rng, n_agents=40, lane_types=["merging", "main", "main"], ego_behavior="merging", ego_lane=0,
+                              spacing=(3, 40))
+        cand = (abi.Candidate * 1)(abi.Candidate(ego, abi.ACTIONS["left"], -1, 0))
+    sp = abi.SimParam(0.2, 900, 900)
+    ds = gpu.DeviceScene(s.c_corridors(), s.c_agents())
+    try:
+        small = bytes(ds.rollouts_range(cand, sp, 5, 0, 2))
+        big = bytes(ds.rollouts_range(cand, sp, 5, 0, 1500))
+        assert big[:128] == small
+        assert any(big[i * 64:(i + 1) * 64] != big[:64] for i in range(1, 1500))
+    finally:
+        ds.close()
