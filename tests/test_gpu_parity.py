@@ -343,7 +343,8 @@ def test_eight_lanes_and_zero_steps(gpu, oracle):
     check_against_oracle(gpu, oracle, s, ego, 0.3, 1, 1, 6, 2, "1step", traj_rollouts=1, actions=("acc",))
 
 
-@pytest.mark.parametrize("block", range(6))
+# MCS_FUZZ_BLOCKS=N widens the sweep to N x 10 scenes for an occasional long run (default 6: 60 scenes)
+@pytest.mark.parametrize("block", range(int(__import__("os").environ.get("MCS_FUZZ_BLOCKS", "6"))))
 def test_many_random_scenes_against_oracle(gpu, oracle, block):
     """Breadth: 60 more random scenes (lane change, merging, exit; sparse to dense) — statuses only."""
     for sc in range(10):
