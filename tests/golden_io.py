@@ -1,5 +1,6 @@
 """Loading of the tests/golden fixtures (written by tests/golden/make_golden.py from the reference binary)."""
 import glob
+import gzip
 import json
 import os
 
@@ -9,9 +10,11 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def load_all(kind=None):
+    """*.json (make_golden.py) and large_*.json.gz (make_large_golden.py: BASELINE-size scenes)."""
     out = []
-    for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.json"))):
-        with open(p) as f:
+    paths = sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.json"))) + sorted(glob.glob(os.path.join(GOLDEN_DIR, "large_*.json.gz")))
+    for p in paths:
+        with (gzip.open(p, "rt") if p.endswith(".gz") else open(p)) as f:
             c = json.load(f)
         if kind is None or c["kind"] == kind:
             out.append(c)
