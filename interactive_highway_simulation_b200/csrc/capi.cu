@@ -281,12 +281,17 @@ int upload_scene(mcs_scene* sc, int pad) {
 // Threads per rollout.  One per vehicle slot is the minimum; a small launch (few rollouts per SM) is latency-bound — each
 // rollout walks its barriers alone — and the phases that are task-parallel inside a rollout (the seven MOBIL sub-tasks
 // per undecided vehicle, the outcome statistics) finish sooner on more threads, so the row length doubles while the
-// launch stays under MCS_WIDE_WARPS_PER_SM resident warps per SM (scripts/kernel_time.py sweeps, 24 vehicles x 5
-// candidates x 160 rollouts: 32 threads 0.66 ms, 64: 0.50, 128: 0.44, 256: 0.55).  The result does not depend on it.
+// launch still fits the SMs in one wave — 24 resident warps per SM for the 80-register lane-change instantiation, 16 for
+// the 128-register merging one (scripts/kernel_time.py / threads_sweep.py, 24 vehicles x 5 candidates x 160 rollouts:
+// 32 threads 0.66 ms, 64: 0.50, 128: 0.44, 256: 0.55; merging, 20 vehicles x 4 gaps x 160 rollouts: 32 threads 0.87 ms,
+// 64: 0.78, 128: 1.05).  The result does not depend on it.
 #ifndef MCS_WIDE_WARPS_PER_SM
 #define MCS_WIDE_WARPS_PER_SM 24
 #endif
-int rollout_threads(const mcs_scene* sc, long long rollouts, bool traj) {
+#ifndef MCS_WIDE_WARPS_PER_SM_MERGE
+#define MCS_WIDE_WARPS_PER_SM_MERGE 16
+#endif
+int rollout_threads(const mcs_scene* sc, long long rollouts, bool traj, bool merge) {
   int t = sc->host.n_pad;
   if (const char* e = getenv("MCS_ROLLOUT_THREADS")) {        // tuning / test override
     const int want = atoi(e);
@@ -294,18 +299,19 @@ int rollout_threads(const mcs_scene* sc, long long rollouts, bool traj) {
     return t;
   }
   if (traj) return t;
-  const long long budget = (long long)MCS_WIDE_WARPS_PER_SM * sc->ctx->n_sm;
+  const long long budget = (long long)(merge ? MCS_WIDE_WARPS_PER_SM_MERGE : MCS_WIDE_WARPS_PER_SM) * sc->ctx->n_sm;
   while (t < 256 && rollouts * (2 * t / 32) <= budget) t *= 2;
   return t;
 }
 
-// Threads per block.  A 256-vehicle rollout owns a 256-thread block.  Smaller rollouts either own a block too (small
-// launches: every rollout gets an SM to itself, nothing to share) or share one and start every step together
-// (rollout_kernel.cuh) — 8 per block; the merging instantiation, the instruction-fetch-bound one, in 512-thread blocks
-// (measured, 4 x 512 rollouts x 40 vehicles: 128 threads 3.42 ms, 256: 2.73 ms, 512: 2.48 ms).  Named barriers limit a
-// block to 15 rollouts.
+// Threads per block.  A rollout of 256 threads owns a 256-thread block.  Narrower rollouts share one and start every
+// step together (rollout_kernel.cuh) — 256 threads per block; the merging instantiation, the instruction-fetch-bound one,
+// 512 (measured, 4 x 512 rollouts x 40 vehicles: 128 threads 3.42 ms, 256: 2.73 ms, 512: 2.48 ms).  Named barriers limit
+// a block to 15 rollouts.  Small launches do not get here with narrow rollouts any more (rollout_threads widens them),
+// so sharing has no lower bound by default: scripts/share_sweep.py — it never loses, and wins up to 27 % where the old
+// bound of 4 rollouts per SM kept 480 128-thread rollouts in blocks of their own (0.86 -> 0.63 ms).
 #ifndef MCS_SHARE_MIN_PER_SM
-#define MCS_SHARE_MIN_PER_SM 4   // rollouts per SM from which sharing a block wins (scripts/kernel_time.py sweep)
+#define MCS_SHARE_MIN_PER_SM 0   // rollouts per SM below which a narrow rollout still owns its block (tuning knob)
 #endif
 template <bool kMerge, int NPS>
 struct BlockThreads { static constexpr int value = NPS == 256 ? 256 : (kMerge && NPS >= 64 ? 512 : 256); };
@@ -368,7 +374,7 @@ int launch_rollouts(mcs_scene* sc, int n_cand, const mcs_sim_param* sp, uint64_t
   lp.dt = sp->dt; lp.steps = sp->steps; lp.min_steps = sp->min_steps;
   lp.seed = seed; lp.first = first; lp.count = count; lp.n_cand = n_cand;
   lp.status = d_status; lp.traj = d_traj; lp.traj_n = d_traj_n; lp.vehicle_steps = d_counter;
-  int rc = upload_scene(sc, rollout_threads(sc, (long long)count * n_cand, d_traj != nullptr));
+  int rc = upload_scene(sc, rollout_threads(sc, (long long)count * n_cand, d_traj != nullptr, merge != 0));
   if (rc != MCS_OK) return rc;
   size_t smem = (rollout_smem_bytes(sc->dev.n_pad, sp->steps) + 15) & ~(size_t)15;   // one rollout's region
   dim3 grid((unsigned)count, (unsigned)n_cand);

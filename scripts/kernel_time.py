@@ -43,6 +43,15 @@ for i in range(4):
     ms, vs = sc.rollouts_device(cands, sp, 77, 0, 4096); best = min(best, ms)
 print("lane-change decision x 4096 rollouts: 5 x 4096 x 24 vehicles %.3f ms (%d vehicle-steps)" % (best, vs))
 sc.close()
+corridors, agents, ego, gaps = synthetic.merging_scene(20, 0)
+sc = backend.DeviceScene(corridors, agents)
+cands = (abi.Candidate * len(gaps))(*[abi.Candidate(ego, abi.ACTIONS["left"], g, 0) for g in gaps])
+sp = abi.SimParam(0.3, 40, 30)
+best = 1e9
+for i in range(4):
+    ms, vs = sc.rollouts_device(cands, sp, 55, 0, 160); best = min(best, ms)
+print("reference-size merging decision: %d x 160 rollouts x 20 vehicles %.3f ms (%d vehicle-steps)" % (len(gaps), best, vs))
+sc.close()
 print("sweep of decision sizes (merging scene, 4 candidates):")
 corridors, agents, ego, gaps = synthetic.merging_scene(40, 0)
 sc = backend.DeviceScene(corridors, agents)
