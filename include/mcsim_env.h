@@ -1,0 +1,96 @@
+/* mcsim_env.h — C ABI of the OUTER environment's lane match, per-lane ordering, leader / follower / side-neighbour search
+ * and Frenet conversion (libmcsim_b200.so, csrc/env_capi.cu + env_kernels.cuh).
+ *
+ * Replaces, for all vehicles of a scene (and for a batch of scenes) in one launch, what the reference's Python does
+ * per vehicle with shapely (SURVEY.md §8 rows a9/a10 Python twins, a13, a14):
+ *   environment.py:40-44    Map.corridor_match            first corridor (dict order) whose polygon holds the point
+ *   environment.py:85-101   match_agents_on_corridor      lane of every vehicle; unmatched vehicles leave the scene
+ *   environment.py:135-143  agents_in_corridor_by_arc_length   per-lane stable sort on the centre-line arc length
+ *   environment.py:166-195  front_agent / following_agent
+ *   environment.py:197-251  neighbor_around_agent         the 8 side neighbours, on the +100 m extended centre line
+ *   environment.py:145-156  sorted_agents_on_corridor_within_range_of_vehicle (from arc_on_lane + lane_order)
+ *   type.py:297-317         LineSimplified.signed_distance / to_frenet_frame on extend_line_both_sides(center, 1000)
+ *   utility.py:88-98        step_along_path                (mce_step_along_path)
+ *
+ * Plain pointers and sizes; caller owns all buffers; HOST buffers in, HOST buffers out (copies inside).  No CPU
+ * fallback: without a CUDA device every compute entry fails with MCE_ERR_CUDA.
+ * The keys of the per-lane vectors stay resident in the handle after mce_env_match, so that later queries for vehicles
+ * that have moved since (the reference plans and moves its vehicles one after the other against the arc lengths of the
+ * last match, environment.py:316-323) are answered against the same stale keys (mce_env_neighbors).
+ */
+#ifndef MCSIM_ENV_H
+#define MCSIM_ENV_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { MCE_OK = 0, MCE_ERR_ARG = -1, MCE_ERR_CUDA = -2, MCE_ERR_CAPACITY = -3 };
+
+#define MCE_MAX_LANES 8
+#define MCE_MAX_POINTS 16   /* points per polyline of a corridor          */
+#define MCE_MAX_AGENTS 1024 /* vehicles per scene                         */
+#define MCE_NEIGHBORS 10    /* Neighbor(...) ctor order, agent.py:203-213 */
+
+/* index into the neighbour tables, the order of the reference's Neighbor constructor */
+enum { MCE_LEFT_FF = 0, MCE_LEFT_F, MCE_LEFT_B, MCE_LEFT_BB, MCE_FRONT, MCE_BACK, MCE_RIGHT_FF, MCE_RIGHT_F, MCE_RIGHT_B,
+       MCE_RIGHT_BB };
+
+/* type.py:140-169 Corridor(idx, t, left, right, center, v_limit) + set_left_and_right_corridor_id.
+ * left_index / right_index: position of the neighbour corridor in the array passed to mce_map_create, -1 = None. */
+typedef struct mce_corridor {
+  int32_t id, left_index, right_index;
+  int32_t n_left, n_right, n_center;
+  double left[MCE_MAX_POINTS][2], right[MCE_MAX_POINTS][2], center[MCE_MAX_POINTS][2];
+} mce_corridor;
+
+typedef struct mce_map mce_map; /* opaque: corridors of one map resident on a device + per-device work buffers */
+
+const char* mce_last_error(void);
+
+/* Map ctor environment.py:21-32 (corridor order = dict insertion order = array order) plus what the Corridor ctor
+ * derives: polygon border (left + reversed right, type.py:160-164), centerExtended (extend_line(center, 100),
+ * type.py:154, utility.py:111-115), and the Frenet reference line of mcs_wrapper.py:42,109,211
+ * (extend_line_both_sides(center, 1000) utility.py:118-126, simplified with tolerance 0.05, type.py:257-272). */
+int mce_map_create(const mce_corridor* corridors, int n_corridors, int device, mce_map** out);
+int mce_map_destroy(mce_map* map);
+
+/* match_agents_on_corridor + every neighbour query of one environment state, for n_scenes scenes of n_agents slots
+ * each on the same map (x, y: [n_scenes][n_agents]; a slot with NaN x is empty).
+ *   lane_out      [n_scenes][n_agents]                 corridor index, -1 = not on any corridor (vehicle removed)
+ *   arc_out       [n_scenes][n_agents]                 arc length on the own lane's centre line
+ *   lane_order_out[n_scenes][n_agents]                 slots grouped by lane (lane 0 first), each lane sorted by arc
+ *                                                       length, ties in slot order (stable sort); -1 padding at the end
+ *   lane_start_out[n_scenes][MCE_MAX_LANES + 1]        offsets of the lanes inside lane_order_out
+ *   arc_on_lane_out [n_scenes][n_corridors][n_agents]  centre-line arc length of every vehicle on every corridor (may be NULL)
+ *   nb_index_out  [n_scenes][MCE_NEIGHBORS][n_agents]  slot of the neighbour, -1 = None
+ *   nb_dis_out    [n_scenes][MCE_NEIGHBORS][n_agents]  IdmMatch.dis (key - own arc on that lane's line)
+ * Any output pointer may be NULL. */
+int mce_env_match(mce_map* map, const double* x, const double* y, int n_agents, int n_scenes, int32_t* lane_out,
+                  double* arc_out, int32_t* lane_order_out, int32_t* lane_start_out, double* arc_on_lane_out,
+                  int32_t* nb_index_out, double* nb_dis_out);
+
+/* front_agent / following_agent / neighbor_around_agent for n_queries vehicles (scene[i], slot[i]) at their CURRENT
+ * positions (qx, qy) against the lanes and keys of the last mce_env_match on this map handle.
+ *   nb_index_out [MCE_NEIGHBORS][n_queries], nb_dis_out likewise. */
+int mce_env_neighbors(mce_map* map, const int32_t* scene, const int32_t* slot, const double* qx, const double* qy,
+                      int n_queries, int32_t* nb_index_out, double* nb_dis_out);
+
+/* LineSimplified(extend_line_both_sides(corridors[ref_lane].center, 1000)).to_frenet_frame([x, y]) for n points. */
+int mce_frenet(mce_map* map, int ref_lane, const double* x, const double* y, int n, double* s_out, double* d_out);
+
+/* utility.py:88-98 step_along_path on the centre line of corridors[ref_lane[i]] (DecoupledAction.ref_path is always a
+ * corridor's centerSimplified, behaviors.py): new x, y, v, yaw of n vehicles.  cos / sin of the segment yaws are
+ * evaluated once on the host at mce_map_create. */
+int mce_step_along_path(mce_map* map, const int32_t* ref_lane, const double* x, const double* y, const double* v,
+                        const double* ax, const double* vy, double dt, int n, double* x_out, double* y_out,
+                        double* v_out, double* yaw_out);
+
+/* average duration (ms, CUDA events on the launching stream) of the kernels of the last mce_env_match call:
+ * out[0] = match + order kernel, out[1] = neighbour kernel */
+int mce_last_kernel_ms(mce_map* map, float* out2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,289 @@
+"""TEST INFRASTRUCTURE ONLY (imported by tests/ and __graft_entry__.smoke(); nothing under the package may import it).
+
+CPU restatement, in plain Python floats (IEEE double, no fused multiply-add — the arithmetic the CUDA kernels of
+csrc/env_kernels.cuh are compiled to with -fmad=false), of the OUTER environment's geometry path of the reference:
+
+    environment.py:40-44    Map.corridor_match
+    environment.py:85-101   Environment.match_agents_on_corridor
+    environment.py:135-143  agents_in_corridor_by_arc_length
+    environment.py:145-156  sorted_agents_on_corridor_within_range_of_vehicle
+    environment.py:166-195  front_agent / following_agent
+    environment.py:197-251  neighbor_around_agent
+    type.py:255-317         LineSimplified (project, get_point_at_length, get_yaw_at_length, is_left_of,
+                            signed_distance, to_frenet_frame)
+    utility.py:83-98        offset_point, step_along_path
+    utility.py:111-126      extend_line, extend_line_both_sides
+
+The geometry the reference takes from shapely (LineString.project / distance / simplify, Point.within) is a third-party
+dependency absent from /root/reference and from this image (shapely, any version — the reference pins none, README.md);
+its published algorithms are restated here: nearest point of each segment, first segment wins ties; even-odd ray
+crossing with boundary points outside; Douglas-Peucker.
+
+Parity pin: tests/golden/env_*.json.gz are written by the reference's OWN environment.py / type.py / mcs_wrapper.py
+(tests/golden/make_env_golden.py; shapely replaced by tests/refshim): lanes, per-lane orders and neighbour ids are
+compared exactly, arc lengths / distances / Frenet coordinates within 1e-9 (the reference evaluates hypot() and
+arctan2/sin where this file evaluates sqrt(dx*dx+dy*dy) and a cross product; see side_of()).
+"""
+import math
+
+NEIGHBORS = 10
+LEFT_FF, LEFT_F, LEFT_B, LEFT_BB, FRONT, BACK, RIGHT_FF, RIGHT_F, RIGHT_B, RIGHT_BB = range(10)
+
+
+# ---- shapely's primitives -------------------------------------------------------------------------------------------
+
+def seg_point(ax, ay, bx, by, px, py):
+    """(distance, t, squared segment length) of the point of segment AB nearest to P"""
+    dx, dy = bx - ax, by - ay
+    d2 = dx * dx + dy * dy
+    if d2 == 0.0:
+        t = 0.0
+    else:
+        t = ((px - ax) * dx + (py - ay) * dy) / d2
+        t = t if t < 1.0 else 1.0
+        t = t if t > 0.0 else 0.0
+    qx, qy = ax + t * dx, ay + t * dy
+    ex, ey = px - qx, py - qy
+    return math.sqrt(ex * ex + ey * ey), t, d2
+
+
+def project_and_distance(line, px, py):
+    """LineString.project + LineString.distance: arc length of the nearest point (first segment wins ties), distance"""
+    best, best_s, run = None, 0.0, 0.0
+    for (ax, ay), (bx, by) in zip(line, line[1:]):
+        d, t, d2 = seg_point(ax, ay, bx, by, px, py)
+        seg = math.sqrt(d2)
+        if best is None or d < best:
+            best, best_s = d, run + t * seg
+        run = run + seg
+    return best_s, best
+
+
+def line_length(line):
+    run = 0.0
+    for (ax, ay), (bx, by) in zip(line, line[1:]):
+        dx, dy = bx - ax, by - ay
+        run = run + math.sqrt(dx * dx + dy * dy)
+    return run
+
+
+def within(shell, px, py):
+    """Point.within(Polygon): even-odd crossing, a point on the boundary is outside"""
+    inside = False
+    n = len(shell)
+    for i in range(n):
+        (x1, y1), (x2, y2) = shell[i], shell[(i + 1) % n]
+        if seg_point(x1, y1, x2, y2, px, py)[0] == 0.0:
+            return False
+        if (y1 > py) != (y2 > py) and px < (x2 - x1) * (py - y1) / (y2 - y1) + x1:
+            inside = not inside
+    return inside
+
+
+def simplify(pts, tol):
+    """LineString.simplify (Douglas-Peucker)"""
+    if len(pts) < 3:
+        return list(pts)
+    a, b = pts[0], pts[-1]
+    imax, dmax = 0, -1.0
+    for i in range(1, len(pts) - 1):
+        d = seg_point(a[0], a[1], b[0], b[1], pts[i][0], pts[i][1])[0]
+        if d > dmax:
+            imax, dmax = i, d
+    if dmax > tol:
+        return simplify(pts[:imax + 1], tol)[:-1] + simplify(pts[imax:], tol)
+    return [a, b]
+
+
+# ---- utility.py / type.py -------------------------------------------------------------------------------------------
+
+def _dist(p, q):                                            # utility.py:8-9
+    dx, dy = p[0] - q[0], p[1] - q[1]
+    return math.sqrt(dx * dx + dy * dy)
+
+
+def extend_line(line, d):                                   # utility.py:111-115
+    k = d / _dist(line[-1], line[-2])
+    return [tuple(p) for p in line] + [(line[-1][0] + k * (line[-1][0] - line[-2][0]), line[-1][1] + k * (line[-1][1] - line[-2][1]))]
+
+
+def extend_line_both_sides(line, d):                        # utility.py:118-126
+    kf = d / _dist(line[0], line[1])
+    kb = d / _dist(line[-1], line[-2])
+    f = (line[0][0] + kf * (line[0][0] - line[1][0]), line[0][1] + kf * (line[0][1] - line[1][1]))
+    b = (line[-1][0] + kb * (line[-1][0] - line[-2][0]), line[-1][1] + kb * (line[-1][1] - line[-2][1]))
+    return [f] + [tuple(p) for p in line] + [b]
+
+
+class LineSimplified:
+    """type.py:255-317.  yaw_list is kept as segment directions: the reference compares angles
+    (sin(arctan2(p - foot) - yaw) > 0), this file and the kernels take the sign of the cross product of the segment
+    direction with (p - foot) — the same sign unless p lies on the line to rounding, where the reference's own answer
+    is decided by the last bit of arctan2."""
+
+    def __init__(self, path):
+        self.path = [(float(p[0]), float(p[1])) for p in path]
+        self.line = simplify(self.path, 0.05)
+        self.path_length = line_length(self.line)
+        self.dis_list = [0.0]
+        run = 0.0
+        for p, q in zip(self.path, self.path[1:]):
+            run = run + _dist(p, q)
+            self.dis_list.append(run)
+        seg0 = (self.path[1][0] - self.path[0][0], self.path[1][1] - self.path[0][1])
+        self.dir_list = [seg0] + [(q[0] - p[0], q[1] - p[1]) for p, q in zip(self.path, self.path[1:])]
+        self.yaw_list = [math.atan2(d[1], d[0]) for d in self.dir_list]
+
+    def _search(self, length):                               # np.searchsorted(dis_list, length), side="left"
+        i = 0
+        while i < len(self.dis_list) and self.dis_list[i] < length:
+            i += 1
+        return i
+
+    def get_yaw_index(self, length):                         # type.py:276-280
+        i = self._search(length)
+        return i if i < len(self.yaw_list) else len(self.yaw_list) - 1
+
+    def get_point_at_length(self, length):                   # type.py:282-295
+        P = self.path
+        if length == 0:
+            return P[0]
+        if length < self.path_length:
+            i = self._search(length)
+            seg = self.dis_list[i] - self.dis_list[i - 1]
+            r = (self.dis_list[i] - length) / seg
+            return (P[i][0] - r * (P[i][0] - P[i - 1][0]), P[i][1] - r * (P[i][1] - P[i - 1][1]))
+        end = self.dis_list[-1] - self.dis_list[-2]
+        r = (length - self.path_length) / end
+        return (P[-1][0] + r * (P[-1][0] - P[-2][0]), P[-1][1] + r * (P[-1][1] - P[-2][1]))
+
+    def side_of(self, s, px, py):
+        """+1 left / -1 right of the line at arc length s (type.py:297-315 without the angles)"""
+        fx, fy = self.get_point_at_length(s)
+        dx, dy = self.dir_list[self.get_yaw_index(s)]
+        return 1 if dx * (py - fy) - dy * (px - fx) > 0.0 else -1
+
+    def to_frenet_frame(self, px, py):                       # type.py:307-317
+        s, dis = project_and_distance(self.line, px, py)
+        if dis <= 0.0:
+            return s, 0.0
+        return s, self.side_of(s, px, py) * dis
+
+
+class PreparedMap:
+    """What Map / Corridor constructors derive (environment.py:21-32, type.py:140-169) for corridors given as dicts
+    {id, left, right, center, left_index, right_index} in dict-insertion order."""
+
+    def __init__(self, corridors):
+        self.n = len(corridors)
+        self.left = [c["left_index"] for c in corridors]
+        self.right = [c["right_index"] for c in corridors]
+        self.center = [[(float(p[0]), float(p[1])) for p in c["center"]] for c in corridors]
+        self.center_ext = [extend_line(c, 100) for c in self.center]                  # type.py:154
+        self.shell = []
+        for c in corridors:                                                           # type.py:160-164
+            pts = [(float(p[0]), float(p[1])) for p in c["left"]] + [(float(p[0]), float(p[1])) for p in reversed(c["right"])]
+            if pts[0] == pts[-1]:
+                pts = pts[:-1]
+            self.shell.append(pts)
+        self.ref = [LineSimplified(extend_line_both_sides(c, 1000)) for c in self.center]   # mcs_wrapper.py:42,109,211
+        self.center_simplified = [LineSimplified(c) for c in self.center]             # type.py:153
+
+
+def match(pm, xs, ys):
+    """environment.py:85-101 + 135-143 for one scene.  -> (lane[n], arc[n], lane_order[n], lane_start[L+1])"""
+    n = len(xs)
+    lane, arc = [-1] * n, [0.0] * n
+    for i in range(n):
+        if xs[i] != xs[i]:
+            continue
+        for c in range(pm.n):                                # corridor_match: first corridor in dict order
+            if within(pm.shell[c], xs[i], ys[i]):
+                lane[i] = c
+                arc[i] = project_and_distance(pm.center[c], xs[i], ys[i])[0]
+                break
+    order, start = [], [0]
+    for c in range(pm.n):
+        members = [i for i in range(n) if lane[i] == c]
+        members.sort(key=lambda i: arc[i])                   # list.sort is stable: ties stay in dict order
+        order += members
+        start.append(len(order))
+    order += [-1] * (n - len(order))
+    start += [start[-1]] * (9 - len(start))
+    return lane, arc, order, start
+
+
+def arc_on_lanes(pm, xs, ys):
+    return [[project_and_distance(pm.center[c], x, y)[0] if x == x else 0.0 for x, y in zip(xs, ys)] for c in range(pm.n)]
+
+
+def neighbors(pm, lane, arc, order, start, i, qx, qy):
+    """front_agent, following_agent, neighbor_around_agent (environment.py:166-251) of slot i standing at (qx, qy),
+    against the per-lane vectors of the last match.  -> ([10 slots or -1], [10 dis])"""
+    idx, dis = [-1] * NEIGHBORS, [0.0] * NEIGHBORS
+    c = lane[i]
+    if c < 0:
+        return idx, dis
+
+    def lane_list(cc):
+        return [(arc[j], j) for j in order[start[cc]:start[cc + 1]]]
+
+    e = project_and_distance(pm.center[c], qx, qy)[0]
+    own = lane_list(c)
+    for key, j in own:                                       # :166-180
+        if key > e:
+            idx[FRONT], dis[FRONT] = j, key - e
+            break
+    for key, j in reversed(own):                             # :182-195
+        if key < e:
+            idx[BACK], dis[BACK] = j, key - e
+            break
+    for side, ff, f, b, bb in ((pm.left[c], LEFT_FF, LEFT_F, LEFT_B, LEFT_BB), (pm.right[c], RIGHT_FF, RIGHT_F, RIGHT_B, RIGHT_BB)):
+        if side < 0:
+            continue
+        lst = lane_list(side)
+        es = project_and_distance(pm.center_ext[side], qx, qy)[0]
+        for key, j in lst:                                   # :213-219
+            if idx[f] < 0 and key >= es:
+                idx[f], dis[f] = j, key - es
+                continue
+            if idx[f] >= 0 and key > dis[f] + es:
+                idx[ff], dis[ff] = j, key - es
+                break
+        for key, j in reversed(lst):                         # :220-226
+            if idx[b] < 0 and key < es:
+                idx[b], dis[b] = j, key - es
+                continue
+            if idx[b] >= 0 and key < dis[b] + es:
+                idx[bb], dis[bb] = j, key - es
+                break
+    return idx, dis
+
+
+def within_range(pm, lane, xs, ys, corridor, ego, max_dis):
+    """environment.py:145-156: slots of `corridor` within max_dis (arc length) of slot `ego`, sorted by arc length"""
+    e = project_and_distance(pm.center[corridor], xs[ego], ys[ego])[0]
+    out = []
+    for j in range(len(xs)):
+        if lane[j] == corridor:
+            a = project_and_distance(pm.center[corridor], xs[j], ys[j])[0]
+            if abs(a - e) <= max_dis:
+                out.append((a, j))
+    out.sort(key=lambda t: t[0])
+    return [j for _, j in out]
+
+
+def step_along_path(pm, ref_lane, x, y, v, ax, vy, dt):
+    """utility.py:88-98 on corridors[ref_lane].centerSimplified"""
+    ls = pm.center_simplified[ref_lane]
+    s, dis = project_and_distance(ls.line, x, y)
+    sign = 1 if (dis > 0.0 and ls.side_of(s, x, y) > 0) else -1       # is_left_of: on the line -> False
+    d = sign * dis
+    s_new = s + v * dt
+    d_new = d + vy * dt
+    v_new = v + ax * dt
+    v_new = v_new if v_new > 0 else 0.0
+    k = ls.get_yaw_index(s_new)
+    yaw = ls.yaw_list[k]
+    px, py = ls.get_point_at_length(s_new)
+    return px - d_new * math.sin(yaw), py + d_new * math.cos(yaw), v_new, yaw

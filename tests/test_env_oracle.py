@@ -1,0 +1,89 @@
+"""oracle/env_oracle.py against the records written by the reference's own environment.py / type.py / utility.py
+(tests/golden/make_env_golden.py): lanes, per-lane orders and neighbour ids exact, arc lengths / distances / Frenet
+coordinates / stepped positions within 1e-9 (the reference evaluates hypot and arctan2/sin, the oracle sqrt and a cross
+product)."""
+import math
+
+import pytest
+
+from env_cases import STATES, prepared, slots, TOL
+from oracle import env_oracle as eo
+
+
+@pytest.mark.parametrize("rec", STATES, ids=[r["tag"] for r in STATES])
+def test_match_and_lane_vectors(rec):
+    pm, ids, xs, ys = prepared(rec)
+    lane, arc, order, start = eo.match(pm, xs, ys)
+    cid = [c["id"] for c in rec["corridors"]]
+    for i, a in enumerate(ids):
+        want = rec["lane"][str(a)]
+        assert (cid[lane[i]] if lane[i] >= 0 else None) == want, (a, lane[i], want)
+    for c, k in enumerate(cid):
+        want = rec["lane_vectors"][str(k)]
+        got = order[start[c]:start[c + 1]]
+        assert [ids[j] for j in got] == [w[1] for w in want], k
+        for j, w in zip(got, want):
+            assert abs(arc[j] - w[0]) <= TOL
+
+
+@pytest.mark.parametrize("rec", STATES, ids=[r["tag"] for r in STATES])
+def test_neighbors_at_match_time_and_after_moves(rec):
+    pm, ids, xs, ys = prepared(rec)
+    lane, arc, order, start = eo.match(pm, xs, ys)
+    slot = slots(ids)
+
+    def check(table, qx, qy):
+        for a, want in table.items():
+            i = slot[int(a)]
+            idx, dis = eo.neighbors(pm, lane, arc, order, start, i, qx[i], qy[i])
+            for k in range(10):
+                if want[k] is None:
+                    assert idx[k] == -1, (a, k, ids[idx[k]])
+                else:
+                    assert idx[k] >= 0 and ids[idx[k]] == want[k][0], (a, k, idx[k], want[k])
+                    assert abs(dis[k] - want[k][1]) <= TOL
+
+    check(rec["neighbors"], xs, ys)
+    qx, qy = list(xs), list(ys)
+    for m in rec["moved"]:
+        qx[slot[m["id"]]], qy[slot[m["id"]]] = m["x"], m["y"]
+    check(rec["neighbors_after_move"], qx, qy)
+
+
+@pytest.mark.parametrize("rec", STATES, ids=[r["tag"] for r in STATES])
+def test_within_range_frenet_and_step(rec):
+    pm, ids, xs, ys = prepared(rec)
+    lane, arc, order, start = eo.match(pm, xs, ys)
+    slot = slots(ids)
+    cpos = {c["id"]: k for k, c in enumerate(rec["corridors"])}
+    for w in rec["within_range"]:
+        got = eo.within_range(pm, lane, xs, ys, cpos[w["corridor"]], slot[w["ego"]], w["max_dis"])
+        assert [ids[j] for j in got] == w["ids"]
+    for c, rows in rec["frenet"].items():
+        for a, (s, d) in zip(rec["frenet_ids"], rows):
+            gs, gd = pm.ref[cpos[int(c)]].to_frenet_frame(xs[slot[a]], ys[slot[a]])
+            assert abs(gs - s) <= TOL and abs(gd - d) <= TOL, (c, a, gs, s, gd, d)
+    by_id = {a["id"]: a for a in rec["agents"]}
+    for st in rec["steps"]:
+        a = by_id[st["id"]]
+        x, y, v, yaw = eo.step_along_path(pm, cpos[st["lane"]], a["x"], a["y"], a["v"], st["ax"], st["vy"], st["dt"])
+        for g, w in zip((x, y, v, yaw), st["out"]):
+            assert abs(g - w) <= TOL
+
+
+def test_cross_product_sign_equals_the_reference_angle_test():
+    """type.py:297-305 decides the side with sin(arctan2(p - foot) - yaw) > 0; the oracle and the kernels with a cross
+    product.  Same answer on a bent polyline for points off the line."""
+    import random
+    rng = random.Random(5)
+    path = [(0.0, 0.0), (50.0, 2.0), (120.0, -6.0), (200.0, 30.0)]
+    ls = eo.LineSimplified(path)
+    for _ in range(4000):
+        px, py = rng.uniform(-40, 240), rng.uniform(-40, 60)
+        s, dis = eo.project_and_distance(ls.line, px, py)
+        if dis < 1e-6:
+            continue
+        fx, fy = ls.get_point_at_length(s)
+        yaw = ls.yaw_list[ls.get_yaw_index(s)]
+        ref = 1 if math.sin(math.atan2(py - fy, px - fx) - yaw) > 0 else -1
+        assert ls.side_of(s, px, py) == ref
