@@ -79,6 +79,10 @@ int mce_env_neighbors(mce_map* map, const int32_t* scene, const int32_t* slot, c
 /* LineSimplified(extend_line_both_sides(corridors[ref_lane].center, 1000)).to_frenet_frame([x, y]) for n points. */
 int mce_frenet(mce_map* map, int ref_lane, const double* x, const double* y, int n, double* s_out, double* d_out);
 
+/* corridors[lane].centerLine.project(Point([x, y])) for n points (environment.py:139,149-152,160-161): arc length and
+ * distance to the (unextended, unsimplified) centre line. */
+int mce_project_center(mce_map* map, int lane, const double* x, const double* y, int n, double* s_out, double* dist_out);
+
 /* utility.py:88-98 step_along_path on the centre line of corridors[ref_lane[i]] (DecoupledAction.ref_path is always a
  * corridor's centerSimplified, behaviors.py): new x, y, v, yaw of n vehicles.  cos / sin of the segment yaws are
  * evaluated once on the host at mce_map_create. */

@@ -1,0 +1,354 @@
+// C ABI of the outer-environment geometry path (include/mcsim_env.h).  CUDA runtime only.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "env_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_env_err;
+int efail(int code, const std::string& msg) { g_env_err = msg; return code; }
+#define ENV_TRY(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (expr);                                                                            \
+    if (e_ != cudaSuccess) return efail(MCE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+typedef std::pair<double, double> Pt;
+
+double dist(const Pt& p, const Pt& q) {                       // utility.py:8-9
+  const double dx = p.first - q.first, dy = p.second - q.second;
+  return std::sqrt(dx * dx + dy * dy);
+}
+
+double seg_point_dist(const Pt& a, const Pt& b, const Pt& p) {
+  const double dx = b.first - a.first, dy = b.second - a.second;
+  const double d2 = dx * dx + dy * dy;
+  double t = 0.0;
+  if (d2 != 0.0) {
+    t = ((p.first - a.first) * dx + (p.second - a.second) * dy) / d2;
+    t = t < 1.0 ? t : 1.0;
+    t = t > 0.0 ? t : 0.0;
+  }
+  const double qx = a.first + t * dx, qy = a.second + t * dy;
+  const double ex = p.first - qx, ey = p.second - qy;
+  return std::sqrt(ex * ex + ey * ey);
+}
+
+// LineString.simplify(0.05) — Douglas-Peucker (type.py:261-262)
+std::vector<Pt> simplify(const std::vector<Pt>& pts, double tol) {
+  if (pts.size() < 3) return pts;
+  size_t imax = 0;
+  double dmax = -1.0;
+  for (size_t i = 1; i + 1 < pts.size(); ++i) {
+    const double d = seg_point_dist(pts.front(), pts.back(), pts[i]);
+    if (d > dmax) { imax = i; dmax = d; }
+  }
+  if (dmax > tol) {
+    std::vector<Pt> a = simplify(std::vector<Pt>(pts.begin(), pts.begin() + imax + 1), tol);
+    std::vector<Pt> b = simplify(std::vector<Pt>(pts.begin() + imax, pts.end()), tol);
+    a.pop_back();
+    a.insert(a.end(), b.begin(), b.end());
+    return a;
+  }
+  return {pts.front(), pts.back()};
+}
+
+double line_length(const std::vector<Pt>& l) {
+  double run = 0.0;
+  for (size_t i = 0; i + 1 < l.size(); ++i) run = run + dist(l[i + 1], l[i]);
+  return run;
+}
+
+Pt extend(const Pt& last, const Pt& prev, double d) {         // utility.py:113 / 120-121
+  const double k = d / dist(last, prev);
+  return Pt(last.first + k * (last.first - prev.first), last.second + k * (last.second - prev.second));
+}
+
+}  // namespace
+
+struct mce_map {
+  int device = 0;
+  int n_lanes = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  mce::EnvMapHead* d_head = nullptr;
+  mce::EnvMapTail* d_tail = nullptr;
+  // state of the last match (resident)
+  int n_agents = 0, n_scenes = 0;
+  size_t cap_slots = 0, cap_scenes = 0, cap_arc_on = 0, cap_q = 0;
+  double *d_x = nullptr, *d_y = nullptr, *d_arc = nullptr, *d_arc_on = nullptr, *d_nbd = nullptr;
+  int32_t *d_lane = nullptr, *d_order = nullptr, *d_start = nullptr, *d_nbi = nullptr;
+  // query / pointwise buffers
+  double* d_qf = nullptr;     // 9 doubles per point
+  int32_t* d_qi = nullptr;    // 2 + 10 ints per point
+  float ms[2] = {0.f, 0.f};
+};
+
+extern "C" {
+
+const char* mce_last_error(void) { return g_env_err.c_str(); }
+
+int mce_map_create(const mce_corridor* corridors, int n_corridors, int device, mce_map** out) {
+  if (!corridors || !out) return efail(MCE_ERR_ARG, "null argument");
+  if (n_corridors < 1 || n_corridors > MCE_MAX_LANES) return efail(MCE_ERR_CAPACITY, "corridor count outside 1..MCE_MAX_LANES");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return efail(MCE_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+  if (device < 0 || device >= n_dev) return efail(MCE_ERR_ARG, "device index out of range");
+  std::vector<mce::EnvMapHead> head(1);
+  std::vector<mce::EnvMapTail> tail(1);
+  mce::EnvMapHead& H = head[0];
+  mce::EnvMapTail& T = tail[0];
+  std::memset(&H, 0, sizeof(H));
+  std::memset(&T, 0, sizeof(T));
+  H.n_lanes = n_corridors;
+  for (int c = 0; c < n_corridors; ++c) {
+    const mce_corridor& k = corridors[c];
+    if (k.n_center < 2 || k.n_center > MCE_MAX_POINTS || k.n_left < 1 || k.n_left > MCE_MAX_POINTS || k.n_right < 1 ||
+        k.n_right > MCE_MAX_POINTS)
+      return efail(MCE_ERR_CAPACITY, "polyline point count outside the compiled limits");
+    if (k.left_index < -1 || k.left_index >= n_corridors || k.right_index < -1 || k.right_index >= n_corridors)
+      return efail(MCE_ERR_ARG, "neighbour corridor index out of range");
+    H.left[c] = k.left_index;
+    H.right[c] = k.right_index;
+    std::vector<Pt> center, shell;
+    for (int i = 0; i < k.n_center; ++i) center.push_back(Pt(k.center[i][0], k.center[i][1]));
+    for (int i = 0; i < k.n_left; ++i) shell.push_back(Pt(k.left[i][0], k.left[i][1]));
+    for (int i = k.n_right - 1; i >= 0; --i) shell.push_back(Pt(k.right[i][0], k.right[i][1]));
+    if (shell.size() > 1 && shell.front() == shell.back()) shell.pop_back();
+    H.n_center[c] = k.n_center;
+    H.n_shell[c] = (int)shell.size();
+    for (size_t i = 0; i < center.size(); ++i) { H.center[c][i][0] = center[i].first; H.center[c][i][1] = center[i].second; }
+    const Pt ext = extend(center[center.size() - 1], center[center.size() - 2], 100.0);   // type.py:154
+    H.center[c][center.size()][0] = ext.first;
+    H.center[c][center.size()][1] = ext.second;
+    for (size_t i = 0; i < shell.size(); ++i) { H.shell[c][i][0] = shell[i].first; H.shell[c][i][1] = shell[i].second; }
+    // Frenet reference line (mcs_wrapper.py:42,109,211)
+    std::vector<Pt> ref;
+    ref.push_back(extend(center[0], center[1], 1000.0));
+    ref.insert(ref.end(), center.begin(), center.end());
+    ref.push_back(extend(center[center.size() - 1], center[center.size() - 2], 1000.0));
+    const std::vector<Pt> refs = simplify(ref, 0.05);
+    T.n_ref[c] = (int)ref.size();
+    T.n_refs[c] = (int)refs.size();
+    double run = 0.0;
+    for (size_t i = 0; i < ref.size(); ++i) {
+      if (i) run = run + dist(ref[i - 1], ref[i]);
+      T.ref[c][i][0] = ref[i].first; T.ref[c][i][1] = ref[i].second; T.ref_dis[c][i] = run;
+    }
+    for (size_t i = 0; i < refs.size(); ++i) { T.refs[c][i][0] = refs[i].first; T.refs[c][i][1] = refs[i].second; }
+    T.refs_len[c] = line_length(refs);
+    // centerSimplified (type.py:153)
+    const std::vector<Pt> cs = simplify(center, 0.05);
+    T.n_center[c] = k.n_center;
+    T.n_cs[c] = (int)cs.size();
+    run = 0.0;
+    for (size_t i = 0; i < center.size(); ++i) {
+      if (i) run = run + dist(center[i - 1], center[i]);
+      T.cpath[c][i][0] = center[i].first; T.cpath[c][i][1] = center[i].second; T.cdis[c][i] = run;
+      const size_t a = i == 0 ? 0 : i - 1, b = i == 0 ? 1 : i;                           // yaw_list, type.py:267-272
+      const double yaw = std::atan2(center[b].second - center[a].second, center[b].first - center[a].first);
+      T.cyaw[c][i] = yaw; T.ccos[c][i] = std::cos(yaw); T.csin[c][i] = std::sin(yaw);
+    }
+    for (size_t i = 0; i < cs.size(); ++i) { T.cs[c][i][0] = cs[i].first; T.cs[c][i][1] = cs[i].second; }
+    T.cs_len[c] = line_length(cs);
+  }
+  ENV_TRY(cudaSetDevice(device));
+  mce_map* m = new mce_map();
+  m->device = device;
+  m->n_lanes = n_corridors;
+  ENV_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 3; ++i) ENV_TRY(cudaEventCreate(&m->ev[i]));
+  ENV_TRY(cudaMalloc(&m->d_head, sizeof(mce::EnvMapHead)));
+  ENV_TRY(cudaMalloc(&m->d_tail, sizeof(mce::EnvMapTail)));
+  ENV_TRY(cudaMemcpyAsync(m->d_head, &H, sizeof(H), cudaMemcpyHostToDevice, m->stream));
+  ENV_TRY(cudaMemcpyAsync(m->d_tail, &T, sizeof(T), cudaMemcpyHostToDevice, m->stream));
+  ENV_TRY(cudaStreamSynchronize(m->stream));
+  *out = m;
+  return MCE_OK;
+}
+
+int mce_map_destroy(mce_map* m) {
+  if (!m) return MCE_OK;
+  cudaSetDevice(m->device);
+  void* bufs[] = {m->d_head, m->d_tail, m->d_x, m->d_y, m->d_arc, m->d_arc_on, m->d_nbd, m->d_lane, m->d_order, m->d_start,
+                  m->d_nbi, m->d_qf, m->d_qi};
+  for (void* b : bufs) if (b) cudaFree(b);
+  for (int i = 0; i < 3; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+  return MCE_OK;
+}
+
+static int ensure_match_buffers(mce_map* m, size_t slots, size_t scenes, size_t arc_on) {
+  if (slots > m->cap_slots) {
+    void* old[] = {m->d_x, m->d_y, m->d_arc, m->d_nbd, m->d_lane, m->d_order, m->d_nbi};
+    for (void* b : old) if (b) cudaFree(b);
+    m->d_x = m->d_y = m->d_arc = m->d_nbd = nullptr; m->d_lane = m->d_order = m->d_nbi = nullptr; m->cap_slots = 0;
+    ENV_TRY(cudaMalloc(&m->d_x, slots * 8)); ENV_TRY(cudaMalloc(&m->d_y, slots * 8)); ENV_TRY(cudaMalloc(&m->d_arc, slots * 8));
+    ENV_TRY(cudaMalloc(&m->d_nbd, slots * 8 * MCE_NEIGHBORS)); ENV_TRY(cudaMalloc(&m->d_nbi, slots * 4 * MCE_NEIGHBORS));
+    ENV_TRY(cudaMalloc(&m->d_lane, slots * 4)); ENV_TRY(cudaMalloc(&m->d_order, slots * 4));
+    m->cap_slots = slots;
+  }
+  if (scenes > m->cap_scenes) {
+    if (m->d_start) cudaFree(m->d_start);
+    m->d_start = nullptr; m->cap_scenes = 0;
+    ENV_TRY(cudaMalloc(&m->d_start, scenes * 4 * (MCE_MAX_LANES + 1)));
+    m->cap_scenes = scenes;
+  }
+  if (arc_on > m->cap_arc_on) {
+    if (m->d_arc_on) cudaFree(m->d_arc_on);
+    m->d_arc_on = nullptr; m->cap_arc_on = 0;
+    ENV_TRY(cudaMalloc(&m->d_arc_on, arc_on * 8));
+    m->cap_arc_on = arc_on;
+  }
+  return MCE_OK;
+}
+
+static int ensure_query_buffers(mce_map* m, size_t n) {
+  if (n > m->cap_q) {
+    if (m->d_qf) cudaFree(m->d_qf);
+    if (m->d_qi) cudaFree(m->d_qi);
+    m->d_qf = nullptr; m->d_qi = nullptr; m->cap_q = 0;
+    ENV_TRY(cudaMalloc(&m->d_qf, n * 8 * 12));
+    ENV_TRY(cudaMalloc(&m->d_qi, n * 4 * 12));
+    m->cap_q = n;
+  }
+  return MCE_OK;
+}
+
+int mce_env_match(mce_map* m, const double* x, const double* y, int n_agents, int n_scenes, int32_t* lane_out, double* arc_out,
+                  int32_t* lane_order_out, int32_t* lane_start_out, double* arc_on_lane_out, int32_t* nb_index_out,
+                  double* nb_dis_out) {
+  if (!m || !x || !y) return efail(MCE_ERR_ARG, "null argument");
+  if (n_agents < 1 || n_scenes < 1) return efail(MCE_ERR_ARG, "empty batch");
+  if (n_agents > MCE_MAX_AGENTS) return efail(MCE_ERR_CAPACITY, "more than MCE_MAX_AGENTS vehicles in a scene");
+  ENV_TRY(cudaSetDevice(m->device));
+  const size_t slots = (size_t)n_agents * n_scenes;
+  const size_t arc_on = arc_on_lane_out ? slots * m->n_lanes : 0;
+  int rc = ensure_match_buffers(m, slots, n_scenes, arc_on);
+  if (rc) return rc;
+  m->n_agents = n_agents; m->n_scenes = n_scenes;
+  cudaStream_t s = m->stream;
+  ENV_TRY(cudaMemcpyAsync(m->d_x, x, slots * 8, cudaMemcpyHostToDevice, s));
+  ENV_TRY(cudaMemcpyAsync(m->d_y, y, slots * 8, cudaMemcpyHostToDevice, s));
+  const size_t dyn = (size_t)n_agents * 12 + 8;
+  ENV_TRY(cudaEventRecord(m->ev[0], s));
+  mce::env_match_kernel<<<n_scenes, mce::kBT, dyn, s>>>(m->d_head, m->d_x, m->d_y, n_agents, m->d_lane, m->d_arc, m->d_order,
+                                                         m->d_start, arc_on_lane_out ? m->d_arc_on : nullptr);
+  ENV_TRY(cudaGetLastError());
+  ENV_TRY(cudaEventRecord(m->ev[1], s));
+  dim3 grid((n_agents + mce::kBT - 1) / mce::kBT, n_scenes);
+  mce::env_neighbors_kernel<<<grid, mce::kBT, 0, s>>>(m->d_head, n_agents, m->d_lane, m->d_arc, m->d_order, m->d_start, nullptr,
+                                                      nullptr, m->d_x, m->d_y, 0, m->d_nbi, m->d_nbd);
+  ENV_TRY(cudaGetLastError());
+  ENV_TRY(cudaEventRecord(m->ev[2], s));
+  if (lane_out) ENV_TRY(cudaMemcpyAsync(lane_out, m->d_lane, slots * 4, cudaMemcpyDeviceToHost, s));
+  if (arc_out) ENV_TRY(cudaMemcpyAsync(arc_out, m->d_arc, slots * 8, cudaMemcpyDeviceToHost, s));
+  if (lane_order_out) ENV_TRY(cudaMemcpyAsync(lane_order_out, m->d_order, slots * 4, cudaMemcpyDeviceToHost, s));
+  if (lane_start_out)
+    ENV_TRY(cudaMemcpyAsync(lane_start_out, m->d_start, (size_t)n_scenes * 4 * (MCE_MAX_LANES + 1), cudaMemcpyDeviceToHost, s));
+  if (arc_on_lane_out) ENV_TRY(cudaMemcpyAsync(arc_on_lane_out, m->d_arc_on, arc_on * 8, cudaMemcpyDeviceToHost, s));
+  if (nb_index_out) ENV_TRY(cudaMemcpyAsync(nb_index_out, m->d_nbi, slots * 4 * MCE_NEIGHBORS, cudaMemcpyDeviceToHost, s));
+  if (nb_dis_out) ENV_TRY(cudaMemcpyAsync(nb_dis_out, m->d_nbd, slots * 8 * MCE_NEIGHBORS, cudaMemcpyDeviceToHost, s));
+  ENV_TRY(cudaStreamSynchronize(s));
+  ENV_TRY(cudaEventElapsedTime(&m->ms[0], m->ev[0], m->ev[1]));
+  ENV_TRY(cudaEventElapsedTime(&m->ms[1], m->ev[1], m->ev[2]));
+  return MCE_OK;
+}
+
+int mce_env_neighbors(mce_map* m, const int32_t* scene, const int32_t* slot, const double* qx, const double* qy, int n_queries,
+                      int32_t* nb_index_out, double* nb_dis_out) {
+  if (!m || !scene || !slot || !qx || !qy || !nb_index_out || !nb_dis_out) return efail(MCE_ERR_ARG, "null argument");
+  if (m->n_scenes == 0) return efail(MCE_ERR_ARG, "mce_env_neighbors before mce_env_match");
+  if (n_queries < 1) return efail(MCE_ERR_ARG, "no queries");
+  for (int i = 0; i < n_queries; ++i)
+    if (scene[i] < 0 || scene[i] >= m->n_scenes || slot[i] < 0 || slot[i] >= m->n_agents)
+      return efail(MCE_ERR_ARG, "query outside the matched batch");
+  ENV_TRY(cudaSetDevice(m->device));
+  int rc = ensure_query_buffers(m, n_queries);
+  if (rc) return rc;
+  cudaStream_t s = m->stream;
+  const size_t q = n_queries;
+  double* d_qx = m->d_qf; double* d_qy = m->d_qf + q; double* d_dis = m->d_qf + 2 * q;
+  int32_t* d_sc = m->d_qi; int32_t* d_sl = m->d_qi + q; int32_t* d_idx = m->d_qi + 2 * q;
+  ENV_TRY(cudaMemcpyAsync(d_qx, qx, q * 8, cudaMemcpyHostToDevice, s));
+  ENV_TRY(cudaMemcpyAsync(d_qy, qy, q * 8, cudaMemcpyHostToDevice, s));
+  ENV_TRY(cudaMemcpyAsync(d_sc, scene, q * 4, cudaMemcpyHostToDevice, s));
+  ENV_TRY(cudaMemcpyAsync(d_sl, slot, q * 4, cudaMemcpyHostToDevice, s));
+  mce::env_neighbors_kernel<<<(n_queries + mce::kBT - 1) / mce::kBT, mce::kBT, 0, s>>>(
+      m->d_head, m->n_agents, m->d_lane, m->d_arc, m->d_order, m->d_start, d_sc, d_sl, d_qx, d_qy, n_queries, d_idx, d_dis);
+  ENV_TRY(cudaGetLastError());
+  ENV_TRY(cudaMemcpyAsync(nb_index_out, d_idx, q * 4 * MCE_NEIGHBORS, cudaMemcpyDeviceToHost, s));
+  ENV_TRY(cudaMemcpyAsync(nb_dis_out, d_dis, q * 8 * MCE_NEIGHBORS, cudaMemcpyDeviceToHost, s));
+  ENV_TRY(cudaStreamSynchronize(s));
+  return MCE_OK;
+}
+
+static int frenet_or_center(mce_map* m, int ref_lane, bool center_line, const double* x, const double* y, int n, double* s_out,
+                            double* d_out) {
+  if (!m || !x || !y || !s_out || !d_out) return efail(MCE_ERR_ARG, "null argument");
+  if (ref_lane < 0 || ref_lane >= m->n_lanes) return efail(MCE_ERR_ARG, "reference corridor index out of range");
+  if (n < 1) return efail(MCE_ERR_ARG, "no points");
+  ENV_TRY(cudaSetDevice(m->device));
+  int rc = ensure_query_buffers(m, n);
+  if (rc) return rc;
+  cudaStream_t s = m->stream;
+  const size_t q = n;
+  double* d = m->d_qf;
+  ENV_TRY(cudaMemcpyAsync(d, x, q * 8, cudaMemcpyHostToDevice, s));
+  ENV_TRY(cudaMemcpyAsync(d + q, y, q * 8, cudaMemcpyHostToDevice, s));
+  mce::env_frenet_kernel<<<(n + mce::kBT - 1) / mce::kBT, mce::kBT, 0, s>>>(m->d_tail, ref_lane, center_line, d, d + q, n, d + 2 * q,
+                                                                            d + 3 * q);
+  ENV_TRY(cudaGetLastError());
+  ENV_TRY(cudaMemcpyAsync(s_out, d + 2 * q, q * 8, cudaMemcpyDeviceToHost, s));
+  ENV_TRY(cudaMemcpyAsync(d_out, d + 3 * q, q * 8, cudaMemcpyDeviceToHost, s));
+  ENV_TRY(cudaStreamSynchronize(s));
+  return MCE_OK;
+}
+
+int mce_frenet(mce_map* m, int ref_lane, const double* x, const double* y, int n, double* s_out, double* d_out) {
+  return frenet_or_center(m, ref_lane, false, x, y, n, s_out, d_out);
+}
+
+int mce_project_center(mce_map* m, int lane, const double* x, const double* y, int n, double* s_out, double* dist_out) {
+  return frenet_or_center(m, lane, true, x, y, n, s_out, dist_out);
+}
+
+int mce_step_along_path(mce_map* m, const int32_t* ref_lane, const double* x, const double* y, const double* v, const double* ax,
+                        const double* vy, double dt, int n, double* x_out, double* y_out, double* v_out, double* yaw_out) {
+  if (!m || !ref_lane || !x || !y || !v || !ax || !vy || !x_out || !y_out || !v_out || !yaw_out) return efail(MCE_ERR_ARG, "null argument");
+  if (n < 1) return efail(MCE_ERR_ARG, "no vehicles");
+  for (int i = 0; i < n; ++i)
+    if (ref_lane[i] < 0 || ref_lane[i] >= m->n_lanes) return efail(MCE_ERR_ARG, "reference corridor index out of range");
+  ENV_TRY(cudaSetDevice(m->device));
+  int rc = ensure_query_buffers(m, n);
+  if (rc) return rc;
+  cudaStream_t s = m->stream;
+  const size_t q = n;
+  double* d = m->d_qf;
+  const double* in[5] = {x, y, v, ax, vy};
+  for (int k = 0; k < 5; ++k) ENV_TRY(cudaMemcpyAsync(d + k * q, in[k], q * 8, cudaMemcpyHostToDevice, s));
+  ENV_TRY(cudaMemcpyAsync(m->d_qi, ref_lane, q * 4, cudaMemcpyHostToDevice, s));
+  mce::env_step_kernel<<<(n + mce::kBT - 1) / mce::kBT, mce::kBT, 0, s>>>(m->d_tail, m->d_qi, d, d + q, d + 2 * q, d + 3 * q, d + 4 * q,
+                                                                           dt, n, d + 5 * q, d + 6 * q, d + 7 * q, d + 8 * q);
+  ENV_TRY(cudaGetLastError());
+  double* outp[4] = {x_out, y_out, v_out, yaw_out};
+  for (int k = 0; k < 4; ++k) ENV_TRY(cudaMemcpyAsync(outp[k], d + (5 + k) * q, q * 8, cudaMemcpyDeviceToHost, s));
+  ENV_TRY(cudaStreamSynchronize(s));
+  return MCE_OK;
+}
+
+int mce_last_kernel_ms(mce_map* m, float* out2) {
+  if (!m || !out2) return efail(MCE_ERR_ARG, "null argument");
+  out2[0] = m->ms[0]; out2[1] = m->ms[1];
+  return MCE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,320 @@
+"""Host mirror of the reference's outer Map / Environment (environment.py:21-251) over the device kernels of
+include/mcsim_env.h: one launch per `match_agents_on_corridor()` answers the lane match, the per-lane ordering and the
+front / following / eight side neighbours of EVERY vehicle; the reference's per-vehicle query methods read those tables.
+
+Same names, arguments and return shapes as the reference (`Map`, `Environment`, `IdmMatch`, `Neighbor`,
+`MatchedAgent`), so the builders of mcs_wrapper.py and the behaviours of behaviors.py run on it unchanged.  Vehicles are
+duck-typed: any object with the reference Agent's attributes (id, x, y, v, vy, a, l, w, idm_param.vd, behavior_model,
+corridor_history, set_behavior_model) works.
+
+The reference plans and moves its vehicles one after the other between two matches (environment.py:316-323): a query
+for a vehicle that has moved since the match is answered by `mce_env_neighbors` against the resident (stale) per-lane
+keys, exactly the reference's semantics.  No CPU fallback: every geometric answer comes from the kernels.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import backend
+
+MCE_MAX_LANES, MCE_MAX_POINTS, MCE_MAX_AGENTS, MCE_NEIGHBORS = 8, 16, 1024, 10
+LEFT_FF, LEFT_F, LEFT_B, LEFT_BB, FRONT, BACK, RIGHT_FF, RIGHT_F, RIGHT_B, RIGHT_BB = range(10)
+
+
+class CorridorPOD(C.Structure):
+    """mce_corridor"""
+    _fields_ = [("id", C.c_int32), ("left_index", C.c_int32), ("right_index", C.c_int32),
+                ("n_left", C.c_int32), ("n_right", C.c_int32), ("n_center", C.c_int32),
+                ("left", C.c_double * 2 * MCE_MAX_POINTS), ("right", C.c_double * 2 * MCE_MAX_POINTS),
+                ("center", C.c_double * 2 * MCE_MAX_POINTS)]
+
+
+class EnvError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("mcsim_env error %d: %s" % (code, msg))
+        self.code = code
+
+
+_bound = False
+_pd = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_pi = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def _lib():
+    global _bound
+    L = backend.lib()
+    if not _bound:
+        V, I, D = C.c_void_p, C.c_int, C.c_double
+        L.mce_last_error.restype = C.c_char_p
+        L.mce_map_create.argtypes = [C.POINTER(CorridorPOD), I, I, C.POINTER(V)]
+        L.mce_map_destroy.argtypes = [V]
+        L.mce_env_match.argtypes = [V, _pd, _pd, I, I, V, V, V, V, V, V, V]
+        L.mce_env_neighbors.argtypes = [V, _pi, _pi, _pd, _pd, I, _pi, _pd]
+        L.mce_frenet.argtypes = [V, I, _pd, _pd, I, _pd, _pd]
+        L.mce_project_center.argtypes = [V, I, _pd, _pd, I, _pd, _pd]
+        L.mce_step_along_path.argtypes = [V, _pi, _pd, _pd, _pd, _pd, _pd, D, I, _pd, _pd, _pd, _pd]
+        L.mce_last_kernel_ms.argtypes = [V, C.POINTER(C.c_float)]
+        for f in ("mce_map_create", "mce_map_destroy", "mce_env_match", "mce_env_neighbors", "mce_frenet", "mce_project_center",
+                  "mce_step_along_path", "mce_last_kernel_ms"):
+            getattr(L, f).restype = I
+        _bound = True
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise EnvError(rc, _lib().mce_last_error().decode("utf-8", "replace"))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def corridor_pods(corridors):
+    """corridors: sequence of objects or dicts with id, left, right, center, left_id, right_id (dict-insertion order)."""
+    get = (lambda c, k: c[k]) if isinstance(corridors[0], dict) else getattr
+    pos = {get(c, "id"): k for k, c in enumerate(corridors)}
+    out = (CorridorPOD * len(corridors))()
+    for k, c in enumerate(corridors):
+        p = out[k]
+        p.id = int(get(c, "id"))
+        li, ri = get(c, "left_id"), get(c, "right_id")
+        p.left_index = pos[li] if li is not None else -1
+        p.right_index = pos[ri] if ri is not None else -1
+        for name in ("left", "right", "center"):
+            pts = get(c, name)
+            if len(pts) > MCE_MAX_POINTS:
+                raise EnvError(-3, "polyline with more than MCE_MAX_POINTS points")
+            setattr(p, "n_" + name, len(pts))
+            arr = getattr(p, name)
+            for i, q in enumerate(pts):
+                arr[i][0], arr[i][1] = float(q[0]), float(q[1])
+    return out
+
+
+class MatchTables:
+    """Outputs of one mce_env_match launch (numpy, host)."""
+    __slots__ = ("lane", "arc", "order", "start", "arc_on_lane", "nb_index", "nb_dis", "n_agents", "n_scenes")
+
+
+class DeviceMap:
+    """mce_map: the corridors of one map resident on a GPU."""
+
+    def __init__(self, corridors, device=0):
+        self._pods = corridor_pods(list(corridors))
+        self.n_lanes = len(self._pods)
+        self._h = C.c_void_p()
+        _check(_lib().mce_map_create(self._pods, self.n_lanes, device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            _lib().mce_map_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def match(self, x, y, n_scenes=1, arc_on_lanes=False):
+        x, y = _f64(x).reshape(n_scenes, -1), _f64(y).reshape(n_scenes, -1)
+        n = x.shape[1]
+        t = MatchTables()
+        t.n_agents, t.n_scenes = n, n_scenes
+        t.lane = np.empty((n_scenes, n), np.int32)
+        t.arc = np.empty((n_scenes, n), np.float64)
+        t.order = np.empty((n_scenes, n), np.int32)
+        t.start = np.empty((n_scenes, MCE_MAX_LANES + 1), np.int32)
+        t.arc_on_lane = np.empty((n_scenes, self.n_lanes, n), np.float64) if arc_on_lanes else None
+        t.nb_index = np.empty((n_scenes, MCE_NEIGHBORS, n), np.int32)
+        t.nb_dis = np.empty((n_scenes, MCE_NEIGHBORS, n), np.float64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        _check(_lib().mce_env_match(self._h, x, y, n, n_scenes, p(t.lane), p(t.arc), p(t.order), p(t.start), p(t.arc_on_lane),
+                                    p(t.nb_index), p(t.nb_dis)))
+        return t
+
+    def neighbors(self, scene, slot, qx, qy):
+        scene, slot = np.ascontiguousarray(scene, np.int32), np.ascontiguousarray(slot, np.int32)
+        qx, qy = _f64(qx), _f64(qy)
+        q = len(slot)
+        idx, dis = np.empty((MCE_NEIGHBORS, q), np.int32), np.empty((MCE_NEIGHBORS, q), np.float64)
+        _check(_lib().mce_env_neighbors(self._h, scene, slot, qx, qy, q, idx, dis))
+        return idx, dis
+
+    def frenet(self, ref_lane, x, y):
+        x, y = _f64(x), _f64(y)
+        s, d = np.empty(len(x)), np.empty(len(x))
+        _check(_lib().mce_frenet(self._h, int(ref_lane), x, y, len(x), s, d))
+        return s, d
+
+    def project_center(self, lane, x, y):
+        x, y = _f64(x), _f64(y)
+        s, d = np.empty(len(x)), np.empty(len(x))
+        _check(_lib().mce_project_center(self._h, int(lane), x, y, len(x), s, d))
+        return s, d
+
+    def step_along_path(self, ref_lane, x, y, v, ax, vy, dt):
+        ref_lane = np.ascontiguousarray(ref_lane, np.int32)
+        n = len(ref_lane)
+        out = [np.empty(n) for _ in range(4)]
+        _check(_lib().mce_step_along_path(self._h, ref_lane, _f64(x), _f64(y), _f64(v), _f64(ax), _f64(vy), float(dt), n, *out))
+        return out
+
+    def last_kernel_ms(self):
+        ms = (C.c_float * 2)()
+        _check(_lib().mce_last_kernel_ms(self._h, ms))
+        return float(ms[0]), float(ms[1])
+
+
+# ---- the reference's value classes (agent.py:203-247, type.py:140-176) ----------------------------------------------
+
+class Corridor:
+    """type.py:140-176 reduced to data (the polygons / shapely lines live on the device)."""
+
+    def __init__(self, idx, t, left, right, center, v_limit):
+        self.id, self.type, self.left, self.right, self.center, self.v_limit = idx, t, left, right, center, v_limit
+        self.left_id = self.right_id = None
+
+    def set_left_and_right_corridor_id(self, left_id, right_id):
+        self.left_id, self.right_id = left_id, right_id
+
+
+class MatchedAgent:                                          # agent.py:229-232
+    def __init__(self, agent, corridor_id):
+        self.agent, self.corridor_id = agent, corridor_id
+
+
+class IdmMatch:                                              # agent.py:235-247
+    def __init__(self, dis, agent):
+        self.id, self.agent, self.dis = agent.id, agent, dis
+        self.x, self.y, self.v, self.vy, self.a, self.l, self.w = agent.x, agent.y, agent.v, agent.vy, agent.a, agent.l, agent.w
+        self.vd = agent.idm_param.vd
+
+
+class Neighbor:                                              # agent.py:203-226
+    def __init__(self, left_ff, left_f, left_b, left_bb, f, b, right_ff, right_f, right_b, right_bb):
+        self.left_ff, self.left_f, self.left_b, self.left_bb, self.f, self.b = left_ff, left_f, left_b, left_bb, f, b
+        self.right_ff, self.right_f, self.right_b, self.right_bb = right_ff, right_f, right_b, right_bb
+        self.lefts = [left_ff, left_f, left_b, left_bb]
+        self.rights = [right_ff, right_f, right_b, right_bb]
+        self.lefts_and_front = [left_ff, left_f, left_b, left_bb, f]
+
+
+class Map:
+    """environment.py:21-56"""
+
+    def __init__(self, corridors, device=0):
+        self.corridors = {}
+        self.corridors_by_type = {}
+        for c in corridors:
+            self.corridors[c.id] = c
+            self.corridors_by_type.setdefault(c.type, []).append(c)
+        self.index_of = {cid: k for k, cid in enumerate(self.corridors)}
+        self.id_at = list(self.corridors)
+        self.device_map = DeviceMap(list(self.corridors.values()), device)
+
+    def truck_lane_id(self):                                 # environment.py:46-56
+        if "merging" in self.corridors_by_type:
+            return self.corridors_by_type["merging"][0].left_id
+        if "exit" in self.corridors_by_type:
+            return self.corridors_by_type["exit"][0].left_id
+        for i, c in self.corridors.items():
+            if c.right_id is None:
+                return i
+
+
+class Environment:
+    """environment.py:70-251: same attributes (`agents`, `removed_agents`, `matched_agents`,
+    `matched_agents_sorted_by_arc_length`) and query methods."""
+
+    def __init__(self, m, agents):
+        self.map = m
+        self.agents = {a.id: a for a in agents}
+        self.removed_agents = {}
+        self.matched_agents = {}
+        self.matched_agents_sorted_by_arc_length = {}
+        self.sim_time = 0
+        self.match_agents_on_corridor()
+
+    def match_agents_on_corridor(self):                      # environment.py:85-101 — one launch
+        objs = list(self.agents.values())
+        self.matched_agents = {}
+        self.matched_agents_sorted_by_arc_length = {c: [] for c in self.map.corridors}
+        self._slot, self._objs = {a.id: i for i, a in enumerate(objs)}, objs
+        if not objs:
+            self._tables = None
+            return
+        self._x0 = np.array([a.x for a in objs], np.float64)
+        self._y0 = np.array([a.y for a in objs], np.float64)
+        t = self._tables = self.map.device_map.match(self._x0, self._y0, 1, arc_on_lanes=True)
+        for i, a in enumerate(objs):
+            lane = int(t.lane[0, i])
+            if lane < 0:
+                self.removed_agents[a.id] = self.agents.pop(a.id)
+                continue
+            c = self.map.corridors[self.map.id_at[lane]]
+            a.corridor_history.append(c.id)
+            if c.type == "main" and "merging" in a.behavior_model:
+                a.set_behavior_model("idm_mobil_lane_change_safe")
+            if c.type == "exit" and "exit" in a.behavior_model:
+                a.set_behavior_model("idm")
+            self.matched_agents[a.id] = MatchedAgent(a, c.id)
+        for lane, cid in enumerate(self.map.id_at):
+            members = t.order[0, t.start[0, lane]:t.start[0, lane + 1]]
+            self.matched_agents_sorted_by_arc_length[cid] = [[float(t.arc[0, j]), objs[j]] for j in members]
+
+    def corridor_for_agent(self, idx):                       # environment.py:103-112
+        if idx not in self.agents or idx not in self.matched_agents:
+            return None
+        return self.map.corridors[self.matched_agents[idx].corridor_id]
+
+    def _neighbor_row(self, idx):
+        """(slots[10], dis[10]) of vehicle idx at its current position against the vectors of the last match"""
+        i = self._slot[idx]
+        a = self._objs[i]
+        if a.x == self._x0[i] and a.y == self._y0[i]:
+            return self._tables.nb_index[0, :, i], self._tables.nb_dis[0, :, i]
+        nb, dis = self.map.device_map.neighbors([0], [i], [a.x], [a.y])
+        return nb[:, 0], dis[:, 0]
+
+    def _match_or_none(self, row, k):
+        j = int(row[0][k])
+        return IdmMatch(float(row[1][k]), self._objs[j]) if j >= 0 else None
+
+    def front_agent(self, idx):                              # environment.py:166-180
+        if idx not in self.agents or idx not in self.matched_agents:
+            return None
+        return self._match_or_none(self._neighbor_row(idx), FRONT)
+
+    def following_agent(self, idx):                          # environment.py:182-195
+        if idx not in self.agents or idx not in self.matched_agents:
+            return None
+        return self._match_or_none(self._neighbor_row(idx), BACK)
+
+    def neighbor_around_agent(self, idx):                    # environment.py:197-251
+        if idx not in self.agents or idx not in self.matched_agents:
+            return Neighbor(*([None] * 10))
+        row = self._neighbor_row(idx)
+        return Neighbor(*[self._match_or_none(row, k) for k in range(MCE_NEIGHBORS)])
+
+    def sorted_agents_on_corridor_within_range_of_vehicle(self, corridor_id, ego_id, max_l_dis):   # environment.py:145-156
+        lane = self.map.index_of[corridor_id]
+        members = [a.agent for a in self.matched_agents.values() if a.corridor_id == corridor_id]
+        ego = self.agents[ego_id]
+        pts = [ego] + members
+        moved = any(p.x != self._x0[self._slot[p.id]] or p.y != self._y0[self._slot[p.id]] for p in pts)
+        if moved:
+            arcs, _ = self.map.device_map.project_center(lane, [p.x for p in pts], [p.y for p in pts])
+        else:
+            arcs = [self._tables.arc_on_lane[0, lane, self._slot[p.id]] for p in pts]
+        e = arcs[0]
+        near = [(arcs[k + 1], k) for k in range(len(members)) if abs(arcs[k + 1] - e) <= max_l_dis]
+        near.sort(key=lambda t: t[0])
+        return [members[k] for _, k in near]
+
+    def agent_to_idm_match(self, ego_id, obj_id):            # environment.py:158-164
+        ego, obj = self.agents[ego_id], self.agents[obj_id]
+        lane = self.map.index_of[self.matched_agents[obj_id].corridor_id]
+        arcs, _ = self.map.device_map.project_center(lane, [ego.x, obj.x], [ego.y, obj.y])
+        return IdmMatch(float(arcs[1] - arcs[0]), obj)

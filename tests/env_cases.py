@@ -27,3 +27,25 @@ def prepared(rec):
 
 def slots(ids):
     return {a: i for i, a in enumerate(ids)}
+
+
+class _NS:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class DuckAgent:
+    """A vehicle with the attributes of the reference's Agent that the environment and the builders read."""
+
+    def __init__(self, r):
+        self.id, self.x, self.y, self.v, self.vy, self.a, self.l, self.w = (r[k] for k in ("id", "x", "y", "v", "vy", "a", "l", "w"))
+        self.behavior_model = r["behavior_model"]
+        i, s, m = r["idm"], r["rss"], r["mobil"]
+        self.idm_param = _NS(vd=i[0], acc_max=i[1], acc_min=i[2], min_dis=i[3], acc_com=i[4], thw=i[5])
+        self.rss_param = _NS(r_t_other=s[0], r_t_ego=s[1], a_min=s[2], a_max=s[3], soft_acc=s[4], soft_dcc=s[5])
+        self.mobil_param = _NS(politeness_factor=m[0], delta_a=m[1], bias_a=m[2])
+        self.yielding_param = list(r["yielding"])
+        self.corridor_history = []
+
+    def set_behavior_model(self, b):
+        self.behavior_model = b

@@ -16,6 +16,35 @@ def declared_functions():
     return sorted(set(re.findall(r"\b(mcs_[a-z0-9_]+)\s*\(", text)))
 
 
+def declared_env_functions():
+    text = open(os.path.join(ROOT, "include", "mcsim_env.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mce_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_env_header_entry_points_are_exported(backend_lib):
+    names = declared_env_functions()
+    for n in ("mce_map_create", "mce_map_destroy", "mce_env_match", "mce_env_neighbors", "mce_frenet", "mce_project_center",
+              "mce_step_along_path", "mce_last_error", "mce_last_kernel_ms"):
+        assert n in names
+    L = C.CDLL(backend_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), "libmcsim_b200.so does not export %s" % n
+    from interactive_highway_simulation_b200 import outer_env
+    assert C.sizeof(outer_env.CorridorPOD) == 24 + 3 * 16 * 16          # mce_corridor
+
+
+def test_env_no_cpu_fallback_without_a_device(backend_lib):
+    if backend_lib.lib().mcs_device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    from interactive_highway_simulation_b200 import outer_env
+    c = {"id": 0, "left": [[0, 3.5], [100, 3.5]], "right": [[0, 0], [100, 0]], "center": [[0, 1.75], [100, 1.75]],
+         "left_id": None, "right_id": None}
+    with pytest.raises(outer_env.EnvError) as e:
+        outer_env.DeviceMap([c])
+    assert e.value.code == -2                                            # MCE_ERR_CUDA
+
+
 def test_header_declares_the_expected_entry_points():
     names = declared_functions()
     for n in ("mcs_scene_create", "mcs_rollouts", "mcs_rollouts_range", "mcs_reduce_features", "mcs_trajectories",
