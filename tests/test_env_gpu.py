@@ -37,7 +37,7 @@ def oracle_tables(pm, xs, ys):
 @pytest.mark.parametrize("rec", STATES, ids=[r["tag"] for r in STATES])
 def test_match_tables_bit_identical_to_the_oracle(oe, rec):
     pm, ids, xs, ys = prepared(rec)
-    dm = oe.DeviceMap(corridor_dicts(rec))
+    dm = oe.DeviceMap(rec["corridors"])
     t = dm.match(xs, ys, 1, arc_on_lanes=True)
     lane, arc, order, start, idx, dis = oracle_tables(pm, xs, ys)
     assert same(t.lane[0], lane) and same(t.arc[0], arc) and same(t.order[0], order) and same(t.start[0], start)
