@@ -84,6 +84,38 @@ def builder_rec(env, name, agent, seed):
             "agents": [ms_agent_rec(a) for a in agents], "possible_actions": [int(v) for v in actions] if actions is not None else None}
 
 
+def decision_recs(env, rng):
+    """behaviors.py:89-176 on the reference's environment with the reference's machine code as inner simulator: the
+    chosen command and the resulting action of a few egos per behaviour."""
+    import behaviors as bh
+    out = []
+    has_exit = any(k.type == "exit" for k in env.map.corridors.values())
+    picks = []
+    for a in env.agents.values():
+        c = env.corridor_for_agent(a.id)
+        if c.type == "merging" and c.left_id is not None:
+            picks.append((a, "merging_learned", "cloned_merging_behavior"))
+            picks.append((a, "merging_closest_gap_policy", "merging_behavior_closest_gap"))
+        elif c.type == "main" and has_exit and a.l <= 7 and rng.random() < 0.2:
+            picks.append((a, "exit_learned", "cloned_exit_behavior"))
+            picks.append((a, "exit", "exit_behavior_closest_gap"))
+        elif c.type == "main" and a.l <= 7 and rng.random() < 0.12:
+            picks.append((a, "lane_change_learned", "lane_change_behavior_learned"))
+    seed = 500
+    for a, model, fn in picks[:8]:
+        before = a.behavior_model
+        a.reset_behavior_model(model)
+        np.random.seed(seed); backend.seed(7000 + seed); backend.RECORD.clear()
+        act = getattr(bh, fn)(env, a)
+        out.append({"fn": fn, "ego": a.id, "np_seed": seed, "backend_seed": 7000 + seed, "agent": agent_rec(a),
+                    "ax": fl(act.ax), "vy": fl(act.vy), "decision": getattr(a, "current_decision", None),
+                    "ref_lane": env.corridor_for_agent(a.id).id, "calls": len(backend.RECORD)})
+        a.reset_behavior_model(before)
+        seed += 1
+    backend.RECORD.clear()
+    return out
+
+
 def state_rec(tag, env, all_agents, rng, builders=True):
     """env was just matched on the positions of all_agents (dict order)."""
     rec = {"tag": tag, "corridors": [corridor_rec(c) for c in env.map.corridors.values()], "agents": all_agents}
@@ -122,6 +154,7 @@ def state_rec(tag, env, all_agents, rng, builders=True):
                 rec["builders"].append(builder_rec(env, "exit_mcs_sim_from_env", a, seed)); seed += 1
             if c.type == "main" and rng.random() < 0.25:
                 rec["builders"].append(builder_rec(env, "lane_change_mcs_sim_from_env", a, seed)); seed += 1
+    rec["decisions"] = decision_recs(env, rng) if builders else []
     # the sequential loop: the first vehicles move, nobody is re-matched, and they and their neighbours are asked again
     moved = []
     for a in list(env.agents.values())[: max(3, len(env.agents) // 3)]:

@@ -222,3 +222,26 @@ def test_capacity_and_argument_errors(oe):
     with pytest.raises(oe.EnvError):
         dm.frenet(5, [0.0], [0.0])
     dm.close()
+
+
+@pytest.mark.parametrize("rec", [r for r in STATES if r["decisions"]], ids=[r["tag"] for r in STATES if r["decisions"]])
+def test_learned_and_closest_gap_behaviours_equal_the_reference(oe, rec):
+    """behaviors.py:89-176 end to end — outer environment, builder, all candidates in one rollout launch, learned model,
+    single-step behaviour — against the reference's own behaviors.py running on the reference's machine code with the
+    same seeds: the same chosen command and bit-identical (ax, vy)."""
+    from interactive_highway_simulation_b200 import behaviors as bh, learned_model as lm, mc_sim_highway as ms
+    env = build_env(oe, rec)
+    for d in rec["decisions"]:
+        a = env.agents[d["ego"]]
+        fresh = DuckAgent(d["agent"])
+        keep = (a.behavior_model, a.rss_param)
+        a.behavior_model, a.rss_param = fresh.behavior_model, fresh.rss_param
+        a.learned_merging_model, a.learned_lane_change_model = lm.LearnedMergingModel(), lm.LearnedLaneChangeModel()
+        a.current_decision = "Initial"
+        np.random.seed(d["np_seed"]); ms.seed(d["backend_seed"])
+        act = getattr(bh, d["fn"])(env, a)
+        assert act.ref_path.id == d["ref_lane"]
+        if d["decision"] is not None and "closest" not in d["fn"]:
+            assert a.current_decision == d["decision"], (d["fn"], d["ego"], a.current_decision, d["decision"])
+        assert (act.ax, act.vy) == (d["ax"], d["vy"]), (d["fn"], d["ego"], act.ax, d["ax"], act.vy, d["vy"])
+        a.behavior_model, a.rss_param = keep
