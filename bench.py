@@ -233,6 +233,72 @@ def decision_latency(torch, dist, world, device, args):
 
 
 # ------------------------------------------------------------------------------------------------ product arm
+def outer_env_workload(n_scenes=512, n_vehicles=200, seed=0):
+    """configs[3]-sized outer scenes on the map of evaluation_exit.py:18-43 (exit lane + 3 main lanes): positions drawn
+    over the whole map, 2 % of the slots off the road."""
+    import numpy as np
+    from interactive_highway_simulation_b200 import traffic_generator as tg
+    spec, _, _, _ = tg.evaluation_map("exit", v_limit=100 / 3.6)
+    corridors = spec
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-200.0, 500.0, (n_scenes, n_vehicles))
+    y = rng.uniform(0.0, 14.0, (n_scenes, n_vehicles))
+    y[rng.random((n_scenes, n_vehicles)) < 0.02] = 30.0
+    return corridors, x, y
+
+
+def outer_env_block(args, reps=10):
+    """Secondary measurement (SURVEY.md §8 rows a9/a10 outer twins, a13, a14): mce_env_match — lane match, per-lane
+    ranking and the 10 neighbours of every vehicle — on 512 scenes x 200 vehicles through the C ABI with host buffers."""
+    import numpy as np
+    from interactive_highway_simulation_b200 import outer_env
+    corridors, x, y = outer_env_workload()
+    dm = outer_env.DeviceMap(corridors, 0)
+    n_scenes, n = x.shape
+    for _ in range(3):
+        t = dm.match(x, y, n_scenes)
+    k_ms, wall = [0.0, 0.0], 0.0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        t = dm.match(x, y, n_scenes)
+        wall += time.perf_counter() - t0
+        ms = dm.last_kernel_ms()
+        k_ms[0] += ms[0]; k_ms[1] += ms[1]
+    k_ms = [v / reps for v in k_ms]
+    vehicles = n_scenes * n
+    alg_bytes = vehicles * (16 + 4 + 8 + 4 + 10 * 12) + n_scenes * 36      # x, y in; lane, arc, order, 10 x (slot, dis) out
+    peak_gbs, peak_src = read_peaks()
+    out = {"workload": "%d scenes x %d vehicles, exit map of evaluation_exit.py (4 lanes)" % (n_scenes, n),
+           "matched_fraction": float((t.lane >= 0).mean()),
+           "kernel_ms": {"env_match_kernel": k_ms[0], "env_neighbors_kernel": k_ms[1]},
+           "vehicles_per_s_kernels": vehicles / ((k_ms[0] + k_ms[1]) * 1e-3),
+           "e2e": {"vehicles_per_s": vehicles * reps / wall, "ms_per_call": wall / reps * 1e3,
+                   "h2d_bytes_per_call": vehicles * 16, "d2h_bytes_per_call": alg_bytes - vehicles * 16},
+           "roofline": {"bound": "hbm", "achieved": alg_bytes / ((k_ms[0] + k_ms[1]) * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                        "frac": alg_bytes / ((k_ms[0] + k_ms[1]) * 1e-3) / 1e9 / peak_gbs, "peak_source": peak_src,
+                        "algorithmic_bytes_per_vehicle": 152,
+                        "note": "152 B per vehicle in and out; the kernels are compute/latency bound (point-in-polygon and "
+                                "projection per corridor, O(n) rank per vehicle), not HBM bound"}}
+    if not args.no_cpu_baseline:
+        from oracle import env_oracle as eo                       # the checker, timed as the CPU baseline only
+        pos = {c["id"]: k for k, c in enumerate(corridors)}
+        pm = eo.PreparedMap([dict(c, left_index=pos[c["left_id"]] if c["left_id"] is not None else -1,
+                                  right_index=pos[c["right_id"]] if c["right_id"] is not None else -1) for c in corridors])
+        t0 = time.perf_counter()
+        done = 0
+        while done < 4 and time.perf_counter() - t0 < 10.0:
+            xs, ys = list(x[done]), list(y[done])
+            lane, arc, order, start = eo.match(pm, xs, ys)
+            for i in range(n):
+                eo.neighbors(pm, lane, arc, order, start, i, xs[i], ys[i])
+            done += 1
+        out["cpu_baseline"] = {"value": done * n / (time.perf_counter() - t0), "unit": "vehicles/s", "cores": 1, "kind": "port",
+                               "sample": "%d scenes of %d vehicles through the Python restatement of environment.py (the reference's "
+                                         "own path is Python + shapely per vehicle)" % (done, n)}
+    dm.close()
+    return out
+
+
 def run_product(args):
     import torch
     from interactive_highway_simulation_b200 import backend, synthetic, _abi as abi
@@ -364,6 +430,12 @@ def run_product(args):
         except Exception as e:    # oracle/_ref is built only where /root/reference exists
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
 
+    outer_env = None
+    if world == 1:
+        try:
+            outer_env = outer_env_block(args)
+        except Exception as e:
+            outer_env = {"error": str(e)}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": workload_config(args),
@@ -371,7 +443,7 @@ def run_product(args):
            "e2e": {"value": e2e_units_total / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h,
                    "note": "mcs_scene_create + mcs_rollouts (8 groups x %d) + feature read-back per step, host buffers" % (e2e_R // 8)},
-           "decision": decision,
+           "decision": decision, "outer_env": outer_env,
            "gpu_launches": args.steps, "wall_s_timed_region": wall,
            "rollouts_per_s": units_total / (N_VEHICLES * SIM_STEPS) / (kernel_ms_max * 1e-3)}
     print(json.dumps(out))
