@@ -1,5 +1,5 @@
 """Selected raw metrics of the (single) kernel in an ncu report -> JSON on stdout (diagnostic; fills profiles/*_ncu_full.json).
-usage: ncu_summary.py report.ncu-rep"""
+usage: ncu_summary.py report.ncu-rep [launch index, default 0]"""
 import csv, io, json, re, subprocess, sys
 KEEP = re.compile(r"^(dram__bytes_(read|write)\.sum|gpu__dram_throughput\.avg\.pct_of_peak_sustained_elapsed|gpu__time_duration\.sum|"
                   r"launch__(block_size|grid_size|occupancy_limit_(registers|shared_mem|warps)|registers_per_thread|shared_mem_per_block)|"
@@ -11,7 +11,7 @@ KEEP = re.compile(r"^(dram__bytes_(read|write)\.sum|gpu__dram_throughput\.avg\.p
                   r"smsp__sass_thread_inst_executed_op_(dadd|dmul|dfma)_pred_on\.sum|sm__sass_inst_executed_op_(shared|local|global)_(ld|st)\.sum)$")
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-names, units, vals = rows[0], rows[1], rows[2]
+names, units, vals = rows[0], rows[1], rows[2 + (int(sys.argv[2]) if len(sys.argv) > 2 else 0)]
 res = {"kernel": vals[names.index("Kernel Name")]}
 for n, u, v in zip(names, units, vals):
     if KEEP.match(n):
