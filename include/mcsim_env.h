@@ -11,6 +11,8 @@
  *   environment.py:145-156  sorted_agents_on_corridor_within_range_of_vehicle (from arc_on_lane + lane_order)
  *   type.py:297-317         LineSimplified.signed_distance / to_frenet_frame on extend_line_both_sides(center, 1000)
  *   utility.py:88-98        step_along_path                (mce_step_along_path)
+ *   type.py:180-206,307-315 distance_to_corridor_end / distance_to_border / centerSimplified.signed_distance
+ *                           (mce_center_distance, mce_border_distance: the geometry idm_behavior and the yielding model read)
  *
  * Plain pointers and sizes; caller owns all buffers; HOST buffers in, HOST buffers out (copies inside).  No CPU
  * fallback: without a CUDA device every compute entry fails with MCE_ERR_CUDA.
@@ -89,6 +91,19 @@ int mce_project_center(mce_map* map, int lane, const double* x, const double* y,
 int mce_step_along_path(mce_map* map, const int32_t* ref_lane, const double* x, const double* y, const double* v,
                         const double* ax, const double* vy, double dt, int n, double* x_out, double* y_out,
                         double* v_out, double* yaw_out);
+
+/* corridors[lane[i]].centerSimplified.signed_distance([x, y]) (type.py:307-315; the lateral "attach to the centre
+ * line" term of idm_behavior, behaviors.py:20-22) and Corridor.distance_to_corridor_end([x, y]) (type.py:180-181; the
+ * yielding features d_to_merging_lane_end, type.py:126-127) for n points, each on its own corridor. */
+int mce_center_distance(mce_map* map, const int32_t* lane, const double* x, const double* y, int n, double* signed_out,
+                        double* to_end_out);
+
+/* Environment.dis_to_lane_border (environment.py:113-115) = Corridor.distance_to_border(hull, direction)
+ * (type.py:183-206) for n vehicle hulls (hull: [n][4][2], the corner order of vehicle_pose_to_rect utility.py:12-20):
+ * minus the largest distance by which a corner has passed the border on that side, else the distance of the hull polygon
+ * to the border line (the yielding feature d_0_lat, type.py:123). */
+enum { MCE_SIDE_LEFT = 0, MCE_SIDE_RIGHT = 1 };
+int mce_border_distance(mce_map* map, const int32_t* lane, const int32_t* side, const double* hull, int n, double* out);
 
 /* average duration (ms, CUDA events on the launching stream) of the kernels of the last mce_env_match call:
  * out[0] = match + order kernel, out[1] = neighbour kernel */

@@ -5,17 +5,71 @@ behaviour kernel.  Same function names, arguments `(observed_model, agent)` and 
 (`current_decision`) as the reference; the returned DecoupledAction carries the ego corridor (whose centre line is the
 reference's `ref_path`) for `DeviceMap.step_along_path`.
 
-The MOBIL / plain-IDM behaviours of the outer loop (behaviors.py:10-86) stay with the reference's Python: they are
-per-vehicle host arithmetic around the yielding model, not part of the rollout path.
+The plain-IDM / MOBIL behaviours of the outer loop (behaviors.py:10-86) are here too: `idm_behavior` is the reference's
+per-vehicle host arithmetic (IDM, yielding intentions, RSS brake) over the device's neighbour tables and border / centre
+distances; `lane_change_behavior_mobil` asks the single-step MOBIL kernel (`laneChangeMobilBehavior`).
 """
 from . import decisions
 from . import mc_sim_highway as ms
 from .mcs_wrapper import exit_mcs_sim_from_env, lane_change_mcs_sim_from_env, merging_mcs_sim_from_env
+from .type import DecoupledAction, YieldingIntention
+from .utility import idm_acc_f_b, idm_p_for_merging_exit_agents, rss_dis
 
 
-class DecoupledAction:                                       # type.py:9-15
-    def __init__(self, ax, vy, ref_path):
-        self.ax, self.vy, self.ref_path = ax, vy, ref_path
+def idm_behavior(observed_model, agent):                     # behaviors.py:10-67
+    corridor = observed_model.corridor_for_agent(agent.id)
+    corridors = observed_model.map.corridors
+    front = observed_model.front_agent(agent.id)
+    ax = idm_acc_f_b([front] if front else [], None, agent.v, corridor.v_limit, agent.idm_param)
+    # lateral: attach to the centre line
+    signed_distance = corridor.centerSimplified.signed_distance([agent.x, agent.y])
+    vy_abs = min(max(abs(signed_distance) * 1.0, 0.1), 1.3)
+    vy = -signed_distance / (abs(signed_distance) + 1e-10) * vy_abs
+    # candidates to yield to: vehicles on a merging lane to the right, exiting vehicles on a main lane to the left
+    matches = []
+    if corridor.right_id is not None and corridors[corridor.right_id].type == "merging":
+        nb = observed_model.neighbor_around_agent(agent.id)
+        matches.extend(v for v in (nb.right_bb, nb.right_b, nb.right_f, nb.right_ff) if v is not None)
+    if corridor.left_id is not None and corridors[corridor.left_id].type == "main":
+        for _, other in observed_model.matched_agents_sorted_by_arc_length[corridor.left_id]:
+            if "exit" in other.behavior_model:
+                matches.append(observed_model.agent_to_idm_match(agent.id, other.id))
+    intentions = agent.yielding_intention_to_others
+    for v in matches:
+        direction = "right" if "exit" in v.agent.behavior_model else "left"
+        p = agent.yielding_model.yielding_probability(v, agent, front, observed_model, direction)
+        if v.id not in intentions:
+            intentions[v.id] = YieldingIntention(v.id, p, change_intention_threshold=agent.change_intention_threshold,
+                                                 random_intention_seed=agent.random_yielding_seed)
+        else:
+            intentions[v.id].update_intention(p)
+    wanted = [v.id for v in matches]
+    for idx in list(intentions):
+        if idx not in wanted:
+            intentions.pop(idx)
+    yielding_to = [v for v in matches if intentions[v.id].yielding]
+    if yielding_to:
+        ax = min(ax, idm_acc_f_b(yielding_to, None, agent.v, corridor.v_limit,
+                                 idm_p_for_merging_exit_agents(agent.random_yielding_seed, agent.idm_param, agent.l > 7)))
+    rp = agent.rss_param
+    if front and rss_dis(front.v, agent.v, rp.r_t_ego, rp.a_min, rp.a_max) > front.dis - 0.5 * (front.l + agent.l):
+        ax = rp.a_min
+    return DecoupledAction(ax, vy, corridor)
+
+
+def lane_change_behavior_mobil(observed_model, agent, require_rss_safety):    # behaviors.py:70-86
+    ego_corridor = observed_model.corridor_for_agent(agent.id)
+    action_idm = idm_behavior(observed_model, agent)
+    mcs_corridors, mcs_agents = lane_change_mcs_sim_from_env(observed_model, agent, ego_corridor)
+    for a in mcs_agents:
+        if a.id == agent.id:
+            a.targetLaneId, a.commitToDecision, a.commitKeepLaneStep = agent.target_lane_id, agent.commit_lane_change, agent.commit_keep_lane_step
+            break
+    action = ms.laneChangeMobilBehavior(ms.Environment(ms.MapMultiLane(mcs_corridors), mcs_agents), agent.id,
+                                        ms.Action(action_idm.ax, action_idm.vy), require_rss_safety)
+    agent.commit_lane_change, agent.commit_keep_lane_step, agent.target_lane_id = \
+        action.commitToDecision, action.commitKeepLaneStep, action.targetLaneId
+    return DecoupledAction(action.ax, action.vy, ego_corridor)
 
 
 def lane_change_behavior_learned(observed_model, agent):     # behaviors.py:89-115

@@ -80,6 +80,7 @@ struct mce_map {
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   mce::EnvMapHead* d_head = nullptr;
   mce::EnvMapTail* d_tail = nullptr;
+  mce::EnvMapBorder* d_border = nullptr;
   // state of the last match (resident)
   int n_agents = 0, n_scenes = 0;
   size_t cap_slots = 0, cap_scenes = 0, cap_arc_on = 0, cap_q = 0;
@@ -103,6 +104,9 @@ int mce_map_create(const mce_corridor* corridors, int n_corridors, int device, m
   if (device < 0 || device >= n_dev) return efail(MCE_ERR_ARG, "device index out of range");
   std::vector<mce::EnvMapHead> head(1);
   std::vector<mce::EnvMapTail> tail(1);
+  std::vector<mce::EnvMapBorder> border(1);
+  mce::EnvMapBorder& B = border[0];
+  std::memset(&B, 0, sizeof(B));
   mce::EnvMapHead& H = head[0];
   mce::EnvMapTail& T = tail[0];
   std::memset(&H, 0, sizeof(H));
@@ -158,6 +162,26 @@ int mce_map_create(const mce_corridor* corridors, int n_corridors, int device, m
     }
     for (size_t i = 0; i < cs.size(); ++i) { T.cs[c][i][0] = cs[i].first; T.cs[c][i][1] = cs[i].second; }
     T.cs_len[c] = line_length(cs);
+    // leftSimplified / rightSimplified (type.py:151-152) and the centre line again, for the distance kernels
+    for (int sd = 0; sd < 2; ++sd) {
+      std::vector<Pt> path;
+      const int np = sd == 0 ? k.n_left : k.n_right;
+      if (np < 2) return efail(MCE_ERR_CAPACITY, "a border polyline needs at least two points");
+      for (int i = 0; i < np; ++i) path.push_back(sd == 0 ? Pt(k.left[i][0], k.left[i][1]) : Pt(k.right[i][0], k.right[i][1]));
+      const std::vector<Pt> sp = simplify(path, 0.05);
+      B.n_path[sd][c] = np;
+      B.n_simp[sd][c] = (int)sp.size();
+      run = 0.0;
+      for (size_t i = 0; i < path.size(); ++i) {
+        if (i) run = run + dist(path[i - 1], path[i]);
+        B.path[sd][c][i][0] = path[i].first; B.path[sd][c][i][1] = path[i].second; B.dis[sd][c][i] = run;
+      }
+      for (size_t i = 0; i < sp.size(); ++i) { B.simp[sd][c][i][0] = sp[i].first; B.simp[sd][c][i][1] = sp[i].second; }
+      B.simp_len[sd][c] = line_length(sp);
+    }
+    B.n_center[c] = T.n_center[c]; B.n_cs[c] = T.n_cs[c]; B.cs_len[c] = T.cs_len[c];
+    std::memcpy(B.cpath[c], T.cpath[c], sizeof(B.cpath[c])); std::memcpy(B.cdis[c], T.cdis[c], sizeof(B.cdis[c]));
+    std::memcpy(B.cs[c], T.cs[c], sizeof(B.cs[c]));
   }
   ENV_TRY(cudaSetDevice(device));
   mce_map* m = new mce_map();
@@ -169,6 +193,8 @@ int mce_map_create(const mce_corridor* corridors, int n_corridors, int device, m
   ENV_TRY(cudaMalloc(&m->d_tail, sizeof(mce::EnvMapTail)));
   ENV_TRY(cudaMemcpyAsync(m->d_head, &H, sizeof(H), cudaMemcpyHostToDevice, m->stream));
   ENV_TRY(cudaMemcpyAsync(m->d_tail, &T, sizeof(T), cudaMemcpyHostToDevice, m->stream));
+  ENV_TRY(cudaMalloc(&m->d_border, sizeof(mce::EnvMapBorder)));
+  ENV_TRY(cudaMemcpyAsync(m->d_border, &B, sizeof(B), cudaMemcpyHostToDevice, m->stream));
   ENV_TRY(cudaStreamSynchronize(m->stream));
   *out = m;
   return MCE_OK;
@@ -177,7 +203,7 @@ int mce_map_create(const mce_corridor* corridors, int n_corridors, int device, m
 int mce_map_destroy(mce_map* m) {
   if (!m) return MCE_OK;
   cudaSetDevice(m->device);
-  void* bufs[] = {m->d_head, m->d_tail, m->d_x, m->d_y, m->d_arc, m->d_arc_on, m->d_nbd, m->d_lane, m->d_order, m->d_start,
+  void* bufs[] = {m->d_head, m->d_tail, m->d_border, m->d_x, m->d_y, m->d_arc, m->d_arc_on, m->d_nbd, m->d_lane, m->d_order, m->d_start,
                   m->d_nbi, m->d_qf, m->d_qi};
   for (void* b : bufs) if (b) cudaFree(b);
   for (int i = 0; i < 3; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
@@ -342,6 +368,54 @@ int mce_step_along_path(mce_map* m, const int32_t* ref_lane, const double* x, co
   double* outp[4] = {x_out, y_out, v_out, yaw_out};
   for (int k = 0; k < 4; ++k) ENV_TRY(cudaMemcpyAsync(outp[k], d + (5 + k) * q, q * 8, cudaMemcpyDeviceToHost, s));
   ENV_TRY(cudaStreamSynchronize(s));
+  return MCE_OK;
+}
+
+int mce_center_distance(mce_map* m, const int32_t* lane, const double* x, const double* y, int n, double* signed_out, double* to_end_out) {
+  if (!m || !lane || !x || !y || !signed_out || !to_end_out) return efail(MCE_ERR_ARG, "null argument");
+  if (n < 1) return efail(MCE_ERR_ARG, "no points");
+  for (int i = 0; i < n; ++i)
+    if (lane[i] < 0 || lane[i] >= m->n_lanes) return efail(MCE_ERR_ARG, "corridor index out of range");
+  ENV_TRY(cudaSetDevice(m->device));
+  int rc = ensure_query_buffers(m, n);
+  if (rc) return rc;
+  cudaStream_t s = m->stream;
+  const size_t q = n;
+  double* d = m->d_qf;
+  ENV_TRY(cudaMemcpyAsync(d, x, q * 8, cudaMemcpyHostToDevice, s));
+  ENV_TRY(cudaMemcpyAsync(d + q, y, q * 8, cudaMemcpyHostToDevice, s));
+  ENV_TRY(cudaMemcpyAsync(m->d_qi, lane, q * 4, cudaMemcpyHostToDevice, s));
+  mce::env_center_kernel<<<(n + mce::kBT - 1) / mce::kBT, mce::kBT, 0, s>>>(m->d_border, m->d_qi, d, d + q, n, d + 2 * q, d + 3 * q);
+  ENV_TRY(cudaGetLastError());
+  ENV_TRY(cudaMemcpyAsync(signed_out, d + 2 * q, q * 8, cudaMemcpyDeviceToHost, s));
+  ENV_TRY(cudaMemcpyAsync(to_end_out, d + 3 * q, q * 8, cudaMemcpyDeviceToHost, s));
+  ENV_TRY(cudaStreamSynchronize(s));
+  return MCE_OK;
+}
+
+int mce_border_distance(mce_map* m, const int32_t* lane, const int32_t* side, const double* hull, int n, double* out) {
+  if (!m || !lane || !side || !hull || !out) return efail(MCE_ERR_ARG, "null argument");
+  if (n < 1) return efail(MCE_ERR_ARG, "no hulls");
+  for (int i = 0; i < n; ++i) {
+    if (lane[i] < 0 || lane[i] >= m->n_lanes) return efail(MCE_ERR_ARG, "corridor index out of range");
+    if (side[i] != MCE_SIDE_LEFT && side[i] != MCE_SIDE_RIGHT) return efail(MCE_ERR_ARG, "side must be MCE_SIDE_LEFT or MCE_SIDE_RIGHT");
+  }
+  ENV_TRY(cudaSetDevice(m->device));
+  int rc = ensure_query_buffers(m, n);
+  if (rc) return rc;
+  cudaStream_t s = m->stream;
+  const size_t q = n;
+  std::vector<double> soa(8 * q);                            // [corner coordinate][hull]: thread i reads element i
+  for (size_t i = 0; i < q; ++i)
+    for (int k = 0; k < 8; ++k) soa[k * q + i] = hull[i * 8 + k];
+  double* d = m->d_qf;
+  ENV_TRY(cudaMemcpyAsync(d, soa.data(), 8 * q * 8, cudaMemcpyHostToDevice, s));
+  ENV_TRY(cudaMemcpyAsync(m->d_qi, lane, q * 4, cudaMemcpyHostToDevice, s));
+  ENV_TRY(cudaMemcpyAsync(m->d_qi + q, side, q * 4, cudaMemcpyHostToDevice, s));
+  mce::env_border_kernel<<<(n + mce::kBT - 1) / mce::kBT, mce::kBT, 0, s>>>(m->d_border, m->d_qi, m->d_qi + q, d, n, d + 8 * q);
+  ENV_TRY(cudaGetLastError());
+  ENV_TRY(cudaMemcpyAsync(out, d + 8 * q, q * 8, cudaMemcpyDeviceToHost, s));
+  ENV_TRY(cudaStreamSynchronize(s));                         // `soa` stays alive until here
   return MCE_OK;
 }
 

@@ -44,6 +44,20 @@ struct EnvMapTail {                          // staged by the Frenet and step ke
   double cyaw[MCE_MAX_LANES][MCE_MAX_POINTS], ccos[MCE_MAX_LANES][MCE_MAX_POINTS], csin[MCE_MAX_LANES][MCE_MAX_POINTS];
 };
 
+struct EnvMapBorder {                        // staged by the centre / border distance kernels
+  int n_path[2][MCE_MAX_LANES];              // [0] left, [1] right border polyline (type.py:144-151)
+  int n_simp[2][MCE_MAX_LANES];              // leftSimplified / rightSimplified .path_line
+  int n_center[MCE_MAX_LANES], n_cs[MCE_MAX_LANES];
+  double path[2][MCE_MAX_LANES][MCE_MAX_POINTS][2];
+  double dis[2][MCE_MAX_LANES][MCE_MAX_POINTS];
+  double simp[2][MCE_MAX_LANES][MCE_MAX_POINTS][2];
+  double simp_len[2][MCE_MAX_LANES];
+  double cpath[MCE_MAX_LANES][MCE_MAX_POINTS][2];
+  double cdis[MCE_MAX_LANES][MCE_MAX_POINTS];
+  double cs[MCE_MAX_LANES][MCE_MAX_POINTS][2];
+  double cs_len[MCE_MAX_LANES];
+};
+
 template <typename T>
 __device__ __forceinline__ void stage(T* dst, const T* src) {
   static_assert(sizeof(T) % 4 == 0, "word copy");
@@ -355,6 +369,103 @@ __global__ void __launch_bounds__(kBT) env_step_kernel(const EnvMapTail* __restr
   y_out[i] = fy + d_new * m.ccos[l][k];
   v_out[i] = v_new;
   yaw_out[i] = m.cyaw[l][k];
+}
+
+// ---- corridor.centerSimplified.signed_distance (type.py:307-315, behaviors.py:20) and Corridor.distance_to_corridor_end
+// (type.py:180-181) of n points, each on its own corridor ---------------------------------------------------------------
+__global__ void __launch_bounds__(kBT) env_center_kernel(const EnvMapBorder* __restrict__ gmap, const int32_t* __restrict__ lane,
+                                                         const double* __restrict__ x, const double* __restrict__ y, int n,
+                                                         double* __restrict__ d_out, double* __restrict__ end_out) {
+  __shared__ EnvMapBorder m;
+  stage(&m, gmap);
+  __syncthreads();
+  const int i = blockIdx.x * kBT + threadIdx.x;
+  if (i >= n) return;
+  const int l = lane[i];
+  const double px = x[i], py = y[i];
+  double s, dis;
+  project_distance(m.cs[l], m.n_cs[l], px, py, s, dis);
+  double d = 0.0;
+  if (dis > 0.0) {
+    LineView lv{m.cpath[l], m.cdis[l], m.n_center[l], m.cs_len[l]};
+    d = lv.side_of(s, px, py) > 0 ? dis : -dis;
+  }
+  d_out[i] = d;
+  end_out[i] = m.cs_len[l] - s;
+}
+
+// shapely: do the closed segments AB and CD share a point
+__device__ __forceinline__ double orient(double ax, double ay, double bx, double by, double cx, double cy) {
+  return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+}
+__device__ __forceinline__ bool on_box(double px, double py, double qx, double qy, double rx, double ry) {
+  return fmin(px, qx) <= rx && rx <= fmax(px, qx) && fmin(py, qy) <= ry && ry <= fmax(py, qy);
+}
+__device__ __forceinline__ bool segments_intersect(double ax, double ay, double bx, double by, double cx, double cy, double dx,
+                                                   double dy) {
+  const double o1 = orient(ax, ay, bx, by, cx, cy), o2 = orient(ax, ay, bx, by, dx, dy);
+  const double o3 = orient(cx, cy, dx, dy, ax, ay), o4 = orient(cx, cy, dx, dy, bx, by);
+  if (((o1 > 0) != (o2 > 0)) && ((o3 > 0) != (o4 > 0)) && o1 != 0 && o2 != 0 && o3 != 0 && o4 != 0) return true;
+  return (o1 == 0 && on_box(ax, ay, bx, by, cx, cy)) || (o2 == 0 && on_box(ax, ay, bx, by, dx, dy)) ||
+         (o3 == 0 && on_box(cx, cy, dx, dy, ax, ay)) || (o4 == 0 && on_box(cx, cy, dx, dy, bx, by));
+}
+__device__ __forceinline__ double seg_seg_distance(double ax, double ay, double bx, double by, double cx, double cy, double dx,
+                                                   double dy) {
+  if (segments_intersect(ax, ay, bx, by, cx, cy, dx, dy)) return 0.0;
+  double d, t, d2, best;
+  seg_point(ax, ay, bx, by, cx, cy, best, t, d2);
+  seg_point(ax, ay, bx, by, dx, dy, d, t, d2); best = d < best ? d : best;
+  seg_point(cx, cy, dx, dy, ax, ay, d, t, d2); best = d < best ? d : best;
+  seg_point(cx, cy, dx, dy, bx, by, d, t, d2); best = d < best ? d : best;
+  return best;
+}
+
+// ---- Corridor.distance_to_border(hull, direction) (type.py:183-206; environment.py:113-115 dis_to_lane_border):
+// < 0 = how far the hull has passed the border on that side, otherwise Polygon(hull).distance(border line) ------------
+__global__ void __launch_bounds__(kBT) env_border_kernel(const EnvMapBorder* __restrict__ gmap, const int32_t* __restrict__ lane,
+                                                         const int32_t* __restrict__ side, const double* __restrict__ hull, int n,
+                                                         double* __restrict__ out) {
+  __shared__ EnvMapBorder m;
+  stage(&m, gmap);
+  __syncthreads();
+  const int i = blockIdx.x * kBT + threadIdx.x;
+  if (i >= n) return;
+  const int l = lane[i], sd = side[i];                       // 0 = "left", 1 = "right"
+  double hx[4], hy[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { hx[k] = hull[(size_t)(2 * k) * n + i]; hy[k] = hull[(size_t)(2 * k + 1) * n + i]; }
+  const double (*simp)[2] = m.simp[sd][l];
+  const int ns = m.n_simp[sd][l];
+  LineView lv{m.path[sd][l], m.dis[sd][l], m.n_path[sd][l], m.simp_len[sd][l]};
+  bool pass = false;
+  double worst = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double s, dis;
+    project_distance(simp, ns, hx[k], hy[k], s, dis);
+    const bool left_of = dis > 0.0 && lv.side_of(s, hx[k], hy[k]) > 0;      // is_left_of type.py:297-305
+    if (sd == 0 ? left_of : !left_of) {
+      pass = true;
+      worst = dis > worst ? dis : worst;
+    }
+  }
+  if (pass) { out[i] = -worst; return; }
+  // Polygon(hull).distance(LineString): 0 when a vertex of the line lies inside the hull, else the nearest edge pair
+  double shell[4][2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { shell[k][0] = hx[k]; shell[k][1] = hy[k]; }
+  for (int k = 0; k < ns; ++k)
+    if (within(shell, 4, simp[k][0], simp[k][1])) { out[i] = 0.0; return; }
+  double best = 0.0;
+  bool have = false;
+  for (int e = 0; e < 4; ++e) {
+    const int e2 = (e + 1) & 3;
+    for (int k = 0; k + 1 < ns; ++k) {
+      const double d = seg_seg_distance(hx[e], hy[e], hx[e2], hy[e2], simp[k][0], simp[k][1], simp[k + 1][0], simp[k + 1][1]);
+      if (!have || d < best) { best = d; have = true; }
+    }
+  }
+  out[i] = best;
 }
 
 }  // namespace mce

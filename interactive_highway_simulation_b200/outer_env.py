@@ -54,7 +54,9 @@ def _lib():
         L.mce_project_center.argtypes = [V, I, _pd, _pd, I, _pd, _pd]
         L.mce_step_along_path.argtypes = [V, _pi, _pd, _pd, _pd, _pd, _pd, D, I, _pd, _pd, _pd, _pd]
         L.mce_last_kernel_ms.argtypes = [V, C.POINTER(C.c_float)]
-        for f in ("mce_map_create", "mce_map_destroy", "mce_env_match", "mce_env_neighbors", "mce_frenet", "mce_project_center",
+        L.mce_center_distance.argtypes = [V, _pi, _pd, _pd, I, _pd, _pd]
+        L.mce_border_distance.argtypes = [V, _pi, _pi, _pd, I, _pd]
+        for f in ("mce_center_distance", "mce_border_distance", "mce_map_create", "mce_map_destroy", "mce_env_match", "mce_env_neighbors", "mce_frenet", "mce_project_center",
                   "mce_step_along_path", "mce_last_kernel_ms"):
             getattr(L, f).restype = I
         _bound = True
@@ -103,6 +105,7 @@ class DeviceMap:
     def __init__(self, corridors, device=0):
         self._pods = corridor_pods(list(corridors))
         self.n_lanes = len(self._pods)
+        self.center_cache = {}                               # (lane, x, y) -> (signed centre distance, distance to the end)
         self._h = C.c_void_p()
         _check(_lib().mce_map_create(self._pods, self.n_lanes, device, C.byref(self._h)))
 
@@ -161,6 +164,21 @@ class DeviceMap:
         _check(_lib().mce_step_along_path(self._h, ref_lane, _f64(x), _f64(y), _f64(v), _f64(ax), _f64(vy), float(dt), n, *out))
         return out
 
+    def center_distance(self, lane, x, y):
+        """(centerSimplified.signed_distance, distance_to_corridor_end) of every point on its own corridor index"""
+        lane, x, y = np.ascontiguousarray(lane, np.int32), _f64(x), _f64(y)
+        d, e = np.empty(len(x)), np.empty(len(x))
+        _check(_lib().mce_center_distance(self._h, lane, x, y, len(x), d, e))
+        return d, e
+
+    def border_distance(self, lane, side, hull):
+        """Corridor.distance_to_border of hulls [n][4][2]; side 0 = left, 1 = right"""
+        lane, side = np.ascontiguousarray(lane, np.int32), np.ascontiguousarray(side, np.int32)
+        hull = _f64(hull).reshape(len(lane), 8)
+        out = np.empty(len(lane))
+        _check(_lib().mce_border_distance(self._h, lane, side, hull, len(lane), out))
+        return out
+
     def last_kernel_ms(self):
         ms = (C.c_float * 2)()
         _check(_lib().mce_last_kernel_ms(self._h, ms))
@@ -169,15 +187,55 @@ class DeviceMap:
 
 # ---- the reference's value classes (agent.py:203-247, type.py:140-176) ----------------------------------------------
 
+class _CenterLine:
+    """corridor.centerSimplified (type.py:153) as far as the behaviours read it: signed_distance, on the device"""
+
+    def __init__(self, corridor):
+        self._c = corridor
+
+    def signed_distance(self, point):                        # type.py:307-315
+        return self._c._center_distance(point)[0]
+
+
 class Corridor:
-    """type.py:140-176 reduced to data (the polygons / shapely lines live on the device)."""
+    """type.py:140-176 reduced to data (the polygons / shapely lines live on the device; `Map` attaches the handle)."""
 
     def __init__(self, idx, t, left, right, center, v_limit):
         self.id, self.type, self.left, self.right, self.center, self.v_limit = idx, t, left, right, center, v_limit
         self.left_id = self.right_id = None
+        self.device_map, self.lane_index = None, -1
+        self.centerSimplified = _CenterLine(self)
 
     def set_left_and_right_corridor_id(self, left_id, right_id):
         self.left_id, self.right_id = left_id, right_id
+
+    def _center_distance(self, point):
+        """(signed distance to the centre line, distance to the corridor end); answers are kept per position — the
+        environment fills them for every vehicle of a step in one launch (Environment.match_agents_on_corridor)"""
+        key = (self.lane_index, float(point[0]), float(point[1]))
+        cache = self.device_map.center_cache
+        if key not in cache:
+            d, e = self.device_map.center_distance([key[0]], [key[1]], [key[2]])
+            cache[key] = (float(d[0]), float(e[0]))
+        return cache[key]
+
+    def distance_to_corridor_end(self, position):            # type.py:180-181
+        return self._center_distance(position)[1]
+
+    def distance_to_border(self, hull, direction):           # type.py:183-206
+        return float(self.device_map.border_distance([self.lane_index], [0 if direction == "left" else 1], [hull])[0])
+
+    def to_dict(self):                                       # environment.py:59-67 (one entry of Map.to_dict)
+        return {"id": self.id, "type": self.type, "left": self.left, "right": self.right, "center": self.center,
+                "v_limit": self.v_limit, "left_id": "none" if self.left_id is None else self.left_id,
+                "right_id": "none" if self.right_id is None else self.right_id}
+
+
+def create_corridor_from_dict(d):                            # environment.py:12-18
+    c = Corridor(d["id"], d["type"], d["left"], d["right"], d["center"], d["v_limit"])
+    c.set_left_and_right_corridor_id(d["left_id"] if d["left_id"] != "none" else None,
+                                     d["right_id"] if d["right_id"] != "none" else None)
+    return c
 
 
 class MatchedAgent:                                          # agent.py:229-232
@@ -213,6 +271,11 @@ class Map:
         self.index_of = {cid: k for k, cid in enumerate(self.corridors)}
         self.id_at = list(self.corridors)
         self.device_map = DeviceMap(list(self.corridors.values()), device)
+        for k, c in enumerate(self.corridors.values()):
+            c.device_map, c.lane_index = self.device_map, k
+
+    def to_dict(self):                                       # environment.py:58-68
+        return {i: c.to_dict() for i, c in self.corridors.items()}
 
     def truck_lane_id(self):                                 # environment.py:46-56
         if "merging" in self.corridors_by_type:
@@ -240,6 +303,7 @@ class Environment:
     def match_agents_on_corridor(self):                      # environment.py:85-101 — one launch
         objs = list(self.agents.values())
         self.matched_agents = {}
+        self._border_cache = {}
         self.matched_agents_sorted_by_arc_length = {c: [] for c in self.map.corridors}
         self._slot, self._objs = {a.id: i for i, a in enumerate(objs)}, objs
         if not objs:
@@ -263,6 +327,16 @@ class Environment:
         for lane, cid in enumerate(self.map.id_at):
             members = t.order[0, t.start[0, lane]:t.start[0, lane + 1]]
             self.matched_agents_sorted_by_arc_length[cid] = [[float(t.arc[0, j]), objs[j]] for j in members]
+        # centre-line distances of every matched vehicle at its matched position, one launch (read by idm_behavior and the
+        # yielding model during the sequential loop; a vehicle that has moved since is asked for again)
+        on = [i for i in range(len(objs)) if t.lane[0, i] >= 0]
+        cache = self.map.device_map.center_cache
+        cache.clear()
+        if on:
+            lanes = [int(t.lane[0, i]) for i in on]
+            d, e = self.map.device_map.center_distance(lanes, self._x0[on], self._y0[on])
+            for k, i in enumerate(on):
+                cache[(lanes[k], float(self._x0[i]), float(self._y0[i]))] = (float(d[k]), float(e[k]))
 
     def corridor_for_agent(self, idx):                       # environment.py:103-112
         if idx not in self.agents or idx not in self.matched_agents:
@@ -318,3 +392,62 @@ class Environment:
         lane = self.map.index_of[self.matched_agents[obj_id].corridor_id]
         arcs, _ = self.map.device_map.project_center(lane, [ego.x, obj.x], [ego.y, obj.y])
         return IdmMatch(float(arcs[1] - arcs[0]), obj)
+
+    def dis_to_lane_border(self, idx, direction):            # environment.py:113-115
+        a = self.matched_agents[idx].agent
+        key = (idx, direction, tuple(map(tuple, a.hull)))
+        if key not in self._border_cache:
+            self._border_cache[key] = self.corridor_for_agent(idx).distance_to_border(a.hull, direction)
+        return self._border_cache[key]
+
+    # ---- bookkeeping of the evaluation scripts (environment.py:253-313) ----
+    def all_finish_merging(self):
+        return all(a.merging_flag.finish_merging for a in self.agents.values() if "merging_flag" in a.__dict__)
+
+    def all_finish_exit(self):
+        return all(self.map.corridors[a.corridor_history[-1]].type == "exit" for a in self.agents.values() if "exit" in a.behavior_model)
+
+    def agents_once_on_merging_lane(self):
+        return [a for a in self.agents.values() if "merging_flag" in a.__dict__]
+
+    def agents_never_on_merging_lane(self):
+        return [a for a in self.agents.values() if "merging_flag" not in a.__dict__]
+
+    def average_normalized_acc_agents(self, agents):
+        total = 0
+        for a in agents:
+            average_acc = sum(a.acceleration_history) / len(a.acceleration_history)
+            total += (average_acc - a.idm_param.acc_min) / (a.idm_param.acc_max - a.idm_param.acc_min)
+        return total / max(len(agents), 1)
+
+    def set_flag(self, agent):                               # environment.py:282-313
+        for b in agent.behavior_model_history:
+            if "merging" in b:
+                if not agent.merging_flag.flag_freeze:
+                    t = self.map.corridors[self.matched_agents[agent.id].corridor_id].type
+                    if t == "main":
+                        agent.merging_flag.finish_merging = True
+                        agent.merging_flag.t_finish_merging = self.sim_time
+                        agent.merging_flag.flag_freeze = True
+                    if t == "merging" and agent.v <= 2 and agent.had_harsh_brake():
+                        agent.merging_flag.once_fallback = True
+                break
+        for b in agent.behavior_model_history:
+            if "exit" in b:
+                if not agent.exit_flag.flag_freeze:
+                    t = self.map.corridors[self.matched_agents[agent.id].corridor_id].type
+                    if t == "exit":
+                        agent.exit_flag.finish_exit = True
+                        agent.exit_flag.t_finish_exit = self.sim_time
+                        agent.exit_flag.flag_freeze = True
+                    if t == "main" and agent.had_harsh_brake():
+                        agent.merging_flag.once_fallback = True       # sic (environment.py:311)
+                break
+
+    def step(self, dt):                                      # environment.py:316-323
+        """Plan and move the vehicles one after the other against the lane vectors of the last match, then re-match."""
+        for a in list(self.agents.values()):
+            a.step(a.plan(self), dt)
+            self.set_flag(a)
+        self.match_agents_on_corridor()
+        self.sim_time += dt

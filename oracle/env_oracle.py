@@ -9,6 +9,7 @@ csrc/env_kernels.cuh are compiled to with -fmad=false), of the OUTER environment
     environment.py:145-156  sorted_agents_on_corridor_within_range_of_vehicle
     environment.py:166-195  front_agent / following_agent
     environment.py:197-251  neighbor_around_agent
+    type.py:180-206         Corridor.distance_to_corridor_end / distance_to_border (environment.py:113-115)
     type.py:255-317         LineSimplified (project, get_point_at_length, get_yaw_at_length, is_left_of,
                             signed_distance, to_frenet_frame)
     utility.py:83-98        offset_point, step_along_path
@@ -188,6 +189,7 @@ class PreparedMap:
             self.shell.append(pts)
         self.ref = [LineSimplified(extend_line_both_sides(c, 1000)) for c in self.center]   # mcs_wrapper.py:42,109,211
         self.center_simplified = [LineSimplified(c) for c in self.center]             # type.py:153
+        self.border = [[LineSimplified(c["left"]), LineSimplified(c["right"])] for c in corridors]   # type.py:151-152
 
 
 def match(pm, xs, ys):
@@ -287,3 +289,60 @@ def step_along_path(pm, ref_lane, x, y, v, ax, vy, dt):
     yaw = ls.yaw_list[k]
     px, py = ls.get_point_at_length(s_new)
     return px - d_new * math.sin(yaw), py + d_new * math.cos(yaw), v_new, yaw
+
+
+def center_distance(pm, lane, x, y):
+    """(centerSimplified.signed_distance type.py:307-315, Corridor.distance_to_corridor_end type.py:180-181) on corridors[lane]"""
+    ls = pm.center_simplified[lane]
+    s, dis = project_and_distance(ls.line, x, y)
+    d = 0.0 if dis <= 0.0 else ls.side_of(s, x, y) * dis
+    return d, ls.path_length - s
+
+
+def _orient(ax, ay, bx, by, cx, cy):
+    return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax)
+
+
+def _on_box(p, q, r):
+    return min(p[0], q[0]) <= r[0] <= max(p[0], q[0]) and min(p[1], q[1]) <= r[1] <= max(p[1], q[1])
+
+
+def segments_intersect(a, b, c, d):
+    """do the closed segments AB and CD share a point (orientation test)"""
+    o1, o2 = _orient(*a, *b, *c), _orient(*a, *b, *d)
+    o3, o4 = _orient(*c, *d, *a), _orient(*c, *d, *b)
+    if ((o1 > 0) != (o2 > 0)) and ((o3 > 0) != (o4 > 0)) and o1 != 0 and o2 != 0 and o3 != 0 and o4 != 0:
+        return True
+    return (o1 == 0 and _on_box(a, b, c)) or (o2 == 0 and _on_box(a, b, d)) or (o3 == 0 and _on_box(c, d, a)) or \
+        (o4 == 0 and _on_box(c, d, b))
+
+
+def seg_seg_distance(a, b, c, d):
+    if segments_intersect(a, b, c, d):
+        return 0.0
+    return min(seg_point(*a, *b, *c)[0], seg_point(*a, *b, *d)[0], seg_point(*c, *d, *a)[0], seg_point(*c, *d, *b)[0])
+
+
+def border_distance(pm, lane, side, hull):
+    """Corridor.distance_to_border(hull, "left" if side == 0 else "right") type.py:183-206; hull = 4 corners"""
+    ls = pm.border[lane][side]
+    passed, worst = False, 0.0
+    for (px, py) in hull:
+        s, dis = project_and_distance(ls.line, px, py)
+        left_of = dis > 0.0 and ls.side_of(s, px, py) > 0                      # is_left_of type.py:297-305
+        if left_of if side == 0 else not left_of:
+            passed = True
+            worst = dis if dis > worst else worst
+    if passed:
+        return -worst
+    shell = [(float(p[0]), float(p[1])) for p in hull]
+    if any(within(shell, qx, qy) for qx, qy in ls.line):                        # Polygon.distance(LineString)
+        return 0.0
+    best = None
+    for e in range(4):
+        a, b = shell[e], shell[(e + 1) % 4]
+        for c, d in zip(ls.line, ls.line[1:]):
+            v = seg_seg_distance(a, b, c, d)
+            if best is None or v < best:
+                best = v
+    return best

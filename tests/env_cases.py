@@ -9,6 +9,8 @@ TOL = 1e-9
 HERE = os.path.dirname(os.path.abspath(__file__))
 with gzip.open(os.path.join(HERE, "golden", "env_states.json.gz"), "rt") as f:
     STATES = json.load(f)
+with gzip.open(os.path.join(HERE, "golden", "env_border.json.gz"), "rt") as f:
+    BORDER = json.load(f)          # tests/golden/make_border_golden.py
 
 
 def corridor_dicts(rec):

@@ -25,7 +25,7 @@ def declared_env_functions():
 def test_env_header_entry_points_are_exported(backend_lib):
     names = declared_env_functions()
     for n in ("mce_map_create", "mce_map_destroy", "mce_env_match", "mce_env_neighbors", "mce_frenet", "mce_project_center",
-              "mce_step_along_path", "mce_last_error", "mce_last_kernel_ms"):
+              "mce_step_along_path", "mce_last_error", "mce_last_kernel_ms", "mce_center_distance", "mce_border_distance"):
         assert n in names
     L = C.CDLL(backend_lib.LIB_PATH)
     for n in names:

@@ -7,7 +7,7 @@ import random
 import numpy as np
 import pytest
 
-from env_cases import STATES, TOL, DuckAgent, corridor_dicts, prepared, slots
+from env_cases import BORDER, STATES, TOL, DuckAgent, corridor_dicts, prepared, slots
 from oracle import env_oracle as eo
 
 pytestmark = pytest.mark.gpu
@@ -245,3 +245,27 @@ def test_learned_and_closest_gap_behaviours_equal_the_reference(oe, rec):
             assert a.current_decision == d["decision"], (d["fn"], d["ego"], a.current_decision, d["decision"])
         assert (act.ax, act.vy) == (d["ax"], d["vy"]), (d["fn"], d["ego"], act.ax, d["ax"], act.vy, d["vy"])
         a.behavior_model, a.rss_param = keep
+
+
+@pytest.mark.parametrize("rec", BORDER, ids=[r["tag"] for r in BORDER])
+def test_border_and_centre_distance_kernels(oe, rec):
+    """mce_center_distance / mce_border_distance: bit-identical to the oracle, and equal (1e-9) to what the reference's own
+    Corridor.distance_to_border / distance_to_corridor_end / centerSimplified.signed_distance answered."""
+    pm = eo.PreparedMap(corridor_dicts(rec))
+    dm = oe.DeviceMap([{**c} for c in rec["corridors"]])
+    pos = {c["id"]: k for k, c in enumerate(rec["corridors"])}
+    S = rec["samples"]
+    lane = [pos[s["corridor"]] for s in S]
+    d, e = dm.center_distance(lane, [s["x"] for s in S], [s["y"] for s in S])
+    want = [eo.center_distance(pm, l, s["x"], s["y"]) for l, s in zip(lane, S)]
+    assert same(d, [w[0] for w in want]) and same(e, [w[1] for w in want])
+    assert all(abs(g - s["signed"]) <= TOL for g, s in zip(d, S)) and all(abs(g - s["to_end"]) <= TOL for g, s in zip(e, S))
+    for side, key in ((0, "left"), (1, "right")):
+        got = dm.border_distance(lane, [side] * len(S), [s["hull"] for s in S])
+        assert same(got, [eo.border_distance(pm, l, side, s["hull"]) for l, s in zip(lane, S)]), key
+        assert all(abs(g - s[key]) <= TOL for g, s in zip(got, S)), key
+    with pytest.raises(oe.EnvError):
+        dm.border_distance([0], [2], [S[0]["hull"]])
+    with pytest.raises(oe.EnvError):
+        dm.center_distance([len(pos)], [0.0], [0.0])
+    dm.close()

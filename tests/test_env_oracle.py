@@ -6,7 +6,7 @@ import math
 
 import pytest
 
-from env_cases import STATES, prepared, slots, TOL
+from env_cases import BORDER, STATES, corridor_dicts, prepared, slots, TOL
 from oracle import env_oracle as eo
 
 
@@ -87,3 +87,18 @@ def test_cross_product_sign_equals_the_reference_angle_test():
         yaw = ls.yaw_list[ls.get_yaw_index(s)]
         ref = 1 if math.sin(math.atan2(py - fy, px - fx) - yaw) > 0 else -1
         assert ls.side_of(s, px, py) == ref
+
+
+@pytest.mark.parametrize("rec", BORDER, ids=[r["tag"] for r in BORDER])
+def test_border_and_centre_distances(rec):
+    """Corridor.distance_to_border / distance_to_corridor_end / centerSimplified.signed_distance as the reference's own
+    type.py answered (tests/golden/make_border_golden.py)"""
+    pm = eo.PreparedMap(corridor_dicts(rec))
+    pos = {c["id"]: k for k, c in enumerate(rec["corridors"])}
+    for s in rec["samples"]:
+        lane = pos[s["corridor"]]
+        d, to_end = eo.center_distance(pm, lane, s["x"], s["y"])
+        assert abs(d - s["signed"]) <= TOL and abs(to_end - s["to_end"]) <= TOL, s
+        for side, key in ((0, "left"), (1, "right")):
+            got = eo.border_distance(pm, lane, side, s["hull"])
+            assert abs(got - s[key]) <= TOL, (s, key, got)
