@@ -299,6 +299,31 @@ def outer_env_block(args, reps=10):
     return out
 
 
+def outer_loop_block(steps=100):
+    """configs[0]: simulation_multilane on the shipped test_scene (21 vehicles, merging lane + 2 main lanes), dt 0.2, 100
+    steps, headless — every step is the sequential plan-and-move loop (device neighbour tables / border distances, the MOBIL
+    and closest-gap decision kernels, device step_along_path) and one re-match.  Wall clock of the public call."""
+    import random
+    import numpy as np
+    from interactive_highway_simulation_b200 import mc_sim_highway as ms, simulation_multilane as sm
+    scene = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "test_scene_epoch0")
+    out = {}
+    for rep in range(2):                                       # the first pass warms the context / allocator
+        random.seed(0); np.random.seed(0); ms.seed(1000)
+        sim = sm.Simulation(None, sm.SimulationParameter(0.2, steps, render=False, write_gif=False))
+        sim.load_initial_scene(scene)
+        n0 = len(sim.environment.agents)
+        t0 = time.perf_counter()
+        sim.run()
+        wall = time.perf_counter() - t0
+        hist = sum(len(a.state_history) - 1 for a in list(sim.environment.agents.values()) + list(sim.environment.removed_agents.values()))
+        out = {"workload": "test_scene epoch0, %d vehicles, dt 0.2, %d steps, render=False" % (n0, steps),
+               "wall_s": wall, "ms_per_step": wall / steps * 1e3, "vehicle_steps": hist, "vehicle_steps_per_s": hist / wall,
+               "vehicles_left_on_map": len(sim.environment.agents),
+               "note": "sequential outer loop of the reference (environment.py:316-323): one small launch per query, latency bound"}
+    return out
+
+
 def run_product(args):
     import torch
     from interactive_highway_simulation_b200 import backend, synthetic, _abi as abi
@@ -436,6 +461,12 @@ def run_product(args):
             outer_env = outer_env_block(args)
         except Exception as e:
             outer_env = {"error": str(e)}
+    outer_loop = None
+    if world == 1:
+        try:
+            outer_loop = outer_loop_block()
+        except Exception as e:
+            outer_loop = {"error": str(e)}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": workload_config(args),
@@ -443,7 +474,7 @@ def run_product(args):
            "e2e": {"value": e2e_units_total / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h,
                    "note": "mcs_scene_create + mcs_rollouts (8 groups x %d) + feature read-back per step, host buffers" % (e2e_R // 8)},
-           "decision": decision, "outer_env": outer_env,
+           "decision": decision, "outer_env": outer_env, "outer_loop": outer_loop,
            "gpu_launches": args.steps, "wall_s_timed_region": wall,
            "rollouts_per_s": units_total / (N_VEHICLES * SIM_STEPS) / (kernel_ms_max * 1e-3)}
     print(json.dumps(out))

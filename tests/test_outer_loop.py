@@ -39,6 +39,69 @@ def learned_overrides(sim_mod, tag):
     return {merging_ids[0]: "merging_learned"}, 2
 
 
+def evaluation_env(kind, seed):
+    """one epoch of generate_random_{merging,lc,exit}_traffic (evaluation_merging.py:4-50, evaluation_lane_change.py:4-55,
+    evaluation_exit.py:4-52) with the package's generator, agents through the yaml dict format as the scripts do"""
+    import numpy as np
+    from interactive_highway_simulation_b200 import agent as ag, outer_env, traffic_generator as tg
+    seed_streams(seed)
+    choices = [80 / 3.6, 60 / 3.6, 100 / 3.6] if kind == "merging" else [100 / 3.6]
+    v_limit = float(np.random.choice(choices, 1)[0])
+    spec, params, unsafe, truck = tg.evaluation_map(kind, v_limit=v_limit)
+    gen = tg.RandomTrafficGenerator()
+    merging, main = gen.random_agents_on_map(tg.lanes_from_spec(spec), {i: tg.RandomDensityAndVelocityParameter(*p) for i, p in params.items()},
+                                             unsafe, truck)
+    agents = ag.create_agents_from_dicts(merging) + ag.create_agents_from_dicts(main)
+    return outer_env.Environment(outer_env.Map([outer_env.create_corridor_from_dict({**c, "left_id": "none" if c["left_id"] is None else c["left_id"],
+                                                                                     "right_id": "none" if c["right_id"] is None else c["right_id"]})
+                                                for c in spec]), agents)
+
+
+EVALUATIONS = {   # tag: (map, seed, steps come from the record, who becomes the ego, fall-back rate)  make_scenario_golden.py main()
+    "eval_merging_learned": ("merging", 3, lambda env: {a.id: "merging_learned" for a in env.agents.values() if "merging" in a.behavior_model}, None),
+    "eval_lane_change_learned": ("lane_change", 4, lambda env: {[a for _, a in env.matched_agents_sorted_by_arc_length[2][2:4] if a.l <= 7][0].id:
+                                                                "lane_change_learned"}, None),
+    "eval_exit_learned": ("exit", 5, lambda env: {[a for _, a in env.matched_agents_sorted_by_arc_length[2][2:4] if a.l <= 7][0].id: "exit_learned"}, 0.2),
+    "eval_exit_closest_gap": ("exit", 6, lambda env: {[a for _, a in env.matched_agents_sorted_by_arc_length[1][2:4] if a.l <= 7][0].id: "exit"}, None),
+}
+
+
+def run_evaluation(tag, rec):
+    """evaluate_recorded_*_scene (evaluation_exit.py:55-64 etc.): reset the ego's behaviour model, step the scene"""
+    kind, seed, egos, fall_back = EVALUATIONS[tag]
+    env = evaluation_env(kind, seed)
+    for i, model in egos(env).items():
+        a = env.agents[i]
+        a.reset_behavior_model(model)
+        if fall_back is not None and "learn" in model and hasattr(a, "learned_merging_model"):
+            a.learned_merging_model.learned_model_parameter.max_fall_back_rate = fall_back
+    worst = 0.0
+    for step in range(rec["steps"]):
+        env.step(rec["dt"])
+        worst = max(worst, compare_trace(env, rec["trace"][step], step))
+    return env, worst
+
+
+@pytest.mark.parametrize("tag", sorted(EVALUATIONS))
+def test_evaluation_epochs_host_logic_reproduces_the_reference_trace(monkeypatch, tag):
+    """configs[1..3]: generator -> environment -> 12-20 steps with the learned / closest-gap ego"""
+    from interactive_highway_simulation_b200 import mc_sim_highway as ms, outer_env
+    monkeypatch.setattr(outer_env, "DeviceMap", OracleDeviceMap)
+    rec = load_scenario(tag)
+    inner = RecordedInnerSimulator(ms, rec["calls"])
+    inner.install(monkeypatch)
+    _, worst = run_evaluation(tag, rec)
+    assert inner.k == len(rec["calls"]) and worst < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", sorted(EVALUATIONS))
+def test_evaluation_epochs_on_the_device_reproduce_the_reference_trace(backend_lib, tag):
+    from interactive_highway_simulation_b200 import mc_sim_highway as ms
+    ms.seed(2000 + EVALUATIONS[tag][1])
+    run_evaluation(tag, load_scenario(tag))
+
+
 @pytest.mark.parametrize("tag", ["test_scene", "lane_change_learned", "merging_learned"])
 def test_outer_loop_host_logic_reproduces_the_reference_trace(monkeypatch, tag):
     from interactive_highway_simulation_b200 import mc_sim_highway as ms, outer_env, simulation_multilane as sim_mod
