@@ -1,0 +1,116 @@
+"""The evaluation scripts' per-scene functions (evaluation_merging.py:53-106, evaluation_lane_change.py:58-101,
+evaluation_exit.py:55-105) on the package's outer loop against the reference's own scripts
+(tests/golden/evaluation_stats.json.gz, written by tests/golden/make_evaluation_golden.py): the scene is written in the
+reference's yaml format, loaded, the ego gets its policy, the scene runs, and the statistics object and the console text
+must come out as the reference's did.  CPU: host logic (oracle geometry, recorded inner answers); GPU: the real thing."""
+import gzip
+import json
+import os
+
+import pytest
+import yaml
+
+from outer_loop_cases import GOLDEN, OracleDeviceMap, RecordedInnerSimulator, seed_streams
+
+with gzip.open(os.path.join(GOLDEN, "evaluation_stats.json.gz"), "rt") as f:
+    RECORDS = json.load(f)
+CASES = [(r, k) for r in RECORDS for k in range(len(r["evaluations"]))]
+IDS = ["%s-%s-%s" % (r["kind"], r["evaluations"][k]["policy"], r["evaluations"][k]["fall_back"]) for r, k in CASES]
+
+
+def write_scene(rec, tmp_path):
+    d = tmp_path / "epoch0"
+    d.mkdir()
+    for name in ("agents", "map"):
+        with open(d / (name + ".yml"), "w") as f:
+            yaml.dump({int(k): v for k, v in rec[name].items()}, f, default_flow_style=False)
+    return str(d)
+
+
+def evaluate(ev_mod, rec, k, path, statistics):
+    """the evaluations of one statistics object run in the recorded order up to evaluation k (they accumulate)"""
+    e = rec["evaluations"][k]
+    sim = ev_mod.Simulation(None, ev_mod.SimulationParameter(0.2, rec["steps"], render=False, write_gif=False, scenario=rec["kind"]))
+    if rec["kind"] == "merging":
+        return sim, ev_mod.evaluate_recorded_merging_scene(path, sim, e["policy"], 0, statistics, e["fall_back"])
+    if rec["kind"] == "lane_change":
+        return sim, ev_mod.evaluate_recorded_lc_scene(path, sim, e["policy"], 0, e["ego"], statistics)
+    return sim, ev_mod.evaluate_recorded_exit_scene(path, sim, e["policy"], 0, e["ego"], statistics, e["fall_back"])
+
+
+def check(ev_mod, rec, k, got_text, statistics, sim, tol):
+    e = rec["evaluations"][k]
+    assert sim.step + 1 == e["executed_steps"]
+    for key, want in e["statistics"].items():
+        got = getattr(statistics, key)
+        if isinstance(want, list):
+            assert len(got) == len(want), key
+            for g, w in zip(got, want):
+                assert g == w if isinstance(w, (list, int)) else abs(g - w) <= tol, (key, got, want)
+        else:
+            assert got == want, (key, got, want)
+    assert got_text == e["text"] or tol > 0      # the console line rounds to 3 digits: identical when the numbers are
+
+
+def fresh_statistics(ev_mod, kind):
+    return ev_mod.LaneChangeStatistics() if kind == "lane_change" else ev_mod.MergingAndExitStatistics()
+
+
+@pytest.mark.parametrize("rec,k", CASES, ids=IDS)
+def test_evaluate_recorded_scene_host_logic(monkeypatch, tmp_path, rec, k):
+    from interactive_highway_simulation_b200 import evaluation as ev_mod, mc_sim_highway as ms, outer_env
+    monkeypatch.setattr(outer_env, "DeviceMap", OracleDeviceMap)
+    e = rec["evaluations"][k]
+    path = write_scene(rec, tmp_path)
+    inner = RecordedInnerSimulator(ms, e["calls"])
+    inner.install(monkeypatch)
+    seed_streams(e["seed"])
+    st = fresh_statistics(ev_mod, rec["kind"])
+    sim, text = evaluate(ev_mod, rec, k, path, st)
+    assert inner.k == len(e["calls"])
+    check(ev_mod, rec, k, text, st, sim, 0.0)
+
+
+def test_ego_candidates_and_generated_epochs(monkeypatch, tmp_path):
+    """ego choice of the three scripts; generate_random_traffic writes epochs the loader reads back unchanged"""
+    from interactive_highway_simulation_b200 import evaluation as ev_mod, outer_env
+    monkeypatch.setattr(outer_env, "DeviceMap", OracleDeviceMap)
+    for rec in RECORDS:
+        sim = ev_mod.Simulation(None, ev_mod.SimulationParameter(0.2, 1, render=False, write_gif=False, scenario=rec["kind"]))
+        sub = tmp_path / rec["kind"]
+        sub.mkdir()
+        sim.load_initial_scene(write_scene(rec, sub))
+        got = ev_mod.ego_candidates(sim.environment, rec["kind"])
+        if rec["kind"] == "merging":
+            assert got == [a["id"] for a in rec["agents"].values() if "merging" in a["behavior_model"]]
+        else:
+            assert got == rec["ego_candidates"]
+    seed_streams(5)
+    sim = ev_mod.Simulation(None, ev_mod.SimulationParameter(0.2, 1, render=False, write_gif=False, scenario="exit"))
+    sim.write_dir = str(tmp_path / "generated")
+    ev_mod.generate_random_traffic("exit", 2, sim)
+    for n in range(2):
+        d = os.path.join(sim.write_dir, "epoch%d" % n)
+        again = ev_mod.Simulation(None, sim.param)
+        again.load_initial_scene(d)
+        with open(os.path.join(d, "agents.yml")) as f:
+            on_disk = yaml.safe_load(f)
+        assert len(on_disk) > 20 and sorted(on_disk) == sorted(again.environment.agents)
+        for i, a in again.environment.agents.items():
+            assert (a.x, a.y, a.v, a.l, a.behavior_model, a.idm_param.vd) == \
+                (on_disk[i]["x"], on_disk[i]["y"], on_disk[i]["v"], on_disk[i]["l"], on_disk[i]["behavior_model"], on_disk[i]["idm_p"]["vd"])
+        with open(os.path.join(d, "map.yml")) as f:
+            assert yaml.safe_load(f) == again.environment.map.to_dict()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rec,k", CASES, ids=IDS)
+def test_evaluate_recorded_scene_on_the_device(backend_lib, tmp_path, rec, k):
+    from interactive_highway_simulation_b200 import evaluation as ev_mod, mc_sim_highway as ms
+    e = rec["evaluations"][k]
+    path = write_scene(rec, tmp_path)
+    seed_streams(e["seed"])
+    ms.seed(e["seed"])
+    st = fresh_statistics(ev_mod, rec["kind"])
+    sim, text = evaluate(ev_mod, rec, k, path, st)
+    check(ev_mod, rec, k, text, st, sim, 1e-7)
