@@ -87,8 +87,8 @@ struct mce_map {
   double *d_x = nullptr, *d_y = nullptr, *d_arc = nullptr, *d_arc_on = nullptr, *d_nbd = nullptr;
   int32_t *d_lane = nullptr, *d_order = nullptr, *d_start = nullptr, *d_nbi = nullptr;
   // query / pointwise buffers
-  double* d_qf = nullptr;     // 9 doubles per point
-  int32_t* d_qi = nullptr;    // 2 + 10 ints per point
+  char* d_q = nullptr;        // inputs then outputs of one query call, 144 bytes per point (+ alignment slack)
+  char* h_q = nullptr;        // pinned mirror: one H2D and one D2H copy per call
   float ms[2] = {0.f, 0.f};
 };
 
@@ -204,7 +204,8 @@ int mce_map_destroy(mce_map* m) {
   if (!m) return MCE_OK;
   cudaSetDevice(m->device);
   void* bufs[] = {m->d_head, m->d_tail, m->d_border, m->d_x, m->d_y, m->d_arc, m->d_arc_on, m->d_nbd, m->d_lane, m->d_order, m->d_start,
-                  m->d_nbi, m->d_qf, m->d_qi};
+                  m->d_nbi, m->d_q};
+  if (m->h_q) cudaFreeHost(m->h_q);
   for (void* b : bufs) if (b) cudaFree(b);
   for (int i = 0; i < 3; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
   if (m->stream) cudaStreamDestroy(m->stream);
@@ -239,15 +240,61 @@ static int ensure_match_buffers(mce_map* m, size_t slots, size_t scenes, size_t 
 
 static int ensure_query_buffers(mce_map* m, size_t n) {
   if (n > m->cap_q) {
-    if (m->d_qf) cudaFree(m->d_qf);
-    if (m->d_qi) cudaFree(m->d_qi);
-    m->d_qf = nullptr; m->d_qi = nullptr; m->cap_q = 0;
-    ENV_TRY(cudaMalloc(&m->d_qf, n * 8 * 12));
-    ENV_TRY(cudaMalloc(&m->d_qi, n * 4 * 12));
-    m->cap_q = n;
+    if (m->d_q) cudaFree(m->d_q);
+    if (m->h_q) cudaFreeHost(m->h_q);
+    m->d_q = nullptr; m->h_q = nullptr; m->cap_q = 0;
+    const size_t cap = n < 64 ? 64 : n;
+    ENV_TRY(cudaMalloc(&m->d_q, cap * 144 + 512));
+    ENV_TRY(cudaMallocHost(&m->h_q, cap * 144 + 512));
+    m->cap_q = cap;
   }
   return MCE_OK;
 }
+
+extern "C++" {
+namespace {
+// One query call: the inputs are packed into the pinned mirror and go up in ONE copy, the outputs come back in ONE copy
+// (a sequential outer loop makes thousands of one-vehicle calls; per-array copies were most of their cost).
+struct Query {
+  mce_map* m;
+  size_t in_bytes = 0, out_bytes = 0;
+  struct Out { void* user; size_t off, bytes; };
+  Out outs[4];
+  int n_outs = 0;
+  explicit Query(mce_map* map) : m(map) {}
+  template <typename T>
+  T* in(const T* src, size_t count) {
+    std::memcpy(m->h_q + in_bytes, src, count * sizeof(T));
+    T* d = reinterpret_cast<T*>(m->d_q + in_bytes);
+    in_bytes += (count * sizeof(T) + 15) & ~size_t(15);
+    return d;
+  }
+  template <typename T>
+  T* in_strided(const T* src, size_t count, size_t stride, size_t offset) {     // element i = src[i * stride + offset]
+    T* h = reinterpret_cast<T*>(m->h_q + in_bytes);
+    for (size_t i = 0; i < count; ++i) h[i] = src[i * stride + offset];
+    T* d = reinterpret_cast<T*>(m->d_q + in_bytes);
+    in_bytes += (count * sizeof(T) + 15) & ~size_t(15);
+    return d;
+  }
+  template <typename T>
+  T* out(T* user, size_t count) {                                               // declare after every in()
+    outs[n_outs++] = Out{user, in_bytes + out_bytes, count * sizeof(T)};
+    T* d = reinterpret_cast<T*>(m->d_q + in_bytes + out_bytes);
+    out_bytes += (count * sizeof(T) + 15) & ~size_t(15);
+    return d;
+  }
+  int upload() { ENV_TRY(cudaMemcpyAsync(m->d_q, m->h_q, in_bytes, cudaMemcpyHostToDevice, m->stream)); return MCE_OK; }
+  int finish() {
+    ENV_TRY(cudaGetLastError());
+    ENV_TRY(cudaMemcpyAsync(m->h_q + in_bytes, m->d_q + in_bytes, out_bytes, cudaMemcpyDeviceToHost, m->stream));
+    ENV_TRY(cudaStreamSynchronize(m->stream));
+    for (int k = 0; k < n_outs; ++k) std::memcpy(outs[k].user, m->h_q + outs[k].off, outs[k].bytes);
+    return MCE_OK;
+  }
+};
+}  // namespace
+}  // extern "C++"
 
 int mce_env_match(mce_map* m, const double* x, const double* y, int n_agents, int n_scenes, int32_t* lane_out, double* arc_out,
                   int32_t* lane_order_out, int32_t* lane_start_out, double* arc_on_lane_out, int32_t* nb_index_out,
@@ -300,21 +347,15 @@ int mce_env_neighbors(mce_map* m, const int32_t* scene, const int32_t* slot, con
   ENV_TRY(cudaSetDevice(m->device));
   int rc = ensure_query_buffers(m, n_queries);
   if (rc) return rc;
-  cudaStream_t s = m->stream;
   const size_t q = n_queries;
-  double* d_qx = m->d_qf; double* d_qy = m->d_qf + q; double* d_dis = m->d_qf + 2 * q;
-  int32_t* d_sc = m->d_qi; int32_t* d_sl = m->d_qi + q; int32_t* d_idx = m->d_qi + 2 * q;
-  ENV_TRY(cudaMemcpyAsync(d_qx, qx, q * 8, cudaMemcpyHostToDevice, s));
-  ENV_TRY(cudaMemcpyAsync(d_qy, qy, q * 8, cudaMemcpyHostToDevice, s));
-  ENV_TRY(cudaMemcpyAsync(d_sc, scene, q * 4, cudaMemcpyHostToDevice, s));
-  ENV_TRY(cudaMemcpyAsync(d_sl, slot, q * 4, cudaMemcpyHostToDevice, s));
-  mce::env_neighbors_kernel<<<(n_queries + mce::kBT - 1) / mce::kBT, mce::kBT, 0, s>>>(
+  Query Q(m);
+  double* d_qx = Q.in(qx, q); double* d_qy = Q.in(qy, q);
+  int32_t* d_sc = Q.in(scene, q); int32_t* d_sl = Q.in(slot, q);
+  int32_t* d_idx = Q.out(nb_index_out, q * MCE_NEIGHBORS); double* d_dis = Q.out(nb_dis_out, q * MCE_NEIGHBORS);
+  if ((rc = Q.upload())) return rc;
+  mce::env_neighbors_kernel<<<(n_queries + mce::kBT - 1) / mce::kBT, mce::kBT, 0, m->stream>>>(
       m->d_head, m->n_agents, m->d_lane, m->d_arc, m->d_order, m->d_start, d_sc, d_sl, d_qx, d_qy, n_queries, d_idx, d_dis);
-  ENV_TRY(cudaGetLastError());
-  ENV_TRY(cudaMemcpyAsync(nb_index_out, d_idx, q * 4 * MCE_NEIGHBORS, cudaMemcpyDeviceToHost, s));
-  ENV_TRY(cudaMemcpyAsync(nb_dis_out, d_dis, q * 8 * MCE_NEIGHBORS, cudaMemcpyDeviceToHost, s));
-  ENV_TRY(cudaStreamSynchronize(s));
-  return MCE_OK;
+  return Q.finish();
 }
 
 static int frenet_or_center(mce_map* m, int ref_lane, bool center_line, const double* x, const double* y, int n, double* s_out,
@@ -325,18 +366,13 @@ static int frenet_or_center(mce_map* m, int ref_lane, bool center_line, const do
   ENV_TRY(cudaSetDevice(m->device));
   int rc = ensure_query_buffers(m, n);
   if (rc) return rc;
-  cudaStream_t s = m->stream;
   const size_t q = n;
-  double* d = m->d_qf;
-  ENV_TRY(cudaMemcpyAsync(d, x, q * 8, cudaMemcpyHostToDevice, s));
-  ENV_TRY(cudaMemcpyAsync(d + q, y, q * 8, cudaMemcpyHostToDevice, s));
-  mce::env_frenet_kernel<<<(n + mce::kBT - 1) / mce::kBT, mce::kBT, 0, s>>>(m->d_tail, ref_lane, center_line, d, d + q, n, d + 2 * q,
-                                                                            d + 3 * q);
-  ENV_TRY(cudaGetLastError());
-  ENV_TRY(cudaMemcpyAsync(s_out, d + 2 * q, q * 8, cudaMemcpyDeviceToHost, s));
-  ENV_TRY(cudaMemcpyAsync(d_out, d + 3 * q, q * 8, cudaMemcpyDeviceToHost, s));
-  ENV_TRY(cudaStreamSynchronize(s));
-  return MCE_OK;
+  Query Q(m);
+  double* dx = Q.in(x, q); double* dy = Q.in(y, q);
+  double* ds = Q.out(s_out, q); double* dd = Q.out(d_out, q);
+  if ((rc = Q.upload())) return rc;
+  mce::env_frenet_kernel<<<(n + mce::kBT - 1) / mce::kBT, mce::kBT, 0, m->stream>>>(m->d_tail, ref_lane, center_line, dx, dy, n, ds, dd);
+  return Q.finish();
 }
 
 int mce_frenet(mce_map* m, int ref_lane, const double* x, const double* y, int n, double* s_out, double* d_out) {
@@ -356,19 +392,14 @@ int mce_step_along_path(mce_map* m, const int32_t* ref_lane, const double* x, co
   ENV_TRY(cudaSetDevice(m->device));
   int rc = ensure_query_buffers(m, n);
   if (rc) return rc;
-  cudaStream_t s = m->stream;
   const size_t q = n;
-  double* d = m->d_qf;
-  const double* in[5] = {x, y, v, ax, vy};
-  for (int k = 0; k < 5; ++k) ENV_TRY(cudaMemcpyAsync(d + k * q, in[k], q * 8, cudaMemcpyHostToDevice, s));
-  ENV_TRY(cudaMemcpyAsync(m->d_qi, ref_lane, q * 4, cudaMemcpyHostToDevice, s));
-  mce::env_step_kernel<<<(n + mce::kBT - 1) / mce::kBT, mce::kBT, 0, s>>>(m->d_tail, m->d_qi, d, d + q, d + 2 * q, d + 3 * q, d + 4 * q,
-                                                                           dt, n, d + 5 * q, d + 6 * q, d + 7 * q, d + 8 * q);
-  ENV_TRY(cudaGetLastError());
-  double* outp[4] = {x_out, y_out, v_out, yaw_out};
-  for (int k = 0; k < 4; ++k) ENV_TRY(cudaMemcpyAsync(outp[k], d + (5 + k) * q, q * 8, cudaMemcpyDeviceToHost, s));
-  ENV_TRY(cudaStreamSynchronize(s));
-  return MCE_OK;
+  Query Q(m);
+  double* dx = Q.in(x, q); double* dy = Q.in(y, q); double* dv = Q.in(v, q); double* dax = Q.in(ax, q); double* dvy = Q.in(vy, q);
+  int32_t* dl = Q.in(ref_lane, q);
+  double* ox = Q.out(x_out, q); double* oy = Q.out(y_out, q); double* ov = Q.out(v_out, q); double* oyaw = Q.out(yaw_out, q);
+  if ((rc = Q.upload())) return rc;
+  mce::env_step_kernel<<<(n + mce::kBT - 1) / mce::kBT, mce::kBT, 0, m->stream>>>(m->d_tail, dl, dx, dy, dv, dax, dvy, dt, n, ox, oy, ov, oyaw);
+  return Q.finish();
 }
 
 int mce_center_distance(mce_map* m, const int32_t* lane, const double* x, const double* y, int n, double* signed_out, double* to_end_out) {
@@ -379,18 +410,14 @@ int mce_center_distance(mce_map* m, const int32_t* lane, const double* x, const 
   ENV_TRY(cudaSetDevice(m->device));
   int rc = ensure_query_buffers(m, n);
   if (rc) return rc;
-  cudaStream_t s = m->stream;
   const size_t q = n;
-  double* d = m->d_qf;
-  ENV_TRY(cudaMemcpyAsync(d, x, q * 8, cudaMemcpyHostToDevice, s));
-  ENV_TRY(cudaMemcpyAsync(d + q, y, q * 8, cudaMemcpyHostToDevice, s));
-  ENV_TRY(cudaMemcpyAsync(m->d_qi, lane, q * 4, cudaMemcpyHostToDevice, s));
-  mce::env_center_kernel<<<(n + mce::kBT - 1) / mce::kBT, mce::kBT, 0, s>>>(m->d_border, m->d_qi, d, d + q, n, d + 2 * q, d + 3 * q);
-  ENV_TRY(cudaGetLastError());
-  ENV_TRY(cudaMemcpyAsync(signed_out, d + 2 * q, q * 8, cudaMemcpyDeviceToHost, s));
-  ENV_TRY(cudaMemcpyAsync(to_end_out, d + 3 * q, q * 8, cudaMemcpyDeviceToHost, s));
-  ENV_TRY(cudaStreamSynchronize(s));
-  return MCE_OK;
+  Query Q(m);
+  double* dx = Q.in(x, q); double* dy = Q.in(y, q);
+  int32_t* dl = Q.in(lane, q);
+  double* od = Q.out(signed_out, q); double* oe = Q.out(to_end_out, q);
+  if ((rc = Q.upload())) return rc;
+  mce::env_center_kernel<<<(n + mce::kBT - 1) / mce::kBT, mce::kBT, 0, m->stream>>>(m->d_border, dl, dx, dy, n, od, oe);
+  return Q.finish();
 }
 
 int mce_border_distance(mce_map* m, const int32_t* lane, const int32_t* side, const double* hull, int n, double* out) {
@@ -403,20 +430,19 @@ int mce_border_distance(mce_map* m, const int32_t* lane, const int32_t* side, co
   ENV_TRY(cudaSetDevice(m->device));
   int rc = ensure_query_buffers(m, n);
   if (rc) return rc;
-  cudaStream_t s = m->stream;
   const size_t q = n;
-  std::vector<double> soa(8 * q);                            // [corner coordinate][hull]: thread i reads element i
-  for (size_t i = 0; i < q; ++i)
-    for (int k = 0; k < 8; ++k) soa[k * q + i] = hull[i * 8 + k];
-  double* d = m->d_qf;
-  ENV_TRY(cudaMemcpyAsync(d, soa.data(), 8 * q * 8, cudaMemcpyHostToDevice, s));
-  ENV_TRY(cudaMemcpyAsync(m->d_qi, lane, q * 4, cudaMemcpyHostToDevice, s));
-  ENV_TRY(cudaMemcpyAsync(m->d_qi + q, side, q * 4, cudaMemcpyHostToDevice, s));
-  mce::env_border_kernel<<<(n + mce::kBT - 1) / mce::kBT, mce::kBT, 0, s>>>(m->d_border, m->d_qi, m->d_qi + q, d, n, d + 8 * q);
-  ENV_TRY(cudaGetLastError());
-  ENV_TRY(cudaMemcpyAsync(out, d + 8 * q, q * 8, cudaMemcpyDeviceToHost, s));
-  ENV_TRY(cudaStreamSynchronize(s));                         // `soa` stays alive until here
-  return MCE_OK;
+  Query Q(m);
+  double* dh = nullptr;                                      // [corner coordinate][hull]: thread i reads element i
+  for (int k = 0; k < 8; ++k) {
+    double* p = Q.in_strided(hull, q, 8, k);
+    if (k == 0) dh = p;
+  }
+  const size_t row = ((q * 8 + 15) & ~size_t(15)) / 8;       // doubles between two corner-coordinate rows
+  int32_t* dl = Q.in(lane, q); int32_t* dsd = Q.in(side, q);
+  double* o = Q.out(out, q);
+  if ((rc = Q.upload())) return rc;
+  mce::env_border_kernel<<<(n + mce::kBT - 1) / mce::kBT, mce::kBT, 0, m->stream>>>(m->d_border, dl, dsd, dh, row, n, o);
+  return Q.finish();
 }
 
 int mce_last_kernel_ms(mce_map* m, float* out2) {

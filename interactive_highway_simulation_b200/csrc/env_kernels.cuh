@@ -423,8 +423,8 @@ __device__ __forceinline__ double seg_seg_distance(double ax, double ay, double 
 // ---- Corridor.distance_to_border(hull, direction) (type.py:183-206; environment.py:113-115 dis_to_lane_border):
 // < 0 = how far the hull has passed the border on that side, otherwise Polygon(hull).distance(border line) ------------
 __global__ void __launch_bounds__(kBT) env_border_kernel(const EnvMapBorder* __restrict__ gmap, const int32_t* __restrict__ lane,
-                                                         const int32_t* __restrict__ side, const double* __restrict__ hull, int n,
-                                                         double* __restrict__ out) {
+                                                         const int32_t* __restrict__ side, const double* __restrict__ hull, size_t row,
+                                                         int n, double* __restrict__ out) {
   __shared__ EnvMapBorder m;
   stage(&m, gmap);
   __syncthreads();
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(kBT) env_border_kernel(const EnvMapBorder* __r
   const int l = lane[i], sd = side[i];                       // 0 = "left", 1 = "right"
   double hx[4], hy[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) { hx[k] = hull[(size_t)(2 * k) * n + i]; hy[k] = hull[(size_t)(2 * k + 1) * n + i]; }
+  for (int k = 0; k < 4; ++k) { hx[k] = hull[(size_t)(2 * k) * row + i]; hy[k] = hull[(size_t)(2 * k + 1) * row + i]; }
   const double (*simp)[2] = m.simp[sd][l];
   const int ns = m.n_simp[sd][l];
   LineView lv{m.path[sd][l], m.dis[sd][l], m.n_path[sd][l], m.simp_len[sd][l]};
