@@ -9,6 +9,10 @@ import random
 from copy import deepcopy
 
 
+def distance(p1, p2):                                                 # utility.py:8-9
+    return math.sqrt((p1[0] - p2[0]) ** 2 + (p1[1] - p2[1]) ** 2)
+
+
 def vehicle_pose_to_rect(pos_x, pos_y, yaw, length, width):           # utility.py:12-20
     head = [pos_x + length / 2 * math.cos(yaw), pos_y + length / 2 * math.sin(yaw)]
     tair = [pos_x - length / 2 * math.cos(yaw), pos_y - length / 2 * math.sin(yaw)]
@@ -35,6 +39,39 @@ def idm_acc_f_b(fs, b, ego_v, v_limit, idm_param, obey_v_limit=True):  # utility
         d_term += acc_max * (d_desire / max(1, -b.dis)) ** 2
     acc = free_road_term + d_term
     return max(min(acc_max, acc), acc_min)
+
+
+def idm_acc_fs_bs(fs, bs, ego_v, v_limit, idm_param, obey_v_limit=True):   # utility.py:52-80: several followers, the strongest push counts
+    acc_max, acc_com = idm_param.acc_max, idm_param.acc_com
+    d_terms_b = []
+    for b in bs:
+        d_desire = (0.7 * (idm_param.min_dis + b.v * idm_param.thw) + b.v * (b.v - ego_v) / (2 * math.sqrt(-acc_max * acc_com)))
+        d_terms_b.append(acc_max * (d_desire / max(1, -b.dis)) ** 2)
+    vd = min(idm_param.vd, 1.1 * v_limit) if obey_v_limit else idm_param.vd
+    free_road_term = acc_max * (1 - (ego_v / vd) ** 4)
+    d_term = 0
+    d_terms_f = []
+    for f in fs:
+        d_desire = (0.7 * (idm_param.min_dis + ego_v * idm_param.thw) + ego_v * (ego_v - f.v) / (2 * math.sqrt(-acc_max * acc_com)))
+        d_terms_f.append(-acc_max * (d_desire / max(1, f.dis)) ** 2)
+    d_term += min(d_terms_f) if d_terms_f else 0
+    d_term += max(d_terms_b) if d_terms_b else 0
+    return max(min(acc_max, free_road_term + d_term), idm_param.acc_min)
+
+
+def offset_point(p, yaw, offset):                                     # utility.py:83-85
+    return [p[0] - offset * math.sin(yaw), p[1] + offset * math.cos(yaw)]
+
+
+def extend_line(line, d):                                             # utility.py:111-115
+    k = d / distance(line[-1], line[-2])
+    return [list(p) for p in line] + [[line[-1][0] + k * (line[-1][0] - line[-2][0]), line[-1][1] + k * (line[-1][1] - line[-2][1])]]
+
+
+def extend_line_both_sides(line, d):                                  # utility.py:118-126
+    kf, kb = d / distance(line[0], line[1]), d / distance(line[-1], line[-2])
+    return [[line[0][0] + kf * (line[0][0] - line[1][0]), line[0][1] + kf * (line[0][1] - line[1][1])]] + [list(p) for p in line] + \
+        [[line[-1][0] + kb * (line[-1][0] - line[-2][0]), line[-1][1] + kb * (line[-1][1] - line[-2][1])]]
 
 
 def step_along_path(ref_path, ego, ax, vy, dt):                       # utility.py:88-98 — one device launch

@@ -116,3 +116,58 @@ def test_prepare_host_rejects_capacity(backend_lib):
         big[k].id = k
     with pytest.raises(Exception):
         backend_lib.prepare_host(cs, big)
+
+
+def test_utility_scalars_equal_the_reference_formulas():
+    """utility.py mirrors: hand-evaluated IDM / RSS values (utility.py:23-80,129-141) and the line helpers"""
+    import math
+    import random
+    from types import SimpleNamespace as NS
+    from interactive_highway_simulation_b200 import utility as u
+    p = NS(acc_max=1.4, acc_min=-4.0, min_dis=2.0, acc_com=-2.0, thw=1.5, vd=30.0)
+    f = NS(v=8.0, dis=20.0)
+    b = NS(v=12.0, dis=-15.0)
+    free = 1.4 * (1 - (10.0 / 27.5) ** 4)
+    dd = 0.7 * (2.0 + 10.0 * 1.5) + 10.0 * (10.0 - 8.0) / (2 * math.sqrt(2.8))
+    want = free - 1.4 * (dd / 20.0) ** 2
+    assert u.idm_acc_f_b([f], None, 10.0, 25.0, p) == max(min(1.4, want), -4.0)
+    db = 0.7 * (2.0 + 12.0 * 1.5) + 12.0 * (12.0 - 10.0) / (2 * math.sqrt(2.8))
+    assert u.idm_acc_f_b([f], b, 10.0, 25.0, p) == max(min(1.4, want + 1.4 * (db / 15.0) ** 2), -4.0)
+    assert u.idm_acc_fs_bs([f], [b], 10.0, 25.0, p) == u.idm_acc_f_b([f], b, 10.0, 25.0, p)
+    assert u.idm_acc_f_b([], None, 10.0, 25.0, p, obey_v_limit=False) == 1.4 * (1 - (10.0 / 30.0) ** 4)
+    assert u.rss_dis(10.0, 12.0, 0.4, -8.0, -10.0) == 12.0 * 0.4 + 144.0 / 16.0 - 100.0 / 20.0
+    assert u.rss_dis(30.0, 1.0, 0.4, -8.0, -10.0) == 0.0
+    assert u.thw_and_ttc(10.0, 0.0, 5.0) == (10.0 / 1e-10, -5.0 / 1e-3)
+    q = u.idm_p_for_merging_exit_agents(17, p, False)
+    random.seed(17)
+    r = random.random()
+    assert (q.acc_max, q.acc_min, p.acc_max) == (1.4 - (0.6 + 0.4 * r), -4.0 + (0.8 + 0.4 * r), 1.4)
+    assert u.idm_p_for_merging_exit_agents(17, p, True).acc_max == 1.4
+    assert u.extend_line([[0, 0], [3, 4]], 5)[-1] == [6.0, 8.0]
+    assert u.extend_line_both_sides([[0, 0], [3, 4]], 5) == [[-3.0, -4.0], [0, 0], [3, 4], [6.0, 8.0]]
+    assert u.vehicle_pose_to_rect(1.0, 2.0, 0.0, 4.0, 2.0) == [[3.0, 3.0], [3.0, 1.0], [-1.0, 1.0], [-1.0, 3.0]]
+
+
+def test_yielding_intention_follows_the_global_random_stream():
+    """type.py:70-90: a truthy seed re-seeds `random`; seed 0 / None draws from the running stream"""
+    import random
+    from interactive_highway_simulation_b200.type import YieldingIntention
+    random.seed(5)
+    want = random.random()
+    a = YieldingIntention(3, 0.5, random_intention_seed=5)
+    assert a.yielding == (want <= 0.5)
+    random.seed(9)
+    first = random.random()
+    random.seed(9)
+    b = YieldingIntention(3, first, random_intention_seed=0)        # not re-seeded: consumes the first draw of the stream
+    assert b.yielding
+    y = YieldingIntention(1, 0.5, random_intention_seed=5)
+    y.yielding = True
+    y.update_intention(0.3126)
+    assert y.yielding
+    y.update_intention(0.3125)                                      # <= threshold * initial probability: gives up yielding
+    assert not y.yielding
+    y.update_intention(0.6874)
+    assert not y.yielding
+    y.update_intention(0.6875)                                      # (1 - p) <= threshold * (1 - initial): yields again
+    assert y.yielding
