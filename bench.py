@@ -299,6 +299,42 @@ def outer_env_block(args, reps=10):
     return out
 
 
+def decision_configs_block(reps=10):
+    """One decision at the size of each remaining BASELINE.json configuration (configs[1] is the `decision` block): kernel
+    time (CUDA events inside mcs_rollouts_device) and end-to-end time of scene upload + all candidates' rollouts + feature
+    read-back through the C ABI with host buffers."""
+    from interactive_highway_simulation_b200 import backend, synthetic, _abi as abi
+    acts = ["keep_lane", "dcc", "acc", "left", "right"]
+    out = []
+
+    def measure(name, corridors, agents, cands, sp, n_per_group, seed):
+        sc = backend.DeviceScene(corridors, agents)
+        R = 8 * n_per_group
+        k_ms, units = 1e9, 0
+        for _ in range(3):
+            ms, units = sc.rollouts_device(cands, sp, seed, 0, R)
+            k_ms = min(k_ms, ms)
+        sc.close()
+        walls = []
+        for i in range(reps + 2):
+            t0 = time.perf_counter()
+            sc = backend.DeviceScene(corridors, agents)
+            sc.rollouts(cands, sp, n_per_group, seed + i)
+            sc.close()
+            walls.append((time.perf_counter() - t0) * 1e3)
+        walls = sorted(walls[2:])
+        out.append({"config": name, "candidates": len(cands), "rollouts_per_candidate": R, "vehicles": len(agents), "horizon_steps": sp.steps,
+                    "kernel_ms": k_ms, "e2e_ms_p50": walls[len(walls) // 2], "vehicle_steps_per_s_kernel": units / k_ms * 1e3})
+
+    c, a, ego = synthetic.lane_change_scene(100, 4, seed=1)
+    measure("configs[2] lane_change_learned, 100 vehicles, 5 actions x 160 rollouts x 40 steps", c, a,
+            (abi.Candidate * 5)(*[abi.Candidate(ego, abi.ACTIONS[x], -2, 0) for x in acts]), abi.SimParam(0.3, 40, 30), 20, 2)
+    c, a, ego, gaps = synthetic.exit_scene(200, 0)
+    measure("configs[3] exit_learned, 200 vehicles, %d gaps x 4096 rollouts x 50 steps" % len(gaps), c, a,
+            (abi.Candidate * len(gaps))(*[abi.Candidate(ego, abi.ACTIONS["right"], g, 0) for g in gaps]), abi.SimParam(0.3, 50, 10), 512, 3)
+    return out
+
+
 def outer_loop_block(steps=100):
     """configs[0]: simulation_multilane on the shipped test_scene (21 vehicles, merging lane + 2 main lanes), dt 0.2, 100
     steps, headless — every step is the sequential plan-and-move loop (device neighbour tables / border distances, the MOBIL
@@ -467,6 +503,12 @@ def run_product(args):
             outer_loop = outer_loop_block()
         except Exception as e:
             outer_loop = {"error": str(e)}
+    decision_configs = None
+    if world == 1:
+        try:
+            decision_configs = decision_configs_block()
+        except Exception as e:
+            decision_configs = {"error": str(e)}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": workload_config(args),
@@ -474,7 +516,7 @@ def run_product(args):
            "e2e": {"value": e2e_units_total / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h,
                    "note": "mcs_scene_create + mcs_rollouts (8 groups x %d) + feature read-back per step, host buffers" % (e2e_R // 8)},
-           "decision": decision, "outer_env": outer_env, "outer_loop": outer_loop,
+           "decision": decision, "decision_configs": decision_configs, "outer_env": outer_env, "outer_loop": outer_loop,
            "gpu_launches": args.steps, "wall_s_timed_region": wall,
            "rollouts_per_s": units_total / (N_VEHICLES * SIM_STEPS) / (kernel_ms_max * 1e-3)}
     print(json.dumps(out))

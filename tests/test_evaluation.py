@@ -113,4 +113,4 @@ def test_evaluate_recorded_scene_on_the_device(backend_lib, tmp_path, rec, k):
     ms.seed(e["seed"])
     st = fresh_statistics(ev_mod, rec["kind"])
     sim, text = evaluate(ev_mod, rec, k, path, st)
-    check(ev_mod, rec, k, text, st, sim, 1e-7)
+    check(ev_mod, rec, k, text, st, sim, 0.0)

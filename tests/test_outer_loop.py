@@ -99,7 +99,8 @@ def test_evaluation_epochs_host_logic_reproduces_the_reference_trace(monkeypatch
 def test_evaluation_epochs_on_the_device_reproduce_the_reference_trace(backend_lib, tag):
     from interactive_highway_simulation_b200 import mc_sim_highway as ms
     ms.seed(2000 + EVALUATIONS[tag][1])
-    run_evaluation(tag, load_scenario(tag))
+    _, worst = run_evaluation(tag, load_scenario(tag))
+    assert worst < 1e-9        # kernels == oracle bit for bit, inner answers == reference bit for bit
 
 
 @pytest.mark.parametrize("tag", ["test_scene", "lane_change_learned", "merging_learned"])
@@ -122,4 +123,5 @@ def test_outer_loop_on_the_device_reproduces_the_reference_trace(backend_lib, ta
     rec = load_scenario(tag)
     overrides, seed = learned_overrides(sim_mod, tag)
     ms.seed(1000 + seed)
-    run_test_scene(sim_mod, rec, overrides, seed)
+    _, worst = run_test_scene(sim_mod, rec, overrides, seed)
+    assert worst < 1e-9
