@@ -548,8 +548,15 @@ template <bool kTraj, bool kMerge, int NPS, int BT>
 #define MCS_MIN_BLOCKS_MERGE 2
 #endif
 // (a block of more than 512 threads is alone on its SM and gets what the register file allows: 896 threads -> 72)
+// A merging rollout that fills a 256-thread block by itself (129-256 vehicles: the exit scenes of configs[3]) comes in
+// launches of many waves, where the third resident block pays as it does for the lane-change path (80 registers, 480 B
+// of spills): 4 gaps x 4096 rollouts x 200 vehicles x 50 steps 28.7 -> 27.1 ms, x 512 rollouts 3.67 -> 3.37 ms.
+#ifndef MCS_MIN_BLOCKS_MERGE_FULL
+#define MCS_MIN_BLOCKS_MERGE_FULL 3
+#endif
+#define MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge) (((kMerge) && (NPS) == 256 && (BT) == 256) ? MCS_MIN_BLOCKS_MERGE_FULL : MCS_RESIDENT_BLOCKS(BT, kMerge))
 #define MCS_RESIDENT_BLOCKS(BT, kMerge) (((kMerge) ? MCS_MIN_BLOCKS_MERGE : MCS_MIN_BLOCKS) * 256 / (BT) > 0 ? ((kMerge) ? MCS_MIN_BLOCKS_MERGE : MCS_MIN_BLOCKS) * 256 / (BT) : 1)
-__global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS(BT, kMerge)) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp, const int region_bytes) {
+__global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp, const int region_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // NPS = sc.n_pad = blockDim.x as a compile-time constant: every shared-memory array address and row stride folds into
   // the instruction's immediate offset instead of living in registers
