@@ -11,6 +11,7 @@ import numpy as np
 
 from . import behaviors
 from .learned_model import LearnedLaneChangeModel, LearnedMergingModel
+from .outer_env import IdmMatch, MatchedAgent, Neighbor, SimpleIdmMatch  # noqa: F401  (agent.py:211-253 live with the environment)
 from .type import DecoupledAction, IdmParameter, MOBILParameter, RSSParameter, YieldingModel
 from .utility import step_along_path, vehicle_pose_to_rect
 

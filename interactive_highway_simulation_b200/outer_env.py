@@ -250,6 +250,11 @@ class IdmMatch:                                              # agent.py:235-247
         self.vd = agent.idm_param.vd
 
 
+class SimpleIdmMatch:                                        # agent.py:250-253
+    def __init__(self, dis, v):
+        self.dis, self.v = dis, v
+
+
 class Neighbor:                                              # agent.py:203-226
     def __init__(self, left_ff, left_f, left_b, left_bb, f, b, right_ff, right_f, right_b, right_bb):
         self.left_ff, self.left_f, self.left_b, self.left_bb, self.f, self.b = left_ff, left_f, left_b, left_bb, f, b
@@ -399,6 +404,14 @@ class Environment:
         if key not in self._border_cache:
             self._border_cache[key] = self.corridor_for_agent(idx).distance_to_border(a.hull, direction)
         return self._border_cache[key]
+
+    def limit_of_vehicles(self):                             # environment.py:117-124
+        xs, ys = [a.x for a in self.agents.values()], [a.y for a in self.agents.values()]
+        return min(xs + [1e10]) - 30, max(xs + [-1e10]) + 30, min(ys + [1e10]) - 10, max(ys + [-1e10]) + 10
+
+    def limit_of_maps(self):                                 # environment.py:126-133 over Corridor.get_x_y_limit type.py:208-215
+        pts = [p for c in self.map.corridors.values() for p in list(c.left) + list(c.right)]
+        return min(p[0] for p in pts), max(p[0] for p in pts), min(p[1] for p in pts), max(p[1] for p in pts)
 
     # ---- bookkeeping of the evaluation scripts (environment.py:253-313) ----
     def all_finish_merging(self):

@@ -15,6 +15,11 @@ class DecoupledAction:                                       # type.py:9-15
         self.ax, self.vy, self.ref_path = ax, vy, ref_path
 
 
+class Trajectory:                                            # type.py:18-21 (accepted by Agent.step, not implemented there either)
+    def __init__(self, trajectory, time_step):
+        self.trajectory, self.time_step = trajectory, time_step
+
+
 class IdmParameter:                                          # type.py:24-33
     def __init__(self, acc_max=1.4, acc_min=-4., min_dis=2, acc_comfort=-2, thw=1.5, vd=None):
         self.acc_max, self.acc_min, self.min_dis, self.acc_com, self.thw, self.vd = acc_max, acc_min, min_dis, acc_comfort, thw, vd
