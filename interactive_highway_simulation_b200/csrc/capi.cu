@@ -313,8 +313,11 @@ int rollout_threads(const mcs_scene* sc, long long rollouts, bool traj, bool mer
 #ifndef MCS_SHARE_MIN_PER_SM
 #define MCS_SHARE_MIN_PER_SM 0   // rollouts per SM below which a narrow rollout still owns its block (tuning knob)
 #endif
+#ifndef MCS_FULL_MERGE_BLOCK
+#define MCS_FULL_MERGE_BLOCK 768   // threads per block for 256-thread merging rollouts in large launches (256 = own block)
+#endif
 template <bool kMerge, int NPS>
-struct BlockThreads { static constexpr int value = NPS == 256 ? 256 : (kMerge && NPS >= 64 ? 512 : 256); };
+struct BlockThreads { static constexpr int value = NPS == 256 ? (kMerge ? MCS_FULL_MERGE_BLOCK : 256) : (kMerge && NPS >= 64 ? 512 : 256); };
 
 template <bool kTraj, bool kMerge, int NPS, int BT>
 int launch_bt(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& lp) {
@@ -342,6 +345,10 @@ int launch_np(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& 
   // while its rollouts fit the SM's shared memory
   const size_t smem_limit = sc->ctx->smem_per_block;
   if (region * (BT / NPS) > smem_limit) return launch_bt<kTraj, kMerge, NPS, NPS>(sc, grid, region, lp);
+  if constexpr (NPS == 256) {
+    // full-width rollouts share a block only when every SM still gets a full block
+    if (rollouts < (long long)sc->ctx->n_sm * (BT / NPS)) return launch_bt<kTraj, kMerge, NPS, NPS>(sc, grid, region, lp);
+  }
   if constexpr (kMerge && NPS == 64) {
     // The merging instantiation is latency-bound per step: a wave of 512-thread blocks (8 rollouts, 128 registers) takes
     // about as long whether the SM holds one rollout or eight, so a launch that needs a second wave is better off in

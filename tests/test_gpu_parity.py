@@ -509,3 +509,22 @@ def test_long_horizon_in_a_large_launch(gpu, kind):
         assert any(big[i * 64:(i + 1) * 64] != big[:64] for i in range(1, 1500))
     finally:
         ds.close()
+
+
+def test_full_width_merging_rollouts_share_a_block_with_identical_results(gpu, monkeypatch):
+    """129-256 vehicles with a merging / exit lane: in a launch that fills every SM three rollouts run in step in one
+    768-thread block (instruction fetches shared); every outcome record equals the one from a block of its own."""
+    from interactive_highway_simulation_b200 import synthetic
+    corridors, agents, ego, gaps = synthetic.exit_scene(200, 0)
+    ds = gpu.DeviceScene(corridors, agents)
+    try:
+        cands = (abi.Candidate * len(gaps))(*[abi.Candidate(ego, abi.ACTIONS["right"], g, 0) for g in gaps])
+        sp = abi.SimParam(0.3, 50, 10)
+        count = 301                                                 # x 4 gaps: not a multiple of 3, last block partly filled
+        shared = bytes(ds.rollouts_range(cands, sp, 77, 5, count))
+        monkeypatch.setenv("MCS_SHARE_MIN_PER_SM", "1000000")       # every rollout in a block of its own
+        own = bytes(ds.rollouts_range(cands, sp, 77, 5, count))
+        assert shared == own
+        assert len({shared[i * 64:(i + 1) * 64] for i in range(count * len(gaps))}) > count
+    finally:
+        ds.close()
