@@ -316,8 +316,14 @@ int rollout_threads(const mcs_scene* sc, long long rollouts, bool traj, bool mer
 #ifndef MCS_FULL_MERGE_BLOCK
 #define MCS_FULL_MERGE_BLOCK 768   // threads per block for 256-thread merging rollouts in large launches (256 = own block)
 #endif
+#ifndef MCS_HALF_MERGE_BLOCK
+// threads per block for 128-thread merging rollouts in large launches: six rollouts at 80 registers instead of four at 128
+// (scripts/merge_width_times.py, 4 gaps x 4096 rollouts x 50 steps: exit scene of 100 vehicles 16.7 -> 15.0 ms, 120 vehicles
+// x 2048 rollouts 6.74 -> 6.14 ms; 896 threads: 15.9 / 6.64; a merging scene of 100 vehicles 11.97 -> 12.19 ms)
+#define MCS_HALF_MERGE_BLOCK 768
+#endif
 template <bool kMerge, int NPS>
-struct BlockThreads { static constexpr int value = NPS == 256 ? (kMerge ? MCS_FULL_MERGE_BLOCK : 256) : (kMerge && NPS >= 64 ? 512 : 256); };
+struct BlockThreads { static constexpr int value = NPS == 256 ? (kMerge ? MCS_FULL_MERGE_BLOCK : 256) : (kMerge && NPS == 128 ? MCS_HALF_MERGE_BLOCK : (kMerge && NPS >= 64 ? 512 : 256)); };
 
 template <bool kTraj, bool kMerge, int NPS, int BT>
 int launch_bt(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& lp) {
