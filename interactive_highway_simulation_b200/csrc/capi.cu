@@ -322,8 +322,11 @@ int rollout_threads(const mcs_scene* sc, long long rollouts, bool traj, bool mer
 // x 2048 rollouts 6.74 -> 6.14 ms; 896 threads: 15.9 / 6.64; a merging scene of 100 vehicles 11.97 -> 12.19 ms)
 #define MCS_HALF_MERGE_BLOCK 768
 #endif
+#ifndef MCS_QUARTER_MERGE_BLOCK
+#define MCS_QUARTER_MERGE_BLOCK 512   // threads per block for 64-thread merging rollouts (896 when that saves a wave, below)
+#endif
 template <bool kMerge, int NPS>
-struct BlockThreads { static constexpr int value = NPS == 256 ? (kMerge ? MCS_FULL_MERGE_BLOCK : 256) : (kMerge && NPS == 128 ? MCS_HALF_MERGE_BLOCK : (kMerge && NPS >= 64 ? 512 : 256)); };
+struct BlockThreads { static constexpr int value = NPS == 256 ? (kMerge ? MCS_FULL_MERGE_BLOCK : 256) : (kMerge && NPS == 128 ? MCS_HALF_MERGE_BLOCK : (kMerge && NPS >= 64 ? MCS_QUARTER_MERGE_BLOCK : 256)); };
 
 template <bool kTraj, bool kMerge, int NPS, int BT>
 int launch_bt(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& lp) {
@@ -350,6 +353,14 @@ int launch_np(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& 
   // a long horizon makes the per-rollout region large (four history arrays of steps + 2 doubles): share a block only
   // while its rollouts fit the SM's shared memory
   const size_t smem_limit = sc->ctx->smem_per_block;
+  if constexpr (kMerge && NPS == 128 && BT != 512) {
+    // six 128-thread rollouts per block pay only when every SM gets a full block; smaller launches keep the four-rollout
+    // 512-thread blocks (4 gaps x 128 rollouts x 40 vehicles, widened to 128 threads: 0.77 ms there, 1.13 ms in 768-thread blocks)
+    if (rollouts < (long long)sc->ctx->n_sm * (BT / NPS) || region * (BT / NPS) > smem_limit) {
+      if (region * 4 <= smem_limit) return launch_bt<kTraj, kMerge, NPS, 512>(sc, grid, region, lp);
+      return launch_bt<kTraj, kMerge, NPS, NPS>(sc, grid, region, lp);
+    }
+  }
   if (region * (BT / NPS) > smem_limit) return launch_bt<kTraj, kMerge, NPS, NPS>(sc, grid, region, lp);
   if constexpr (NPS == 256) {
     // full-width rollouts share a block only when every SM still gets a full block
