@@ -177,7 +177,7 @@ def run_reference(args):
            "decision": {"latency_ms": dec_ms, "candidates": n_gaps, "rollouts_per_candidate": 8 * DEC_N_PER_GROUP,
                         "vehicles": DEC_VEHICLES, "note": "sum of one runMultiThreads call per candidate gap"},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    print(json.dumps(out), file=RESULT_OUT, flush=True)
     return 0
 
 
@@ -519,10 +519,13 @@ def run_product(args):
            "decision": decision, "decision_configs": decision_configs, "outer_env": outer_env, "outer_loop": outer_loop,
            "gpu_launches": args.steps, "wall_s_timed_region": wall,
            "rollouts_per_s": units_total / (N_VEHICLES * SIM_STEPS) / (kernel_ms_max * 1e-3)}
-    print(json.dumps(out))
+    print(json.dumps(out), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+RESULT_OUT = sys.stdout
 
 
 def main():
@@ -537,6 +540,12 @@ def main():
     ap.add_argument("--scene-seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # exactly ONE line on stdout: whatever libraries write to file descriptor 1 (NCCL prints its version banner there when
+    # NCCL_DEBUG is set in the environment) goes to stderr; the JSON line goes to the saved descriptor
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     return run_reference(args) if args.impl == "reference" else run_product(args)

@@ -541,6 +541,9 @@ template <bool kTraj, bool kMerge, int NPS, int BT>
 // resident 256-thread-equivalents per SM the register allocation aims at: 3 (80 registers) for the lane-change path —
 // the kernel is latency-bound, the third block hides more than its few spills cost (measured 6.26e9 -> 7.06e9
 // vehicle-steps/s) — and 2 (128 registers) for the much larger merging instantiation
+#ifndef MCS_ALIGN_STEPS
+#define MCS_ALIGN_STEPS 1   // rollouts that share a block re-align every this many steps
+#endif
 #ifndef MCS_MIN_BLOCKS
 #define MCS_MIN_BLOCKS 3
 #endif
@@ -653,12 +656,20 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
   yt.n = 0; yt.yielding = 0u;
 
   bool running = true;
+  int window = 0;   // steps left until the block's next alignment point
   while (true) {
     if (G > 1) {
-      // the rollouts of a block start every step together, so their warps run through the same code at about the same
-      // time and share its instruction fetches; a finished rollout idles here until the last one is done
-      if (!__syncthreads_or((running && lp.steps > step) ? 1 : 0)) break;
-      if (!(running && lp.steps > step)) continue;
+      // the rollouts of a block start every MCS_ALIGN_STEPS-th step together, so their warps run through the same code at
+      // about the same time and share its instruction fetches; a finished rollout idles here until the last one is done
+      if (MCS_ALIGN_STEPS == 1 || window == 0) {
+        if (!__syncthreads_or((running && lp.steps > step) ? 1 : 0)) break;
+        if (!(running && lp.steps > step)) continue;
+        window = MCS_ALIGN_STEPS;
+      }
+      if (MCS_ALIGN_STEPS > 1) {
+        if (!(running && lp.steps > step)) { window = 0; continue; }
+        --window;
+      }
     } else if (!(lp.steps > step)) {
       break;
     }
