@@ -316,6 +316,9 @@ int rollout_threads(const mcs_scene* sc, long long rollouts, bool traj, bool mer
 #ifndef MCS_FULL_MERGE_BLOCK
 #define MCS_FULL_MERGE_BLOCK 768   // threads per block for 256-thread merging rollouts in large launches (256 = own block)
 #endif
+#ifndef MCS_FULL_LC_BLOCK
+#define MCS_FULL_LC_BLOCK 256      // a 256-thread lane-change rollout owns its block (768: three in step, measured below)
+#endif
 #ifndef MCS_HALF_MERGE_BLOCK
 // threads per block for 128-thread merging rollouts in large launches: six rollouts at 80 registers instead of four at 128
 // (scripts/merge_width_times.py, 4 gaps x 4096 rollouts x 50 steps: exit scene of 100 vehicles 16.7 -> 15.0 ms, 120 vehicles
@@ -326,7 +329,7 @@ int rollout_threads(const mcs_scene* sc, long long rollouts, bool traj, bool mer
 #define MCS_QUARTER_MERGE_BLOCK 512   // threads per block for 64-thread merging rollouts (896 when that saves a wave, below)
 #endif
 template <bool kMerge, int NPS>
-struct BlockThreads { static constexpr int value = NPS == 256 ? (kMerge ? MCS_FULL_MERGE_BLOCK : 256) : (kMerge && NPS == 128 ? MCS_HALF_MERGE_BLOCK : (kMerge && NPS >= 64 ? MCS_QUARTER_MERGE_BLOCK : 256)); };
+struct BlockThreads { static constexpr int value = NPS == 256 ? (kMerge ? MCS_FULL_MERGE_BLOCK : MCS_FULL_LC_BLOCK) : (kMerge && NPS == 128 ? MCS_HALF_MERGE_BLOCK : (kMerge && NPS >= 64 ? MCS_QUARTER_MERGE_BLOCK : 256)); };
 
 template <bool kTraj, bool kMerge, int NPS, int BT>
 int launch_bt(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& lp) {
