@@ -325,6 +325,9 @@ int rollout_threads(const mcs_scene* sc, long long rollouts, bool traj, bool mer
 // x 2048 rollouts 6.74 -> 6.14 ms; 896 threads: 15.9 / 6.64; a merging scene of 100 vehicles 11.97 -> 12.19 ms)
 #define MCS_HALF_MERGE_BLOCK 768
 #endif
+#ifndef MCS_NARROW_MERGE_WAVE_BLOCK
+#define MCS_NARROW_MERGE_WAVE_BLOCK 896   // 14 rollouts of 64 threads per SM in one block (448: the same 14 in two blocks of 7)
+#endif
 #ifndef MCS_QUARTER_MERGE_BLOCK
 #define MCS_QUARTER_MERGE_BLOCK 512   // threads per block for 64-thread merging rollouts (896 when that saves a wave, below)
 #endif
@@ -376,7 +379,7 @@ int launch_np(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& 
     // 2.03 -> 1.86 ms; 4 x 1024: 3.90 -> 3.42; but 4 x 256, one wave either way: 1.07 vs 1.74).
     const long long sm = sc->ctx->n_sm;
     const long long waves8 = ((rollouts + 7) / 8 + sm - 1) / sm, waves14 = ((rollouts + 13) / 14 + sm - 1) / sm;
-    if (waves14 * 17 < waves8 * 10 && region * 14 <= smem_limit) return launch_bt<kTraj, kMerge, NPS, 896>(sc, grid, region, lp);
+    if (waves14 * 17 < waves8 * 10 && region * 14 <= smem_limit) return launch_bt<kTraj, kMerge, NPS, MCS_NARROW_MERGE_WAVE_BLOCK>(sc, grid, region, lp);
   }
   return launch_bt<kTraj, kMerge, NPS, BT>(sc, grid, region, lp);
 }

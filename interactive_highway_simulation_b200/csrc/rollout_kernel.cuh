@@ -557,7 +557,7 @@ template <bool kTraj, bool kMerge, int NPS, int BT>
 #ifndef MCS_MIN_BLOCKS_MERGE_FULL
 #define MCS_MIN_BLOCKS_MERGE_FULL 3
 #endif
-#define MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge) (((kMerge) && (NPS) == 256 && (BT) == 256) ? MCS_MIN_BLOCKS_MERGE_FULL : MCS_RESIDENT_BLOCKS(BT, kMerge))
+#define MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge) (((kMerge) && (NPS) == 256 && (BT) == 256) ? MCS_MIN_BLOCKS_MERGE_FULL : ((kMerge) && (BT) == 448) ? 2 : MCS_RESIDENT_BLOCKS(BT, kMerge))
 #define MCS_RESIDENT_BLOCKS(BT, kMerge) (((kMerge) ? MCS_MIN_BLOCKS_MERGE : MCS_MIN_BLOCKS) * 256 / (BT) > 0 ? ((kMerge) ? MCS_MIN_BLOCKS_MERGE : MCS_MIN_BLOCKS) * 256 / (BT) : 1)
 __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) rollout_kernel(const SceneDev sc, const CandDev* __restrict__ cands, const LaunchParams lp, const int region_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
