@@ -14,7 +14,9 @@
  *   type.py:180-206,307-315 distance_to_corridor_end / distance_to_border / centerSimplified.signed_distance
  *                           (mce_center_distance, mce_border_distance: the geometry idm_behavior and the yielding model read)
  *
- * Plain pointers and sizes; caller owns all buffers; HOST buffers in, HOST buffers out (copies inside).  No CPU
+ * Plain pointers and sizes; caller owns all buffers; HOST buffers in, HOST buffers out (copies inside; every query entry
+ * stages its arguments through one pinned buffer of the handle: one H2D and one D2H copy per call).  Calls on one handle
+ * must not run concurrently (use one handle per thread); different handles are independent.  No CPU
  * fallback: without a CUDA device every compute entry fails with MCE_ERR_CUDA.
  * The keys of the per-lane vectors stay resident in the handle after mce_env_match, so that later queries for vehicles
  * that have moved since (the reference plans and moves its vehicles one after the other against the arc lengths of the

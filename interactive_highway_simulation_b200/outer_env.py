@@ -215,6 +215,8 @@ class Corridor:
         key = (self.lane_index, float(point[0]), float(point[1]))
         cache = self.device_map.center_cache
         if key not in cache:
+            if len(cache) > 65536:                           # a map used without an Environment never gets its cache reset
+                cache.clear()
             d, e = self.device_map.center_distance([key[0]], [key[1]], [key[2]])
             cache[key] = (float(d[0]), float(e[0]))
         return cache[key]
