@@ -22,6 +22,7 @@ __device__ __forceinline__ double idm_acc_list(const Smem& s, const IdmP& p, con
   const double dDes = (egoV * p.thw + p.minDis) * 0.7;
   bool any = false;
   double d = 0.0;
+#pragma unroll 1
   for (int q = 0; q < nf; ++q) {
     const int f = fronts[q];
     if (f < 0) continue;

@@ -846,6 +846,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
                        ypC = F[(size_t)F_YP_C * np + k];
           int ylist[5];
           int ny = 0;
+#pragma unroll 1
           for (int q = 0; q < nY; ++q) {
             const int j = ycand[q];
             double p = 0.0;
