@@ -94,14 +94,17 @@ typedef struct mcs_status { /* StatusOneSim of one rollout + bookkeeping; 64 byt
   int32_t finishStep;
   int32_t executedSteps;  /* steps actually simulated (≤ steps) */
   uint32_t draws;         /* random draws consumed, incl. the N aggressive-flag draws */
-  uint8_t finish, fallBack, ok, overflow;  /* overflow: 0 fine, 1 yielding table full, 2 reference undefined here (→ error codes) */
+  uint8_t finish, fallBack, ok, overflow;  /* overflow: 0 fine, 1 yielding table full, 2 reference undefined here.  Every
+                                              entry point returns the error code if ANY rollout of its launch is marked
+                                              (a launch-wide word the kernel ORs into), whichever rollout it was. */
   int32_t reserved[4];
 } mcs_status;
 
 typedef struct mcs_group_partial { /* one runMTimes group = one thread's BehaviorFeature inside runMultiThreads; 64 bytes */
   double f[7];       /* group means: fallBackRate successRate utility comfort expectedStepRatio utilityObjects comfortObjects */
   int32_t fromNSims; /* n_per_group, or 0 when setEgoAgentIdAndDrivingBehavior failed (group skipped by the mean) */
-  int32_t reserved;
+  int32_t reserved;  /* max of mcs_status.overflow over the group's rollouts: a scene-error mark survives the all-gather and
+                        makes mcs_combine_groups fail (MCS_ERR_SCENE / MCS_ERR_CAPACITY) on every rank */
 } mcs_group_partial;
 
 typedef struct mcs_action { double ax, vy; } mcs_action;

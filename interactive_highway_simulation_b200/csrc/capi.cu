@@ -34,6 +34,9 @@ __host__ __device__ inline void group_partial(const mcs_status* p, int m, int st
   mcs_group_partial g;
   for (int t = 0; t < 7; ++t) g.f[t] = 0.0;
   g.fromNSims = 0; g.reserved = 0;
+  // the scene-error mark of ANY rollout of the group travels with the partial (and through the all-gather of the sharded
+  // path): mcs_combine_groups refuses such a group whichever rank simulated it
+  for (int i = 0; i < m; ++i) if (p[i].overflow > g.reserved) g.reserved = p[i].overflow;
   if (m > 0 && p[0].ok) {
     int nFall = 0, nFin = 0, sumStep = 0;
     double u = 0.0, c = 0.0, uo = 0.0, co = 0.0;
@@ -61,6 +64,7 @@ __host__ __device__ inline void combine_groups(const mcs_group_partial* g, int g
   out->fallBackRate = acc[0] / d; out->successRate = acc[1] / d; out->utility = acc[2] / d; out->comfort = acc[3] / d;
   out->expectedStepRatio = acc[4] / d; out->utilityObjects = acc[5] / d; out->comfortObjects = acc[6] / d;
   out->fromNSims = nOk * m; out->reserved = 0;
+  for (int q = 0; q < groups; ++q) if (g[q].reserved > out->reserved) out->reserved = g[q].reserved;
 }
 
 // one thread per (candidate, group): statuses [n_cand][groups*m] -> partials [n_cand][groups]
@@ -95,6 +99,14 @@ struct DeviceCtx {
   mcs_feature* h_feat = nullptr;         // pinned
   mcs_status* d_status = nullptr; size_t status_cap = 0;
   unsigned long long* d_counter = nullptr;
+  unsigned int* d_err = nullptr;         // launch-wide scene-error word (LaunchParams::err_flags)
+  struct Small {                         // pinned landing zone of every small read-back: a failing call may return while
+    unsigned int err;                    // copies are still in flight, and they must not land in a dead stack frame
+    int32_t n_states;
+    unsigned long long steps;
+    mcs_status status;
+    mcs::DecideOut decide;
+  }* h_small = nullptr;
   void* d_decide = nullptr;              // mcs::DecideOut
   unsigned char* h_stage = nullptr; size_t stage_cap = 0;   // pinned staging of the scene blob
   std::mutex mu;
@@ -127,6 +139,8 @@ int get_ctx(int device, DeviceCtx** out) {
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
         (e = cudaMalloc(&c->d_counter, sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_err, sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMallocHost(&c->h_small, sizeof(DeviceCtx::Small))) != cudaSuccess ||
         (e = cudaMalloc(&c->d_decide, sizeof(mcs::DecideOut))) != cudaSuccess) {
       delete c;
       return fail(MCS_ERR_CUDA, cudaGetErrorString(e));
@@ -404,25 +418,52 @@ int launch_rollouts(mcs_scene* sc, int n_cand, const mcs_sim_param* sp, uint64_t
   lp.dt = sp->dt; lp.steps = sp->steps; lp.min_steps = sp->min_steps;
   lp.seed = seed; lp.first = first; lp.count = count; lp.n_cand = n_cand;
   lp.status = d_status; lp.traj = d_traj; lp.traj_n = d_traj_n; lp.vehicle_steps = d_counter;
+  lp.err_flags = sc->ctx->d_err;
+  CUDA_TRY(cudaMemsetAsync(sc->ctx->d_err, 0, sizeof(unsigned int), sc->ctx->stream));
   int rc = upload_scene(sc, rollout_threads(sc, (long long)count * n_cand, d_traj != nullptr, merge != 0));
   if (rc != MCS_OK) return rc;
   size_t smem = (rollout_smem_bytes(sc->dev.n_pad, sp->steps) + 15) & ~(size_t)15;   // one rollout's region
   dim3 grid((unsigned)count, (unsigned)n_cand);
   // the trajectory-writing variant is a test / Simulation.run() path: one instantiation (the merging superset) serves it
-  if (d_traj) return launch_one<true, true>(sc, grid, smem, lp);
-  return merge ? launch_one<false, true>(sc, grid, smem, lp) : launch_one<false, false>(sc, grid, smem, lp);
-}
-
-int check_unsupported(const mcs_status* st, size_t n) {
-  for (size_t i = 0; i < n; ++i) {
-    if (st[i].overflow == 2)
-      return fail(MCS_ERR_SCENE, "the reference's behaviour is undefined for this scene (vehicle without a usable behaviour, or a "
-                                 "merging command without a lane on that side)");
-    if (st[i].overflow == 1)
-      return fail(MCS_ERR_CAPACITY, "a vehicle met more distinct yielding candidates than the device table holds");
-  }
+  if (d_traj) rc = launch_one<true, true>(sc, grid, smem, lp);
+  else rc = merge ? launch_one<false, true>(sc, grid, smem, lp) : launch_one<false, false>(sc, grid, smem, lp);
+  if (rc != MCS_OK) return rc;
+  // the launch-wide scene-error word follows the kernel on the stream; callers read it after their synchronisation
+  CUDA_TRY(cudaMemcpyAsync(&sc->ctx->h_small->err, sc->ctx->d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, sc->ctx->stream));
   return MCS_OK;
 }
+
+int scene_error(unsigned int bits) {
+  if (bits & 2u)
+    return fail(MCS_ERR_SCENE, "the reference's behaviour is undefined for this scene (vehicle without a usable behaviour, or a "
+                               "merging command without a lane on that side)");
+  if (bits & 1u)
+    return fail(MCS_ERR_CAPACITY, "a vehicle met more distinct yielding candidates than the device table holds");
+  return MCS_OK;
+}
+// after the stream has been synchronised: did ANY rollout of the last launch hit a case the reference leaves undefined?
+int check_launch(const mcs_scene* sc) { return scene_error(sc->ctx->h_small->err); }
+
+// synchronise; on failure the stream is drained as far as possible before the error is reported
+int sync_stream(mcs_scene* sc) {
+  cudaError_t e = cudaStreamSynchronize(sc->ctx->stream);
+  if (e != cudaSuccess) return fail(MCS_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+  return MCS_OK;
+}
+// an entry point that has queued copies into caller memory must not return before they have landed or been abandoned
+#define TRY_SYNCED(expr)                                               \
+  do {                                                                 \
+    int rc_ = (expr);                                                  \
+    if (rc_ != MCS_OK) { cudaStreamSynchronize(sc->ctx->stream); return rc_; } \
+  } while (0)
+#define CUDA_TRY_SYNCED(expr)                                                                                   \
+  do {                                                                                                          \
+    cudaError_t e_ = (expr);                                                                                    \
+    if (e_ != cudaSuccess) {                                                                                    \
+      cudaStreamSynchronize(sc->ctx->stream);                                                                   \
+      return fail(MCS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                            \
+    }                                                                                                           \
+  } while (0)
 
 }  // namespace
 
@@ -508,12 +549,15 @@ int mcs_reduce_features(const mcs_status* statuses, int n_candidates, int groups
                         mcs_feature* features_out) {
   if (!statuses || !features_out || n_candidates < 0 || groups <= 0 || n_per_group <= 0) return fail(MCS_ERR_ARG, "bad arguments");
   std::vector<mcs_group_partial> part(groups);
+  unsigned int bits = 0;
   for (int c = 0; c < n_candidates; ++c) {
     for (int g = 0; g < groups; ++g)
       group_partial(statuses + ((size_t)c * groups + g) * n_per_group, n_per_group, steps, &part[g]);
     combine_groups(part.data(), groups, features_out + c);
+    bits |= (unsigned int)features_out[c].reserved;
+    features_out[c].reserved = 0;
   }
-  return MCS_OK;
+  return scene_error(bits);     // statuses gathered from other ranks carry their scene-error marks with them
 }
 
 int mcs_group_partials(const mcs_status* statuses, int n_candidates, int groups, int n_per_group, int steps,
@@ -526,12 +570,18 @@ int mcs_group_partials(const mcs_status* statuses, int n_candidates, int groups,
 
 int mcs_combine_groups(const mcs_group_partial* partials, int n_candidates, int groups, mcs_feature* features_out) {
   if (!partials || !features_out || n_candidates < 0 || groups <= 0) return fail(MCS_ERR_ARG, "bad arguments");
-  for (int c = 0; c < n_candidates; ++c) combine_groups(partials + (size_t)c * groups, groups, features_out + c);
-  return MCS_OK;
+  unsigned int bits = 0;
+  for (int c = 0; c < n_candidates; ++c) {
+    combine_groups(partials + (size_t)c * groups, groups, features_out + c);
+    bits |= (unsigned int)features_out[c].reserved;
+    features_out[c].reserved = 0;
+  }
+  return scene_error(bits);     // a rollout of some group (simulated on whichever rank) hit an undefined case
 }
 
 int mcs_scene_sync(mcs_scene* sc) {
   if (!sc) return fail(MCS_ERR_ARG, "scene is null");
+  std::lock_guard<std::mutex> lock(sc->ctx->mu);
   CUDA_TRY(cudaSetDevice(sc->device));
   CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
   return MCS_OK;
@@ -539,7 +589,7 @@ int mcs_scene_sync(mcs_scene* sc) {
 
 // shared by mcs_rollouts_groups{,_device}: rollouts of groups [first_group, first_group+n_groups) -> partials in `d_out`
 static int groups_on_device(mcs_scene* sc, const mcs_candidate* cands, int n_cand, const mcs_sim_param* sp, int n_per_group,
-                            uint64_t seed, int first_group, int n_groups, mcs_group_partial* d_out, mcs_status* probe) {
+                            uint64_t seed, int first_group, int n_groups, mcs_group_partial* d_out) {
   if (first_group < 0 || n_groups <= 0 || first_group + n_groups > MCS_GROUPS) return fail(MCS_ERR_ARG, "bad group range");
   const int64_t count = (int64_t)n_groups * n_per_group;
   const size_t n_status = (size_t)n_cand * count;
@@ -553,8 +603,6 @@ static int groups_on_device(mcs_scene* sc, const mcs_candidate* cands, int n_can
   group_partials_kernel<<<(total + 63) / 64, 64, 0, sc->ctx->stream>>>(sc->ctx->d_status, n_cand, n_groups, n_per_group, sp->steps,
                                                                    d_out ? d_out : sc->ctx->d_part);
   CUDA_TRY(cudaGetLastError());
-  for (int c = 0; c < n_cand; ++c)   // the scene-error marker lives in the statuses: fetch the first rollout of each candidate
-    CUDA_TRY(cudaMemcpyAsync(probe + c, sc->ctx->d_status + (size_t)c * count, sizeof(mcs_status), cudaMemcpyDeviceToHost, sc->ctx->stream));
   return MCS_OK;
 }
 
@@ -563,12 +611,11 @@ int mcs_rollouts_groups(mcs_scene* sc, const mcs_candidate* cands, int n_cand, c
   if (!sc || !cands || !sp || !partials_out || n_cand <= 0 || n_per_group <= 0) return fail(MCS_ERR_ARG, "bad arguments");
   std::lock_guard<std::mutex> lock(sc->ctx->mu);
   CUDA_TRY(cudaSetDevice(sc->device));
-  std::vector<mcs_status> probe(n_cand);
-  int rc = groups_on_device(sc, cands, n_cand, sp, n_per_group, seed, first_group, n_groups, nullptr, probe.data());
+  int rc = groups_on_device(sc, cands, n_cand, sp, n_per_group, seed, first_group, n_groups, nullptr);
   if (rc != MCS_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(partials_out, sc->ctx->d_part, sizeof(mcs_group_partial) * n_cand * n_groups, cudaMemcpyDeviceToHost, sc->ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
-  return check_unsupported(probe.data(), probe.size());
+  CUDA_TRY_SYNCED(cudaMemcpyAsync(partials_out, sc->ctx->d_part, sizeof(mcs_group_partial) * n_cand * n_groups, cudaMemcpyDeviceToHost, sc->ctx->stream));
+  if ((rc = sync_stream(sc)) != MCS_OK) return rc;
+  return check_launch(sc);
 }
 
 int mcs_rollouts_groups_device(mcs_scene* sc, const mcs_candidate* cands, int n_cand, const mcs_sim_param* sp, int n_per_group,
@@ -576,12 +623,13 @@ int mcs_rollouts_groups_device(mcs_scene* sc, const mcs_candidate* cands, int n_
   if (!sc || !cands || !sp || !d_partials_out || n_cand <= 0 || n_per_group <= 0) return fail(MCS_ERR_ARG, "bad arguments");
   std::lock_guard<std::mutex> lock(sc->ctx->mu);
   CUDA_TRY(cudaSetDevice(sc->device));
-  std::vector<mcs_status> probe(n_cand);
-  int rc = groups_on_device(sc, cands, n_cand, sp, n_per_group, seed, first_group, n_groups, (mcs_group_partial*)d_partials_out,
-                            probe.data());
+  int rc = groups_on_device(sc, cands, n_cand, sp, n_per_group, seed, first_group, n_groups, (mcs_group_partial*)d_partials_out);
   if (rc != MCS_OK) return rc;
-  CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
-  return check_unsupported(probe.data(), probe.size());
+  if ((rc = sync_stream(sc)) != MCS_OK) return rc;
+  // Sharded callers exchange the partials next (a collective every rank must enter): the mark also travels inside them
+  // (mcs_group_partial::reserved) and mcs_combine_groups refuses it on every rank, so this rank's own error is not lost
+  // if its caller postpones the check until after the exchange.
+  return check_launch(sc);
 }
 
 int mcs_rollouts(mcs_scene* sc, const mcs_candidate* cands, int n_cand, const mcs_sim_param* sp, int n_per_group,
@@ -601,17 +649,11 @@ int mcs_rollouts(mcs_scene* sc, const mcs_candidate* cands, int n_cand, const mc
   combine_groups_kernel<<<(n_cand + 31) / 32, 32, 0, sc->ctx->stream>>>(sc->ctx->d_part, n_cand, MCS_GROUPS, sc->ctx->d_feat);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(sc->ctx->h_feat, sc->ctx->d_feat, sizeof(mcs_feature) * n_cand, cudaMemcpyDeviceToHost, sc->ctx->stream));
-  std::vector<mcs_status> first_status;
-  if (status_out) CUDA_TRY(cudaMemcpyAsync(status_out, sc->ctx->d_status, sizeof(mcs_status) * n_status, cudaMemcpyDeviceToHost, sc->ctx->stream));
-  else {
-    // the "unsupported" marker lives in the statuses; fetch the first rollout of each candidate
-    first_status.resize(n_cand);
-    for (int c = 0; c < n_cand; ++c)
-      CUDA_TRY(cudaMemcpyAsync(&first_status[c], sc->ctx->d_status + (size_t)c * count, sizeof(mcs_status), cudaMemcpyDeviceToHost, sc->ctx->stream));
-  }
-  CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
+  if (status_out) CUDA_TRY_SYNCED(cudaMemcpyAsync(status_out, sc->ctx->d_status, sizeof(mcs_status) * n_status, cudaMemcpyDeviceToHost, sc->ctx->stream));
+  if ((rc = sync_stream(sc)) != MCS_OK) return rc;
   memcpy(features_out, sc->ctx->h_feat, sizeof(mcs_feature) * n_cand);
-  return status_out ? check_unsupported(status_out, n_status) : check_unsupported(first_status.data(), first_status.size());
+  for (int c = 0; c < n_cand; ++c) features_out[c].reserved = 0;
+  return check_launch(sc);     // any rollout of any candidate, not only the first
 }
 
 int mcs_rollouts_range(mcs_scene* sc, const mcs_candidate* cands, int n_cand, const mcs_sim_param* sp, uint64_t seed,
@@ -625,9 +667,9 @@ int mcs_rollouts_range(mcs_scene* sc, const mcs_candidate* cands, int n_cand, co
   int merge = 0;
   if ((rc = stage_candidates(sc, cands, n_cand, &merge)) != MCS_OK) return rc;
   if ((rc = launch_rollouts(sc, n_cand, sp, seed, first, count, sc->ctx->d_status, nullptr, nullptr, nullptr, merge)) != MCS_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(status_out, sc->ctx->d_status, sizeof(mcs_status) * n_status, cudaMemcpyDeviceToHost, sc->ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
-  return check_unsupported(status_out, n_status);
+  CUDA_TRY_SYNCED(cudaMemcpyAsync(status_out, sc->ctx->d_status, sizeof(mcs_status) * n_status, cudaMemcpyDeviceToHost, sc->ctx->stream));
+  if ((rc = sync_stream(sc)) != MCS_OK) return rc;
+  return check_launch(sc);
 }
 
 int mcs_rollouts_device(mcs_scene* sc, const mcs_candidate* cands, int n_cand, const mcs_sim_param* sp, uint64_t seed,
@@ -647,14 +689,11 @@ int mcs_rollouts_device(mcs_scene* sc, const mcs_candidate* cands, int n_cand, c
   CUDA_TRY(cudaEventRecord(sc->ctx->ev0, sc->ctx->stream));
   if ((rc = launch_rollouts(sc, n_cand, sp, seed, first, count, dst, nullptr, nullptr, sc->ctx->d_counter, merge)) != MCS_OK) return rc;
   CUDA_TRY(cudaEventRecord(sc->ctx->ev1, sc->ctx->stream));
-  unsigned long long steps = 0;
-  CUDA_TRY(cudaMemcpyAsync(&steps, sc->ctx->d_counter, sizeof steps, cudaMemcpyDeviceToHost, sc->ctx->stream));
-  mcs_status probe;
-  CUDA_TRY(cudaMemcpyAsync(&probe, dst, sizeof probe, cudaMemcpyDeviceToHost, sc->ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(&sc->ctx->h_small->steps, sc->ctx->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sc->ctx->stream));
+  if ((rc = sync_stream(sc)) != MCS_OK) return rc;
   if (kernel_ms_out) CUDA_TRY(cudaEventElapsedTime(kernel_ms_out, sc->ctx->ev0, sc->ctx->ev1));
-  if (vehicle_steps_out) *vehicle_steps_out = steps;
-  return check_unsupported(&probe, 1);
+  if (vehicle_steps_out) *vehicle_steps_out = sc->ctx->h_small->steps;
+  return check_launch(sc);
 }
 
 int mcs_trajectories(mcs_scene* sc, const mcs_candidate* cand, const mcs_sim_param* sp, uint64_t seed, int64_t rollout,
@@ -667,26 +706,26 @@ int mcs_trajectories(mcs_scene* sc, const mcs_candidate* cand, const mcs_sim_par
   int merge = 0;
   if ((rc = stage_candidates(sc, cand, 1, &merge)) != MCS_OK) return rc;
   const size_t n_d = (size_t)sc->host.n * (sp->steps + 1) * 4;
-  double* d_traj = nullptr; int32_t* d_n = nullptr;
-  CUDA_TRY(cudaMalloc(&d_traj, n_d * sizeof(double)));
-  CUDA_TRY(cudaMalloc(&d_n, sizeof(int32_t)));
-  cudaMemsetAsync(d_traj, 0, n_d * sizeof(double), sc->ctx->stream);
-  cudaMemsetAsync(d_n, 0, sizeof(int32_t), sc->ctx->stream);
-  rc = launch_rollouts(sc, 1, sp, seed, rollout, 1, sc->ctx->d_status, d_traj, d_n, nullptr, merge);
-  mcs_status st{};
-  int32_t ns = 0;
-  if (rc == MCS_OK) {
-    cudaMemcpyAsync(states_out, d_traj, n_d * sizeof(double), cudaMemcpyDeviceToHost, sc->ctx->stream);
-    cudaMemcpyAsync(&ns, d_n, sizeof ns, cudaMemcpyDeviceToHost, sc->ctx->stream);
-    cudaMemcpyAsync(&st, sc->ctx->d_status, sizeof st, cudaMemcpyDeviceToHost, sc->ctx->stream);
-  }
-  cudaError_t e = cudaStreamSynchronize(sc->ctx->stream);
-  cudaFree(d_traj); cudaFree(d_n);
-  if (rc != MCS_OK) return rc;
-  if (e != cudaSuccess) return fail(MCS_ERR_CUDA, cudaGetErrorString(e));
-  if (n_states_out) *n_states_out = ns;
-  if (status_out) *status_out = st;
-  return check_unsupported(&st, 1);
+  // one allocation for the states and their count; released on every path out of this function
+  struct Scratch {
+    unsigned char* p = nullptr;
+    cudaStream_t stream;
+    ~Scratch() { if (p) { cudaStreamSynchronize(stream); cudaFree(p); } }
+  } scratch;
+  scratch.stream = sc->ctx->stream;
+  CUDA_TRY(cudaMalloc(&scratch.p, n_d * sizeof(double) + 16));
+  double* d_traj = (double*)scratch.p;
+  int32_t* d_n = (int32_t*)(scratch.p + n_d * sizeof(double));
+  CUDA_TRY(cudaMemsetAsync(scratch.p, 0, n_d * sizeof(double) + 16, sc->ctx->stream));
+  if ((rc = launch_rollouts(sc, 1, sp, seed, rollout, 1, sc->ctx->d_status, d_traj, d_n, nullptr, merge)) != MCS_OK) return rc;
+  DeviceCtx::Small* hs = sc->ctx->h_small;
+  CUDA_TRY_SYNCED(cudaMemcpyAsync(states_out, d_traj, n_d * sizeof(double), cudaMemcpyDeviceToHost, sc->ctx->stream));
+  CUDA_TRY_SYNCED(cudaMemcpyAsync(&hs->n_states, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, sc->ctx->stream));
+  CUDA_TRY_SYNCED(cudaMemcpyAsync(&hs->status, sc->ctx->d_status, sizeof(mcs_status), cudaMemcpyDeviceToHost, sc->ctx->stream));
+  if ((rc = sync_stream(sc)) != MCS_OK) return rc;
+  if (n_states_out) *n_states_out = hs->n_states;
+  if (status_out) *status_out = hs->status;
+  return check_launch(sc);
 }
 
 static int run_decision(mcs_scene* sc, int32_t agent_id, mcs::DecideParams dp, int32_t gap_id, mcs::DecideOut* res) {
@@ -706,8 +745,9 @@ static int run_decision(mcs_scene* sc, int32_t agent_id, mcs::DecideParams dp, i
   CUDA_TRY(cudaFuncSetAttribute(mcs::decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mcs::decide_kernel<<<1, sc->dev.n_pad, smem, sc->ctx->stream>>>(sc->dev, dp, (mcs::DecideOut*)sc->ctx->d_decide);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(res, sc->ctx->d_decide, sizeof *res, cudaMemcpyDeviceToHost, sc->ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(sc->ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(&sc->ctx->h_small->decide, sc->ctx->d_decide, sizeof *res, cudaMemcpyDeviceToHost, sc->ctx->stream));
+  { const int rc = sync_stream(sc); if (rc != MCS_OK) return rc; }
+  *res = sc->ctx->h_small->decide;
   if (res->status != MCS_OK)
     return fail(res->status, "the reference's behaviour is undefined here (vehicle not on a lane, or no lane on that side)");
   return MCS_OK;

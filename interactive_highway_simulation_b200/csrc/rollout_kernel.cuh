@@ -62,6 +62,7 @@ struct LaunchParams {
   double* traj;       // optional [n_cand][count][n][steps+1][4] in INPUT agent order, or nullptr
   int32_t* traj_n;    // optional [n_cand][count]
   unsigned long long* vehicle_steps;  // optional global counter
+  unsigned int* err_flags;            // per-launch word: bit 0 = a yielding table overflowed, bit 1 = scene unsupported (any rollout)
 };
 
 #define MCS_MINSD(a, b) (((a) < (b)) ? (a) : (b))   /* x86 vminsd: second source when not less / unordered */
@@ -1152,7 +1153,12 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
   }
   sub_sync<NPS, G == 1>(sub);
   const int anyUnsupported = s.flags[6], anyFull = s.flags[7];
-  if ((anyUnsupported || anyFull) && isEgo) st_out->overflow = (uint8_t)(anyUnsupported ? 2 : 1);   // the caller fails loudly (MCS_ERR_SCENE / MCS_ERR_CAPACITY)
+  if ((anyUnsupported || anyFull) && isEgo) {
+    // the caller fails loudly (MCS_ERR_SCENE / MCS_ERR_CAPACITY): the record carries the mark, and so does the launch-wide
+    // word every entry point checks after its synchronisation — whichever rollout of whichever candidate it happened in
+    st_out->overflow = (uint8_t)(anyUnsupported ? 2 : 1);
+    if (lp.err_flags) atomicOr(lp.err_flags, anyUnsupported ? 2u : 1u);
+  }
 }
 
 }  // namespace mcs

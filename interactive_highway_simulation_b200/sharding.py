@@ -55,7 +55,14 @@ def simulation_multi_thread_sharded(scene, candidates, sim_param, n_per_group, s
     first, per = group_range(rank, world)
     dev = torch.device("cuda", torch.cuda.current_device())
     mine = torch.empty((nc * per, 8), dtype=torch.float64, device=dev)
-    scene.rollouts_groups(candidates, sim_param, n_per_group, seed, first, per, d_partials_ptr=mine.data_ptr())
+    try:
+        scene.rollouts_groups(candidates, sim_param, n_per_group, seed, first, per, d_partials_ptr=mine.data_ptr())
+    except backend.McsimError as e:
+        # A rollout of THIS rank's groups hit a case the reference leaves undefined.  The exchange below is a collective
+        # every rank has to enter, and the mark travels inside the partials (GroupPartial.reserved): mcs_combine_groups
+        # then refuses them on every rank alike.  Anything else (CUDA failure, bad arguments) is raised right away.
+        if e.code not in (abi.MCS_ERR_SCENE, abi.MCS_ERR_CAPACITY):
+            raise
     if world > 1:
         gathered = torch.empty((world * nc * per, 8), dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(gathered, mine, group=group)

@@ -109,6 +109,68 @@ def test_scene_errors_where_the_reference_is_undefined(gpu):
         ds.close()
 
 
+def late_error_scene():
+    """Two stacked merging lanes: the `merging` vehicle 1 moves left as soon as the gap in front of vehicle 2 is safe
+    (which depends on vehicle 2's acceleration noise, i.e. on the rollout's draws), and from the upper lane there is no
+    lane further left — mergingBehaviorClosestGap then reads a missing corridor in the reference (so:0xfe757 region).  With seed 5 and a
+    14-step horizon rollouts 0..6 never get there, rollout 7 is the first that does (found with the oracle)."""
+    from oracle.pyoracle import SceneSpec
+    s = SceneSpec()
+    s.add_corridor(1, "merging", 3.5, 0.0, 1.75, 27.78)
+    s.add_corridor(2, "merging", 7.0, 3.5, 5.25, 27.78)
+    s.add_agent(0, 300.0, 5.25, 25.0, 27.0, "idm")
+    s.add_agent(1, 100.0, 1.75, 20.0, 22.0, "merging")
+    s.add_agent(2, 88.0, 5.25, 26.0, 27.0, "idm")
+    return s
+
+
+def test_scene_error_in_a_later_rollout_is_reported(gpu, oracle):
+    """The reference's behaviour can become undefined in ANY rollout (it depends on the trajectory, hence on the draws):
+    every entry point must report it, not only when it happens in the first rollout of a candidate."""
+    s = late_error_scene()
+    cs, as_ = s.c_corridors(), s.c_agents()
+    cand = (abi.Candidate * 1)(abi.Candidate(0, abi.ACTIONS["keep_lane"], -2, 0))
+    sp = abi.SimParam(0.3, 14, 14)
+    first_bad = None
+    for r in range(32):
+        one = (abi.Status * 1)()
+        rc = oracle.lib.orc_rollouts(cs, len(cs), as_, len(as_), C.byref(cand[0]), C.byref(sp), 5, r, 1, one, None, None)
+        if rc != 0:
+            first_bad = r
+            break
+    assert first_bad == 7
+    ds = gpu.DeviceScene(cs, as_)
+    try:
+        good = ds.rollouts_range(cand, sp, 5, 0, first_bad)                    # the rollouts before it are fine
+        o, _ = oracle.rollouts(s, 0, "keep_lane", -2, 0.3, 14, 14, 5, 0, first_bad)
+        for i in range(first_bad):
+            for k in STATUS_KEYS:
+                assert same(status_dict(good[i])[k], o[i][k]), (i, k)
+        raw = (abi.Status * 32)()
+        rc = gpu.lib().mcs_rollouts_range(ds._h, cand, 1, C.byref(sp), 5, 0, 32, raw)
+        assert rc == abi.MCS_ERR_SCENE
+        assert raw[0].overflow == 0 and raw[first_bad].overflow == 2           # not in the first record
+        with pytest.raises(gpu.McsimError) as e:
+            ds.rollouts(cand, sp, 4, 5)                                        # simulationMultiThread: statuses not requested
+        assert e.value.code == abi.MCS_ERR_SCENE
+        with pytest.raises(gpu.McsimError) as e:
+            ds.rollouts_device(cand, sp, 5, 0, 32)
+        assert e.value.code == abi.MCS_ERR_SCENE
+        ds.rollouts_groups(cand, sp, 4, 5, 0, 1)                               # group 0 = rollouts 0..3: fine
+        with pytest.raises(gpu.McsimError) as e:
+            ds.rollouts_groups(cand, sp, 4, 5, 1, 1)                           # group 1 = rollouts 4..7
+        assert e.value.code == abi.MCS_ERR_SCENE
+        # the sharded path: the mark travels inside the partials, the combine refuses them on every rank
+        parts = (abi.GroupPartial * 8)()
+        rc = gpu.lib().mcs_rollouts_groups(ds._h, cand, 1, C.byref(sp), 4, 5, 0, 8, parts)
+        assert rc == abi.MCS_ERR_SCENE and parts[0].reserved == 0 and parts[1].reserved == 2
+        with pytest.raises(gpu.McsimError) as e:
+            gpu.combine_groups(parts, 1, 8)
+        assert e.value.code == abi.MCS_ERR_SCENE
+    finally:
+        ds.close()
+
+
 @pytest.mark.parametrize("case", ROLLOUT_CASES, ids=golden_io.ids(ROLLOUT_CASES))
 def test_against_reference_golden_vectors(gpu, case):
     """The CUDA path against what the reference's machine code returned (no oracle in between)."""

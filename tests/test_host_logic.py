@@ -53,6 +53,23 @@ def test_reduce_features_rejects_bad_arguments(backend_lib):
     assert backend_lib.lib().mcs_reduce_features(None, 1, 8, 1, 40, feats) == abi.MCS_ERR_ARG
 
 
+def test_a_marked_rollout_anywhere_fails_the_reduction(backend_lib):
+    """mcs_status.overflow of ANY rollout (not only a candidate's first) travels into its group's partial and makes the
+    combine fail on whichever rank runs it (the mark used to be read from rollout 0 only)."""
+    rng = random.Random(2)
+    groups, m = 8, 4
+    for bad, code in ((17, abi.MCS_ERR_SCENE), (31, abi.MCS_ERR_CAPACITY)):
+        st = random_statuses(rng, groups * m, [True] * groups, m)
+        st[bad].overflow = 2 if code == abi.MCS_ERR_SCENE else 1
+        feats = (abi.Feature * 1)()
+        assert backend_lib.lib().mcs_reduce_features(st, 1, groups, m, 40, feats) == code
+        parts = backend_lib.group_partials(st, 1, groups, m, 40)
+        assert [p.reserved for p in parts] == [st[bad].overflow if g == bad // m else 0 for g in range(groups)]
+        assert backend_lib.lib().mcs_combine_groups(parts, 1, groups, feats) == code
+        st[bad].overflow = 0
+        assert backend_lib.lib().mcs_reduce_features(st, 1, groups, m, 40, feats) == abi.MCS_OK
+
+
 # ---- scene preparation on the host (MapMultiLane ctor so:0x109f00, matchAgentsOnCorridor so:0x10b810) ----
 import math
 
