@@ -109,6 +109,43 @@ def test_scene_errors_where_the_reference_is_undefined(gpu):
         ds.close()
 
 
+import libm_check  # noqa: E402
+
+LIBM_CASES = libm_check.load_cases()
+
+
+@pytest.mark.parametrize("case", LIBM_CASES, ids=[c["tag"] for c in LIBM_CASES])
+def test_against_the_stock_reference(gpu, case, record_property):
+    """The CUDA path against the reference AS SHIPPED (its machine code with the platform libm's exp / pow, no pinned math
+    interposed), at the shape of every BASELINE.json configuration: zero discrete mismatches (finish, fallBack,
+    finishStep, draw count, state count, lane and lateral direction of every vehicle at every step) and every state of
+    every vehicle within libm_check.STATE_TOL per step.  The measured deviation is recorded with the test."""
+    s = golden_io.scene_of(case)
+    ds = gpu.DeviceScene(s.c_corridors(), s.c_agents())
+    try:
+        cand = (abi.Candidate * 1)(abi.Candidate(case["ego"], abi.ACTIONS[case["action"]], case["gap"], 0))
+        sp = abi.SimParam(case["dt"], case["steps"], case["min_steps"])
+        st = ds.rollouts_range(cand, sp, case["seed"], case["first"], case["count"])
+        statuses = [status_dict(st[i]) for i in range(case["count"])]
+        hist = {}
+        for i, r in enumerate(case["rollouts"]):
+            if "hist" not in r:
+                continue
+            buf, ns, _ = ds.trajectories(cand[0], sp, case["seed"], case["first"] + i)
+            stride = case["steps"] + 1
+            hist[i] = {a["id"]: [tuple(buf[(ai * stride + t) * 4:(ai * stride + t) * 4 + 4]) for t in range(ns)]
+                       for ai, a in enumerate(s.agents)}
+        mismatches, dev_state, dev_stat = libm_check.compare(case, statuses, hist)
+        record_property("max_state_deviation", dev_state)
+        record_property("max_statistic_deviation", dev_stat)
+        print("%s: discrete mismatches %d, max |state deviation| %.3g, max |statistic deviation| %.3g"
+              % (case["tag"], len(mismatches), dev_state, dev_stat))
+        assert mismatches == []
+        assert dev_state <= libm_check.STATE_TOL and dev_stat <= libm_check.STAT_TOL, (dev_state, dev_stat)
+    finally:
+        ds.close()
+
+
 def late_error_scene():
     """Two stacked merging lanes: the `merging` vehicle 1 moves left as soon as the gap in front of vehicle 2 is safe
     (which depends on vehicle 2's acceleration noise, i.e. on the rollout's draws), and from the upper lane there is no
