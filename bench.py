@@ -7,9 +7,12 @@ reference's own CPU path.
 
 Throughput (the JSON line's `value`): a "step" is one launch of the rollout kernel over one batch of rollouts of
 BASELINE.json's throughput configuration (configs[4]): 256 vehicles x 100 steps, every non-ego vehicle `idm_lc`, ego
-`keep_lane`, minSteps = steps (no early exit); `--rollouts` rollouts per step per GPU (default 65536 = 1/16 of the 1M
-sweep, so the default run ends in minutes).  Rollouts are independent, so ranks shard the rollout index range with no
-data-path collective (weak scaling: per-GPU batch fixed).
+`keep_lane`, minSteps = steps (no early exit), on a scene of the reference's own generator (synthetic.generated_scene:
+RandomTrafficGenerator with np.random.seed(s), random.seed(s), s = --scene-seed; `scene_seeds` repeats it for s = 0..9);
+`--rollouts` rollouts per step per GPU (default 65536 = 1/16 of the 1M sweep, so the default run ends in minutes).
+Rollouts are independent, so ranks shard the rollout index range with no data-path collective (weak scaling: per-GPU
+batch fixed).  `roofline` is against the FP64 multiply-add rate measured in the same run (the FP64 pipe,
+not HBM, bounds this path); `roofline_hbm` keeps the HBM view.
 
 Decision latency (`decision`): BASELINE.json configs[1] — merging lane + 3 main lanes, 40 vehicles, 512 rollouts per
 candidate gap, 4 candidates, SimParameter(0.3, 40, 10) — through the public API: scene upload, one launch for all
@@ -40,8 +43,21 @@ def workload_config(args):
     return {"workload": "configs[4]: synthetic throughput sweep, %d vehicles x %d steps IDM/MOBIL/RSS, ego keep_lane, "
                         "minSteps=steps" % (N_VEHICLES, SIM_STEPS),
             "vehicles": N_VEHICLES, "lanes": N_LANES, "horizon_steps": SIM_STEPS, "dt": SIM_DT,
-            "rollouts_per_step_per_gpu": args.rollouts, "scene_seed": args.scene_seed,
+            "scene": "RandomTrafficGenerator (random_traffic_generator.py:77-136 restated, pinned on the reference's records) "
+                     "on the lanes of evaluation_lane_change.py:18-44 made %d vehicles long; np.random.seed = random.seed = scene_seed"
+                     % (N_VEHICLES // N_LANES),
+            "scene_seed": args.scene_seed,
+            "rollouts_per_step_per_gpu": args.rollouts,
+            "reference_arm_rollouts_per_step": 8 * max(1, args.ref_rollouts // 8),
+            "note": "both arms run this workload; the product arm times rollouts_per_step_per_gpu rollouts per step, the "
+                    "reference arm (--impl reference, host CPU) a bounded sample of reference_arm_rollouts_per_step rollouts "
+                    "per step; the metric is a rate (vehicle-steps/s)",
             "l2": "flushed between timed steps (256 MiB write); the 66 KB scene is re-read by every block by design"}
+
+
+def throughput_scene(args, seed=None):
+    from interactive_highway_simulation_b200 import synthetic
+    return synthetic.generated_scene(args.scene_seed if seed is None else seed, N_VEHICLES, N_LANES)
 
 
 def read_peaks():
@@ -135,9 +151,38 @@ def reference_time(spec, dt, steps, min_steps, mode, m, ego, action, gap, reps=1
 
 
 def reference_throughput(args, m, mode):
-    from interactive_highway_simulation_b200 import synthetic
-    corridors, agents, ego = synthetic.lane_change_scene(N_VEHICLES, N_LANES, seed=args.scene_seed)
+    corridors, agents, ego = throughput_scene(args)
     return reference_time(scene_spec(corridors, agents), SIM_DT, SIM_STEPS, SIM_STEPS, mode, m, ego, "keep_lane", -2)
+
+
+def port_throughput(args, seconds=12.0):
+    """BASELINE.md §3 item 3, the fair best-CPU number: the C++ restatement (oracle/mcsim_oracle.cpp — scalar, no
+    shared_ptr / strings, one counter stream per rollout) on every host core (std::thread x nproc), same scene, same
+    workload, bounded sample; best of the passes that fit the time budget."""
+    from oracle.pyoracle import Oracle, ORACLE_SO
+    from interactive_highway_simulation_b200 import _abi as abi
+    if not os.path.exists(ORACLE_SO):
+        subprocess.run(["make", "-s", "-C", os.path.join(HERE, "oracle"), "libmcsim_oracle.so"], check=True)
+    corridors, agents, ego = throughput_scene(args)
+    orc = Oracle(0)
+    cores = os.cpu_count() or 1
+    cand = abi.Candidate(ego, abi.ACTIONS["keep_lane"], -2, 0)
+    sp = abi.SimParam(SIM_DT, SIM_STEPS, SIM_STEPS)
+    count = 64 * cores
+    st = (abi.Status * count)()
+    best, passes, t_all = 1e30, 0, time.perf_counter()
+    while passes < 5 and (passes == 0 or time.perf_counter() - t_all < seconds):
+        t0 = time.perf_counter()
+        rc = orc.lib.orc_rollouts_mt(corridors, len(corridors), agents, len(agents), C.byref(cand), C.byref(sp), 2026,
+                                     passes * count, count, cores, st)
+        dt = time.perf_counter() - t0
+        if rc != 0:
+            raise RuntimeError("oracle error %d" % rc)
+        best = min(best, dt); passes += 1
+    units = sum(s_.executedSteps for s_ in st) * N_VEHICLES
+    return {"value": units / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d rollouts of the same scene per pass, %d passes (best), oracle/mcsim_oracle.cpp on %d std::threads, "
+                      "one counter stream per rollout" % (count, passes, cores)}
 
 
 def reference_decision_ms(args):
@@ -169,10 +214,15 @@ def run_reference(args):
     sample = "%d rollouts per step through the reference's runMultiThreads (8 std::threads x %d), platform libm, " \
              "lock-free interposed rand()" % (8 * m, m)
     dec_ms, n_gaps = reference_decision_ms(args)
+    try:
+        port = port_throughput(args)
+    except Exception as e:
+        port = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "unavailable: %s" % e}
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(8, cores), "kind": "reference", "sample": sample},
+           "cpu_baseline_port": port,
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "decision": {"latency_ms": dec_ms, "candidates": n_gaps, "rollouts_per_candidate": 8 * DEC_N_PER_GROUP,
                         "vehicles": DEC_VEHICLES, "note": "sum of one runMultiThreads call per candidate gap"},
@@ -182,8 +232,9 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ FP64 peak probe
-def fp64_peak_tflops(torch, device):
-    """Measured FP64 rate of this GPU via a torch DGEMM (cuBLAS); the denominator of the FP64 view of the roofline."""
+def fp64_dgemm_tflops(torch, device):
+    """FP64 rate of a cuBLAS DGEMM (tensor-core DMMA) — a note beside the roofline, NOT its denominator: the rollout kernels
+    issue scalar FP64 instructions, whose ceiling is the multiply-add stream measured by mcs_fp64_peak."""
     n = 4096
     a = torch.randn(n, n, dtype=torch.float64, device=device)
     b = torch.randn(n, n, dtype=torch.float64, device=device)
@@ -222,10 +273,23 @@ def decision_latency(torch, dist, world, device, args):
         if i >= 5:
             times.append(t1 - t0)
     t = torch.tensor(times, dtype=torch.float64, device=device)
+    parity = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # the N-GPU features against the 1-GPU ones, byte for byte: every rank simulates all 8 groups on its own GPU once
+        # and compares with what the sharded path (its 8/N groups + the all-gather) gave it; the verdicts are AND-ed
+        scene = backend.DeviceScene(corridors, agents, device=device)
+        sharded = sharding.simulation_multi_thread_sharded(scene, cands, sp, DEC_N_PER_GROUP, 4242)
+        single, _ = scene.rollouts(cands, sp, DEC_N_PER_GROUP, 4242)
+        scene.close()
+        same = all(bytes(sharded[c]) == bytes(single[c]) for c in range(len(gaps)))
+        flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity = bool(int(flag[0]))
+        if not parity:
+            raise SystemExit("bench.py: features on %d GPUs differ from the 1-GPU features" % world)
     ts = sorted(t.tolist())
-    return {"latency_ms_p50": 1e3 * ts[len(ts) // 2], "latency_ms_p90": 1e3 * ts[int(len(ts) * 0.9)], "decisions": len(ts),
+    return {"parity_vs_1gpu": parity, "latency_ms_p50": 1e3 * ts[len(ts) // 2], "latency_ms_p90": 1e3 * ts[int(len(ts) * 0.9)], "decisions": len(ts),
             "candidates": len(gaps), "rollouts_per_candidate": 8 * DEC_N_PER_GROUP, "vehicles": DEC_VEHICLES,
             "horizon_steps": DEC_STEPS, "last_decision_gap_id": decision, "last_action": [act.ax, act.vy],
             "h2d_bytes": C.sizeof(corridors) + C.sizeof(agents) + C.sizeof(cands), "d2h_bytes": 64 * 8 * len(gaps) + 16,
@@ -357,6 +421,9 @@ def outer_loop_block(steps=100):
                "wall_s": wall, "ms_per_step": wall / steps * 1e3, "vehicle_steps": hist, "vehicle_steps_per_s": hist / wall,
                "vehicles_left_on_map": len(sim.environment.agents),
                "note": "sequential outer loop of the reference (environment.py:316-323): one small launch per query, latency bound"}
+    rec = os.path.join(HERE, "profiles", "r02_reference_outer_loop_cpu.json")
+    if os.path.exists(rec):
+        out["cpu_baseline"] = json.load(open(rec))     # scripts/time_reference_outer_loop.py (cannot run on the GPU box)
     return out
 
 
@@ -379,7 +446,7 @@ def run_product(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    corridors, agents, ego = synthetic.lane_change_scene(N_VEHICLES, N_LANES, seed=args.scene_seed)
+    corridors, agents, ego = throughput_scene(args)
     scene = backend.DeviceScene(corridors, agents, device=device)
     cand = (abi.Candidate * 1)(abi.Candidate(ego, abi.ACTIONS["keep_lane"], -2, 0))
     sp = abi.SimParam(SIM_DT, SIM_STEPS, SIM_STEPS)
@@ -413,7 +480,7 @@ def run_product(args):
     e2e_R = max(8, (R // 8) * 8)
     h2d = C.sizeof(corridors) + C.sizeof(agents) + C.sizeof(cand)
     d2h = C.sizeof(abi.Feature)
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = args.steps             # as many timed end-to-end steps as kernel-timed ones
     sc2 = backend.DeviceScene(corridors, agents, device=device); sc2.rollouts(cand, sp, 8, seed); sc2.close()   # warm-up
     barrier()
     e2e_t0 = time.perf_counter()
@@ -443,35 +510,63 @@ def run_product(args):
         return 0
 
     value = units_total / (kernel_ms_max * 1e-3)
-    # roofline of the rollout kernel (one launch = one step)
+    # ---- roofline of the rollout kernel (one launch = one step).  SURVEY.md §8(d): the binding resource is the FP64 pipe
+    # (and instruction issue), not HBM and not the tensor cores.  achieved = algorithmic flop per launch (100 per
+    # vehicle-step x the vehicle-steps the launch executed, counted on the device) / the launch's average duration (CUDA
+    # events on the kernel's stream inside the timed region); peak = a stream of independent FP64 fused multiply-adds
+    # measured by libmcsim_b200's own probe kernel in this run (MEASURED_PEAKS.json holds no FP64 figure).
     peak_gbs, peak_src = read_peaks()
     launch_s = kernel_ms / args.steps * 1e-3
+    fp64_peak, fp64_ms = backend.fp64_peak_tflops(device)
+    fp64_achieved = (vsteps / args.steps) * FLOP_PER_VEHICLE_STEP / launch_s / 1e12
+    traffic = None
+    prof = os.path.join(HERE, "profiles", "r02_rollout_kernel_dram.json")
+    if not os.path.exists(prof):
+        prof = os.path.join(HERE, "profiles", "r01_rollout_kernel_dram.json")
+    try:
+        pj = json.load(open(prof))
+        traffic = pj.get("dram_bytes_per_rollout", 0) * R or None
+    except Exception:
+        pj = {}
+    roofline = {"bound": "fp64", "achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak,
+                "traffic": traffic,
+                "flop_per_vehicle_step": FLOP_PER_VEHICLE_STEP,
+                "peak_source": "measured in this run: mcs_fp64_peak, 8 independent DFMA chains per thread, 2048 threads per SM "
+                               "(%.2f ms); the CUDA-core FP64 rate, which is what a scalar FP64 kernel can reach" % fp64_ms,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel "
+                                  "(%s), scaled to this launch's rollouts; bytes, not flop — see roofline_hbm" % os.path.basename(prof),
+                "fp64_tensor_dgemm_tflops": fp64_dgemm_tflops(torch, device),
+                "note": "100 algorithmic FP64 flop per vehicle-step (63 base IDM + RSS + lateral + integration, + 380 per MOBIL "
+                        "evaluation at ~1/10 duty); the kernel's own limiter is instruction issue and dependent-instruction "
+                        "latency of FP64 / control code (profiles/: issue slots, FP64 pipe, stall breakdown)"}
     scene_bytes = C.sizeof(corridors) + 30 * 8 * 256 + 8 * 4 * 256 + 256     # SoA scene read once (L2-shared)
     alg_bytes = R * 64 + scene_bytes
     achieved_gbs = alg_bytes / launch_s / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs,
-                "traffic": None, "peak_source": peak_src,
-                "note": "algorithmic HBM traffic is 64 B per rollout + one scene read (state lives in registers/shared "
-                        "memory for the whole rollout): by design the kernel is nowhere near the HBM roof; its limiter is "
-                        "FP64/control instruction issue and barrier latency, see `issue` and `fp64`"}
-    issue = None
-    prof = os.path.join(HERE, "profiles", "r01_rollout_kernel_dram.json")
-    if os.path.exists(prof):
-        try:
-            pj = json.load(open(prof))
-            roofline["traffic"] = pj.get("dram_bytes_per_rollout", 0) * R or None
-            ipv = pj.get("warp_inst_per_vehicle_step")
-            if ipv and clocks and clocks.get("sm_mhz"):
-                per_gpu = value / world
-                issue = {"achieved_warp_inst_per_s": per_gpu * ipv, "peak_warp_inst_per_s": N_SM * 4 * clocks["sm_mhz"] * 1e6,
-                         "frac": per_gpu * ipv / (N_SM * 4 * clocks["sm_mhz"] * 1e6), "warp_inst_per_vehicle_step": ipv,
-                         "source": "instruction count per vehicle-step from the committed ncu capture (%s), rate from this run" % pj.get("source")}
-        except Exception:
-            pass
-    fp64_peak = fp64_peak_tflops(torch, device)
-    fp64_achieved = (vsteps / args.steps) * FLOP_PER_VEHICLE_STEP / launch_s / 1e12
-    fp64 = {"achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak,
-            "flop_per_vehicle_step": FLOP_PER_VEHICLE_STEP, "peak_source": "cuBLAS DGEMM 4096^3 measured in this run"}
+    roofline_hbm = {"bound": "hbm", "achieved": achieved_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "note": "algorithmic HBM traffic is 64 B per rollout + one scene read (state lives in registers / shared "
+                            "memory for the whole rollout): by design the kernel is nowhere near the HBM roof"}
+
+    # ---- the same workload on the scenes of generator seeds 0..9: one warm-up + two timed launches each
+    scene_seeds = None
+    if world == 1 and args.seed_sweep:
+        per_seed = []
+        Rs = min(R, 16384)
+        for sd in range(10):
+            c2, a2, ego2 = throughput_scene(args, seed=sd)
+            sc = backend.DeviceScene(c2, a2, device=device)
+            cd = (abi.Candidate * 1)(abi.Candidate(ego2, abi.ACTIONS["keep_lane"], -2, 0))
+            sc.rollouts_device(cd, sp, seed, 0, Rs)
+            ms_sum, vs_sum = 0.0, 0
+            for rep in range(2):
+                flush.zero_(); torch.cuda.synchronize(device)
+                ms, vs = sc.rollouts_device(cd, sp, seed, (rep + 1) * Rs, Rs)
+                ms_sum += ms; vs_sum += vs
+            sc.close()
+            per_seed.append(vs_sum / (ms_sum * 1e-3))
+        srt = sorted(per_seed)
+        scene_seeds = {"seeds": list(range(10)), "rollouts_per_launch": Rs, "vehicle_steps_per_s": per_seed,
+                       "median": 0.5 * (srt[4] + srt[5]), "min": srt[0], "max": srt[-1]}
 
     # ---- CPU baseline: the reference's own machine code on this box's host cores, bounded sample
     cpu = None
@@ -482,14 +577,20 @@ def run_product(args):
             r1, s1 = reference_throughput(args, max(1, m), "m")
             cpu = {"value": rollouts * N_VEHICLES * SIM_STEPS / secs, "unit": UNIT, "cores": min(8, os.cpu_count() or 1),
                    "kind": "reference",
-                   "sample": "%d rollouts of the same scene through the reference's runMultiThreads (8 threads), platform "
-                             "libm; single-thread runMTimes on %d rollouts: %.3g vehicle-steps/s"
-                             % (rollouts, r1, r1 * N_VEHICLES * SIM_STEPS / s1)}
+                   "sample": "%d rollouts of the same scene through the reference's runMultiThreads (its hard-wired 8 threads; "
+                             "this box has %d cores), platform libm; single-thread runMTimes on %d rollouts: %.3g vehicle-steps/s"
+                             % (rollouts, os.cpu_count() or 1, r1, r1 * N_VEHICLES * SIM_STEPS / s1)}
             if decision is not None:
                 dec_ms, _ = reference_decision_ms(args)
                 decision["cpu_reference_latency_ms"] = dec_ms
         except Exception as e:    # oracle/_ref is built only where /root/reference exists
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+    cpu_port = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu_port = port_throughput(args)
+        except Exception as e:
+            cpu_port = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "unavailable: %s" % e}
 
     outer_env = None
     if world == 1:
@@ -512,7 +613,12 @@ def run_product(args):
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-           "roofline": roofline, "issue": issue, "fp64": fp64, "cpu_baseline": cpu, "clocks": clocks,
+           "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "cpu_baseline_port": cpu_port,
+           "scene_seeds": scene_seeds, "clocks": clocks,
+           "value_wall": {"value": units_total / wall, "unit": UNIT,
+                          "note": "the same vehicle-steps over the wall clock of the timed region (barrier to barrier: L2 flush, "
+                                  "candidate upload, launch and read-back overheads included); `value` divides by the CUDA-event "
+                                  "time of the kernels alone; compare CPU baselines (wall clock) with this or with `e2e`"},
            "e2e": {"value": e2e_units_total / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h,
                    "note": "mcs_scene_create + mcs_rollouts (8 groups x %d) + feature read-back per step, host buffers" % (e2e_R // 8)},
@@ -539,6 +645,7 @@ def main():
     ap.add_argument("--decisions", type=int, default=40, help="timed decisions for the latency figure (0 = skip)")
     ap.add_argument("--scene-seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-seed-sweep", dest="seed_sweep", action="store_false", help="skip the scene seeds 0..9 block")
     args = ap.parse_args()
     # exactly ONE line on stdout: whatever libraries write to file descriptor 1 (NCCL prints its version banner there when
     # NCCL_DEBUG is set in the environment) goes to stderr; the JSON line goes to the saved descriptor

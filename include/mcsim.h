@@ -185,6 +185,11 @@ int mcs_rollouts_device(mcs_scene* scene, const mcs_candidate* candidates, int n
                         uint64_t seed, int64_t first, int64_t count, void* d_status_out, void* cuda_stream,
                         float* kernel_ms_out, uint64_t* vehicle_steps_out);
 
+/* Measurement helper (no reference counterpart): the FP64 rate of device `device` on a stream of independent
+ * fused multiply-adds — what a CUDA-core FP64 kernel like the rollout kernel can reach at best; the denominator of
+ * bench.py's `roofline` (FP64 pipe, not HBM, bounds this path).  iters x 64 DFMA per thread. */
+int mcs_fp64_peak(int device, int iters, double* tflops_out, float* ms_out);
+
 /* ---- Simulation.run() + agentsStatesHistory() for one rollout ----
  * states_out: [n_agents][steps+1][4] (x y v a), agent order = input order; n_states_out = states per agent */
 int mcs_trajectories(mcs_scene* scene, const mcs_candidate* candidate, const mcs_sim_param* param, uint64_t seed,

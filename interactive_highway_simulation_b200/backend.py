@@ -17,7 +17,7 @@ EXPORTS = [
     "mcs_scene_visit_order", "mcs_scene_prepare_host", "mcs_rollouts", "mcs_rollouts_range", "mcs_reduce_features", "mcs_rollouts_device",
     "mcs_rollouts_groups", "mcs_rollouts_groups_device", "mcs_scene_sync", "mcs_group_partials", "mcs_combine_groups",
     "mcs_trajectories", "mcs_decide_mobil", "mcs_decide_fixed_direction", "mcs_decide_fixed_gap",
-    "mcs_decide_closest_gap",
+    "mcs_decide_closest_gap", "mcs_fp64_peak",
 ]
 
 
@@ -85,6 +85,8 @@ def lib():
     L.mcs_decide_fixed_gap.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, P(abi.Action)]
     L.mcs_decide_closest_gap.restype = C.c_int
     L.mcs_decide_closest_gap.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(abi.Action)]
+    L.mcs_fp64_peak.restype = C.c_int
+    L.mcs_fp64_peak.argtypes = [C.c_int, C.c_int, P(C.c_double), P(C.c_float)]
     _lib = L
     return L
 
@@ -186,6 +188,13 @@ class DeviceScene:
         out = abi.Action()
         check(lib().mcs_decide_closest_gap(self._h, agent_id, direction, C.byref(out)))
         return out
+
+
+def fp64_peak_tflops(device=0, iters=20000):
+    """Measured FP64 multiply-add rate of the device (TFLOP/s, kernel ms): the roofline denominator of the rollout kernels."""
+    tf, ms = C.c_double(), C.c_float()
+    check(lib().mcs_fp64_peak(device, iters, C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value
 
 
 def prepare_host(corridors, agents):

@@ -82,6 +82,23 @@ __global__ void combine_groups_kernel(const mcs_group_partial* __restrict__ g, i
   combine_groups(g + (size_t)c * groups, groups, out + c);
 }
 
+// Roofline denominator of the rollout kernels (the binding resource is the FP64 pipe, and
+// MEASURED_PEAKS.json holds no FP64 figure): a stream of independent double-precision fused multiply-adds, eight
+// accumulator chains per thread so that neither latency nor issue limits it, no memory traffic.  2 flop per DFMA.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* __restrict__ out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (r == 12345.678) out[0] = r;      // never true for the arguments used; keeps the chains alive
+}
+
 }  // namespace
 
 // Everything a call needs besides the scene itself lives in one grow-only context per device: creating and destroying
@@ -476,6 +493,32 @@ int mcs_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
+}
+
+int mcs_fp64_peak(int device, int iters, double* tflops_out, float* ms_out) {
+  if (!tflops_out || iters <= 0) return fail(MCS_ERR_ARG, "bad arguments");
+  if (mcs_device_count() <= device || device < 0) return fail(MCS_ERR_CUDA, "no such CUDA device");
+  DeviceCtx* c = nullptr;
+  int rc = get_ctx(device, &c);
+  if (rc != MCS_OK) return rc;
+  std::lock_guard<std::mutex> lock(c->mu);
+  CUDA_TRY(cudaSetDevice(device));
+  const int blocks = c->n_sm * 8, threads = 256;            // 2048 resident threads per SM
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {                        // the first repetition warms the clocks up
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    fp64_peak_kernel<<<blocks, threads, 0, c->stream>>>((double*)c->d_counter, iters, 0.999999, 1e-6);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  const double flop = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+  *tflops_out = flop / ((double)best * 1e-3) / 1e12;
+  if (ms_out) *ms_out = best;
+  return MCS_OK;
 }
 
 int mcs_scene_create(const mcs_corridor* corridors, int n_corridors, const mcs_agent* agents, int n_agents, int device,

@@ -152,3 +152,68 @@ def exit_scene(n_vehicles=200, seed=0, n_main=3):
     right = sorted((a for a in agents if 0.0 <= a.y < LANE_WIDTH), key=lambda a: abs(a.x - ego.x))[:3]
     gaps = [-1] + [a.id for a in sorted(right, key=lambda a: -a.x)]
     return corridors, agents, ego.id, gaps
+
+
+def generated_scene(seed, n_vehicles=256, n_lanes=4):
+    """The throughput workload (BASELINE.json configs[4]) on a scene of the reference's own generator, as BASELINE.md §3 /
+    SURVEY.md §8(d) prescribe: `np.random.seed(seed); random.seed(seed)`, then RandomTrafficGenerator.random_agents_on_map
+    (traffic_generator.py, pinned on the reference's random_traffic_generator.py) on the lanes of
+    evaluation_lane_change.py:18-44 — speed limits 100/3.6, 100/3.6, +20/3.6, +30/3.6, headway parameters (1.8, 0.4) on
+    the two right lanes and (2.0, 1.0) on the two left ones, truck ratio 0.4 on the rightmost lane — made long enough for
+    n_vehicles / n_lanes vehicles per lane (the shipped 500 m hold about ten) and with the ramp replaced by a fourth main
+    lane (configs[4] is IDM / MOBIL only).  Marshalled like lane_change_mcs_sim_from_env (mcs_wrapper.py:193-283) without
+    its 80 m cut: Frenet frame of the ego lane's centre line extended by 1000 m, the ego keeps its own parameters, every
+    other vehicle becomes `idm_lc` with idm_param(l) / rss_param(False) / YieldingParam() and vd + N(0, 1) drawn in
+    list order.  Returns (corridors, agents, ego_id) as ctypes arrays."""
+    import random
+    from . import traffic_generator as tg
+    np.random.seed(seed)
+    random.seed(seed)
+    base = 100 / 3.6
+    limits = [base, base, base + 20 / 3.6, base + 30 / 3.6]
+    headway = [(1.8, 0.4), (1.8, 0.4), (2.0, 1.0), (2.0, 1.0)]
+    while len(limits) < n_lanes:
+        limits.append(limits[-1]); headway.append(headway[-1])
+    per_lane = [n_vehicles // n_lanes + (1 if k < n_vehicles % n_lanes else 0) for k in range(n_lanes)]
+    x0, x1 = -200.0, 200.0 + max(per_lane) * 120.0
+    lanes, params = {}, {}
+    for k in range(n_lanes):
+        lo, hi, mid = k * LANE_WIDTH, (k + 1) * LANE_WIDTH, (k + 0.5) * LANE_WIDTH
+        lanes[k] = tg.StraightLane(k, "main", [[x0, hi], [x1, hi]], [[x0, lo], [x1, lo]], [[x0, mid], [x1, mid]], limits[k],
+                                   k + 1 if k + 1 < n_lanes else None, k - 1 if k > 0 else None)
+        params[k] = tg.RandomDensityAndVelocityParameter(headway[k][0], headway[k][1], 0, 2, [0, x1 - x0], per_lane[k])
+    _, vehicles = tg.RandomTrafficGenerator().random_agents_on_map(lanes, params, unsafe_lc_ratio=0., truck_ratio=0.4)
+    if len(vehicles) != n_vehicles:
+        raise ValueError("generator produced %d vehicles, wanted %d" % (len(vehicles), n_vehicles))
+    ego_lane = min(1, n_lanes - 1)
+    mid_y = (ego_lane + 0.5) * LANE_WIDTH
+    in_lane = sorted((v for v in vehicles if ego_lane * LANE_WIDTH <= v["y"] < (ego_lane + 1) * LANE_WIDTH), key=lambda v: v["x"])
+    ego = in_lane[len(in_lane) // 2]
+    s_of = lambda x: x - (x0 - 1000.0)            # arc length on the ego lane's centre line extended by 1000 m
+    corridors = (abi.Corridor * n_lanes)()
+    for o, k in zip(corridors, range(n_lanes)):
+        o.id = k; o.type = abi.LANE_TYPES["main"]
+        o.left[:] = [s_of(x0), (k + 1) * LANE_WIDTH - mid_y, s_of(x1), (k + 1) * LANE_WIDTH - mid_y]
+        o.right[:] = [s_of(x0), k * LANE_WIDTH - mid_y, s_of(x1), k * LANE_WIDTH - mid_y]
+        o.center[:] = [s_of(x0), (k + 0.5) * LANE_WIDTH - mid_y, s_of(x1), (k + 0.5) * LANE_WIDTH - mid_y]
+        o.v_limit = limits[k]
+    agents = (abi.Agent * n_vehicles)()
+    order = [ego] + [v for v in vehicles if v is not ego]         # the builders put the ego first
+    for o, v in zip(agents, order):
+        o.id = v["id"]
+        o.x, o.y, o.v, o.vy, o.a, o.l, o.w = s_of(v["x"]), v["y"] - mid_y, v["v"], v["vy"], v["a"], v["l"], v["w"]
+        o.commit = abi.COMMITS["not_decided"]; o.commit_keep_lane_step = 0; o.target_lane_id = -1
+        if v is ego:
+            ip, mp, yp = v["idm_p"], v["mobil_param"], v["yielding_param"]
+            o.behavior = abi.BEHAVIORS["idm"]
+            o.vd = ip["vd"]
+            o.idm[:] = [ip["acc_max"], ip["min_dis"], ip["acc_min"], ip["acc_com"], -8.0, ip["thw"]]
+            o.rss[:] = EGO_RSS
+            o.yp[:] = [yp[0], yp[1], yp[2], yp[3], mp["politeness_factor"], mp["delta_a"], mp["bias_a"]]
+        else:
+            o.behavior = abi.BEHAVIORS["idm_lc"]
+            o.vd = v["idm_p"]["vd"] + np.random.normal(0., 1)
+            o.idm[:] = generic_idm(v["l"])
+            o.rss[:] = GENERIC_RSS
+            o.yp[:] = GENERIC_YP
+    return corridors, agents, ego["id"]
