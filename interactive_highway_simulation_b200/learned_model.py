@@ -61,20 +61,18 @@ class LearnedLaneChangeModel:
         by delta_to_last_decision."""
         if len(feature) != len(commands):
             print("Dimension of features do not match possible commands!")
+        side_cost = {"left": self.left_cost, "right": self.right_cost}
         q_values = []
-        q_last = -1e10
         for command, f in zip(commands, feature):
             q = np.dot(self.weights, np.array(f))
-            if command == "left":
-                q += self.left_cost
-            if command == "right":
-                q += self.right_cost
-            if command == last_decision:
-                q_last = q
+            if command in side_cost:
+                q += side_cost[command]
             q_values.append([command, q])
+        bar = dict(q_values).get(last_decision, -1e10) + self.delta_to_last_decision   # what a new command has to reach
         q_values.sort(key=lambda cq: cq[1], reverse=True)
-        if q_values[0][0] != last_decision:
-            for command, q in q_values:
-                if q >= q_last + self.delta_to_last_decision:
-                    return q_values, command
+        if q_values[0][0] == last_decision:
+            return q_values, last_decision
+        for command, q in q_values:
+            if q >= bar:
+                return q_values, command
         return q_values, last_decision

@@ -81,121 +81,122 @@ def truck_lane_id(lanes):
     return None
 
 
-def _at_least(mean, var, lo):
-    return max(lo, np.random.normal(mean, var))
+# ---- parameter draws.  What matters for reproducing the reference's scenes is WHICH global stream each quantity comes
+# from and in which order; the tables below carry the distributions, the functions only walk them in that order.
 
+# IDM families (random_traffic_generator.py:8-35): acc_max ~ U, acc_min ~ U, then min_dis ~ max(2, N(4, 1)),
+# acc_com ~ N(-2, 0.1), thw ~ max(1, N(thw_mean, 0.1)), vd = desired + N(0, vd_sigma) — six numpy draws in this order
+IDM_FAMILIES = {
+    "car": {"acc_max": (1.8, 2.2), "acc_min": (-2., -4.), "thw_mean": 1.5, "vd_sigma": 0.5},
+    "truck": {"acc_max": (0.8, 1.1), "acc_min": (-1.0, -2.0), "thw_mean": 1.2, "vd_sigma": 1.},
+    "merging": {"acc_max": (2.0, 2.5), "acc_min": (-3., -4.), "thw_mean": 1.5, "vd_sigma": 0.5},
+}
 
-def random_idm_p(desired_v):
-    acc_max = np.random.uniform(1.8, 2.2)
-    acc_min = np.random.uniform(-2., -4.)
-    min_dis = _at_least(4, 1, 2)
-    acc_com = np.random.normal(-2.0, 0.1)
-    thw = _at_least(1.5, 0.1, 1.0)
-    vd = desired_v + np.random.normal(0., 0.5)
-    return {"acc_max": acc_max, "acc_min": acc_min, "min_dis": min_dis, "acc_com": acc_com, "thw": thw, "vd": vd}
-
-
-def random_idm_p_truck(desired_v):
-    acc_max = np.random.uniform(0.8, 1.1)
-    acc_min = np.random.uniform(-1.0, -2.0)
-    min_dis = _at_least(4, 1, 2)
-    acc_com = np.random.normal(-2.0, 0.1)
-    thw = _at_least(1.2, 0.1, 1.0)
-    vd = desired_v + np.random.normal(0., 1.)
-    return {"acc_max": acc_max, "acc_min": acc_min, "min_dis": min_dis, "acc_com": acc_com, "thw": thw, "vd": vd}
-
-
-def random_idm_p_merging(desired_v):
-    acc_max = np.random.uniform(2.0, 2.5)
-    acc_min = np.random.uniform(-3., -4.)
-    min_dis = _at_least(4, 1, 2)
-    acc_com = np.random.normal(-2.0, 0.1)
-    thw = _at_least(1.5, 0.1, 1.0)
-    vd = desired_v + np.random.normal(0., 0.5)
-    return {"acc_max": acc_max, "acc_min": acc_min, "min_dis": min_dis, "acc_com": acc_com, "thw": thw, "vd": vd}
-
-
+# the 13 weights of the reference's yielding model (random_traffic_generator.py:39-41); a vehicle gets each one
+# perturbed by 20 % (one numpy normal draw per weight, in order)
 YIELDING_PARAMETER = [1.70968573, 0.00582201, 0.40742229, 1.02390871, -0.32091885, 1.48127062, -0.69499426, -0.34547462,
                       -0.56578542, -1.911662, -0.03998742, 0.02613949, -0.02392805]
 
 
-def random_yielding_p():
-    return [np.random.normal(p, abs(p) * 0.2) for p in YIELDING_PARAMETER]
+def draw_idm(family, desired_v):
+    f = IDM_FAMILIES[family]
+    p = {"acc_max": np.random.uniform(*f["acc_max"]), "acc_min": np.random.uniform(*f["acc_min"])}
+    p["min_dis"] = max(2, np.random.normal(4, 1))
+    p["acc_com"] = np.random.normal(-2.0, 0.1)
+    p["thw"] = max(1.0, np.random.normal(f["thw_mean"], 0.1))
+    p["vd"] = desired_v + np.random.normal(0., f["vd_sigma"])
+    return p
 
 
-def random_mobil_p():
-    politeness_f = np.random.uniform(0, 1)
-    delta_a = np.random.normal(0.5, 0.2)
-    bias_a = delta_a + np.random.normal(0.1, 0.05)
-    return {"politeness_factor": politeness_f, "delta_a": delta_a, "bias_a": bias_a}
+def draw_yielding():
+    return [np.random.normal(w, abs(w) * 0.2) for w in YIELDING_PARAMETER]
+
+
+def draw_mobil():
+    """politeness ~ U(0, 1), delta_a ~ N(0.5, 0.2), bias_a = delta_a + N(0.1, 0.05) (random_traffic_generator.py:47-51)"""
+    p = {"politeness_factor": np.random.uniform(0, 1), "delta_a": np.random.normal(0.5, 0.2)}
+    p["bias_a"] = p["delta_a"] + np.random.normal(0.1, 0.05)
+    return p
+
+
+def _plain(d):
+    return {k: float(v) for k, v in d.items()}
 
 
 class RandomTrafficGenerator:
-    """random_traffic_generator.py:74-136"""
+    """random_traffic_generator.py:74-136: vehicles are placed lane by lane from the lane's start, each a random time
+    headway ahead of the previous one; ids count up across lanes and calls."""
+
+    CAR_SHAPES = [[4.5, 1.9], [4.8, 2], [4.9, 2.1], [5.2, 2.2], [5.9, 2.4]]
+    TRUCK_SHAPES = [[11.5, 2.5], [12, 2.5], [10, 2.5]]
 
     def __init__(self):
         self.vehicle_id = 0
-        self.shapes = [[4.5, 1.9], [4.8, 2], [4.9, 2.1], [5.2, 2.2], [5.9, 2.4]]
-        self.truck_shape = [[11.5, 2.5], [12, 2.5], [10, 2.5]]
+        self.shapes = self.CAR_SHAPES
+        self.truck_shape = self.TRUCK_SHAPES
 
     def random_agents_on_map(self, lanes, parameter, unsafe_lc_ratio=0., truck_ratio=0.):
-        """lanes: {id: StraightLane} in the map's insertion order -> (agents on merging lanes, agents on main lanes)"""
-        agents_merging, agents_main = [], []
-        truck_lane = truck_lane_id(lanes)
-        v_limit_candidates = [c.v_limit for c in lanes.values() if c.type == "main"]
-        for i, c in lanes.items():
-            if c.type == "main":
-                agents_main.extend(self.random_agents_on_lane(c, parameter[i], v_limit_candidates, "idm", unsafe_lc_ratio=unsafe_lc_ratio,
-                                                              truck_ratio=truck_ratio if i == truck_lane else 0.))
-            if c.type == "merging":
-                agents_merging.extend(self.random_agents_on_lane(c, parameter[i], v_limit_candidates, "merging_closest_gap_policy"))
-        return agents_merging, agents_main
+        """lanes: {id: StraightLane} in the map's insertion order -> (agents on merging lanes, agents on main lanes).
+        Only the truck lane (Map.truck_lane_id) gets trucks; exit lanes get nobody."""
+        speed_limits = [lane.v_limit for lane in lanes.values() if lane.type == "main"]
+        trucks_on = truck_lane_id(lanes)
+        on_ramp, on_main = [], []
+        for lane_id, lane in lanes.items():
+            if lane.type == "main":
+                on_main += self.random_agents_on_lane(lane, parameter[lane_id], speed_limits, "idm", unsafe_lc_ratio,
+                                                      truck_ratio if lane_id == trucks_on else 0.)
+            elif lane.type == "merging":
+                on_ramp += self.random_agents_on_lane(lane, parameter[lane_id], speed_limits, "merging_closest_gap_policy")
+        return on_ramp, on_main
 
     def random_agents_on_lane(self, corridor, params, v_limit_candidates, behavior_model, unsafe_lc_ratio=0., truck_ratio=0.):
-        vehicles = []
-        s_range = [0, corridor.path_length]
-        num_vehicles = 1e10
+        first, last = 0, corridor.path_length
         if params.s_range:
-            s_range = [max(s_range[0], params.s_range[0]), min(s_range[1], params.s_range[1])]
-        if params.num_vehicles:
-            num_vehicles = params.num_vehicles
-        x_frenet = np.random.uniform(s_range[0], 0.3 * corridor.v_limit * params.thw_mean)
-        while x_frenet < s_range[1] and len(vehicles) < num_vehicles:
-            y_frenet = np.random.normal(0, 0.2)
-            v = np.random.normal(corridor.v_limit + params.mean_v_diff_to_limit, params.v_var)
-            x, y, yaw = corridor.to_global_coordinate(x_frenet, y_frenet)
-            random_num = np.random.uniform(0, 1)
-            if random_num < truck_ratio:
-                l, w = random.choice(self.truck_shape)
-                idm_p = random_idm_p_truck(min(v_limit_candidates))
-            else:
-                l, w = random.choice(self.shapes)
-                idm_p = random_idm_p(random.choice(v_limit_candidates))
-            change_intention_threshold = np.random.uniform(0.4, 0.7)
-            b_model = behavior_model
-            if behavior_model == "idm":     # 10 % plain idm
-                random_num = np.random.uniform(0, 1)
-                if 1 - unsafe_lc_ratio >= random_num > 0.1:
-                    b_model = "idm_mobil_lane_change_safe"
-                elif random_num > 1 - unsafe_lc_ratio:
-                    b_model = "idm_mobil_lane_change"
-            yielding_p = random_yielding_p()
-            mobil_p = random_mobil_p()
-            yielding_seed = int(random.random() * 100)            # Agent.__init__ (agent.py:73-76)
-            if "merging" in behavior_model:
-                idm_p = random_idm_p_merging(random.choice(v_limit_candidates))
-            vehicles.append({"id": int(self.vehicle_id), "x": float(x), "y": float(y), "v": float(v), "vy": 0.0,
-                             "yaw": float(np.rad2deg(np.deg2rad(yaw))), "a": 0.0, "l": float(l), "w": float(w),
-                             "idm_p": {k: float(val) for k, val in idm_p.items()},
-                             "mobil_param": {k: float(val) for k, val in mobil_p.items()},
-                             "yielding_param": [float(p) for p in yielding_p],
-                             "behavior_model": b_model,
-                             "change_intention_threshold": float(change_intention_threshold),
-                             "random_yielding_seed": yielding_seed})
-            x_frenet += np.random.uniform(corridor.v_limit * (params.thw_mean - params.thw_var),
-                                          corridor.v_limit * (params.thw_mean + params.thw_var)) + l
+            first, last = max(first, params.s_range[0]), min(last, params.s_range[1])
+        room = params.num_vehicles if params.num_vehicles else 1e10
+        gap_lo = corridor.v_limit * (params.thw_mean - params.thw_var)
+        gap_hi = corridor.v_limit * (params.thw_mean + params.thw_var)
+        out = []
+        s = np.random.uniform(first, 0.3 * corridor.v_limit * params.thw_mean)
+        while s < last and len(out) < room:
+            vehicle = self._spawn(corridor, params, s, v_limit_candidates, behavior_model, unsafe_lc_ratio, truck_ratio)
+            out.append(vehicle)
+            s += np.random.uniform(gap_lo, gap_hi) + vehicle["l"]
             self.vehicle_id += 1
-        return vehicles
+        return out
+
+    def _spawn(self, lane, params, s, speed_limits, base_model, unsafe_lc_ratio, truck_ratio):
+        """One vehicle at arc length `s`.  Draw order (numpy unless noted): lateral offset, speed, truck?, shape (`random`),
+        IDM (cars pick their desired-speed limit with `random`), intention threshold, behaviour model (main lanes only),
+        13 yielding weights, 3 MOBIL values, yielding seed (`random`), and for ramps a second IDM set that replaces the first."""
+        lateral = np.random.normal(0, 0.2)
+        speed = np.random.normal(lane.v_limit + params.mean_v_diff_to_limit, params.v_var)
+        x, y, yaw = lane.to_global_coordinate(s, lateral)
+        if np.random.uniform(0, 1) < truck_ratio:
+            length, width = random.choice(self.truck_shape)
+            idm = draw_idm("truck", min(speed_limits))
+        else:
+            length, width = random.choice(self.shapes)
+            idm = draw_idm("car", random.choice(speed_limits))
+        threshold = np.random.uniform(0.4, 0.7)
+        model = base_model
+        if base_model == "idm":
+            # a tenth stay plain IDM; the rest change lanes by MOBIL, `unsafe_lc_ratio` of them without the RSS check
+            u = np.random.uniform(0, 1)
+            if u > 1 - unsafe_lc_ratio:
+                model = "idm_mobil_lane_change"
+            elif u > 0.1:
+                model = "idm_mobil_lane_change_safe"
+        yielding = draw_yielding()
+        mobil = draw_mobil()
+        yielding_seed = int(random.random() * 100)            # drawn by Agent.__init__ (agent.py:73-76)
+        if "merging" in base_model:
+            idm = draw_idm("merging", random.choice(speed_limits))
+        return {"id": int(self.vehicle_id), "x": float(x), "y": float(y), "v": float(speed), "vy": 0.0,
+                "yaw": float(np.rad2deg(np.deg2rad(yaw))), "a": 0.0, "l": float(length), "w": float(width),
+                "idm_p": _plain(idm), "mobil_param": _plain(mobil), "yielding_param": [float(w) for w in yielding],
+                "behavior_model": model, "change_intention_threshold": float(threshold),
+                "random_yielding_seed": yielding_seed}
 
 
 def evaluation_map(name, v_limit=100 / 3.6):

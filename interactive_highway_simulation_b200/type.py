@@ -46,12 +46,13 @@ class YieldingIntention:                                     # type.py:70-90
         self.yielding = random.random() <= initial_probability
 
     def update_intention(self, new_probability):
-        if not self.yielding:
-            if (1 - new_probability) <= self.change_intention_threshold * (1 - self.initial_probability):
-                self.yielding = True
+        """Hysteresis around the first estimate p0: a yielding vehicle stops yielding once the probability has fallen to
+        threshold * p0, a non-yielding one starts once the complement has fallen to threshold * (1 - p0)."""
+        p0, k = self.initial_probability, self.change_intention_threshold
+        if self.yielding:
+            self.yielding = not (new_probability <= k * p0)
         else:
-            if new_probability <= self.change_intention_threshold * self.initial_probability:
-                self.yielding = False
+            self.yielding = (1 - new_probability) <= k * (1 - p0)
 
     def __repr__(self):
         return "Yielding {}, initial_p: {}".format(self.yielding, self.initial_probability)
@@ -75,19 +76,25 @@ class YieldingModel:                                         # type.py:93-137
         return 1 / (1 + math.exp(-r))
 
     def yielding_probability(self, idm_match, ego, ego_f, env, direction):
-        if idm_match.dis + 0.5 * (ego.l + idm_match.l) < 0:
+        """Probability that `ego` (on the main lane, own leader `ego_f` or None) yields to the vehicle `idm_match` that
+        wants to move in from the side lane in `direction`; 0 once that vehicle is completely behind (type.py:111-137)."""
+        half_lengths = 0.5 * (ego.l + idm_match.l)
+        if idm_match.dis + half_lengths < 0:
             return 0.
-        v_kf = ego_f.v if ego_f else 20
-        v_k = ego.v
-        s_diff_kf_f = ego_f.dis if ego_f else 200
-        s_diff_0_k = idm_match.dis - 0.5 * (ego.l + idm_match.l)
-        v_0 = ego.v                                          # sic (type.py:122)
-        d_0_lat = env.dis_to_lane_border(idm_match.id, direction)
-        v_0_lat = idm_match.vy
-        corridor_merging_vehicle = env.corridor_for_agent(idm_match.id)
-        d_to_merging_lane_end = corridor_merging_vehicle.distance_to_corridor_end([idm_match.x, idm_match.y])
-        t_to_merging_lane_end = d_to_merging_lane_end / max(v_0, 0.0001)
-        predicted_remaining_length = d_to_merging_lane_end * (1 - v_k / max(v_0, 0.0001))
-        thw, d_thw = thw_and_ttc(idm_match.dis - 0.5 * (ego.l + idm_match.l), ego.v, idm_match.v)
-        return self.logistic_function((s_diff_kf_f, s_diff_0_k, v_0, d_0_lat, v_0_lat, v_k, v_kf, thw, d_thw,
-                                       d_to_merging_lane_end, t_to_merging_lane_end, predicted_remaining_length))
+        gap = idm_match.dis - half_lengths
+        own_v = ego.v                      # the reference feeds the yielding vehicle's speed as BOTH v_0 and v_k (type.py:122)
+        v_floor = max(own_v, 0.0001)
+        border = env.dis_to_lane_border(idm_match.id, direction)
+        to_end = env.corridor_for_agent(idm_match.id).distance_to_corridor_end([idm_match.x, idm_match.y])
+        thw, d_thw = thw_and_ttc(gap, own_v, idm_match.v)
+        return self.logistic_function((ego_f.dis if ego_f else 200,          # s_diff_kf_f   gap to the own leader
+                                       gap,                                  # s_diff_0_k
+                                       own_v,                                # v_0
+                                       border,                               # d_0_lat       its hull to the lane border
+                                       idm_match.vy,                         # v_0_lat
+                                       own_v,                                # v_k
+                                       ego_f.v if ego_f else 20,             # v_kf
+                                       thw, d_thw,
+                                       to_end,                               # d_to_merging_lane_end
+                                       to_end / v_floor,                     # t_to_merging_lane_end
+                                       to_end * (1 - own_v / v_floor)))      # predicted_remaining_length

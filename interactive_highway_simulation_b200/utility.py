@@ -14,49 +14,43 @@ def distance(p1, p2):                                                 # utility.
 
 
 def vehicle_pose_to_rect(pos_x, pos_y, yaw, length, width):           # utility.py:12-20
-    head = [pos_x + length / 2 * math.cos(yaw), pos_y + length / 2 * math.sin(yaw)]
-    tair = [pos_x - length / 2 * math.cos(yaw), pos_y - length / 2 * math.sin(yaw)]
-    head_left = [head[0] - width / 2 * math.sin(yaw), head[1] + width / 2 * math.cos(yaw)]
-    head_right = [head[0] + width / 2 * math.sin(yaw), head[1] - width / 2 * math.cos(yaw)]
-    tair_left = [tair[0] - width / 2 * math.sin(yaw), tair[1] + width / 2 * math.cos(yaw)]
-    tair_right = [tair[0] + width / 2 * math.sin(yaw), tair[1] - width / 2 * math.cos(yaw)]
-    return [head_left, head_right, tair_right, tair_left]
+    """Corners [front-left, front-right, rear-right, rear-left] of the vehicle's rectangle."""
+    c, s = math.cos(yaw), math.sin(yaw)
+    along = (length / 2 * c, length / 2 * s)          # centre -> front bumper
+    across = (width / 2 * s, width / 2 * c)           # (minus x, plus y) components of centre line -> left side
+    front = (pos_x + along[0], pos_y + along[1])
+    rear = (pos_x - along[0], pos_y - along[1])
+
+    def corner(p, left):
+        return [p[0] - across[0], p[1] + across[1]] if left else [p[0] + across[0], p[1] - across[1]]
+    return [corner(front, True), corner(front, False), corner(rear, False), corner(rear, True)]
 
 
-def idm_acc_f_b(fs, b, ego_v, v_limit, idm_param, obey_v_limit=True):  # utility.py:23-49
-    acc_max, acc_min, min_dis = idm_param.acc_max, idm_param.acc_min, idm_param.min_dis
-    acc_com, thw = idm_param.acc_com, idm_param.thw
-    vd = min(idm_param.vd, 1.1 * v_limit) if obey_v_limit else idm_param.vd
-    free_road_term = acc_max * (1 - (ego_v / vd) ** 4)
-    d_term = 0
-    d_terms_f = []
-    for f in fs:
-        d_desire = (0.7 * (min_dis + ego_v * thw) + ego_v * (ego_v - f.v) / (2 * math.sqrt(-acc_max * acc_com)))
-        d_terms_f.append(-acc_max * (d_desire / max(1, f.dis)) ** 2)
-    d_term += min(d_terms_f) if d_terms_f else 0
-    if b:
-        d_desire = (0.7 * (min_dis + b.v * thw) + b.v * (b.v - ego_v) / (2 * math.sqrt(-acc_max * acc_com)))
-        d_term += acc_max * (d_desire / max(1, -b.dis)) ** 2
-    acc = free_road_term + d_term
-    return max(min(acc_max, acc), acc_min)
+def _idm_interaction(p, v_behind, v_ahead, gap):
+    """(desired gap of the vehicle behind / actual gap, at least 1 m)^2 — the IDM interaction term without its sign and
+    scale; the desired gap is 0.7 (min_dis + v thw) + v dv / (2 sqrt(-acc_max acc_com)) (utility.py:35,42)."""
+    wish = (0.7 * (p.min_dis + v_behind * p.thw) + v_behind * (v_behind - v_ahead) / (2 * math.sqrt(-p.acc_max * p.acc_com)))
+    return (wish / max(1, gap)) ** 2
 
 
-def idm_acc_fs_bs(fs, bs, ego_v, v_limit, idm_param, obey_v_limit=True):   # utility.py:52-80: several followers, the strongest push counts
-    acc_max, acc_com = idm_param.acc_max, idm_param.acc_com
-    d_terms_b = []
-    for b in bs:
-        d_desire = (0.7 * (idm_param.min_dis + b.v * idm_param.thw) + b.v * (b.v - ego_v) / (2 * math.sqrt(-acc_max * acc_com)))
-        d_terms_b.append(acc_max * (d_desire / max(1, -b.dis)) ** 2)
-    vd = min(idm_param.vd, 1.1 * v_limit) if obey_v_limit else idm_param.vd
-    free_road_term = acc_max * (1 - (ego_v / vd) ** 4)
-    d_term = 0
-    d_terms_f = []
-    for f in fs:
-        d_desire = (0.7 * (idm_param.min_dis + ego_v * idm_param.thw) + ego_v * (ego_v - f.v) / (2 * math.sqrt(-acc_max * acc_com)))
-        d_terms_f.append(-acc_max * (d_desire / max(1, f.dis)) ** 2)
-    d_term += min(d_terms_f) if d_terms_f else 0
-    d_term += max(d_terms_b) if d_terms_b else 0
-    return max(min(acc_max, free_road_term + d_term), idm_param.acc_min)
+def idm_acc_fs_bs(fs, bs, ego_v, v_limit, idm_param, obey_v_limit=True):   # utility.py:52-80
+    """IDM acceleration with leaders `fs` (the most restrictive one counts) and followers `bs` (the strongest push
+    counts); `dis` of a match is the bumper-to-bumper gap, positive ahead, negative behind."""
+    p = idm_param
+    vd = min(p.vd, 1.1 * v_limit) if obey_v_limit else p.vd
+    acc = p.acc_max * (1 - (ego_v / vd) ** 4)
+    pull = [-p.acc_max * _idm_interaction(p, ego_v, f.v, f.dis) for f in fs]
+    push = [p.acc_max * _idm_interaction(p, b.v, ego_v, -b.dis) for b in bs]
+    interaction = 0
+    if pull:
+        interaction += min(pull)
+    if push:
+        interaction += max(push)
+    return max(min(p.acc_max, acc + interaction), p.acc_min)
+
+
+def idm_acc_f_b(fs, b, ego_v, v_limit, idm_param, obey_v_limit=True):  # utility.py:23-49: at most one follower
+    return idm_acc_fs_bs(fs, [b] if b else [], ego_v, v_limit, idm_param, obey_v_limit)
 
 
 def offset_point(p, yaw, offset):                                     # utility.py:83-85
@@ -81,23 +75,24 @@ def step_along_path(ref_path, ego, ax, vy, dt):                       # utility.
 
 
 def thw_and_ttc(d, ego_v, obj_v):                                     # utility.py:101-108
-    thw = d / max(ego_v, 1e-10)
-    if ego_v > 0:
-        ttc = (ego_v - obj_v) / ego_v
-    else:
-        ttc = (ego_v - obj_v) / 1e-3
-    return thw, ttc
+    """Time headway over the gap `d` and the closing speed relative to the own speed (speeds below 1 mm/s count as 1 mm/s)."""
+    return d / max(ego_v, 1e-10), (ego_v - obj_v) / (ego_v if ego_v > 0 else 1e-3)
 
 
 def rss_dis(vf, vb, rt, a_min, a_max):                                # utility.py:129-130
-    return max(vb * rt + vb * vb / (-2 * a_min) - vf * vf / (-2 * a_max), 0.)
+    """RSS gap: what the rear vehicle covers in its reaction time and braking at a_min, less the leader's braking path at a_max."""
+    rear_path = vb * rt + vb * vb / (-2 * a_min)
+    return max(rear_path - vf * vf / (-2 * a_max), 0.)
 
 
-def idm_p_for_merging_exit_agents(random_seed, idm_p_origin, is_truck):   # utility.py:133-141 (re-seeds `random`)
+def idm_p_for_merging_exit_agents(random_seed, idm_p_origin, is_truck):   # utility.py:133-141
+    """The softened IDM parameters a vehicle yields with.  Re-seeds the global `random` stream like the reference — callers
+    downstream depend on where that leaves it."""
     random.seed(random_seed)
-    random_number = random.random()
-    idm_p_yielding = deepcopy(idm_p_origin)
-    if not is_truck:
-        idm_p_yielding.acc_max -= (0.6 + 0.4 * random_number)
-        idm_p_yielding.acc_min += (0.8 + 0.4 * random_number)
-    return idm_p_yielding
+    u = random.random()
+    softened = deepcopy(idm_p_origin)
+    if is_truck:
+        return softened
+    softened.acc_max -= (0.6 + 0.4 * u)
+    softened.acc_min += (0.8 + 0.4 * u)
+    return softened
