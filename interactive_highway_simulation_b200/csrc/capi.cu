@@ -1,6 +1,7 @@
 // C ABI of libmcsim_b200.so (include/mcsim.h).  CUDA runtime only — no torch types cross this boundary.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -10,6 +11,7 @@
 #include <vector>
 
 #include "rollout_kernel.cuh"
+#include "bundle_kernel.cuh"
 #include "decide_kernel.cuh"
 #include "scene.hpp"
 
@@ -136,6 +138,7 @@ struct mcs_scene {
   mcs::SceneDev dev{};
   unsigned char* d_blob = nullptr;   // f | i | lane_vec in one allocation, rows dev.n_pad long (0 = not uploaded yet)
   size_t blob_cap = 0;
+  int slot_table = -1;               // which thread -> slot table the blob carries: 0 rollout_kernel, 1 bundle_kernel
 };
 
 namespace {
@@ -260,12 +263,28 @@ void thread_slots(const mcs::SceneHost& h, int pad, unsigned char* out) {
   for (int q = 0; q < pad; ++q) out[q] = (unsigned char)(slot_of[q] >= 0 ? slot_of[q] : dead++);
 }
 
+// Slot of every slot thread of a rollout in bundle_kernel: the live slots sorted by (initial lane, initial behaviour, ego
+// last within its lane) — threads that sit side by side in a warp then run the same behaviour code — then the padding
+// slots.  Any permutation is correct (the draw positions come from a table indexed by slot, not from the thread order).
+void bundle_slots(const mcs::SceneHost& h, int pad, unsigned char* out) {
+  std::vector<int> order;
+  for (int k = 0; k < h.n; ++k) order.push_back(k);
+  auto cls = [&](int k) {
+    const int lane = h.i[(size_t)mcs::I_LANE * h.n_pad + k], beh = h.i[(size_t)mcs::I_BEH * h.n_pad + k];
+    return (lane < 0 ? 255 : lane) * 16 + beh;
+  };
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cls(a) < cls(b); });
+  int q = 0;
+  for (int k : order) out[q++] = (unsigned char)k;
+  for (int k = h.n; q < pad; ++k) out[q++] = (unsigned char)k;
+}
+
 // Copy the scene to the device with rows `pad` slots long (pad >= host.n_pad; the kernels index rows with their block
 // size as a compile-time stride).  The upload happens at the first use and again only if a later launch wants another
 // row length: one blob (doubles | ints | lane vector), staged through pinned memory, one stream-ordered allocation,
 // one copy.  Caller holds the context lock and has selected the device.
-int upload_scene(mcs_scene* sc, int pad) {
-  if (sc->dev.n_pad == pad) return MCS_OK;
+int upload_scene(mcs_scene* sc, int pad, int slot_table = 0) {
+  if (sc->dev.n_pad == pad && sc->slot_table == slot_table) return MCS_OK;
   DeviceCtx* c = sc->ctx;
   const mcs::SceneHost& h = sc->host;
   if (pad < h.n_pad) return fail(MCS_ERR_ARG, "row length below the scene's");
@@ -293,7 +312,8 @@ int upload_scene(mcs_scene* sc, int pad) {
       memcpy(c->h_stage + bf + (size_t)q * pad * sizeof(int32_t), h.i.data() + (size_t)q * h.n_pad, (size_t)h.n_pad * sizeof(int32_t));
     memcpy(c->h_stage + bf + bi, h.lane_vec.data(), (size_t)h.n_pad);
   }
-  thread_slots(h, pad, c->h_stage + bf + bi + ((bv + 15) & ~(size_t)15));
+  if (slot_table == 1) bundle_slots(h, pad, c->h_stage + bf + bi + ((bv + 15) & ~(size_t)15));
+  else thread_slots(h, pad, c->h_stage + bf + bi + ((bv + 15) & ~(size_t)15));
   if (total > sc->blob_cap) {
     if (sc->d_blob) CUDA_TRY(cudaFreeAsync(sc->d_blob, c->stream));
     sc->d_blob = nullptr; sc->blob_cap = 0; sc->dev.n_pad = 0;
@@ -306,6 +326,7 @@ int upload_scene(mcs_scene* sc, int pad) {
   d.f = (const double*)sc->d_blob; d.i = (const int32_t*)(sc->d_blob + bf); d.lane_vec = sc->d_blob + bf + bi;
   d.thread_slot = d.lane_vec + ((bv + 15) & ~(size_t)15);
   d.n_pad = pad;     // the copy is ordered before every later launch on the context's stream
+  sc->slot_table = slot_table;
   return MCS_OK;
 }
 
@@ -426,6 +447,66 @@ int launch_one(mcs_scene* sc, dim3 grid, size_t smem, const mcs::LaunchParams& l
   }
 }
 
+// ---- bundle_kernel (scenes of up to 64 vehicles): rollouts per block RW (a power of two: the lanes of a warp are RW
+// rollouts x 32/RW vehicle slots), slot threads per rollout NS, threads per block NS * RW <= 1024.  The wider the bundle the
+// more lanes of a warp run the same code; the launch should still give every SM a block.
+#ifndef MCS_BUNDLE_MAX_RW_LOG2
+#define MCS_BUNDLE_MAX_RW_LOG2 4
+#endif
+#ifndef MCS_BUNDLE_MIN_SLOTS
+#define MCS_BUNDLE_MIN_SLOTS 49152    // rollouts x vehicles from which a merging launch goes to bundle_kernel
+#endif
+template <bool kMerge, int MAXT>
+int launch_bundle_t(mcs_scene* sc, dim3 grid, int threads, size_t smem, const mcs::LaunchParams& lp, const mcs::BundleParams& bp) {
+  CUDA_TRY(cudaFuncSetAttribute(mcs::bundle_kernel<kMerge, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mcs::bundle_kernel<kMerge, MAXT><<<grid, dim3(threads), smem, sc->ctx->stream>>>(sc->dev, sc->ctx->d_cand, lp, bp);
+  CUDA_TRY(cudaGetLastError());
+  return MCS_OK;
+}
+
+// returns 1 when the launch went to bundle_kernel, 0 when this launch is not for it, < 0 on error
+int try_launch_bundle(mcs_scene* sc, int n_cand, const mcs::LaunchParams& lp, bool merge) {
+  const int n = sc->host.n;
+  // capability: up to 64 vehicle slots, no trajectory output, a horizon the per-rollout pool of yielding intentions is sized
+  // for (longer ones go to rollout_kernel's per-vehicle tables)
+  if (n > mcs::BNP || lp.traj || lp.steps > 128) return 0;
+  const long long total = (long long)lp.count * n_cand;
+  const char* forced = getenv("MCS_KERNEL");               // tests run every scene through both kernels
+  if (forced && !strcmp(forced, "rollout")) return 0;
+  if (!(forced && !strcmp(forced, "bundle"))) {
+    // Where it pays (scripts/bundle_sweep.py, B200): merging / exit scenes once the launch is past what rollout_kernel runs
+    // in one wave — 40 vehicles x 4 gaps x 512 rollouts 1.60 -> 1.30 ms, x 2048 rollouts 6.7 -> 4.7 ms.  Below that a
+    // rollout's own warps finish a step sooner (4 x 64 rollouts 0.75 vs 1.12 ms), and in plain lane-change scenes
+    // rollout_kernel's compacted MOBIL sub-tasks win (64 vehicles x 5 x 512: 0.98 vs 1.62 ms).
+    if (!merge || total * n < MCS_BUNDLE_MIN_SLOTS) return 0;
+  }
+  const size_t region = mcs::bundle_region_bytes(lp.steps, merge);
+  int max_log2 = MCS_BUNDLE_MAX_RW_LOG2;
+  if (const char* e = getenv("MCS_BUNDLE_RW_LOG2")) { const int v = atoi(e); if (v >= 0 && v <= 5) max_log2 = v; }   // tuning / tests
+  int rw_log2 = -1;
+  for (int l = max_log2; l >= 0; --l) {
+    const int rw = 1 << l, hslots = 32 >> l, ns = (n + hslots - 1) / hslots * hslots;
+    if (ns * rw > 1024) continue;
+    if (mcs::BUNDLE_STATIC_BYTES + (size_t)rw * region > sc->ctx->smem_per_block) continue;
+    rw_log2 = l;
+    // wide enough once every SM has a block (a forced width is taken as it is)
+    if (getenv("MCS_BUNDLE_RW_LOG2") || (total + rw - 1) / rw >= sc->ctx->n_sm * 3 / 4) break;
+  }
+  if (rw_log2 < 0) return 0;                      // horizon too long for even one rollout per block: rollout_kernel decides
+  const int rw = 1 << rw_log2, hslots = 32 >> rw_log2, ns = (n + hslots - 1) / hslots * hslots;
+  int rc = upload_scene(sc, mcs::BNP, 1);
+  if (rc != MCS_OK) return rc;
+  mcs::BundleParams bp{rw_log2, ns, (int)region, 0};
+  const int threads = ns * rw;
+  const size_t smem = mcs::BUNDLE_STATIC_BYTES + (size_t)rw * region;
+  dim3 grid((unsigned)((lp.count + rw - 1) / rw), (unsigned)n_cand);
+  if (threads <= 384) rc = merge ? launch_bundle_t<true, 384>(sc, grid, threads, smem, lp, bp) : launch_bundle_t<false, 384>(sc, grid, threads, smem, lp, bp);
+  else if (threads <= 512) rc = merge ? launch_bundle_t<true, 512>(sc, grid, threads, smem, lp, bp) : launch_bundle_t<false, 512>(sc, grid, threads, smem, lp, bp);
+  else if (threads <= 768) rc = merge ? launch_bundle_t<true, 768>(sc, grid, threads, smem, lp, bp) : launch_bundle_t<false, 768>(sc, grid, threads, smem, lp, bp);
+  else rc = merge ? launch_bundle_t<true, 1024>(sc, grid, threads, smem, lp, bp) : launch_bundle_t<false, 1024>(sc, grid, threads, smem, lp, bp);
+  return rc == MCS_OK ? 1 : rc;
+}
+
 // launch the rollout kernel for rollouts [first, first+count) of every candidate; statuses → d_status (device)
 int launch_rollouts(mcs_scene* sc, int n_cand, const mcs_sim_param* sp, uint64_t seed, int64_t first, int64_t count,
                     mcs_status* d_status, double* d_traj, int32_t* d_traj_n, unsigned long long* d_counter, int merge) {
@@ -437,7 +518,13 @@ int launch_rollouts(mcs_scene* sc, int n_cand, const mcs_sim_param* sp, uint64_t
   lp.status = d_status; lp.traj = d_traj; lp.traj_n = d_traj_n; lp.vehicle_steps = d_counter;
   lp.err_flags = sc->ctx->d_err;
   CUDA_TRY(cudaMemsetAsync(sc->ctx->d_err, 0, sizeof(unsigned int), sc->ctx->stream));
-  int rc = upload_scene(sc, rollout_threads(sc, (long long)count * n_cand, d_traj != nullptr, merge != 0));
+  int rc = try_launch_bundle(sc, n_cand, lp, merge != 0);
+  if (rc < 0) return rc;
+  if (rc == 1) {
+    CUDA_TRY(cudaMemcpyAsync(&sc->ctx->h_small->err, sc->ctx->d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, sc->ctx->stream));
+    return MCS_OK;
+  }
+  rc = upload_scene(sc, rollout_threads(sc, (long long)count * n_cand, d_traj != nullptr, merge != 0));
   if (rc != MCS_OK) return rc;
   size_t smem = (rollout_smem_bytes(sc->dev.n_pad, sp->steps) + 15) & ~(size_t)15;   // one rollout's region
   dim3 grid((unsigned)count, (unsigned)n_cand);

@@ -72,9 +72,9 @@ __global__ void __launch_bounds__(256, 1) decide_kernel(const SceneDev sc, const
       if (canL || canR) {
         const int bpos = lane_reverse(s, lo, cnt, x);
         const int back = bpos > 0 ? (int)s.vec[lo + bpos - 1] : -1;
-        for (int part = 0; part < MOBIL_PARTS; ++part) mobil_geometry(s, sc, laneStart, np, k, front, back, part, false);
+        const MobilGeo geo = mobil_geometry_all(s, sc, laneStart, np, k, front, back);
         const double u = (double)mcs_rand31(dp.key, (uint64_t)n) / 2147483647.0;
-        mobil_decide(s, sc, np, k, lane, v, el, aMin, F[(size_t)F_YP_PF * np + k], F[(size_t)F_YP_DA * np + k],
+        mobil_decide(geo, sc, np, k, lane, v, el, aMin, F[(size_t)F_YP_PF * np + k], F[(size_t)F_YP_DA * np + k],
                      F[(size_t)F_YP_BA * np + k], dp.require_rss ? 2 : 3, false, F + (size_t)F_PRIOR_L * np, u, ms, ax, avy);
       }
     }

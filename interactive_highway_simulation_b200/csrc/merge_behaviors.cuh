@@ -343,13 +343,97 @@ __device__ __forceinline__ bool merging_closest_gap(const Smem& s, const SceneDe
   return merging_behavior(s, sc, laneStart, a, evd, false, isEgo, left, -1, ax, vy);
 }
 
-// ---- yielding intentions (Agent+0x238: unordered_map<int, YieldingIntention>) as a small per-thread table ----
+// ---- yielding intentions (Agent+0x238: unordered_map<int, YieldingIntention{id, p0, threshold 0.625, yielding}>) ----
+// Two stores with one interface.  update(): `p` = yielding probability now, `y0` = the initial intention drawn for a first
+// encounter (0x10469c-0x1046ec); returns the intention after the hysteresis update (0x104724: a non-yielding vehicle starts
+// once (1-p0) 0.625 >= 1-p, a yielding one stops once 0.625 p0 >= p).  A full store sets flags[7] (MCS_ERR_CAPACITY) and
+// drops the entry.
+__device__ __forceinline__ bool yield_hysteresis(bool yl, double p0, double p) {
+  if (!yl) { if ((1.0 - p0) * 0.625 >= 1.0 - p) yl = true; }
+  else { if (0.625 * p0 >= p) yl = false; }
+  return yl;
+}
+
+// rollout_kernel: a table of 32 entries per vehicle thread (local memory; L1-resident).  The shared-memory pool below was
+// measured in its place and is slower there: 3 KB more per rollout no longer fit fourteen 64-thread rollouts per block
+// (configs[1] 1.60 -> 1.82 ms), and a pool sized per rollout overflows on long horizons where 32 per vehicle do not.
 #define MCS_YCAP 32
-struct YieldTable {
+struct YieldLocal {
   uint8_t key[MCS_YCAP];
   double p0[MCS_YCAP];
   uint32_t yielding;   // bit per entry
   int n;
+  __device__ __forceinline__ void init() { n = 0; yielding = 0u; }
+  __device__ __forceinline__ bool update(const Smem& s, int j, double p, bool y0) {
+    int e = -1;
+    for (int t = 0; t < n; ++t) if (key[t] == (uint8_t)j) { e = t; break; }
+    if (e < 0) {
+      if (n >= MCS_YCAP) { s.flags[7] = 1; return false; }
+      e = n++;
+      key[e] = (uint8_t)j; p0[e] = p;
+      if (y0) yielding |= 1u << e; else yielding &= ~(1u << e);
+    }
+    const bool yl = yield_hysteresis((yielding >> e) & 1u, p0[e], p);
+    if (yl) yielding |= 1u << e; else yielding &= ~(1u << e);
+    return yl;
+  }
 };
+
+// bundle_kernel: ONE pool of entries per rollout in shared memory (Smem::yp0 / ykey / ynext / yflag, handed out by an
+// atomic counter); every vehicle threads its own entries into a chain whose head lives in a register.  Chains are short (a
+// vehicle meets a handful of distinct candidates per rollout) and nothing sits in local memory.
+struct YieldChain {
+  int head;
+  __device__ __forceinline__ void init() { head = YIELD_END; }
+  __device__ __forceinline__ bool update(const Smem& s, int j, double p, bool y0) {
+    int e = head;
+    while (e != YIELD_END && s.ykey[e] != (uint8_t)j) e = s.ynext[e];
+    if (e == YIELD_END) {
+      e = atomicAdd(&s.flags[8], 1);
+      if (e >= s.ycap) { s.flags[7] = 1; return false; }
+      s.ykey[e] = (uint8_t)j; s.yp0[e] = p; s.ynext[e] = (uint16_t)head; s.yflag[e] = y0 ? 1 : 0;
+      head = e;
+    }
+    const bool yl = yield_hysteresis(s.yflag[e] != 0, s.yp0[e], p);
+    s.yflag[e] = yl ? 1 : 0;
+    return yl;
+  }
+};
+
+// The part of idmBehaviorAndYieldingToMergingAgents that looks at the yielding candidates (0x1045b0-0x1048f4): per
+// candidate the intention probability — logistic of (time headway, relative speed, own initial acceleration) — one draw
+// each (draws drawBase .. drawBase + nY - 1), the hysteresis update, then idmAccFrontBack with the softened parameters
+// `py` over the candidates the vehicle currently yields to.
+template <class YieldStore>
+__device__ __forceinline__ double yielding_acc(const Smem& s, const double* __restrict__ F, int np, int k, const IdmP& py,
+                                               const int* ycand, int nY, uint64_t key, uint64_t drawBase, YieldStore& yt, double x,
+                                               double v, double el, double pw) {
+  const double ypBias = F[(size_t)F_YP_BIAS * np + k], ypA = F[(size_t)F_YP_A * np + k], ypB = F[(size_t)F_YP_B * np + k],
+               ypC = F[(size_t)F_YP_C * np + k];
+  int ylist[5];
+  int ny = 0;
+#pragma unroll 1
+  for (int q = 0; q < nY; ++q) {
+    const int j = ycand[q];
+    double p = 0.0;
+    const double half = (el + s.l[j]) * 0.5;
+    const double dx = s.x[j] - x;
+    if (!(0.0 > dx + half)) {
+      const double thw = (dx - half) / MCS_MAXSD(1e-10, v);
+      const double rel = (v - s.v[j]) / MCS_MAXSD(v, 0.001);
+      double r = thw * ypA + ypBias;
+      r = r + rel * ypB;
+      r = r + F[(size_t)F_A * np + k] * ypC;     // Agent::statesHistory[0].a
+      double arg;
+      if (100.0 > r) arg = (-100.0 > r) ? 100.0 : -r;
+      else arg = -100.0;
+      p = 1.0 / (mcs_exp(arg) + 1.0);
+    }
+    const int rnd = mcs_rand31(key, drawBase + (uint64_t)q);
+    const bool y0 = (100.0 * p) >= (double)(rnd % 100);
+    if (yt.update(s, j, p, y0)) ylist[ny++] = j;
+  }
+  return idm_acc_list(s, py, ylist, ny, -1, x, v, el, pw);
+}
 
 }  // namespace mcs

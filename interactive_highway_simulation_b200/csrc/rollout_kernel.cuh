@@ -107,12 +107,23 @@ struct Smem {
   int* cnt;        // [2][16] lane starts, double-buffered across rebuilds
   int* flags;      // [8] per-rollout scalars: 0 ego reached its target lane, 1 movers queued, 2 ego behaviour, 3 thw samples,
                    //     4 ego's gap slot, 5 finish step, 6 scene unsupported, 7 yield table full
+                   //     (bundle_kernel: [16], 1 = a lane membership changed, 8 = yield pool entries in use, 9 = fall-back seen)
   int* tasks;      // [n_pad] MOBIL task queue
   uint8_t* lane;   // [n_pad] lane slot of each vehicle (0xff = none)
   uint8_t* vec;    // [n_pad] concatenated per-lane vectors
   uint8_t* mflag;  // [2][n_pad] MOBIL flags per vehicle (left part, right part)
   uint8_t* pos;    // [n_pad] position of each vehicle inside vec
+  // yielding intentions in bundle_kernel: one pool of entries per rollout, chained per vehicle (merge_behaviors.cuh)
+  double* yp0;      // [ycap] probability at the first encounter
+  uint16_t* ynext;  // [ycap] next entry of the same yielding vehicle, YIELD_END = end of the chain
+  uint8_t* ykey;    // [ycap] slot of the vehicle yielded to
+  uint8_t* yflag;   // [ycap] current intention
+  int ycap;
 };
+constexpr int YIELD_END = 0xffff;
+// entries of a rollout's pool in bundle_kernel (<= 64 vehicles; a vehicle next to a ramp meets the ramp's [BB, B, F, FF]
+// and, while it overtakes or is overtaken, a few more; vehicles elsewhere meet nobody)
+constexpr int BUNDLE_YCAP = 256;
 
 // shared-memory layout of one rollout (host twin: rollout_smem_bytes in capi.cu)
 __device__ __forceinline__ void carve_smem(Smem& s, unsigned char* p, int np, int steps) {
@@ -133,6 +144,7 @@ __device__ __forceinline__ void carve_smem(Smem& s, unsigned char* p, int np, in
   s.vec = p; p += np;
   s.mflag = p; p += 2 * np;
   s.pos = p; p += np;      // 5 * np bytes so far, np a multiple of 32: still 8-byte aligned
+  s.ycap = 0; s.yp0 = nullptr; s.ynext = nullptr; s.ykey = nullptr; s.yflag = nullptr;
   // the arrays whose size depends on the horizon come last: everything above sits at a compile-time offset (np is the
   // block-size template constant), so the per-step accesses need no address arithmetic
   s.chist = (double*)p; p += sizeof(double) * ((steps + 2) & ~1);
@@ -301,8 +313,14 @@ __device__ __forceinline__ void side_leader_follower(const Smem& s, const int* l
 // independent sub-tasks of similar cost (part 0: old follower delta; 1-3: left lane own IDM / RSS gates / follower
 // delta; 4-6: the same for the right lane) executed by whichever threads picked them from the queue; results go to
 // shared memory.
-__device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc, const int* laneStart, int np, int k,
-                                               int front, int back, int part, bool ordered) {
+// Everything mobil_decide needs from the seven sub-tasks of one vehicle
+struct MobilGeo { double accNewL, accNewR, dNewL, dNewR, deltaOld; int mf; };
+
+// one sub-task.  kStore: the result goes to the vehicle's cell of the shared arrays (the task queue of rollout_kernel);
+// otherwise it comes back in `value` (parts 0, 1, 3, 4, 6) or `mfOut` (parts 2, 5: the side's flag bits)
+template <bool kStore>
+__device__ __forceinline__ void mobil_geometry_core(const Smem& s, const SceneDev& sc, const int* laneStart, int np, int k,
+                                                    int front, int back, int part, bool ordered, double& value, int& mfOut) {
   const LaneDev& L = sc.lanes[s.lane[k]];
   // Which IDM evaluation is this sub-task?  Parts 0, 3, 6 are all "what does vehicle j lose when k drives between it
   // and F" (j = old follower / would-be follower on the left / right); parts 1, 3 are k's own acceleration behind the
@@ -323,7 +341,7 @@ __device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc
       const double vdCap = MCS_MINSD(s.vd[k], 1.1 * sc.lanes[sl].vLimit);
       accNew = idm_acc(s, load_idm(s, np, k), leader, -1, follower, s.x[k], ev, s.l[k], mcs_pow4(ev / vdCap));
     }
-    s.mob[side * np + k] = accNew;
+    if (kStore) s.mob[side * np + k] = accNew; else value = accNew;
     return;
   }
   if (sub == 1) {
@@ -339,7 +357,7 @@ __device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc
         if (ok) mf |= (side == 0 ? MF_STRICT_L : MF_STRICT_R) << relaxed;
       }
     }
-    s.mflag[side * np + k] = (uint8_t)mf;
+    if (kStore) s.mflag[side * np + k] = (uint8_t)mf; else mfOut = mf;
     return;
   }
   const int j = part == 0 ? back : follower;
@@ -377,7 +395,41 @@ __device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc
     ro = MCS_MAXSD(pj.accMin, ro);
     delta = part == 0 ? ro - rw : rw - ro;       // old follower: without - with (0xf4583); new follower: with - without
   }
-  s.mob[(part == 0 ? 4 : 2 + side) * np + k] = delta;
+  if (kStore) s.mob[(part == 0 ? 4 : 2 + side) * np + k] = delta; else value = delta;
+}
+
+// the sub-task as the task queue of rollout_kernel runs it
+__device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc, const int* laneStart, int np, int k,
+                                               int front, int back, int part, bool ordered) {
+  double value;
+  int mf;
+  mobil_geometry_core<true>(s, sc, laneStart, np, k, front, back, part, ordered, value, mf);
+}
+__device__ __forceinline__ MobilGeo load_mobil_geo(const Smem& s, int np, int k) {
+  MobilGeo g;
+  g.accNewL = s.mob[k]; g.accNewR = s.mob[np + k]; g.dNewL = s.mob[2 * np + k]; g.dNewR = s.mob[3 * np + k];
+  g.deltaOld = s.mob[4 * np + k];
+  g.mf = s.mflag[k] | s.mflag[np + k];
+  return g;
+}
+// all seven sub-tasks in one thread (bundle_kernel: the lanes of a warp are the same vehicle in different rollouts)
+__device__ __forceinline__ MobilGeo mobil_geometry_all(const Smem& s, const SceneDev& sc, const int* laneStart, int np, int k,
+                                                       int front, int back) {
+  MobilGeo g;
+  g.accNewL = g.accNewR = g.dNewL = g.dNewR = g.deltaOld = 0.0; g.mf = 0;
+#pragma unroll 1
+  for (int part = 0; part < MOBIL_PARTS; ++part) {
+    double value = 0.0;
+    int mf = 0;
+    mobil_geometry_core<false>(s, sc, laneStart, np, k, front, back, part, false, value, mf);
+    if (part == 0) g.deltaOld = value;
+    else if (part == 1) g.accNewL = value;
+    else if (part == 3) g.dNewL = value;
+    else if (part == 4) g.accNewR = value;
+    else if (part == 6) g.dNewR = value;
+    else g.mf |= mf;
+  }
+  return g;
 }
 
 // Agent fields laneChangeBehaviorMOBIL writes back (commitToDecision 0x90, commitKeepLaneStep 0xb0, targetLaneId 0x68)
@@ -387,15 +439,15 @@ struct MobilState { int commit, keepStep, targetLane; };
 // vehicle k and the keep-lane counter test (0xf434c) has passed.  `u` = the uniform draw of 0xf510f (consumed only when
 // the vehicle does not continue a committed change).  mode: 0 = inside a rollout at the vehicle's first step (lateral-offset
 // prior blended in, 0xf58a0), 1 = inside a rollout later, 2 = Python-facing with requireRssSafety (0xf5858), 3 = without (0xf5053).
-__device__ __forceinline__ void mobil_decide(const Smem& s, const SceneDev& sc, int np, int k, int lane, double v, double el,
+__device__ __forceinline__ void mobil_decide(const MobilGeo& geo, const SceneDev& sc, int np, int k, int lane, double v, double el,
                                              double aMin, double pf, double dA, double bA, int mode, bool aggressive,
                                              const double* __restrict__ priors /* F_PRIOR_L row, stride np */, double u, MobilState& ms,
                                              double& ax, double& avy) {
-  const int mf = s.mflag[k] | s.mflag[np + k];
+  const int mf = geo.mf;
   const bool canL = mf & MF_CAN_L, canR = mf & MF_CAN_R;
   const bool strictL = mf & MF_STRICT_L, relaxL = mf & MF_RELAX_L, strictR = mf & MF_STRICT_R, relaxR = mf & MF_RELAX_R;
-  const double accNewL = s.mob[k], accNewR = s.mob[np + k], dNewL = s.mob[2 * np + k], dNewR = s.mob[3 * np + k];
-  const double deltaOld = s.mob[4 * np + k];
+  const double accNewL = geo.accNewL, accNewR = geo.accNewR, dNewL = geo.dNewL, dNewR = geo.dNewR;
+  const double deltaOld = geo.deltaOld;
   const double axIdm = ax, vyIdm = avy;
   double axLeft = axIdm, vyLeft = vyIdm, axRight = 0.0, vyRight = 0.0;
   double incL = -10000000000.0, incR = -10000000000.0;
@@ -653,8 +705,8 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
   int step = 0;
   // scalars only the ego thread touches (arrival, gap slot, finish step) and the two sticky error marks live in s.flags:
   // registers are what limits the resident rollouts per SM
-  YieldTable yt;
-  yt.n = 0; yt.yielding = 0u;
+  YieldLocal yt;
+  yt.init();
 
   bool running = true;
   int window = 0;   // steps left until the block's next alignment point
@@ -842,51 +894,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
         py.accMax = F[(size_t)F_IDMY_ACCMAX * np + k]; py.accMin = F[(size_t)F_IDMY_ACCMIN * np + k];
         double axY;
         if (kMerge && nY > 0) {
-          // intention per candidate: logistic of (thw, relative speed, own initial acceleration), one draw each, hysteresis 0.625
-          const double ypBias = F[(size_t)F_YP_BIAS * np + k], ypA = F[(size_t)F_YP_A * np + k], ypB = F[(size_t)F_YP_B * np + k],
-                       ypC = F[(size_t)F_YP_C * np + k];
-          int ylist[5];
-          int ny = 0;
-#pragma unroll 1
-          for (int q = 0; q < nY; ++q) {
-            const int j = ycand[q];
-            double p = 0.0;
-            const double half = (el + s.l[j]) * 0.5;
-            const double dx = s.x[j] - x;
-            if (!(0.0 > dx + half)) {
-              const double thw = (dx - half) / MCS_MAXSD(1e-10, v);
-              const double rel = (v - s.v[j]) / MCS_MAXSD(v, 0.001);
-              double r = thw * ypA + ypBias;
-              r = r + rel * ypB;
-              r = r + F[(size_t)F_A * np + k] * ypC;     // Agent::statesHistory[0].a
-              double arg;
-              if (100.0 > r) arg = (-100.0 > r) ? 100.0 : -r;
-              else arg = -100.0;
-              p = 1.0 / (mcs_exp(arg) + 1.0);
-            }
-            const int rnd = mcs_rand31(key, drawBase + (uint64_t)q);
-            const bool y0 = (100.0 * p) >= (double)(rnd % 100);
-            int e = -1;
-            for (int t = 0; t < yt.n; ++t) if (yt.key[t] == (uint8_t)j) { e = t; break; }
-            if (e < 0) {
-              if (yt.n < MCS_YCAP) {
-                e = yt.n++;
-                yt.key[e] = (uint8_t)j; yt.p0[e] = p;
-                if (y0) yt.yielding |= 1u << e; else yt.yielding &= ~(1u << e);
-              } else {
-                s.flags[7] = 1;
-              }
-            }
-            if (e >= 0) {
-              bool yl = (yt.yielding >> e) & 1u;
-              const double p0 = yt.p0[e];
-              if (!yl) { if ((1.0 - p0) * 0.625 >= 1.0 - p) yl = true; }
-              else { if (0.625 * p0 >= p) yl = false; }
-              if (yl) yt.yielding |= 1u << e; else yt.yielding &= ~(1u << e);
-              if (yl) ylist[ny++] = j;
-            }
-          }
-          axY = idm_acc_list(s, py, ylist, ny, -1, x, v, el, pw);
+          axY = yielding_acc(s, F, np, k, py, ycand, nY, key, drawBase, yt, x, v, el, pw);
         } else {
           // no yielding candidate: idmAccFrontBack over an empty list is the clamped free-road term
           const double r = MCS_MINSD(0.0 + (1.0 - pw) * py.accMax, py.accMax);
@@ -902,7 +910,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
           } else if (needMobil) {
             const double u = (double)mcs_rand31(key, drawBase + (uint64_t)nY + 1) / 2147483647.0;
             MobilState ms{commit, keepStep, targetLane};
-            mobil_decide(s, sc, np, k, lane, v, el, aMin, F[(size_t)F_YP_PF * np + k], F[(size_t)F_YP_DA * np + k],
+            mobil_decide(load_mobil_geo(s, np, k), sc, np, k, lane, v, el, aMin, F[(size_t)F_YP_PF * np + k], F[(size_t)F_YP_DA * np + k],
                          F[(size_t)F_YP_BA * np + k], /*mode=*/(step == 0) ? 0 : 1, aggressive, F + (size_t)F_PRIOR_L * np, u, ms, ax, avy);
             commit = ms.commit; keepStep = ms.keepStep; targetLane = ms.targetLane;
           }

@@ -23,15 +23,26 @@ def gpu(backend_lib):
     return backend_lib
 
 
-@pytest.fixture(autouse=True, params=["one_thread_per_slot", "launch_sized"])
-def threads_per_rollout(request, monkeypatch):
-    """Every test runs twice: with the minimum block size of its scene (32 / 64 / 128 / 256 threads per rollout, so each
-    kernel instantiation and the shared-block path are exercised by the small scenes too) and with the library's own
-    choice, which widens the rollouts of a small launch (capi.cu rollout_threads).  Results must not depend on it."""
-    if request.param == "one_thread_per_slot":
-        monkeypatch.setenv("MCS_ROLLOUT_THREADS", "32")      # below every scene's minimum = the minimum
+@pytest.fixture(autouse=True, params=["rollout_min_threads", "rollout_launch_sized", "bundle", "bundle_32_wide", "bundle_2_wide"])
+def kernel_variant(request, monkeypatch):
+    """Every test runs through both kernels and their launch shapes; results must not depend on any of it.
+    rollout_kernel (one rollout's vehicles on the lanes of a warp; the only kernel for scenes above 64 vehicles): with the
+    minimum block size of the scene (32 / 64 / 128 / 256 threads per rollout, so each instantiation and the shared-block
+    path are exercised by the small scenes too) and with the library's own choice, which widens the rollouts of a small
+    launch (capi.cu rollout_threads).  bundle_kernel (scenes up to 64 vehicles: the lanes of a warp are RW rollouts x 32/RW
+    vehicles): the library's own width, 32 rollouts per warp (one vehicle per warp) and 2 rollouts per warp."""
+    for name in ("MCS_ROLLOUT_THREADS", "MCS_KERNEL", "MCS_BUNDLE_RW_LOG2"):
+        monkeypatch.delenv(name, raising=False)
+    if request.param.startswith("rollout"):
+        monkeypatch.setenv("MCS_KERNEL", "rollout")
+        if request.param == "rollout_min_threads":
+            monkeypatch.setenv("MCS_ROLLOUT_THREADS", "32")      # below every scene's minimum = the minimum
     else:
-        monkeypatch.delenv("MCS_ROLLOUT_THREADS", raising=False)
+        monkeypatch.setenv("MCS_KERNEL", "bundle")               # whatever the launch size (the library's own rule: large merging launches)
+        if request.param == "bundle_32_wide":
+            monkeypatch.setenv("MCS_BUNDLE_RW_LOG2", "5")
+        elif request.param == "bundle_2_wide":
+            monkeypatch.setenv("MCS_BUNDLE_RW_LOG2", "1")
     return request.param
 
 
@@ -583,6 +594,44 @@ def test_result_is_independent_of_threads_per_rollout(gpu, monkeypatch, kind):
                     ref = got
                     assert any(x != bytes(64) for x in ref)
                 assert got == ref, (kind, threads, count)
+    finally:
+        ds.close()
+
+
+@pytest.mark.parametrize("kind", ["lane_change", "merging", "exit"])
+def test_bundle_kernel_equals_rollout_kernel(gpu, monkeypatch, kind):
+    """The two kernels on the same rollouts — bundle_kernel at every width (1 .. 32 rollouts per warp) against
+    rollout_kernel: byte-identical outcome records, in launches of 3, 700 and 2000 rollouts per candidate."""
+    rng = random.Random(777)
+    if kind == "lane_change":
+        s, ego = random_scene(rng, 4, 30, spacing=(3, 40))
+        cands = [(ego, a, -2) for a in ("keep_lane", "left", "right", "acc", "dcc")]
+    elif kind == "merging":
+        s, ego = random_scene(rng, n_agents=40, lane_types=["merging", "main", "main", "main"], ego_behavior="merging", ego_lane=0,
+                              spacing=(3, 40))
+        ids = [a["id"] for a in s.agents if 3.5 <= a["y"] < 7.0]
+        cands = [(ego, "left", -1)] + [(ego, "left", g) for g in ids[:2]]
+    else:
+        s, ego = random_scene(rng, n_agents=33, lane_types=["exit", "main", "main"], ego_behavior="exit", ego_lane=1, spacing=(3, 40))
+        cands = [(ego, "right", -1)]
+    cand = (abi.Candidate * len(cands))(*[abi.Candidate(e, abi.ACTIONS[a], g, 0) for e, a, g in cands])
+    sp = abi.SimParam(0.3, 40, 10)
+    ds = gpu.DeviceScene(s.c_corridors(), s.c_agents())
+    try:
+        for count in (3, 700, 2000):
+            monkeypatch.setenv("MCS_KERNEL", "rollout")
+            monkeypatch.delenv("MCS_ROLLOUT_THREADS", raising=False)
+            want = bytes(ds.rollouts_range(cand, sp, 4711, 0, count))
+            assert any(want[i * 64:(i + 1) * 64] != want[:64] for i in range(1, count))
+            monkeypatch.setenv("MCS_KERNEL", "bundle")
+            for width in (None, 0, 1, 2, 3, 4, 5):
+                if width is None:
+                    monkeypatch.delenv("MCS_BUNDLE_RW_LOG2", raising=False)
+                else:
+                    monkeypatch.setenv("MCS_BUNDLE_RW_LOG2", str(width))
+                got = bytes(ds.rollouts_range(cand, sp, 4711, 0, count))
+                bad = [i for i in range(len(cands) * count) if got[i * 64:(i + 1) * 64] != want[i * 64:(i + 1) * 64]]
+                assert not bad, (kind, count, width, len(bad), bad[:5])
     finally:
         ds.close()
 
