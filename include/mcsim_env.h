@@ -35,6 +35,7 @@ enum { MCE_OK = 0, MCE_ERR_ARG = -1, MCE_ERR_CUDA = -2, MCE_ERR_CAPACITY = -3 };
 #define MCE_MAX_POINTS 16   /* points per polyline of a corridor          */
 #define MCE_MAX_AGENTS 1024 /* vehicles per scene                         */
 #define MCE_NEIGHBORS 10    /* Neighbor(...) ctor order, agent.py:203-213 */
+#define MCE_BUILD_MAX_AGENTS 48 /* vehicles one builder call can marshal (the reference's selection gives <= ~25) */
 
 /* index into the neighbour tables, the order of the reference's Neighbor constructor */
 enum { MCE_LEFT_FF = 0, MCE_LEFT_F, MCE_LEFT_B, MCE_LEFT_BB, MCE_FRONT, MCE_BACK, MCE_RIGHT_FF, MCE_RIGHT_F, MCE_RIGHT_B,
@@ -106,6 +107,41 @@ int mce_center_distance(mce_map* map, const int32_t* lane, const double* x, cons
  * to the border line (the yielding feature d_0_lat, type.py:123). */
 enum { MCE_SIDE_LEFT = 0, MCE_SIDE_RIGHT = 1 };
 int mce_border_distance(mce_map* map, const int32_t* lane, const int32_t* side, const double* hull, int n, double* out);
+
+/* ---- mcs_wrapper.py:24-283 on the device: the three builders of the inner simulator's scene ------------------------
+ * Corridor.id / .type (MCS_LANE_*) / .v_limit of every corridor of the map, in the order of mce_map_create — the values
+ * the builders copy into the CorridorMS records and the exit builder's lane arithmetic (mcs_wrapper.py:96-118). */
+struct mcs_corridor;
+struct mcs_agent;
+struct mcs_scene;
+int mce_map_set_lane_info(mce_map* map, const int32_t* ids, const int32_t* types, const double* v_limits, int n_corridors);
+
+typedef struct mce_build_request {
+  int32_t kind;            /* 0 merging_mcs_sim_from_env, 1 exit_mcs_sim_from_env, 2 lane_change_mcs_sim_from_env */
+  int32_t scene, ego_slot; /* against the tables of the last mce_env_match on this handle */
+  int32_t ego_behavior;    /* MCS_BEH_* of the ego's AgentMS ("merging" / "idm" / "exit", mcs_wrapper.py:45,187,277) */
+  int32_t others_merging;  /* merging builder: behaviour of the collected main-lane vehicles, 1 "merging" / 0 "idm_lc" (:50) */
+  int32_t ego_commit, ego_keep_step, ego_target_lane; /* what behaviors.py:75-78 pokes into the ego's AgentMS */
+  double ego_vd;
+  double ego_idm[6], ego_rss[6], ego_yp[7];           /* memory order of mcs_agent */
+} mce_build_request;
+
+/* One builder call on the device: neighbour selection (FF / F / B / BB per side, front, front of the front, follower,
+ * +-80 m on the second lanes) over the resident match tables at the vehicles' CURRENT positions, XY -> Frenet of the
+ * builder's reference line, parameter assignment, candidate gap ids — all in one launch; the records come back in the
+ * reference's append order, and (scene_out != NULL) the marshalled scene is created on `device` right away
+ * (mcs_scene_create), ready for mcs_rollouts / mcs_decide_*.
+ *   ids    [n_agents]        Agent.id of every slot of the matched scene
+ *   attrs  [8][n_agents]     x y v vy a l w vd (idm_param.vd) of every slot NOW (vehicles moved since the match included)
+ *   noise  [n_noise]         np.random.normal(0., 1) draws added to the vd of the non-ego vehicles, in append order; NULL:
+ *                            the records carry the plain vd and the caller, who only now knows how many vehicles were
+ *                            collected, draws *n_agents_out - 1 values and adds them itself (what the Python layer does:
+ *                            the reference draws one value per appended vehicle from numpy's global stream)
+ *   corridors_out [MCE_MAX_LANES], agents_out [MCE_BUILD_MAX_AGENTS], actions_out [4]   (host; any may be NULL) */
+int mce_build_rollout_scene(mce_map* map, const mce_build_request* request, const int32_t* ids, const double* attrs,
+                            const double* noise, int n_noise, struct mcs_corridor* corridors_out, int32_t* n_corridors_out,
+                            struct mcs_agent* agents_out, int32_t* n_agents_out, int32_t* actions_out, int32_t* n_actions_out,
+                            int device, struct mcs_scene** scene_out);
 
 /* average duration (ms, CUDA events on the launching stream) of the kernels of the last mce_env_match call:
  * out[0] = match + order kernel, out[1] = neighbour kernel */

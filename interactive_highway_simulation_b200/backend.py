@@ -107,6 +107,13 @@ class DeviceScene:
         self._agents = agents
         check(lib().mcs_scene_create(corridors, len(corridors), agents, len(agents), device, C.byref(self._h)))
 
+    @classmethod
+    def adopt(cls, handle, n_agents, n_corridors):
+        """Wrap an mcs_scene* another entry point created (mce_build_rollout_scene); this object now owns it."""
+        self = cls.__new__(cls)
+        self._h, self.n_agents, self.n_corridors, self._corridors, self._agents = handle, n_agents, n_corridors, None, None
+        return self
+
     def close(self):
         if self._h:
             lib().mcs_scene_destroy(self._h)

@@ -9,9 +9,12 @@ The plain-IDM / MOBIL behaviours of the outer loop (behaviors.py:10-86) are here
 per-vehicle host arithmetic (IDM, yielding intentions, RSS brake) over the device's neighbour tables and border / centre
 distances; `lane_change_behavior_mobil` asks the single-step MOBIL kernel (`laneChangeMobilBehavior`).
 """
+from . import _abi as abi
+from . import backend
 from . import decisions
 from . import mc_sim_highway as ms
-from .mcs_wrapper import exit_mcs_sim_from_env, lane_change_mcs_sim_from_env, merging_mcs_sim_from_env
+from .mcs_wrapper import exit_mcs_sim_from_env, lane_change_mcs_sim_from_env, merging_mcs_sim_from_env  # noqa: F401  (reference's import list)
+from .outer_env import BUILD_EXIT, BUILD_LANE_CHANGE, BUILD_MERGING
 from .type import DecoupledAction, YieldingIntention
 from .utility import idm_acc_f_b, idm_p_for_merging_exit_agents, rss_dis
 
@@ -57,19 +60,30 @@ def idm_behavior(observed_model, agent):                     # behaviors.py:10-6
     return DecoupledAction(ax, vy, corridor)
 
 
+class _Marshalled:
+    """The inner simulator's scene of one vehicle, built on the device by the environment (mcs_wrapper's builder as ONE
+    launch, outer_env.Environment.marshal) and handed to the decision / rollout kernels without passing through Python
+    value objects; `actions` = the builder's candidate gap ids."""
+
+    def __init__(self, observed_model, agent, kind, poke_commit=False):
+        _, nc, _, na, self.actions, handle = observed_model.marshal(agent, kind, poke_commit=poke_commit)
+        self.scene = backend.DeviceScene.adopt(handle, na, nc)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.scene.close()
+
+
 def lane_change_behavior_mobil(observed_model, agent, require_rss_safety):    # behaviors.py:70-86
     ego_corridor = observed_model.corridor_for_agent(agent.id)
     action_idm = idm_behavior(observed_model, agent)
-    mcs_corridors, mcs_agents = lane_change_mcs_sim_from_env(observed_model, agent, ego_corridor)
-    for a in mcs_agents:
-        if a.id == agent.id:
-            a.targetLaneId, a.commitToDecision, a.commitKeepLaneStep = agent.target_lane_id, agent.commit_lane_change, agent.commit_keep_lane_step
-            break
-    action = ms.laneChangeMobilBehavior(ms.Environment(ms.MapMultiLane(mcs_corridors), mcs_agents), agent.id,
-                                        ms.Action(action_idm.ax, action_idm.vy), require_rss_safety)
+    with _Marshalled(observed_model, agent, BUILD_LANE_CHANGE, poke_commit=True) as m:
+        out = m.scene.decide_mobil(agent.id, action_idm.ax, action_idm.vy, bool(require_rss_safety), ms._next_seed())
     agent.commit_lane_change, agent.commit_keep_lane_step, agent.target_lane_id = \
-        action.commitToDecision, action.commitKeepLaneStep, action.targetLaneId
-    return DecoupledAction(action.ax, action.vy, ego_corridor)
+        abi.COMMIT_NAMES[out.commit], out.commit_keep_lane_step, out.target_lane_id
+    return DecoupledAction(out.ax, out.vy, ego_corridor)
 
 
 def lane_change_behavior_learned(observed_model, agent):     # behaviors.py:89-115
@@ -80,41 +94,40 @@ def lane_change_behavior_learned(observed_model, agent):     # behaviors.py:89-1
         possible_actions.append("left")
     if ego_corridor.right_id and corridors[ego_corridor.right_id].type == "main":
         possible_actions.append("right")
-    mcs_corridors, mcs_agents = lane_change_mcs_sim_from_env(observed_model, agent, ego_corridor)
-    action, decision, _, _ = decisions.lane_change_decision(mcs_corridors, mcs_agents, agent.id, possible_actions,
-                                                            agent.current_decision, agent.learned_lane_change_model, 20,
-                                                            ms.SimParameter(0.3, 40, 30))
+    with _Marshalled(observed_model, agent, BUILD_LANE_CHANGE) as m:
+        action, decision, _, _ = decisions.lane_change_decision_on(m.scene, agent.id, possible_actions, agent.current_decision,
+                                                                   agent.learned_lane_change_model, 20, ms.SimParameter(0.3, 40, 30))
     agent.current_decision = decision
     return DecoupledAction(action.ax, action.vy, ego_corridor)
 
 
 def cloned_merging_behavior(observed_model, agent):          # behaviors.py:118-137
     ego_corridor = observed_model.corridor_for_agent(agent.id)
-    mcs_corridors, mcs_agents, possible_actions = merging_mcs_sim_from_env(observed_model, agent, ego_corridor)
-    action, decision, _, _ = decisions.gap_decision(mcs_corridors, mcs_agents, agent.id, possible_actions, "left",
-                                                    agent.learned_merging_model, 30, ms.SimParameter(0.3, 40, 10))
+    with _Marshalled(observed_model, agent, BUILD_MERGING) as m:
+        action, decision, _, _ = decisions.gap_decision_on(m.scene, agent.id, m.actions, "left", agent.learned_merging_model, 30,
+                                                           ms.SimParameter(0.3, 40, 10))
     agent.current_decision = decision
     return DecoupledAction(action.ax, action.vy, ego_corridor)
 
 
 def merging_behavior_closest_gap(observed_model, agent):     # behaviors.py:140-145
     ego_corridor = observed_model.corridor_for_agent(agent.id)
-    mcs_corridors, mcs_agents, _ = merging_mcs_sim_from_env(observed_model, agent, ego_corridor)
-    action = ms.closestGapMergingBehavior(ms.Environment(ms.MapMultiLane(mcs_corridors), mcs_agents), agent.id, "left")
+    with _Marshalled(observed_model, agent, BUILD_MERGING) as m:
+        action = m.scene.decide_closest_gap(agent.id, abi.ACTIONS["left"])
     return DecoupledAction(action.ax, action.vy, ego_corridor)
 
 
 def exit_behavior_closest_gap(observed_model, agent):        # behaviors.py:148-153
     ego_corridor = observed_model.corridor_for_agent(agent.id)
-    mcs_corridors, mcs_agents, _ = exit_mcs_sim_from_env(observed_model, agent, ego_corridor)
-    action = ms.closestGapMergingBehavior(ms.Environment(ms.MapMultiLane(mcs_corridors), mcs_agents), agent.id, "right")
+    with _Marshalled(observed_model, agent, BUILD_EXIT) as m:
+        action = m.scene.decide_closest_gap(agent.id, abi.ACTIONS["right"])
     return DecoupledAction(action.ax, action.vy, ego_corridor)
 
 
 def cloned_exit_behavior(observed_model, agent):             # behaviors.py:156-176
     ego_corridor = observed_model.corridor_for_agent(agent.id)
-    mcs_corridors, mcs_agents, possible_actions = exit_mcs_sim_from_env(observed_model, agent, ego_corridor)
-    action, decision, _, _ = decisions.gap_decision(mcs_corridors, mcs_agents, agent.id, possible_actions, "right",
-                                                    agent.learned_merging_model, 20, ms.SimParameter(0.3, 40, 10))
+    with _Marshalled(observed_model, agent, BUILD_EXIT) as m:
+        action, decision, _, _ = decisions.gap_decision_on(m.scene, agent.id, m.actions, "right", agent.learned_merging_model, 20,
+                                                           ms.SimParameter(0.3, 40, 10))
     agent.current_decision = decision
     return DecoupledAction(action.ax, action.vy, ego_corridor)

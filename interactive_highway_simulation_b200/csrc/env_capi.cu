@@ -81,6 +81,7 @@ struct mce_map {
   mce::EnvMapHead* d_head = nullptr;
   mce::EnvMapTail* d_tail = nullptr;
   mce::EnvMapBorder* d_border = nullptr;
+  mce::EnvLaneInfo* d_info = nullptr;   // Corridor.id / type / v_limit (mce_map_set_lane_info), read by the builders
   // state of the last match (resident)
   int n_agents = 0, n_scenes = 0;
   size_t cap_slots = 0, cap_scenes = 0, cap_arc_on = 0, cap_q = 0;
@@ -203,7 +204,7 @@ int mce_map_create(const mce_corridor* corridors, int n_corridors, int device, m
 int mce_map_destroy(mce_map* m) {
   if (!m) return MCE_OK;
   cudaSetDevice(m->device);
-  void* bufs[] = {m->d_head, m->d_tail, m->d_border, m->d_x, m->d_y, m->d_arc, m->d_arc_on, m->d_nbd, m->d_lane, m->d_order, m->d_start,
+  void* bufs[] = {m->d_info, m->d_head, m->d_tail, m->d_border, m->d_x, m->d_y, m->d_arc, m->d_arc_on, m->d_nbd, m->d_lane, m->d_order, m->d_start,
                   m->d_nbi, m->d_q};
   if (m->h_q) cudaFreeHost(m->h_q);
   for (void* b : bufs) if (b) cudaFree(b);
@@ -443,6 +444,67 @@ int mce_border_distance(mce_map* m, const int32_t* lane, const int32_t* side, co
   if ((rc = Q.upload())) return rc;
   mce::env_border_kernel<<<(n + mce::kBT - 1) / mce::kBT, mce::kBT, 0, m->stream>>>(m->d_border, dl, dsd, dh, row, n, o);
   return Q.finish();
+}
+
+int mce_map_set_lane_info(mce_map* m, const int32_t* ids, const int32_t* types, const double* v_limits, int n_corridors) {
+  if (!m || !ids || !types || !v_limits) return efail(MCE_ERR_ARG, "null argument");
+  if (n_corridors != m->n_lanes) return efail(MCE_ERR_ARG, "one entry per corridor of the map");
+  ENV_TRY(cudaSetDevice(m->device));
+  mce::EnvLaneInfo info;
+  std::memset(&info, 0, sizeof info);
+  for (int c = 0; c < n_corridors; ++c) { info.id[c] = ids[c]; info.type[c] = types[c]; info.v_limit[c] = v_limits[c]; }
+  if (!m->d_info) ENV_TRY(cudaMalloc(&m->d_info, sizeof info));
+  ENV_TRY(cudaMemcpyAsync(m->d_info, &info, sizeof info, cudaMemcpyHostToDevice, m->stream));
+  ENV_TRY(cudaStreamSynchronize(m->stream));
+  return MCE_OK;
+}
+
+int mce_build_rollout_scene(mce_map* m, const mce_build_request* request, const int32_t* ids, const double* attrs, const double* noise,
+                            int n_noise, mcs_corridor* corridors_out, int32_t* n_corridors_out, mcs_agent* agents_out,
+                            int32_t* n_agents_out, int32_t* actions_out, int32_t* n_actions_out, int device, mcs_scene** scene_out) {
+  if (!m || !request || !ids || !attrs) return efail(MCE_ERR_ARG, "null argument");
+  if (!noise) n_noise = 0;
+  if (scene_out) *scene_out = nullptr;
+  if (m->n_scenes == 0) return efail(MCE_ERR_ARG, "mce_build_rollout_scene before mce_env_match");
+  if (!m->d_info) return efail(MCE_ERR_ARG, "mce_build_rollout_scene before mce_map_set_lane_info");
+  if (request->kind < 0 || request->kind > 2) return efail(MCE_ERR_ARG, "kind must be 0 (merging), 1 (exit) or 2 (lane change)");
+  if (request->scene < 0 || request->scene >= m->n_scenes || request->ego_slot < 0 || request->ego_slot >= m->n_agents)
+    return efail(MCE_ERR_ARG, "request outside the matched batch");
+  if (n_noise < 0) return efail(MCE_ERR_ARG, "negative noise count");
+  ENV_TRY(cudaSetDevice(m->device));
+  const size_t n = (size_t)m->n_agents;
+  const size_t bytes = sizeof(mce_build_request) + n * 4 + n * 64 + (size_t)n_noise * 8 + sizeof(mce::BuildOut) + 256;
+  int rc = ensure_query_buffers(m, bytes / 144 + 1);
+  if (rc) return rc;
+  Query Q(m);
+  mce_build_request* d_req = Q.in(request, 1);
+  int32_t* d_ids = Q.in(ids, n);
+  double* d_attrs = Q.in(attrs, 8 * n);
+  double* d_noise = noise ? Q.in(noise, (size_t)n_noise) : nullptr;
+  static thread_local mce::BuildOut host_out;
+  mce::BuildOut* d_out = Q.out(&host_out, 1);
+  if ((rc = Q.upload())) return rc;
+  mce::env_build_kernel<<<1, 64, 0, m->stream>>>(m->d_head, m->d_tail, m->d_border, m->d_info, m->n_agents, m->d_lane, m->d_arc,
+                                                 m->d_order, m->d_start, d_req, d_ids, d_attrs, d_noise, n_noise, d_out);
+  if ((rc = Q.finish())) return rc;
+  const mce::BuildOut& o = host_out;
+  if (o.status == 1) return efail(MCE_ERR_CAPACITY, "the builder collected more vehicles than MCE_BUILD_MAX_AGENTS or than noise draws were passed");
+  if (o.status == 2) return efail(MCE_ERR_ARG, "no corridor on the side the builder needs (the reference raises here)");
+  if (o.status == 3) return efail(MCE_ERR_ARG, "the ego is on no corridor");
+  if (n_corridors_out) *n_corridors_out = o.n_corridors;
+  if (n_agents_out) *n_agents_out = o.n_agents;
+  if (n_actions_out) *n_actions_out = o.n_actions;
+  if (corridors_out) std::memcpy(corridors_out, o.corridors, sizeof(mcs_corridor) * o.n_corridors);
+  if (agents_out) std::memcpy(agents_out, o.agents, sizeof(mcs_agent) * o.n_agents);
+  if (actions_out) std::memcpy(actions_out, o.actions, sizeof(int32_t) * 4);
+  if (scene_out) {
+    // MapMultiLane + Environment ctor of the inner simulator (host bookkeeping of <= 48 vehicles: visit order, first lane
+    // match, priors — scene.cpp); the scene's rows go to the device at its first launch
+    const int src = mcs_scene_create(o.corridors, o.n_corridors, o.agents, o.n_agents, device, scene_out);
+    if (src != MCS_OK) return efail(src == MCS_ERR_CUDA ? MCE_ERR_CUDA : (src == MCS_ERR_CAPACITY ? MCE_ERR_CAPACITY : MCE_ERR_ARG),
+                                    std::string("mcs_scene_create: ") + mcs_last_error());
+  }
+  return MCE_OK;
 }
 
 int mce_last_kernel_ms(mce_map* m, float* out2) {

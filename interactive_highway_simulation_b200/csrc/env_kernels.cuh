@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #include "../../include/mcsim_env.h"
+#include "../../include/mcsim.h"
 
 namespace mce {
 
@@ -222,39 +223,15 @@ __global__ void __launch_bounds__(kBT) env_match_kernel(const EnvMapHead* __rest
   if (threadIdx.x <= MCE_MAX_LANES) start_out[(size_t)blockIdx.x * (MCE_MAX_LANES + 1) + threadIdx.x] = start[threadIdx.x];
 }
 
-// ---- front_agent / following_agent / neighbor_around_agent (environment.py:166-251) ---------------------------------
-// One thread per query.  q_scene == nullptr: every slot of every scene at the matched positions (grid.y = scene);
-// otherwise a list of (scene, slot, x, y) queries against the resident vectors of the last match.
-__global__ void __launch_bounds__(kBT) env_neighbors_kernel(const EnvMapHead* __restrict__ gmap, int n,
-                                                            const int32_t* __restrict__ lane, const double* __restrict__ arc,
-                                                            const int32_t* __restrict__ order, const int32_t* __restrict__ start,
-                                                            const int32_t* __restrict__ q_scene, const int32_t* __restrict__ q_slot,
-                                                            const double* __restrict__ qx, const double* __restrict__ qy,
-                                                            int n_queries, int32_t* __restrict__ nb_index, double* __restrict__ nb_dis) {
-  __shared__ EnvMapHead m;
-  stage(&m, gmap);
-  __syncthreads();
-  const int t = blockIdx.x * kBT + threadIdx.x;
-  int scene, slot;
-  size_t out, stride;
-  double px, py;
-  if (q_scene == nullptr) {
-    if (t >= n) return;
-    scene = blockIdx.y; slot = t;
-    px = qx[(size_t)scene * n + slot]; py = qy[(size_t)scene * n + slot];
-    out = (size_t)scene * MCE_NEIGHBORS * n + slot; stride = n;
-  } else {
-    if (t >= n_queries) return;
-    scene = q_scene[t]; slot = q_slot[t];
-    px = qx[t]; py = qy[t];
-    out = t; stride = n_queries;
-  }
+// front_agent / following_agent / neighbor_around_agent of vehicle (scene, slot) at position (px, py) against the lanes and
+// keys of the last match (environment.py:166-251); idx / dis in the order of the reference's Neighbor constructor
+__device__ __forceinline__ void neighbor_row(const EnvMapHead& m, int n, const int32_t* __restrict__ lane, const double* __restrict__ arc,
+                                             const int32_t* __restrict__ order, const int32_t* __restrict__ start, int scene, int slot,
+                                             double px, double py, int* idx, double* dis) {
   const size_t base = (size_t)scene * n;
   const int32_t* ord = order + base;
   const double* key = arc + base;
   const int32_t* st = start + (size_t)scene * (MCE_MAX_LANES + 1);
-  int idx[MCE_NEIGHBORS];
-  double dis[MCE_NEIGHBORS];
 #pragma unroll
   for (int k = 0; k < MCE_NEIGHBORS; ++k) { idx[k] = -1; dis[k] = 0.0; }
   const int c = lane[base + slot];
@@ -304,6 +281,38 @@ __global__ void __launch_bounds__(kBT) env_neighbors_kernel(const EnvMapHead* __
       }
     }
   }
+}
+
+// ---- front_agent / following_agent / neighbor_around_agent (environment.py:166-251) ---------------------------------
+// One thread per query.  q_scene == nullptr: every slot of every scene at the matched positions (grid.y = scene);
+// otherwise a list of (scene, slot, x, y) queries against the resident vectors of the last match.
+__global__ void __launch_bounds__(kBT) env_neighbors_kernel(const EnvMapHead* __restrict__ gmap, int n,
+                                                            const int32_t* __restrict__ lane, const double* __restrict__ arc,
+                                                            const int32_t* __restrict__ order, const int32_t* __restrict__ start,
+                                                            const int32_t* __restrict__ q_scene, const int32_t* __restrict__ q_slot,
+                                                            const double* __restrict__ qx, const double* __restrict__ qy,
+                                                            int n_queries, int32_t* __restrict__ nb_index, double* __restrict__ nb_dis) {
+  __shared__ EnvMapHead m;
+  stage(&m, gmap);
+  __syncthreads();
+  const int t = blockIdx.x * kBT + threadIdx.x;
+  int scene, slot;
+  size_t out, stride;
+  double px, py;
+  if (q_scene == nullptr) {
+    if (t >= n) return;
+    scene = blockIdx.y; slot = t;
+    px = qx[(size_t)scene * n + slot]; py = qy[(size_t)scene * n + slot];
+    out = (size_t)scene * MCE_NEIGHBORS * n + slot; stride = n;
+  } else {
+    if (t >= n_queries) return;
+    scene = q_scene[t]; slot = q_slot[t];
+    px = qx[t]; py = qy[t];
+    out = t; stride = n_queries;
+  }
+  int idx[MCE_NEIGHBORS];
+  double dis[MCE_NEIGHBORS];
+  neighbor_row(m, n, lane, arc, order, start, scene, slot, px, py, idx, dis);
 #pragma unroll
   for (int k = 0; k < MCE_NEIGHBORS; ++k) {
     nb_index[out + k * stride] = idx[k];
@@ -466,6 +475,226 @@ __global__ void __launch_bounds__(kBT) env_border_kernel(const EnvMapBorder* __r
     }
   }
   out[i] = best;
+}
+
+
+// ---- mcs_wrapper.py:24-283 — the three builders of the inner simulator's scene, on the device ----------------------
+// One block per request.  Thread 0 walks the reference's selection logic over the resident match tables (the neighbour
+// slots FF / F / B / BB per side, front, front of the front, follower, the vehicles within 80 m on the second lanes, the
+// candidate gaps) and lists the vehicles and corridors in the reference's append order; then every thread converts one
+// listed point — vehicles at their CURRENT positions, six corner points per corridor — to the Frenet frame of the builder's
+// reference line (extend_line_both_sides(center, 1000), simplified) and writes its AgentMS / CorridorMS record.
+struct EnvLaneInfo { int id[MCE_MAX_LANES], type[MCE_MAX_LANES]; double v_limit[MCE_MAX_LANES]; };   // Corridor.id / .type / .v_limit
+
+constexpr int kBuildMaxAgents = MCE_BUILD_MAX_AGENTS;
+struct BuildOut {
+  int32_t n_agents, n_corridors, n_actions, status;     // status: 0 ok, 1 too many vehicles, 2 no lane on the needed side, 3 ego unmatched
+  int32_t actions[4];
+  mcs_corridor corridors[MCE_MAX_LANES];
+  mcs_agent agents[kBuildMaxAgents];
+};
+
+// LineSimplified(extend_line_both_sides(center, 1000)).to_frenet_frame (type.py:307-317) — the body of env_frenet_kernel
+__device__ __forceinline__ void to_frenet(const EnvMapTail& t, int ref_lane, double px, double py, double& s, double& d) {
+  double dis;
+  project_distance(t.refs[ref_lane], t.n_refs[ref_lane], px, py, s, dis);
+  d = 0.0;
+  if (dis > 0.0) {
+    LineView lv{t.ref[ref_lane], t.ref_dis[ref_lane], t.n_ref[ref_lane], t.refs_len[ref_lane]};
+    d = lv.side_of(s, px, py) > 0 ? dis : -dis;
+  }
+}
+
+__global__ void __launch_bounds__(64) env_build_kernel(const EnvMapHead* __restrict__ head, const EnvMapTail* __restrict__ tail,
+                                                       const EnvMapBorder* __restrict__ border, const EnvLaneInfo* __restrict__ info,
+                                                       int n, const int32_t* __restrict__ lane, const double* __restrict__ arc,
+                                                       const int32_t* __restrict__ order, const int32_t* __restrict__ start,
+                                                       const mce_build_request* __restrict__ reqs, const int32_t* __restrict__ ids,
+                                                       const double* __restrict__ attrs /* [8][n]: x y v vy a l w vd, current */,
+                                                       const double* __restrict__ noise, int n_noise, BuildOut* __restrict__ outs) {
+  __shared__ int item_slot[kBuildMaxAgents], item_beh[kBuildMaxAgents];
+  __shared__ int corr_lane[MCE_MAX_LANES];
+  __shared__ int n_items, n_corr, n_act, status, ref_lane;
+  __shared__ int acts[4];
+  __shared__ double ego_s_sh, x_limit_sh;
+  const mce_build_request& rq = reqs[blockIdx.x];
+  BuildOut& out = outs[blockIdx.x];
+  const EnvMapHead& H = *head;
+  const EnvMapTail& T = *tail;
+  const int scene = rq.scene, ego = rq.ego_slot;
+  const double* ax = attrs; const double* ay = attrs + n;
+  const int ego_lane = lane[(size_t)scene * n + ego];
+  if (threadIdx.x == 0) {
+    n_items = 0; n_corr = 0; n_act = 1; acts[0] = -1; status = 0; ref_lane = ego_lane;
+    auto add = [&](int slot, int beh) {
+      if (n_items >= kBuildMaxAgents - 1) { status = 1; return; }
+      item_slot[n_items] = slot; item_beh[n_items] = beh; n_items++;
+    };
+    auto corridor = [&](int l) { if (n_corr < MCE_MAX_LANES) corr_lane[n_corr++] = l; };
+    auto gap = [&](int slot) { if (slot >= 0 && n_act < 4) acts[n_act++] = ids[slot]; };
+    // sorted_agents_on_corridor_within_range_of_vehicle (environment.py:145-156): the vehicles matched on lane l whose arc
+    // length on that lane's centre line is within 80 m of the ego's, by arc length (ties in dict order)
+    auto within_range = [&](int l, int beh) {
+      double e, d;
+      project_distance(T.cpath[l], T.n_center[l], ax[ego], ay[ego], e, d);
+      const int first = n_items;
+      for (int j = 0; j < n; ++j) {
+        if (lane[(size_t)scene * n + j] != l) continue;
+        double a;
+        project_distance(T.cpath[l], T.n_center[l], ax[j], ay[j], a, d);
+        if (!(fabs(a - e) <= 80.0)) continue;
+        if (n_items >= kBuildMaxAgents - 1) { status = 1; return; }
+        // insertion by arc length, stable
+        int p = n_items;
+        while (p > first) {
+          double ap;
+          project_distance(T.cpath[l], T.n_center[l], ax[item_slot[p - 1]], ay[item_slot[p - 1]], ap, d);
+          if (!(ap > a)) break;
+          item_slot[p] = item_slot[p - 1]; item_beh[p] = item_beh[p - 1]; --p;
+        }
+        item_slot[p] = j; item_beh[p] = beh; n_items++;
+      }
+    };
+    if (ego_lane < 0) status = 3;
+    else {
+      int idx[MCE_NEIGHBORS];
+      double dis[MCE_NEIGHBORS];
+      neighbor_row(H, n, lane, arc, order, start, scene, ego, ax[ego], ay[ego], idx, dis);
+      if (rq.kind == 0) {                                   // merging_mcs_sim_from_env, mcs_wrapper.py:24-75
+        const int left = H.left[ego_lane];
+        if (left < 0) status = 2;
+        else {
+          ref_lane = left;                                  // reference line: the main lane next to the ramp
+          const int beh = rq.others_merging ? MCS_BEH_MERGING : MCS_BEH_IDM_LC;
+          const int laf[5] = {MCE_LEFT_FF, MCE_LEFT_F, MCE_LEFT_B, MCE_LEFT_BB, MCE_FRONT};
+          for (int q = 0; q < 5; ++q) if (idx[laf[q]] >= 0) add(idx[laf[q]], beh);
+          gap(idx[MCE_LEFT_BB]); gap(idx[MCE_LEFT_B]); gap(idx[MCE_LEFT_F]); gap(idx[MCE_LEFT_FF]);
+          corridor(ego_lane); corridor(left);
+          const int ll = H.left[left];
+          if (ll >= 0) { within_range(ll, MCS_BEH_IDM_LC); corridor(ll); }
+        }
+      } else {                                              // exit_ (:78-190) and lane_change_mcs_sim_from_env (:193-283)
+        if (rq.kind == 1) {
+          int r = H.right[ego_lane], ex = -1;
+          while (r >= 0) { if (info->type[r] == MCS_LANE_EXIT) { ex = r; break; } r = H.right[r]; }
+          if (ex < 0) status = 2;
+          else corridor(ex);                                // plan index 0: only its far centre point is used (:113-115)
+        }
+        corridor(ego_lane);
+        if (idx[MCE_FRONT] >= 0) {
+          add(idx[MCE_FRONT], MCS_BEH_IDM_LC);
+          int i2[MCE_NEIGHBORS];
+          double d2[MCE_NEIGHBORS];
+          const int f = idx[MCE_FRONT];
+          neighbor_row(H, n, lane, arc, order, start, scene, f, ax[f], ay[f], i2, d2);
+          if (i2[MCE_FRONT] >= 0) add(i2[MCE_FRONT], MCS_BEH_IDM_LC);
+        }
+        if (idx[MCE_BACK] >= 0) add(idx[MCE_BACK], MCS_BEH_IDM_LC);
+        const int left = H.left[ego_lane];
+        if (left >= 0) {
+          for (int q = MCE_LEFT_FF; q <= MCE_LEFT_BB; ++q) if (idx[q] >= 0) add(idx[q], MCS_BEH_IDM_LC);
+          corridor(left);
+          const int ll = H.left[left];
+          if (ll >= 0) { within_range(ll, MCS_BEH_IDM_LC); corridor(ll); }
+        }
+        if (rq.kind == 1) { gap(idx[MCE_RIGHT_BB]); gap(idx[MCE_RIGHT_B]); gap(idx[MCE_RIGHT_F]); gap(idx[MCE_RIGHT_FF]); }
+        const int right = H.right[ego_lane];
+        if (right >= 0) {
+          const int beh = info->type[right] == MCS_LANE_MERGING ? MCS_BEH_MERGING : MCS_BEH_IDM_LC;
+          for (int q = MCE_RIGHT_FF; q <= MCE_RIGHT_BB; ++q) if (idx[q] >= 0) add(idx[q], beh);
+          corridor(right);
+          const int rr = H.right[right];
+          if (rr >= 0) { within_range(rr, info->type[rr] == MCS_LANE_MERGING ? MCS_BEH_MERGING : MCS_BEH_IDM_LC); corridor(rr); }
+        }
+      }
+      if (noise != nullptr && n_items > n_noise) status = 1;
+    }
+  }
+  __syncthreads();
+  if (status != 0) {
+    if (threadIdx.x == 0) { out.status = status; out.n_agents = 0; out.n_corridors = 0; out.n_actions = 0; }
+    return;
+  }
+  // ---- the ego and the listed vehicles, one per thread
+  for (int q = threadIdx.x; q <= n_items; q += blockDim.x) {
+    const int slot = q == 0 ? ego : item_slot[q - 1];
+    double s, d;
+    to_frenet(T, ref_lane, ax[slot], ay[slot], s, d);
+    if (q == 0) ego_s_sh = s;
+    mcs_agent a;
+    a.id = ids[slot];
+    a.x = s; a.y = d;
+    a.v = attrs[2 * (size_t)n + slot]; a.vy = attrs[3 * (size_t)n + slot]; a.a = attrs[4 * (size_t)n + slot];
+    a.l = attrs[5 * (size_t)n + slot]; a.w = attrs[6 * (size_t)n + slot];
+    a.reserved = 0;
+    if (q == 0) {
+      a.behavior = rq.ego_behavior; a.vd = rq.ego_vd;
+      for (int t = 0; t < 6; ++t) { a.idm[t] = rq.ego_idm[t]; a.rss[t] = rq.ego_rss[t]; }
+      for (int t = 0; t < 7; ++t) a.yp[t] = rq.ego_yp[t];
+      a.commit = rq.ego_commit; a.commit_keep_lane_step = rq.ego_keep_step; a.target_lane_id = rq.ego_target_lane;
+    } else {
+      const int beh = item_beh[q - 1];
+      a.behavior = beh;
+      a.vd = attrs[7 * (size_t)n + slot];
+      if (noise != nullptr) a.vd = a.vd + noise[q - 1];                        // vd + np.random.normal(0., 1), append order
+      const bool truck = a.l > 7.0;                                            // idm_param(l), mcs_wrapper.py:8-13 (memory order)
+      a.idm[0] = truck ? 0.8 : 1.6; a.idm[1] = 2.0; a.idm[2] = truck ? -1.5 : -3.0; a.idm[3] = -2.0; a.idm[4] = -8.0; a.idm[5] = 1.2;
+      const bool m = beh == MCS_BEH_MERGING;                                   // rss_param(behavior == "merging"), :16-21
+      a.rss[0] = 0.7; a.rss[1] = 0.4; a.rss[2] = m ? -8.0 : -6.0; a.rss[3] = m ? -10.0 : -6.0; a.rss[4] = 1.8; a.rss[5] = 1.2;
+      a.yp[0] = -0.5; a.yp[1] = 1.81; a.yp[2] = -4.8; a.yp[3] = -1.1; a.yp[4] = 0.9; a.yp[5] = 0.5; a.yp[6] = 0.51;   // YieldingParam()
+      a.commit = MCS_COMMIT_NOT_DECIDED; a.commit_keep_lane_step = 0; a.target_lane_id = -1;
+    }
+    out.agents[q] = a;
+  }
+  // ---- corridors: Corridor.to_frenet_corridor (type.py:207-237) — the far points take the lateral offset of the near ones
+  __shared__ double cs_[MCE_MAX_LANES][6], cd_[MCE_MAX_LANES][6];
+  for (int q = threadIdx.x; q < n_corr * 6; q += blockDim.x) {
+    const int c = q / 6, w = q - 6 * c, l = corr_lane[c];
+    const EnvMapBorder& B = *border;
+    double px, py;
+    if (w < 4) {
+      const int sd = w >> 1, last = (w & 1) ? B.n_path[sd][l] - 1 : 0;
+      px = B.path[sd][l][last][0]; py = B.path[sd][l][last][1];
+    } else {
+      const int last = (w & 1) ? T.n_center[l] - 1 : 0;
+      px = T.cpath[l][last][0]; py = T.cpath[l][last][1];
+    }
+    to_frenet(T, ref_lane, px, py, cs_[c][w], cd_[c][w]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // exit builder: the centre corridor ends where the exit has to be reached (mcs_wrapper.py:113-118)
+    int first = 0;
+    x_limit_sh = 0.0;
+    bool limited = false;
+    if (rq.kind == 1) {
+      const int ex = corr_lane[0], el = corr_lane[1];
+      const double vl = info->v_limit[el];
+      const double by_speed = vl * vl / 6.25;
+      const int lanes_between = abs(info->id[ex] - info->id[el]) - 1;
+      const double by_exit = (cs_[0][5] - (double)(lanes_between * 50)) - ego_s_sh;
+      const double max_length = by_speed < by_exit ? by_speed : by_exit;       // min(a, b): a unless b < a
+      x_limit_sh = ego_s_sh + max_length;
+      limited = true;
+      first = 1;
+    }
+    int w = 0;
+    for (int c = first; c < n_corr; ++c, ++w) {
+      const int l = corr_lane[c];
+      mcs_corridor o;
+      o.id = info->id[l]; o.type = info->type[l]; o.v_limit = info->v_limit[l];
+      double far0 = cs_[c][1], far1 = cs_[c][3], far2 = cs_[c][5];
+      if (limited && c == first) {
+        far0 = far0 < x_limit_sh ? far0 : x_limit_sh; far1 = far1 < x_limit_sh ? far1 : x_limit_sh; far2 = far2 < x_limit_sh ? far2 : x_limit_sh;
+      }
+      o.left[0] = cs_[c][0]; o.left[1] = cd_[c][0]; o.left[2] = far0; o.left[3] = cd_[c][0];
+      o.right[0] = cs_[c][2]; o.right[1] = cd_[c][2]; o.right[2] = far1; o.right[3] = cd_[c][2];
+      o.center[0] = cs_[c][4]; o.center[1] = cd_[c][4]; o.center[2] = far2; o.center[3] = cd_[c][4];
+      out.corridors[w] = o;
+    }
+    out.n_corridors = w; out.n_agents = n_items + 1; out.n_actions = n_act; out.status = 0;
+    for (int q = 0; q < 4; ++q) out.actions[q] = q < n_act ? acts[q] : 0;
+  }
 }
 
 }  // namespace mce

@@ -29,6 +29,18 @@ class CorridorPOD(C.Structure):
                 ("center", C.c_double * 2 * MCE_MAX_POINTS)]
 
 
+class BuildRequest(C.Structure):
+    """mce_build_request"""
+    _fields_ = [("kind", C.c_int32), ("scene", C.c_int32), ("ego_slot", C.c_int32), ("ego_behavior", C.c_int32),
+                ("others_merging", C.c_int32), ("ego_commit", C.c_int32), ("ego_keep_step", C.c_int32),
+                ("ego_target_lane", C.c_int32), ("ego_vd", C.c_double), ("ego_idm", C.c_double * 6),
+                ("ego_rss", C.c_double * 6), ("ego_yp", C.c_double * 7)]
+
+
+BUILD_MERGING, BUILD_EXIT, BUILD_LANE_CHANGE = 0, 1, 2
+MCE_BUILD_MAX_AGENTS = 48
+
+
 class EnvError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("mcsim_env error %d: %s" % (code, msg))
@@ -52,11 +64,14 @@ def _lib():
         L.mce_env_neighbors.argtypes = [V, _pi, _pi, _pd, _pd, I, _pi, _pd]
         L.mce_frenet.argtypes = [V, I, _pd, _pd, I, _pd, _pd]
         L.mce_project_center.argtypes = [V, I, _pd, _pd, I, _pd, _pd]
-        L.mce_step_along_path.argtypes = [V, _pi, _pd, _pd, _pd, _pd, _pd, D, I, _pd, _pd, _pd, _pd]
+        L.mce_step_along_path.argtypes = [V, V, V, V, V, V, V, D, I, V, V, V, V]
         L.mce_last_kernel_ms.argtypes = [V, C.POINTER(C.c_float)]
         L.mce_center_distance.argtypes = [V, _pi, _pd, _pd, I, _pd, _pd]
         L.mce_border_distance.argtypes = [V, _pi, _pi, _pd, I, _pd]
-        for f in ("mce_center_distance", "mce_border_distance", "mce_map_create", "mce_map_destroy", "mce_env_match", "mce_env_neighbors", "mce_frenet", "mce_project_center",
+        L.mce_map_set_lane_info.argtypes = [V, _pi, _pi, _pd, I]
+        L.mce_build_rollout_scene.argtypes = [V, C.POINTER(BuildRequest), V, V, V, I, V, C.POINTER(C.c_int32), V,
+                                              C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), I, C.POINTER(V)]
+        for f in ("mce_map_set_lane_info", "mce_build_rollout_scene", "mce_center_distance", "mce_border_distance", "mce_map_create", "mce_map_destroy", "mce_env_match", "mce_env_neighbors", "mce_frenet", "mce_project_center",
                   "mce_step_along_path", "mce_last_kernel_ms"):
             getattr(L, f).restype = I
         _bound = True
@@ -106,6 +121,8 @@ class DeviceMap:
         self._pods = corridor_pods(list(corridors))
         self.n_lanes = len(self._pods)
         self.center_cache = {}                               # (lane, x, y) -> (signed centre distance, distance to the end)
+        self._build_out = None
+        self._step_io = None
         self._h = C.c_void_p()
         _check(_lib().mce_map_create(self._pods, self.n_lanes, device, C.byref(self._h)))
 
@@ -161,8 +178,20 @@ class DeviceMap:
         ref_lane = np.ascontiguousarray(ref_lane, np.int32)
         n = len(ref_lane)
         out = [np.empty(n) for _ in range(4)]
-        _check(_lib().mce_step_along_path(self._h, ref_lane, _f64(x), _f64(y), _f64(v), _f64(ax), _f64(vy), float(dt), n, *out))
+        ins = [ref_lane, _f64(x), _f64(y), _f64(v), _f64(ax), _f64(vy)]
+        _check(_lib().mce_step_along_path(self._h, *[a.ctypes.data for a in ins], float(dt), n, *[a.ctypes.data for a in out]))
         return out
+
+    def step_one(self, ref_lane, x, y, v, ax, vy, dt):
+        """step_along_path for one vehicle (the sequential outer loop moves them one by one) without numpy in between"""
+        if self._step_io is None:
+            self._step_io = ((C.c_int32 * 1)(), [(C.c_double * 1)() for _ in range(9)])
+        lane, d = self._step_io
+        lane[0] = ref_lane
+        d[0][0], d[1][0], d[2][0], d[3][0], d[4][0] = x, y, v, ax, vy
+        _check(_lib().mce_step_along_path(self._h, C.addressof(lane), *[C.addressof(a) for a in d[:5]], dt, 1,
+                                          *[C.addressof(a) for a in d[5:]]))
+        return d[5][0], d[6][0], d[7][0], d[8][0]
 
     def center_distance(self, lane, x, y):
         """(centerSimplified.signed_distance, distance_to_corridor_end) of every point on its own corridor index"""
@@ -178,6 +207,42 @@ class DeviceMap:
         out = np.empty(len(lane))
         _check(_lib().mce_border_distance(self._h, lane, side, hull, len(lane), out))
         return out
+
+    def set_lane_info(self, ids, types, v_limits):
+        """Corridor.id / type (MCS_LANE_*) / v_limit per corridor, for the builders (mce_map_set_lane_info)"""
+        _check(_lib().mce_map_set_lane_info(self._h, np.ascontiguousarray(ids, np.int32), np.ascontiguousarray(types, np.int32),
+                                            _f64(v_limits), len(ids)))
+
+    def build_scene(self, request, ids, attrs, noise, device=0, records=True, scene=True):
+        """mce_build_rollout_scene: one of mcs_wrapper's builders on the device.  Returns (corridors, agents, actions, handle):
+        ctypes arrays of abi.Corridor / abi.Agent cut to their lengths (None unless `records`), the candidate gap ids, and
+        the handle of the marshalled inner scene (None unless `scene`; the caller owns it: backend.DeviceScene.adopt)."""
+        from . import _abi as abi
+        # `ids` / `attrs`: numpy arrays (int32 [n], float64 [8][n]) or raw addresses of such arrays (a caller in a loop
+        # caches them).  The record arrays are the map's own and are overwritten by the next call.
+        if self._build_out is None:
+            self._build_out = ((abi.Corridor * MCE_MAX_LANES)(), (abi.Agent * MCE_BUILD_MAX_AGENTS)(), C.c_int32(), C.c_int32(),
+                               C.c_int32(), (C.c_int32 * 4)())
+        cs, ag, nc, na, nact, acts = self._build_out
+        if not isinstance(ids, int):
+            ids = np.ascontiguousarray(ids, np.int32).ctypes.data
+        if not isinstance(attrs, int):
+            attrs = _f64(attrs).ctypes.data
+        pn, nn = None, 0
+        if noise is not None:
+            noise = _f64(noise)
+            pn, nn = noise.ctypes.data, len(noise)
+        h = C.c_void_p()
+        _check(_lib().mce_build_rollout_scene(self._h, request, ids, attrs, pn, nn, cs, nc, ag, na, acts, nact, device,
+                                              C.byref(h) if scene else None))
+        return cs, nc.value, ag, na.value, list(acts[:nact.value]), (h if scene else None)
+
+    @staticmethod
+    def create_scene(corridors, n_corridors, agents, n_agents, device=0):
+        """mcs_scene_create over the first n_corridors / n_agents records of the builder's arrays -> mcs_scene*"""
+        handle = C.c_void_p()
+        backend.check(backend.lib().mcs_scene_create(corridors, n_corridors, agents, n_agents, device, C.byref(handle)))
+        return handle
 
     def last_kernel_ms(self):
         ms = (C.c_float * 2)()
@@ -277,9 +342,14 @@ class Map:
             self.corridors_by_type.setdefault(c.type, []).append(c)
         self.index_of = {cid: k for k, cid in enumerate(self.corridors)}
         self.id_at = list(self.corridors)
+        self.device = device
         self.device_map = DeviceMap(list(self.corridors.values()), device)
         for k, c in enumerate(self.corridors.values()):
             c.device_map, c.lane_index = self.device_map, k
+        from . import _abi as abi
+        self.device_map.set_lane_info([int(c.id) for c in self.corridors.values()],
+                                      [abi.LANE_TYPES.get(c.type, abi.LANE_OTHER) for c in self.corridors.values()],
+                                      [float(c.v_limit) for c in self.corridors.values()])
 
     def to_dict(self):                                       # environment.py:58-68
         return {i: c.to_dict() for i, c in self.corridors.items()}
@@ -318,6 +388,12 @@ class Environment:
             return
         self._x0 = np.array([a.x for a in objs], np.float64)
         self._y0 = np.array([a.y for a in objs], np.float64)
+        # structure-of-arrays mirror of what the builders read of every vehicle (mce_build_rollout_scene): x y v vy a l w vd
+        self._ids = np.array([a.id for a in objs], np.int32)
+        self._attr = np.array([self._x0, self._y0, [a.v for a in objs], [a.vy for a in objs], [a.a for a in objs],
+                               [a.l for a in objs], [a.w for a in objs], [a.idm_param.vd for a in objs]], np.float64)
+        self._ids_p, self._attr_p = self._ids.ctypes.data, self._attr.ctypes.data
+        self._mirror_live = False
         t = self._tables = self.map.device_map.match(self._x0, self._y0, 1, arc_on_lanes=True)
         for i, a in enumerate(objs):
             lane = int(t.lane[0, i])
@@ -459,10 +535,69 @@ class Environment:
                         agent.merging_flag.once_fallback = True       # sic (environment.py:311)
                 break
 
+    def _mirror(self):
+        """The vehicles' current x y v vy a in the builders' mirror: rows are kept up to date by step(); outside of it (a
+        caller that moved vehicles by hand) they are read again."""
+        if not self._mirror_live:
+            at = self._attr
+            for i, a in enumerate(self._objs):
+                at[0, i] = a.x; at[1, i] = a.y; at[2, i] = a.v; at[3, i] = a.vy; at[4, i] = a.a
+        return self._ids_p, self._attr_p
+
+    def marshal(self, agent, kind, records=False, scene=True, poke_commit=False):
+        """One of mcs_wrapper's builders for `agent` on the device (mce_build_rollout_scene): `kind` = BUILD_MERGING /
+        BUILD_EXIT / BUILD_LANE_CHANGE.  Consumes numpy's global stream like the reference: one np.random.normal(0., 1) per
+        collected vehicle.  Returns (corridors, n_corridors, agents, n_agents, possible_actions, scene handle): ctypes arrays
+        of abi.Corridor / abi.Agent (valid up to their counts) and, with `scene`, the mcs_scene* of the marshalled inner scene
+        (the caller owns it: backend.DeviceScene.adopt)."""
+        if agent.id not in self._slot or agent.id not in self.matched_agents:
+            raise EnvError(-1, "agent %r is not matched on any corridor" % (agent.id,))
+        from . import _abi as abi
+        ip, mp, yp = agent.idm_param, agent.mobil_param, agent.yielding_param
+        merging_model = "merging" in agent.behavior_model
+        rq = BuildRequest()
+        rq.kind, rq.scene, rq.ego_slot = kind, 0, self._slot[agent.id]
+        if kind == BUILD_EXIT:
+            rq.ego_behavior = abi.BEHAVIORS["exit"]
+        else:
+            rq.ego_behavior = abi.BEHAVIORS["merging" if merging_model else "idm"]
+        rq.others_merging = 1 if merging_model else 0
+        if poke_commit:       # lane_change_behavior_mobil hands the vehicle's commit state to the inner agent (behaviors.py:75-78)
+            rq.ego_commit = abi.COMMITS[agent.commit_lane_change]
+            rq.ego_keep_step, rq.ego_target_lane = int(agent.commit_keep_lane_step), int(agent.target_lane_id)
+        else:
+            rq.ego_commit, rq.ego_keep_step, rq.ego_target_lane = abi.COMMITS["not_decided"], 0, -1
+        rq.ego_vd = ip.vd
+        rq.ego_idm[:] = (ip.acc_max, ip.min_dis, ip.acc_min, ip.acc_com, -8., ip.thw)         # IdmParam memory order
+        if kind == BUILD_LANE_CHANGE:
+            rp = agent.rss_param
+            rq.ego_rss[:] = (rp.r_t_other, rp.r_t_ego, rp.a_min, rp.a_max, rp.soft_acc, rp.soft_dcc)
+        else:
+            rq.ego_rss[:] = (0.7, 0.4, -8., -10., 1.8, 1.2)                                    # rss_param(True)
+        rq.ego_yp[:] = (yp[0], yp[1], yp[2], yp[3], mp.politeness_factor, mp.delta_a, mp.bias_a)
+        ids, attrs = self._mirror()
+        cs, nc, ag, na, actions, _ = self.map.device_map.build_scene(rq, ids, attrs, None, device=self.map.device, records=True,
+                                                                     scene=False)
+        # the reference draws one np.random.normal(0., 1) per vehicle while it appends them: now that their number is known
+        # the same draws come from the same stream and are added where the reference adds them (vd + noise, IEEE add)
+        if na > 1:
+            noise = np.random.normal(0., 1, na - 1)
+            for q in range(1, na):
+                ag[q].vd += noise[q - 1]
+        handle = self.map.device_map.create_scene(cs, nc, ag, na, self.map.device) if scene else None
+        return cs, nc, ag, na, actions, handle
+
     def step(self, dt):                                      # environment.py:316-323
         """Plan and move the vehicles one after the other against the lane vectors of the last match, then re-match."""
-        for a in list(self.agents.values()):
-            a.step(a.plan(self), dt)
-            self.set_flag(a)
+        self._mirror()
+        self._mirror_live = True
+        try:
+            for a in list(self.agents.values()):
+                a.step(a.plan(self), dt)
+                i, at = self._slot[a.id], self._attr
+                at[0, i] = a.x; at[1, i] = a.y; at[2, i] = a.v; at[3, i] = a.vy; at[4, i] = a.a
+                self.set_flag(a)
+        finally:
+            self._mirror_live = False
         self.match_agents_on_corridor()
         self.sim_time += dt

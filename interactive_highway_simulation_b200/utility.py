@@ -70,8 +70,7 @@ def extend_line_both_sides(line, d):                                  # utility.
 
 def step_along_path(ref_path, ego, ax, vy, dt):                       # utility.py:88-98 — one device launch
     """ref_path: the corridor whose centre line is the reference's `DecoupledAction.ref_path` (behaviors.py)."""
-    x, y, v, yaw = ref_path.device_map.step_along_path([ref_path.lane_index], [ego.x], [ego.y], [ego.v], [ax], [vy], dt)
-    return float(x[0]), float(y[0]), float(v[0]), float(yaw[0])
+    return ref_path.device_map.step_one(ref_path.lane_index, ego.x, ego.y, ego.v, ax, vy, dt)
 
 
 def thw_and_ttc(d, ego_v, obj_v):                                     # utility.py:101-108

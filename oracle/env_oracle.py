@@ -190,6 +190,7 @@ class PreparedMap:
         self.ref = [LineSimplified(extend_line_both_sides(c, 1000)) for c in self.center]   # mcs_wrapper.py:42,109,211
         self.center_simplified = [LineSimplified(c) for c in self.center]             # type.py:153
         self.border = [[LineSimplified(c["left"]), LineSimplified(c["right"])] for c in corridors]   # type.py:151-152
+        self.raw = [{k: [(float(p[0]), float(p[1])) for p in c[k]] for k in ("left", "right", "center")} for c in corridors]
 
 
 def match(pm, xs, ys):
@@ -346,3 +347,124 @@ def border_distance(pm, lane, side, hull):
             if best is None or v < best:
                 best = v
     return best
+
+
+# ---- mcs_wrapper.py:8-283: the three builders of the inner simulator's scene ------------------------------------------
+BEH_IDM, BEH_IDM_LC, BEH_MERGING, BEH_EXIT = 0, 1, 2, 3          # include/mcsim.h MCS_BEH_*
+LANE_MAIN, LANE_MERGING, LANE_EXIT = 0, 1, 2                      # MCS_LANE_*
+
+
+def build_scene(pm, info, tables, xs, ys, attrs, ids, kind, ego, ego_rec, others_merging, noise):
+    """merging_ (kind 0, mcs_wrapper.py:24-75), exit_ (1, :78-190), lane_change_mcs_sim_from_env (2, :193-283) for slot
+    `ego` at the vehicles' current positions xs / ys against the match `tables` = (lane, arc, order, start).
+    info: per corridor {"id", "type" (LANE_*), "v_limit"}; attrs: per slot {"v", "vy", "a", "l", "w", "vd"}; ego_rec: the
+    ego's {"behavior", "vd", "idm", "rss", "yp", "commit", "keep", "target"} (memory-order tuples); noise: the
+    np.random.normal(0., 1) draws in append order (None: plain vd, the caller adds them).  -> (corridors, agents, possible_actions) as plain records:
+    corridor = (id, type, [l.p1.x, l.p1.y, l.p2.x, l.p2.y], [r...], [c...], v_limit), agent = dict of mcs_agent fields."""
+    lane, arc, order, start = tables
+    ego_lane = lane[ego]
+    items, corr, actions = [], [], [-1]
+
+    def nb(i):
+        return neighbors(pm, lane, arc, order, start, i, xs[i], ys[i])[0]
+
+    def gap(j):
+        if j >= 0 and len(actions) < 4:
+            actions.append(ids[j])
+
+    def in_range(l, beh):
+        for j in within_range(pm, lane, xs, ys, l, ego, 80):
+            items.append((j, beh))
+
+    idx = nb(ego)
+    if kind == 0:
+        left = pm.left[ego_lane]
+        ref = left                                                 # :42 reference line: the main lane next to the ramp
+        beh = BEH_MERGING if others_merging else BEH_IDM_LC
+        for k in (LEFT_FF, LEFT_F, LEFT_B, LEFT_BB, FRONT):         # neighbor.lefts_and_front, :47-54
+            if idx[k] >= 0:
+                items.append((idx[k], beh))
+        for k in (LEFT_BB, LEFT_B, LEFT_F, LEFT_FF):                # reversed(neighbor.lefts), :57-59
+            gap(idx[k])
+        corr += [ego_lane, left]
+        ll = pm.left[left]
+        if ll >= 0:                                                # :64-72
+            in_range(ll, BEH_IDM_LC)
+            corr.append(ll)
+    else:
+        ref = ego_lane
+        if kind == 1:                                              # :96-103 the exit lane somewhere to the right
+            r, ex = pm.right[ego_lane], -1
+            while r >= 0:
+                if info[r]["type"] == LANE_EXIT:
+                    ex = r
+                    break
+                r = pm.right[r]
+            if ex < 0:
+                raise ValueError("no exit lane to the right of the ego's lane")
+            corr.append(ex)
+        corr.append(ego_lane)
+        if idx[FRONT] >= 0:                                        # :120-137 / :219-236 front, front of the front, follower
+            items.append((idx[FRONT], BEH_IDM_LC))
+            ff = nb(idx[FRONT])[FRONT]
+            if ff >= 0:
+                items.append((ff, BEH_IDM_LC))
+        if idx[BACK] >= 0:
+            items.append((idx[BACK], BEH_IDM_LC))
+        left = pm.left[ego_lane]
+        if left >= 0:                                              # :139-160 / :238-258
+            for k in (LEFT_FF, LEFT_F, LEFT_B, LEFT_BB):
+                if idx[k] >= 0:
+                    items.append((idx[k], BEH_IDM_LC))
+            corr.append(left)
+            ll = pm.left[left]
+            if ll >= 0:
+                in_range(ll, BEH_IDM_LC)
+                corr.append(ll)
+        if kind == 1:                                              # :155-157 candidate gaps on the right
+            for k in (RIGHT_BB, RIGHT_B, RIGHT_F, RIGHT_FF):
+                gap(idx[k])
+        right = pm.right[ego_lane]
+        if right >= 0:                                             # :162-189 / :260-282
+            beh = BEH_MERGING if info[right]["type"] == LANE_MERGING else BEH_IDM_LC
+            for k in (RIGHT_FF, RIGHT_F, RIGHT_B, RIGHT_BB):
+                if idx[k] >= 0:
+                    items.append((idx[k], beh))
+            corr.append(right)
+            rr = pm.right[right]
+            if rr >= 0:
+                in_range(rr, BEH_MERGING if info[rr]["type"] == LANE_MERGING else BEH_IDM_LC)
+                corr.append(rr)
+    line = pm.ref[ref]
+    ego_s, ego_d = line.to_frenet_frame(xs[ego], ys[ego])
+
+    def corridor_ms(l, x_limit=None):                              # Corridor.to_frenet_corridor[_limit_length], type.py:207-237
+        raw = pm.raw[l]
+        pts = [raw["left"][0], raw["left"][-1], raw["right"][0], raw["right"][-1], raw["center"][0], raw["center"][-1]]
+        sd = [line.to_frenet_frame(p[0], p[1]) for p in pts]
+        far = [sd[1][0], sd[3][0], sd[5][0]]
+        if x_limit is not None:
+            far = [min(v, x_limit) for v in far]
+        return (info[l]["id"], info[l]["type"], [sd[0][0], sd[0][1], far[0], sd[0][1]], [sd[2][0], sd[2][1], far[1], sd[2][1]],
+                [sd[4][0], sd[4][1], far[2], sd[4][1]], info[l]["v_limit"])
+
+    if kind == 1:
+        exit_ms = corridor_ms(corr[0])
+        el = corr[1]
+        max_length = min(info[el]["v_limit"] ** 2 / 2.5 ** 2,
+                         exit_ms[4][2] - (abs(exit_ms[0] - info[el]["id"]) - 1) * 50 - ego_s)              # :113-116
+        corridors = [corridor_ms(el, ego_s + max_length)] + [corridor_ms(l) for l in corr[2:]]
+    else:
+        corridors = [corridor_ms(l) for l in corr]
+    a = attrs[ego]
+    agents = [dict(id=ids[ego], behavior=ego_rec["behavior"], x=ego_s, y=ego_d, v=a["v"], vy=a["vy"], vd=ego_rec["vd"], a=a["a"],
+                   l=a["l"], w=a["w"], idm=tuple(ego_rec["idm"]), rss=tuple(ego_rec["rss"]), yp=tuple(ego_rec["yp"]),
+                   commit=ego_rec["commit"], keep=ego_rec["keep"], target=ego_rec["target"])]
+    for q, (j, beh) in enumerate(items):
+        a = attrs[j]
+        s_, d_ = line.to_frenet_frame(xs[j], ys[j])
+        idm = (0.8, 2.0, -1.5, -2.0, -8.0, 1.2) if a["l"] > 7 else (1.6, 2.0, -3.0, -2.0, -8.0, 1.2)     # idm_param(l), :8-13
+        rss = (0.7, 0.4, -8.0, -10.0, 1.8, 1.2) if beh == BEH_MERGING else (0.7, 0.4, -6.0, -6.0, 1.8, 1.2)   # rss_param, :16-21
+        agents.append(dict(id=ids[j], behavior=beh, x=s_, y=d_, v=a["v"], vy=a["vy"], vd=a["vd"] + noise[q] if noise is not None else a["vd"], a=a["a"], l=a["l"],
+                           w=a["w"], idm=idm, rss=rss, yp=(-0.5, 1.81, -4.8, -1.1, 0.9, 0.5, 0.51), commit=0, keep=0, target=-1))
+    return corridors, agents, actions

@@ -144,6 +144,78 @@ def test_marshalling_builders_equal_the_reference(oe, rec):
             assert all(abs(x - y) <= TOL for x, y in zip(g[1:-1], w[1:-1])), (b["builder"], b["ego"], g, w)
 
 
+@pytest.mark.parametrize("rec", STATES, ids=[r["tag"] for r in STATES])
+def test_device_builder_bit_identical_to_the_oracle(oe, rec):
+    """mce_build_rollout_scene against oracle build_scene (itself pinned on the reference's builders, test_env_oracle.py):
+    all three builders for every vehicle that has the lanes the builder needs, at the matched positions and again after some
+    vehicles have moved (stale lane vectors, current positions) — every field of every record identical."""
+    from interactive_highway_simulation_b200 import _abi as abi
+    from interactive_highway_simulation_b200 import outer_env
+    pm, ids, xs, ys = prepared(rec)
+    tables = eo.match(pm, xs, ys)
+    slot = slots(ids)
+    cds = corridor_dicts(rec)
+    info = [{"id": c["id"], "type": abi.LANE_TYPES.get(c["type"], abi.LANE_OTHER), "v_limit": c["v_limit"]} for c in rec["corridors"]]
+    dm = oe.DeviceMap(rec["corridors"])
+    dm.set_lane_info([c["id"] for c in info], [c["type"] for c in info], [c["v_limit"] for c in info])
+    dm.match(xs, ys, 1)
+    agents = rec["agents"]
+    n = len(agents)
+    rng = random.Random(5)
+    checked = 0
+    for moved in (False, True):
+        qx, qy = list(xs), list(ys)
+        if moved:
+            for m in rec["moved"]:
+                if m["id"] in slot:
+                    qx[slot[m["id"]]], qy[slot[m["id"]]] = m["x"], m["y"]
+        attrs = np.array([qx, qy, [a["v"] for a in agents], [a["vy"] for a in agents], [a["a"] for a in agents],
+                          [a["l"] for a in agents], [a["w"] for a in agents], [a["idm"][0] for a in agents]], np.float64)
+        per = [dict(v=a["v"], vy=a["vy"], a=a["a"], l=a["l"], w=a["w"], vd=a["idm"][0]) for a in agents]
+        idarr = np.array(ids, np.int32)
+        for e in range(n):
+            lane = tables[0][e]
+            if lane < 0:
+                continue
+            for kind in (0, 1, 2):
+                if kind == 0 and pm.left[lane] < 0:
+                    continue
+                if kind == 1:
+                    r, ex = pm.right[lane], -1
+                    while r >= 0 and ex < 0:
+                        ex, r = (r if info[r]["type"] == abi.LANE_TYPES["exit"] else -1), pm.right[r]
+                    if ex < 0:
+                        continue
+                a = agents[e]
+                i, s_, m_, y = a["idm"], a["rss"], a["mobil"], a["yielding"]
+                rq = outer_env.BuildRequest()
+                rq.kind, rq.scene, rq.ego_slot = kind, 0, e
+                rq.ego_behavior = rng.choice([0, 2, 3])
+                rq.others_merging = rng.choice([0, 1])
+                rq.ego_commit, rq.ego_keep_step, rq.ego_target_lane = rng.choice([0, 1, 2, 3]), rng.randrange(12), rng.choice([-1, 1, 2])
+                rq.ego_vd = i[0]
+                rq.ego_idm[:] = (i[1], i[3], i[2], i[4], -8.0, i[5])
+                rq.ego_rss[:] = tuple(s_)
+                rq.ego_yp[:] = (y[0], y[1], y[2], y[3], m_[0], m_[1], m_[2])
+                noise = np.array([rng.gauss(0, 1) for _ in range(48)])
+                cs, nc, ag, na, actions, _ = dm.build_scene(rq, idarr, attrs, noise, records=True, scene=False)
+                ego = dict(behavior=rq.ego_behavior, vd=rq.ego_vd, idm=tuple(rq.ego_idm), rss=tuple(rq.ego_rss), yp=tuple(rq.ego_yp),
+                           commit=rq.ego_commit, keep=rq.ego_keep_step, target=rq.ego_target_lane)
+                wc, wa, wact = eo.build_scene(pm, info, tables, qx, qy, per, ids, kind, e, ego, bool(rq.others_merging), list(noise))
+                assert actions == wact and nc == len(wc) and na == len(wa), (kind, e, actions, wact, nc, na)
+                for c, w in zip(cs[:nc], wc):
+                    assert (c.id, c.type, list(c.left), list(c.right), list(c.center), c.v_limit) == (w[0], w[1], w[2], w[3], w[4], w[5]), (kind, e)
+                for g, w in zip(ag[:na], wa):
+                    got = (g.id, g.behavior, g.x, g.y, g.v, g.vy, g.vd, g.a, g.l, g.w, tuple(g.idm), tuple(g.rss), tuple(g.yp), g.commit,
+                           g.commit_keep_lane_step, g.target_lane_id)
+                    want = (w["id"], w["behavior"], w["x"], w["y"], w["v"], w["vy"], w["vd"], w["a"], w["l"], w["w"], w["idm"], w["rss"],
+                            w["yp"], w["commit"], w["keep"], w["target"])
+                    assert got == want, (kind, e, got, want)
+                checked += 1
+    assert checked > 0
+    dm.close()
+
+
 def bent_map():
     """three lanes following a bent centre line (4-point polylines), lane 0 right-most"""
     base = [(0.0, 0.0), (300.0, 0.0), (600.0, 40.0), (1000.0, 40.0)]

@@ -102,3 +102,45 @@ def test_border_and_centre_distances(rec):
         for side, key in ((0, "left"), (1, "right")):
             got = eo.border_distance(pm, lane, side, s["hull"])
             assert abs(got - s[key]) <= TOL, (s, key, got)
+
+
+BUILDER_RECS = [r for r in STATES if r["builders"]]
+
+
+@pytest.mark.parametrize("rec", BUILDER_RECS, ids=[r["tag"] for r in BUILDER_RECS])
+def test_builders_equal_the_reference(rec):
+    """oracle build_scene (the restatement of mcs_wrapper.py:24-283 the device builder is checked against) on the records
+    the reference's own three builders wrote: same corridors, vehicles (order, ids, behaviours, parameters, vd noise) and
+    candidate gaps."""
+    import numpy as np
+    from interactive_highway_simulation_b200 import _abi as abi
+    pm, ids, xs, ys = prepared(rec)
+    tables = eo.match(pm, xs, ys)
+    slot = slots(ids)
+    info = [{"id": c["id"], "type": abi.LANE_TYPES.get(c["type"], abi.LANE_OTHER), "v_limit": c["v_limit"]} for c in rec["corridors"]]
+    attrs = [dict(v=a["v"], vy=a["vy"], a=a["a"], l=a["l"], w=a["w"], vd=a["idm"][0]) for a in rec["agents"]]
+    kinds = {"merging_mcs_sim_from_env": 0, "exit_mcs_sim_from_env": 1, "lane_change_mcs_sim_from_env": 2}
+    lane_names = {v: k for k, v in abi.LANE_TYPES.items()}
+    beh_names = {v: k for k, v in abi.BEHAVIORS.items()}
+    for b in rec["builders"]:
+        a = next(x for x in rec["agents"] if x["id"] == b["ego"])
+        kind = kinds[b["builder"]]
+        merging_model = "merging" in a["behavior_model"]
+        i, s, m, y = a["idm"], a["rss"], a["mobil"], a["yielding"]
+        ego = dict(behavior=abi.BEHAVIORS["exit" if kind == 1 else ("merging" if merging_model else "idm")], vd=i[0],
+                   idm=(i[1], i[3], i[2], i[4], -8.0, i[5]), rss=tuple(s) if kind == 2 else (0.7, 0.4, -8.0, -10.0, 1.8, 1.2),
+                   yp=(y[0], y[1], y[2], y[3], m[0], m[1], m[2]), commit=0, keep=0, target=-1)
+        np.random.seed(b["np_seed"])
+        noise = list(np.random.normal(0., 1, 48))
+        cs, ag, actions = eo.build_scene(pm, info, tables, xs, ys, attrs, ids, kind, slot[b["ego"]], ego, merging_model, noise)
+        assert (actions if kind != 2 else None) == b["possible_actions"], b["builder"]
+        assert len(cs) == len(b["corridors"]) and len(ag) == len(b["agents"]), (b["builder"], b["ego"])
+        for c, w in zip(cs, b["corridors"]):
+            assert [c[0], lane_names[c[1]]] == w[:2]
+            g = c[2] + c[3] + c[4] + [c[5]]
+            assert all(abs(p - q) <= TOL for p, q in zip(g, w[2:])), (b["builder"], b["ego"], g, w)
+        for r, w in zip(ag, b["agents"]):
+            g = [r["id"], r["x"], r["y"], r["v"], r["vy"], r["vd"], r["a"], r["l"], r["w"]] + list(r["idm"]) + list(r["rss"]) + \
+                list(r["yp"]) + [beh_names[r["behavior"]]]
+            assert g[0] == w[0] and g[-1] == w[-1], (b["builder"], b["ego"], g[0], w[0])
+            assert all(abs(p - q) <= TOL for p, q in zip(g[1:-1], w[1:-1])), (b["builder"], b["ego"], g, w)
