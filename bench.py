@@ -427,6 +427,56 @@ def outer_loop_block(steps=100):
     return out
 
 
+def evaluation_block(steps=100):
+    """the evaluation scripts' per-scene functions (evaluation_merging.py:53-106,
+    evaluation_lane_change.py:58-101, evaluation_exit.py:55-105) with the LEARNED ego policy through the public API — yaml scene
+    on disk -> headless outer loop on the device (lane match, builders, decisions, rollouts) -> statistics — on the epochs of
+    tests/golden/evaluation_stats.json.gz, for the scripts' own horizon (dt 0.2, 100 steps); beside it the reference's own
+    functions on the same epochs (recorded in the build container, scripts/time_reference_evaluation.py)."""
+    import gzip
+    import random
+    import tempfile
+    import numpy as np
+    import yaml
+    from interactive_highway_simulation_b200 import evaluation as ev, mc_sim_highway as ms
+    with gzip.open(os.path.join(HERE, "tests", "golden", "evaluation_stats.json.gz"), "rt") as f:
+        records = json.load(f)
+    learned = {"merging": "merging_learned", "lane_change": "lane_change_learned", "exit": "exit_learned"}
+    tmp = tempfile.mkdtemp(prefix="bench_eval")
+    out = {}
+    for rec in records:
+        kind = rec["kind"]
+        path = os.path.join(tmp, kind, "epoch0")
+        os.makedirs(path)
+        for name in ("agents", "map"):
+            with open(os.path.join(path, name + ".yml"), "w") as f:
+                yaml.dump({int(k): v for k, v in rec[name].items()}, f, default_flow_style=False)
+        best, info = 1e30, None
+        for rep in range(2):                     # the first pass warms the context
+            sim = ev.Simulation(None, ev.SimulationParameter(0.2, steps, render=False, write_gif=False, scenario=kind))
+            st = ev.LaneChangeStatistics() if kind == "lane_change" else ev.MergingAndExitStatistics()
+            random.seed(7); np.random.seed(7); ms.seed(7)
+            t0 = time.perf_counter()
+            if kind == "merging":
+                ev.evaluate_recorded_merging_scene(path, sim, learned[kind], 0, st, 1.0)
+            elif kind == "lane_change":
+                ev.evaluate_recorded_lc_scene(path, sim, learned[kind], 0, rec["ego_candidates"][0], st)
+            else:
+                ev.evaluate_recorded_exit_scene(path, sim, learned[kind], 0, rec["ego_candidates"][0], st, 1.0)
+            wall = time.perf_counter() - t0
+            if wall < best:
+                best, info = wall, {"policy": learned[kind], "vehicles": len(rec["agents"]), "executed_steps": sim.step + 1,
+                                    "wall_s": wall, "evaluations_per_s": 1.0 / wall}
+        out[kind] = info
+    res = {"horizon": "dt 0.2, %d steps" % steps, "kinds": out,
+           "note": "one evaluation = load the yaml epoch, give the ego its learned policy, run the scene, accumulate the statistics; "
+                   "every step the ego makes one learned decision (4-5 candidates x 160-240 rollouts in one launch)"}
+    recf = os.path.join(HERE, "profiles", "r02_reference_evaluation_cpu.json")
+    if os.path.exists(recf):
+        res["cpu_baseline"] = json.load(open(recf))
+    return res
+
+
 def run_product(args):
     import torch
     from interactive_highway_simulation_b200 import backend, synthetic, _abi as abi
@@ -610,6 +660,12 @@ def run_product(args):
             decision_configs = decision_configs_block()
         except Exception as e:
             decision_configs = {"error": str(e)}
+    evaluation = None
+    if world == 1:
+        try:
+            evaluation = evaluation_block()
+        except Exception as e:
+            evaluation = {"error": str(e)}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": workload_config(args),
@@ -623,6 +679,7 @@ def run_product(args):
                    "d2h_bytes_per_step": d2h,
                    "note": "mcs_scene_create + mcs_rollouts (8 groups x %d) + feature read-back per step, host buffers" % (e2e_R // 8)},
            "decision": decision, "decision_configs": decision_configs, "outer_env": outer_env, "outer_loop": outer_loop,
+           "evaluation": evaluation,
            "gpu_launches": args.steps, "wall_s_timed_region": wall,
            "rollouts_per_s": units_total / (N_VEHICLES * SIM_STEPS) / (kernel_ms_max * 1e-3)}
     print(json.dumps(out), file=RESULT_OUT, flush=True)

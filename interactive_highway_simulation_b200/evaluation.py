@@ -28,7 +28,8 @@ def random_environment(kind, device=0, generator=None):
     gen = generator or tg.RandomTrafficGenerator()
     merging, main = gen.random_agents_on_map(tg.lanes_from_spec(spec), {i: tg.RandomDensityAndVelocityParameter(*p) for i, p in params.items()},
                                              unsafe, truck)
-    gen.vehicle_id = 0
+    if kind != "merging":      # evaluation_lane_change.py:56, evaluation_exit.py:52 restart the ids every epoch; evaluation_merging.py
+        gen.vehicle_id = 0     # never does: its epochs after the first carry cumulative vehicle ids
     corridors = [create_corridor_from_dict({**c, "left_id": "none" if c["left_id"] is None else c["left_id"],
                                             "right_id": "none" if c["right_id"] is None else c["right_id"]}) for c in spec]
     return Environment(Map(corridors, device), create_agents_from_dicts(merging) + create_agents_from_dicts(main))

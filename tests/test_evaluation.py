@@ -101,6 +101,19 @@ def test_ego_candidates_and_generated_epochs(monkeypatch, tmp_path):
                 (on_disk[i]["x"], on_disk[i]["y"], on_disk[i]["v"], on_disk[i]["l"], on_disk[i]["behavior_model"], on_disk[i]["idm_p"]["vd"])
         with open(os.path.join(d, "map.yml")) as f:
             assert yaml.safe_load(f) == again.environment.map.to_dict()
+    # vehicle ids across epochs: evaluation_merging.py never resets its generator's counter (ids run on from epoch to
+    # epoch), evaluation_lane_change.py:56 / evaluation_exit.py:52 restart at 0 every epoch
+    for kind, restarts in (("merging", False), ("lane_change", True)):
+        seed_streams(6)
+        sim = ev_mod.Simulation(None, ev_mod.SimulationParameter(0.2, 1, render=False, write_gif=False, scenario=kind))
+        sim.write_dir = str(tmp_path / ("ids_" + kind))
+        ev_mod.generate_random_traffic(kind, 2, sim)
+        ids = []
+        for n in range(2):
+            with open(os.path.join(sim.write_dir, "epoch%d" % n, "agents.yml")) as f:
+                ids.append(sorted(yaml.safe_load(f)))
+        assert ids[0][0] == 0
+        assert ids[1][0] == (0 if restarts else ids[0][-1] + 1), (kind, ids[0][-1], ids[1][0])
 
 
 @pytest.mark.gpu
