@@ -201,6 +201,16 @@ class _Statistics:
         return (("utility_ego", "_utility_ego.npy"), ("comfort_ego", "_comfort_ego.npy"), ("utility_other", "_utility_others.npy"),
                 ("comfort_other", "_comfort_others.npy")) + self._extra + (("epoch_and_ego_id_history", "_epoch_and_ego_id_history.npy"),)
 
+    def remove_invalid_data(self, index_list):               # agent.py:325-331 / 432-438
+        """Drop the samples at the given positions from every per-sample list.  As in the reference the ego-utility list
+        is cut first and the other lists are then read only up to ITS new length (its loops all range over
+        len(self.utility_ego)), so removing k samples also drops the last k entries of the other lists."""
+        self.utility_ego = [v for i, v in enumerate(self.utility_ego) if i not in index_list]
+        keep = [i for i in range(len(self.utility_ego)) if i not in index_list]
+        for attr, _ in self._files()[1:]:
+            values = getattr(self, attr)
+            setattr(self, attr, [values[i] for i in keep])
+
     def save(self, path, name):
         for attr, suffix in self._files():
             np.save(os.path.join(path, name + suffix), np.array(getattr(self, attr)))

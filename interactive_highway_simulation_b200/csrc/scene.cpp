@@ -23,7 +23,9 @@ void prior_from_offset(double y, double vy, double centerY, double out[3]) {
 
 int build_scene_host(const mcs_corridor* cs, int nc, const mcs_agent* as, int na, SceneHost& s) {
   if (!cs || !as || nc <= 0 || na <= 0) { s.error = "empty scene"; return MCS_ERR_ARG; }
-  if (nc > MCS_MAX_LANES || na > MCS_MAX_AGENTS) { s.error = "scene exceeds MCS_MAX_LANES / MCS_MAX_AGENTS"; return MCS_ERR_CAPACITY; }
+  if (nc > MCS_MAX_LANES || na > MCS_MAX_AGENTS) { s.error = "scene exceeds the compiled limits: at most " + std::to_string(MCS_MAX_AGENTS) + " vehicles per rollout and " +
+                                                               std::to_string(MCS_MAX_LANES) + " corridors (got " + std::to_string(na) + " / " + std::to_string(nc) + ")";
+                                                     return MCS_ERR_CAPACITY; }
   // ---- lanes: hash order, neighbours by ascending centre y (MapMultiLane ctor)
   std::unordered_map<int, int> lane_order;
   for (int k = 0; k < nc; ++k) lane_order.emplace(cs[k].id, k);

@@ -137,18 +137,21 @@ class DeviceMap:
         except Exception:
             pass
 
-    def match(self, x, y, n_scenes=1, arc_on_lanes=False):
+    def match(self, x, y, n_scenes=1, arc_on_lanes=False, fetch=("lane", "arc", "order", "start", "neighbors")):
+        """mce_env_match.  `fetch`: which tables come back to the host (the others stay None; all of them stay resident on
+        the device for mce_env_neighbors / mce_build_rollout_scene either way — a caller that only needs the lanes of a
+        large batch does not pay for 120 bytes of neighbour tables per vehicle)."""
         x, y = _f64(x).reshape(n_scenes, -1), _f64(y).reshape(n_scenes, -1)
         n = x.shape[1]
         t = MatchTables()
         t.n_agents, t.n_scenes = n, n_scenes
-        t.lane = np.empty((n_scenes, n), np.int32)
-        t.arc = np.empty((n_scenes, n), np.float64)
-        t.order = np.empty((n_scenes, n), np.int32)
-        t.start = np.empty((n_scenes, MCE_MAX_LANES + 1), np.int32)
+        t.lane = np.empty((n_scenes, n), np.int32) if "lane" in fetch else None
+        t.arc = np.empty((n_scenes, n), np.float64) if "arc" in fetch else None
+        t.order = np.empty((n_scenes, n), np.int32) if "order" in fetch else None
+        t.start = np.empty((n_scenes, MCE_MAX_LANES + 1), np.int32) if "start" in fetch else None
         t.arc_on_lane = np.empty((n_scenes, self.n_lanes, n), np.float64) if arc_on_lanes else None
-        t.nb_index = np.empty((n_scenes, MCE_NEIGHBORS, n), np.int32)
-        t.nb_dis = np.empty((n_scenes, MCE_NEIGHBORS, n), np.float64)
+        t.nb_index = np.empty((n_scenes, MCE_NEIGHBORS, n), np.int32) if "neighbors" in fetch else None
+        t.nb_dis = np.empty((n_scenes, MCE_NEIGHBORS, n), np.float64) if "neighbors" in fetch else None
         p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
         _check(_lib().mce_env_match(self._h, x, y, n, n_scenes, p(t.lane), p(t.arc), p(t.order), p(t.start), p(t.arc_on_lane),
                                     p(t.nb_index), p(t.nb_dis)))
@@ -274,6 +277,47 @@ class Corridor:
     def set_left_and_right_corridor_id(self, left_id, right_id):
         self.left_id, self.right_id = left_id, right_id
 
+    # ---- what the reference's Corridor derives in its constructor (type.py:157-169), as cheap host values.  Not on the
+    # hot path (plot limits, sanity checks); the device holds its own copies of the geometry.
+    @property
+    def border(self):
+        """left + reversed right: the shell of the corridor polygon"""
+        return [list(p) for p in self.left] + [list(p) for p in reversed(self.right)]
+
+    @property
+    def length(self):
+        """centerSimplified.path_length = the distance from the first centre point to the corridor end"""
+        return self.distance_to_corridor_end(self.center[0])
+
+    @property
+    def width(self):
+        """leftLine.distance(rightLine): smallest distance between the two border polylines"""
+        return min(_segment_distance(self.left[i], self.left[i + 1], self.right[j], self.right[j + 1])
+                   for i in range(len(self.left) - 1) for j in range(len(self.right) - 1))
+
+    def get_x_y_limit(self):                                 # type.py:208-215
+        pts = list(self.left) + list(self.right)
+        return min(p[0] for p in pts), max(p[0] for p in pts), min(p[1] for p in pts), max(p[1] for p in pts)
+
+    x_min = property(lambda self: self.get_x_y_limit()[0])
+    x_max = property(lambda self: self.get_x_y_limit()[1])
+    y_min = property(lambda self: self.get_x_y_limit()[2])
+    y_max = property(lambda self: self.get_x_y_limit()[3])
+
+    def contains(self, point):
+        """Point(point).within(self.polygon): even-odd rule, points on the boundary are outside (the rule of the device's
+        lane match, env_kernels.cuh `within`)"""
+        px, py = float(point[0]), float(point[1])
+        shell = self.border
+        inside = False
+        for k in range(len(shell)):
+            (x1, y1), (x2, y2) = shell[k], shell[(k + 1) % len(shell)]
+            if _point_segment_distance(px, py, x1, y1, x2, y2) == 0.0:
+                return False
+            if (y1 > py) != (y2 > py) and px < (x2 - x1) * (py - y1) / (y2 - y1) + x1:
+                inside = not inside
+        return inside
+
     def _center_distance(self, point):
         """(signed distance to the centre line, distance to the corridor end); answers are kept per position — the
         environment fills them for every vehicle of a step in one launch (Environment.match_agents_on_corridor)"""
@@ -296,6 +340,25 @@ class Corridor:
         return {"id": self.id, "type": self.type, "left": self.left, "right": self.right, "center": self.center,
                 "v_limit": self.v_limit, "left_id": "none" if self.left_id is None else self.left_id,
                 "right_id": "none" if self.right_id is None else self.right_id}
+
+
+def _point_segment_distance(px, py, ax, ay, bx, by):
+    dx, dy = bx - ax, by - ay
+    d2 = dx * dx + dy * dy
+    t = 0.0 if d2 == 0.0 else min(1.0, max(0.0, ((px - ax) * dx + (py - ay) * dy) / d2))
+    ex, ey = px - (ax + t * dx), py - (ay + t * dy)
+    return (ex * ex + ey * ey) ** 0.5
+
+
+def _segment_distance(a, b, c, d):
+    """distance between the closed segments ab and cd (0 when they touch)"""
+    def orient(p, q, r):
+        return (q[0] - p[0]) * (r[1] - p[1]) - (q[1] - p[1]) * (r[0] - p[0])
+    o1, o2, o3, o4 = orient(a, b, c), orient(a, b, d), orient(c, d, a), orient(c, d, b)
+    if (o1 > 0) != (o2 > 0) and (o3 > 0) != (o4 > 0) and 0 not in (o1, o2, o3, o4):
+        return 0.0
+    return min(_point_segment_distance(c[0], c[1], a[0], a[1], b[0], b[1]), _point_segment_distance(d[0], d[1], a[0], a[1], b[0], b[1]),
+               _point_segment_distance(a[0], a[1], c[0], c[1], d[0], d[1]), _point_segment_distance(b[0], b[1], c[0], c[1], d[0], d[1]))
 
 
 def create_corridor_from_dict(d):                            # environment.py:12-18
@@ -353,6 +416,15 @@ class Map:
 
     def to_dict(self):                                       # environment.py:58-68
         return {i: c.to_dict() for i, c in self.corridors.items()}
+
+    def corridor_match(self, vehicle):                       # environment.py:35-39 (one vehicle, host; the scene-wide match is the kernel's)
+        for corridor in self.corridors.values():
+            if corridor.contains([vehicle.x, vehicle.y]):
+                return corridor
+        return False
+
+    def on_merging_lane(self, point):                        # environment.py:41-45
+        return any(c.contains(point) for c in self.corridors_by_type["merging"])
 
     def truck_lane_id(self):                                 # environment.py:46-56
         if "merging" in self.corridors_by_type:

@@ -177,3 +177,20 @@ def test_decision_helpers_follow_behaviors_py(oracle, backend_lib):
     cs, as_ = s2.c_corridors(), s2.c_agents()
     assert oracle.lib.orc_decide_fixed_gap(cs, len(cs), as_, len(as_), ego, abi.ACTIONS["left"], chosen, 0, C.byref(want)) == 0
     assert (act.ax, act.vy) == (want.ax, want.vy)
+
+
+@pytest.mark.gpu
+def test_more_than_256_vehicles_is_a_clear_error(backend_lib):
+    """The inner simulator holds up to MCS_MAX_AGENTS = 256 vehicles per rollout (one thread per vehicle of a 256-thread
+    rollout); the reference has no such limit (its callers pass 10-25).  The drop-in says so instead of truncating."""
+    from interactive_highway_simulation_b200 import mc_sim_highway as ms
+    lanes = [ms.Corridor(k, "main", ms.Line(ms.Point(-1000, 3.5 * (k + 1)), ms.Point(9000, 3.5 * (k + 1))),
+                         ms.Line(ms.Point(-1000, 3.5 * k), ms.Point(9000, 3.5 * k)),
+                         ms.Line(ms.Point(-1000, 3.5 * k + 1.75), ms.Point(9000, 3.5 * k + 1.75)), 30.0) for k in range(2)]
+    agents = [ms.Agent(i, 30.0 * (i // 2), 1.75 + 3.5 * (i % 2), 20.0, 0.0, 25.0, 0.0, 4.8, 2.0, ms.IdmParam(), ms.RSSParam(),
+                       ms.YieldingParam(), "idm" if i == 0 else "idm_lc") for i in range(257)]
+    with pytest.raises(backend_lib.McsimError) as e:
+        ms.simulationMultiThread(1, ms.SimParameter(0.3, 5, 5), ms.MapMultiLane(lanes), agents, 0, "keep_lane", -2)
+    assert e.value.code == -3 and "256" in str(e.value)
+    f = ms.simulationMultiThread(1, ms.SimParameter(0.3, 5, 5), ms.MapMultiLane(lanes), agents[:256], 0, "keep_lane", -2)
+    assert f.fromNSims == 8

@@ -188,3 +188,20 @@ def test_yielding_intention_follows_the_global_random_stream():
     assert not y.yielding
     y.update_intention(0.6875)                                      # (1 - p) <= threshold * (1 - initial): yields again
     assert y.yielding
+
+
+def test_corridor_host_values_and_statistics_trimming():
+    """the cheap host values of the reference's Corridor (type.py:157-169, 208-215) and remove_invalid_data
+    (agent.py:325-331) as user scripts touch them"""
+    from interactive_highway_simulation_b200 import agent, outer_env as oe
+    c = oe.Corridor(1, "main", [[0, 3.5], [50, 3.5], [100, 4.5]], [[0, 0], [100, 1.0]], [[0, 1.75], [100, 2.75]], 30)
+    assert c.border == [[0, 3.5], [50, 3.5], [100, 4.5], [100, 1.0], [0, 0]]
+    assert (c.x_min, c.x_max, c.y_min, c.y_max) == (0, 100, 0, 4.5) == c.get_x_y_limit()
+    assert abs(c.width - 3.0 * 100 / math.hypot(100, 1)) < 1e-12            # left's middle vertex (50, 3.5) against the slanted right border
+    assert c.contains([10, 1]) and not c.contains([10, 3.5]) and not c.contains([10, 5]) and not c.contains([-1, 1])
+    st = agent.MergingAndExitStatistics()
+    st.utility_ego, st.comfort_ego, st.utility_other, st.comfort_other = [1, 2, 3, 4], [5, 6, 7, 8], [1, 1, 1, 1], [2, 2, 2, 2]
+    st.total_t, st.epoch_and_ego_id_history = [9, 9, 9, 9], [[0, 1], [0, 2], [0, 3], [0, 4]]
+    st.remove_invalid_data([1])
+    # the reference ranges every later list over the ALREADY shortened utility_ego: one sample removed, one more cut off the end
+    assert st.utility_ego == [1, 3, 4] and st.comfort_ego == [5, 7] and st.epoch_and_ego_id_history == [[0, 1], [0, 3]]
