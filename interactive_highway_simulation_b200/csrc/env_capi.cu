@@ -484,7 +484,8 @@ int mce_build_rollout_scene(mce_map* m, const mce_build_request* request, const 
   static thread_local mce::BuildOut host_out;
   mce::BuildOut* d_out = Q.out(&host_out, 1);
   if ((rc = Q.upload())) return rc;
-  mce::env_build_kernel<<<1, 64, 0, m->stream>>>(m->d_head, m->d_tail, m->d_border, m->d_info, m->n_agents, m->d_lane, m->d_arc,
+  const size_t dyn = n * 36 + 64;
+  mce::env_build_kernel<<<1, 128, dyn, m->stream>>>(m->d_head, m->d_tail, m->d_border, m->d_info, m->n_agents, m->d_lane, m->d_arc,
                                                  m->d_order, m->d_start, d_req, d_ids, d_attrs, d_noise, n_noise, d_out);
   if ((rc = Q.finish())) return rc;
   const mce::BuildOut& o = host_out;

@@ -505,25 +505,39 @@ __device__ __forceinline__ void to_frenet(const EnvMapTail& t, int ref_lane, dou
   }
 }
 
-__global__ void __launch_bounds__(64) env_build_kernel(const EnvMapHead* __restrict__ head, const EnvMapTail* __restrict__ tail,
-                                                       const EnvMapBorder* __restrict__ border, const EnvLaneInfo* __restrict__ info,
-                                                       int n, const int32_t* __restrict__ lane, const double* __restrict__ arc,
-                                                       const int32_t* __restrict__ order, const int32_t* __restrict__ start,
-                                                       const mce_build_request* __restrict__ reqs, const int32_t* __restrict__ ids,
-                                                       const double* __restrict__ attrs /* [8][n]: x y v vy a l w vd, current */,
-                                                       const double* __restrict__ noise, int n_noise, BuildOut* __restrict__ outs) {
+// The selection walks dependent look-ups (binary searches over the lane vectors, projections on the centre lines): the
+// map head and the scene's match tables are staged into shared memory first, so that one thread's chain runs at
+// shared-memory latency.  Dynamic shared memory: n x (8 arc + 8 x + 8 y + 4 lane + 4 order + 4 spare) bytes + 9 lane starts.
+__global__ void __launch_bounds__(128) env_build_kernel(const EnvMapHead* __restrict__ head, const EnvMapTail* __restrict__ tail,
+                                                        const EnvMapBorder* __restrict__ border, const EnvLaneInfo* __restrict__ info,
+                                                        int n, const int32_t* __restrict__ g_lane, const double* __restrict__ g_arc,
+                                                        const int32_t* __restrict__ g_order, const int32_t* __restrict__ g_start,
+                                                        const mce_build_request* __restrict__ reqs, const int32_t* __restrict__ ids,
+                                                        const double* __restrict__ attrs /* [8][n]: x y v vy a l w vd, current */,
+                                                        const double* __restrict__ noise, int n_noise, BuildOut* __restrict__ outs) {
+  __shared__ EnvMapHead H;
   __shared__ int item_slot[kBuildMaxAgents], item_beh[kBuildMaxAgents];
   __shared__ int corr_lane[MCE_MAX_LANES];
   __shared__ int n_items, n_corr, n_act, status, ref_lane;
   __shared__ int acts[4];
   __shared__ double ego_s_sh, x_limit_sh;
+  extern __shared__ double build_dyn[];
   const mce_build_request& rq = reqs[blockIdx.x];
   BuildOut& out = outs[blockIdx.x];
-  const EnvMapHead& H = *head;
   const EnvMapTail& T = *tail;
   const int scene = rq.scene, ego = rq.ego_slot;
-  const double* ax = attrs; const double* ay = attrs + n;
-  const int ego_lane = lane[(size_t)scene * n + ego];
+  // this scene's tables and the current positions, staged (indexed like a one-scene batch below: scene 0)
+  double* arc = build_dyn; double* sx = arc + n; double* sy = sx + n;
+  int32_t* lane = reinterpret_cast<int32_t*>(sy + n); int32_t* order = lane + n; int32_t* start = order + n;
+  stage(&H, head);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    arc[j] = g_arc[(size_t)scene * n + j]; lane[j] = g_lane[(size_t)scene * n + j]; order[j] = g_order[(size_t)scene * n + j];
+    sx[j] = attrs[j]; sy[j] = attrs[(size_t)n + j];
+  }
+  if (threadIdx.x <= MCE_MAX_LANES) start[threadIdx.x] = g_start[(size_t)scene * (MCE_MAX_LANES + 1) + threadIdx.x];
+  __syncthreads();
+  const double* ax = sx; const double* ay = sy;
+  const int ego_lane = lane[ego];
   if (threadIdx.x == 0) {
     n_items = 0; n_corr = 0; n_act = 1; acts[0] = -1; status = 0; ref_lane = ego_lane;
     auto add = [&](int slot, int beh) {
@@ -536,19 +550,19 @@ __global__ void __launch_bounds__(64) env_build_kernel(const EnvMapHead* __restr
     // length on that lane's centre line is within 80 m of the ego's, by arc length (ties in dict order)
     auto within_range = [&](int l, int beh) {
       double e, d;
-      project_distance(T.cpath[l], T.n_center[l], ax[ego], ay[ego], e, d);
+      project_distance(H.center[l], H.n_center[l], ax[ego], ay[ego], e, d);
       const int first = n_items;
       for (int j = 0; j < n; ++j) {
-        if (lane[(size_t)scene * n + j] != l) continue;
+        if (lane[j] != l) continue;
         double a;
-        project_distance(T.cpath[l], T.n_center[l], ax[j], ay[j], a, d);
+        project_distance(H.center[l], H.n_center[l], ax[j], ay[j], a, d);
         if (!(fabs(a - e) <= 80.0)) continue;
         if (n_items >= kBuildMaxAgents - 1) { status = 1; return; }
         // insertion by arc length, stable
         int p = n_items;
         while (p > first) {
           double ap;
-          project_distance(T.cpath[l], T.n_center[l], ax[item_slot[p - 1]], ay[item_slot[p - 1]], ap, d);
+          project_distance(H.center[l], H.n_center[l], ax[item_slot[p - 1]], ay[item_slot[p - 1]], ap, d);
           if (!(ap > a)) break;
           item_slot[p] = item_slot[p - 1]; item_beh[p] = item_beh[p - 1]; --p;
         }
@@ -559,7 +573,7 @@ __global__ void __launch_bounds__(64) env_build_kernel(const EnvMapHead* __restr
     else {
       int idx[MCE_NEIGHBORS];
       double dis[MCE_NEIGHBORS];
-      neighbor_row(H, n, lane, arc, order, start, scene, ego, ax[ego], ay[ego], idx, dis);
+      neighbor_row(H, n, lane, arc, order, start, 0, ego, ax[ego], ay[ego], idx, dis);
       if (rq.kind == 0) {                                   // merging_mcs_sim_from_env, mcs_wrapper.py:24-75
         const int left = H.left[ego_lane];
         if (left < 0) status = 2;
@@ -586,7 +600,7 @@ __global__ void __launch_bounds__(64) env_build_kernel(const EnvMapHead* __restr
           int i2[MCE_NEIGHBORS];
           double d2[MCE_NEIGHBORS];
           const int f = idx[MCE_FRONT];
-          neighbor_row(H, n, lane, arc, order, start, scene, f, ax[f], ay[f], i2, d2);
+          neighbor_row(H, n, lane, arc, order, start, 0, f, ax[f], ay[f], i2, d2);
           if (i2[MCE_FRONT] >= 0) add(i2[MCE_FRONT], MCS_BEH_IDM_LC);
         }
         if (idx[MCE_BACK] >= 0) add(idx[MCE_BACK], MCS_BEH_IDM_LC);
