@@ -18,12 +18,9 @@ struct DecideParams {
 };
 struct DecideOut { double ax, vy; int commit, keepStep, targetLane, status; };
 
-__global__ void __launch_bounds__(256, 1) decide_kernel(const SceneDev sc, const DecideParams dp, DecideOut* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int np = sc.n_pad, n = sc.n, k = threadIdx.x;
-  Smem s;
-  carve_smem(s, smem_raw, np, 0);
-  int* laneStart = s.cnt;
+// Stage one vehicle slot of the scene into the rollout kernels' shared-memory layout (every thread k < np of the block)
+__device__ __forceinline__ void decide_stage(const SceneDev& sc, const Smem& s, int* laneStart, int k) {
+  const int np = sc.n_pad, n = sc.n;
   const double* F = sc.f;
   const int32_t* I = sc.i;
   const bool live = k < n;
@@ -41,15 +38,20 @@ __global__ void __launch_bounds__(256, 1) decide_kernel(const SceneDev sc, const
   s.lane[k] = (uint8_t)(lane < 0 ? 0xff : lane);
   s.vec[k] = sc.lane_vec[k];
   if (k <= sc.n_lanes) laneStart[k] = sc.lane_start[k];
-  __syncthreads();
-  if (k != dp.slot) return;
+}
 
+// One decision of vehicle dp.slot on the staged scene (one thread)
+__device__ __forceinline__ void decide_eval(const SceneDev& sc, const Smem& s, const int* laneStart, const DecideParams& dp, DecideOut& out) {
+  const int np = sc.n_pad, n = sc.n, k = dp.slot;
+  const double* F = sc.f;
+  const int32_t* I = sc.i;
+  const int lane = I[(size_t)I_LANE * np + k];
   DecideOut o;
   o.ax = 0.0; o.vy = 0.0; o.status = MCS_OK;
   o.commit = I[(size_t)I_COMMIT * np + k]; o.keepStep = I[(size_t)I_KEEPSTEP * np + k]; o.targetLane = I[(size_t)I_TARGETLANE * np + k];
   if (lane < 0) {       // "is not matched!" — the wrappers return a zero action; MOBIL dereferences an empty history
     o.status = dp.kind == 0 ? MCS_ERR_SCENE : MCS_OK;
-    *out = o;
+    out = o;
     return;
   }
   const LaneDev& L = sc.lanes[lane];
@@ -97,6 +99,20 @@ __global__ void __launch_bounds__(256, 1) decide_kernel(const SceneDev sc, const
     if (!ok) o.status = MCS_ERR_SCENE;     // no corridor on that side: the reference reads a missing corridor
     o.ax = ax; o.vy = avy;
   }
+  out = o;
+}
+
+__global__ void __launch_bounds__(256, 1) decide_kernel(const SceneDev sc, const DecideParams dp, DecideOut* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int k = threadIdx.x;
+  Smem s;
+  carve_smem(s, smem_raw, sc.n_pad, 0);
+  int* laneStart = s.cnt;
+  decide_stage(sc, s, laneStart, k);
+  __syncthreads();
+  if (k != dp.slot) return;
+  DecideOut o;
+  decide_eval(sc, s, laneStart, dp, o);
   *out = o;
 }
 

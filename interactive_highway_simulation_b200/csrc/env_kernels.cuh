@@ -505,38 +505,35 @@ __device__ __forceinline__ void to_frenet(const EnvMapTail& t, int ref_lane, dou
   }
 }
 
-// The selection walks dependent look-ups (binary searches over the lane vectors, projections on the centre lines): the
-// map head and the scene's match tables are staged into shared memory first, so that one thread's chain runs at
-// shared-memory latency.  Dynamic shared memory: n x (8 arc + 8 x + 8 y + 4 lane + 4 order + 4 spare) bytes + 9 lane starts.
-__global__ void __launch_bounds__(128) env_build_kernel(const EnvMapHead* __restrict__ head, const EnvMapTail* __restrict__ tail,
-                                                        const EnvMapBorder* __restrict__ border, const EnvLaneInfo* __restrict__ info,
-                                                        int n, const int32_t* __restrict__ g_lane, const double* __restrict__ g_arc,
-                                                        const int32_t* __restrict__ g_order, const int32_t* __restrict__ g_start,
-                                                        const mce_build_request* __restrict__ reqs, const int32_t* __restrict__ ids,
-                                                        const double* __restrict__ attrs /* [8][n]: x y v vy a l w vd, current */,
-                                                        const double* __restrict__ noise, int n_noise, BuildOut* __restrict__ outs) {
-  __shared__ EnvMapHead H;
-  __shared__ int item_slot[kBuildMaxAgents], item_beh[kBuildMaxAgents];
-  __shared__ int corr_lane[MCE_MAX_LANES];
-  __shared__ int n_items, n_corr, n_act, status, ref_lane;
-  __shared__ int acts[4];
-  __shared__ double ego_s_sh, x_limit_sh;
-  extern __shared__ double build_dyn[];
-  const mce_build_request& rq = reqs[blockIdx.x];
-  BuildOut& out = outs[blockIdx.x];
+// The body of one builder call, executed by every thread of a block (it synchronises the block).  H: the map head in
+// shared memory; lane / arc / order / start: ONE scene's match tables, ax / ay: the vehicles' current positions (shared
+// memory: the selection walks dependent look-ups — binary searches over the lane vectors, projections on the centre
+// lines — which run at shared-memory latency there); attrs [8][n] / ids: global; out: global or shared.
+struct BuildScratch {
+  int item_slot[kBuildMaxAgents], item_beh[kBuildMaxAgents];
+  int corr_lane[MCE_MAX_LANES];
+  int n_items, n_corr, n_act, status, ref_lane;
+  int acts[4];
+  double ego_s, x_limit;
+  double cs[MCE_MAX_LANES][6], cd[MCE_MAX_LANES][6];
+};
+
+__device__ __forceinline__ void build_scene_block(const EnvMapHead& H, const EnvMapTail* __restrict__ tail,
+                                                  const EnvMapBorder* __restrict__ border, const EnvLaneInfo* __restrict__ info, int n,
+                                                  const int32_t* lane, const double* arc, const int32_t* order, const int32_t* start,
+                                                  const double* ax, const double* ay, const mce_build_request& rq,
+                                                  const int32_t* __restrict__ ids, const double* __restrict__ attrs,
+                                                  const double* __restrict__ noise, int n_noise, BuildScratch& w, BuildOut& out) {
+  int (&item_slot)[kBuildMaxAgents] = w.item_slot;
+  int (&item_beh)[kBuildMaxAgents] = w.item_beh;
+  int (&corr_lane)[MCE_MAX_LANES] = w.corr_lane;
+  int& n_items = w.n_items; int& n_corr = w.n_corr; int& n_act = w.n_act; int& status = w.status; int& ref_lane = w.ref_lane;
+  int (&acts)[4] = w.acts;
+  double& ego_s_sh = w.ego_s; double& x_limit_sh = w.x_limit;
+  double (&cs_)[MCE_MAX_LANES][6] = w.cs;
+  double (&cd_)[MCE_MAX_LANES][6] = w.cd;
   const EnvMapTail& T = *tail;
-  const int scene = rq.scene, ego = rq.ego_slot;
-  // this scene's tables and the current positions, staged (indexed like a one-scene batch below: scene 0)
-  double* arc = build_dyn; double* sx = arc + n; double* sy = sx + n;
-  int32_t* lane = reinterpret_cast<int32_t*>(sy + n); int32_t* order = lane + n; int32_t* start = order + n;
-  stage(&H, head);
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    arc[j] = g_arc[(size_t)scene * n + j]; lane[j] = g_lane[(size_t)scene * n + j]; order[j] = g_order[(size_t)scene * n + j];
-    sx[j] = attrs[j]; sy[j] = attrs[(size_t)n + j];
-  }
-  if (threadIdx.x <= MCE_MAX_LANES) start[threadIdx.x] = g_start[(size_t)scene * (MCE_MAX_LANES + 1) + threadIdx.x];
-  __syncthreads();
-  const double* ax = sx; const double* ay = sy;
+  const int ego = rq.ego_slot;
   const int ego_lane = lane[ego];
   if (threadIdx.x == 0) {
     n_items = 0; n_corr = 0; n_act = 1; acts[0] = -1; status = 0; ref_lane = ego_lane;
@@ -661,7 +658,6 @@ __global__ void __launch_bounds__(128) env_build_kernel(const EnvMapHead* __rest
     out.agents[q] = a;
   }
   // ---- corridors: Corridor.to_frenet_corridor (type.py:207-237) — the far points take the lateral offset of the near ones
-  __shared__ double cs_[MCE_MAX_LANES][6], cd_[MCE_MAX_LANES][6];
   for (int q = threadIdx.x; q < n_corr * 6; q += blockDim.x) {
     const int c = q / 6, w = q - 6 * c, l = corr_lane[c];
     const EnvMapBorder& B = *border;
@@ -709,6 +705,33 @@ __global__ void __launch_bounds__(128) env_build_kernel(const EnvMapHead* __rest
     out.n_corridors = w; out.n_agents = n_items + 1; out.n_actions = n_act; out.status = 0;
     for (int q = 0; q < 4; ++q) out.actions[q] = q < n_act ? acts[q] : 0;
   }
+}
+
+
+// one block per request: stage the map head, the request's scene tables and the current positions, then build
+// Dynamic shared memory: n x (8 arc + 8 x + 8 y + 4 lane + 4 order + 4 spare) bytes + 9 lane starts.
+__global__ void __launch_bounds__(128) env_build_kernel(const EnvMapHead* __restrict__ head, const EnvMapTail* __restrict__ tail,
+                                                        const EnvMapBorder* __restrict__ border, const EnvLaneInfo* __restrict__ info,
+                                                        int n, const int32_t* __restrict__ g_lane, const double* __restrict__ g_arc,
+                                                        const int32_t* __restrict__ g_order, const int32_t* __restrict__ g_start,
+                                                        const mce_build_request* __restrict__ reqs, const int32_t* __restrict__ ids,
+                                                        const double* __restrict__ attrs /* [8][n]: x y v vy a l w vd, current */,
+                                                        const double* __restrict__ noise, int n_noise, BuildOut* __restrict__ outs) {
+  __shared__ EnvMapHead H;
+  __shared__ BuildScratch w;
+  extern __shared__ double build_dyn[];
+  const mce_build_request& rq = reqs[blockIdx.x];
+  const int scene = rq.scene;
+  double* arc = build_dyn; double* sx = arc + n; double* sy = sx + n;
+  int32_t* lane = reinterpret_cast<int32_t*>(sy + n); int32_t* order = lane + n; int32_t* start = order + n;
+  stage(&H, head);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    arc[j] = g_arc[(size_t)scene * n + j]; lane[j] = g_lane[(size_t)scene * n + j]; order[j] = g_order[(size_t)scene * n + j];
+    sx[j] = attrs[j]; sy[j] = attrs[(size_t)n + j];
+  }
+  if (threadIdx.x <= MCE_MAX_LANES) start[threadIdx.x] = g_start[(size_t)scene * (MCE_MAX_LANES + 1) + threadIdx.x];
+  __syncthreads();
+  build_scene_block(H, tail, border, info, n, lane, arc, order, start, sx, sy, rq, ids, attrs, noise, n_noise, w, outs[blockIdx.x]);
 }
 
 }  // namespace mce
