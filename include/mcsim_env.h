@@ -143,6 +143,48 @@ int mce_build_rollout_scene(mce_map* map, const mce_build_request* request, cons
                             struct mcs_agent* agents_out, int32_t* n_agents_out, int32_t* actions_out, int32_t* n_actions_out,
                             int device, struct mcs_scene** scene_out);
 
+/* ---- environment.py:316-323 on the device: the sequential plan-and-move walk over the vehicles of a scene ------------
+ * One launch walks slots [first, last) in dict order against the tables of the last mce_env_match (csrc/walk_kernel.cuh):
+ * idm_behavior (behaviors.py:10-67, yielding intentions included), the MOBIL / closest-gap behaviours through the device
+ * builder and the single-step decision, Agent.step.  It stops at the first vehicle that needs the host (behaviour
+ * MCE_WB_HOST — the learned behaviours — or a yielding seed of 0) and says where; the host handles that vehicle and calls
+ * again behind it. */
+enum { MCE_WB_HOST = 0, MCE_WB_IDM = 1, MCE_WB_MOBIL = 2, MCE_WB_MOBIL_SAFE = 3, MCE_WB_MERGE_CLOSEST = 4, MCE_WB_EXIT_CLOSEST = 5 };
+enum { MCE_WF_MERGING_MODEL = 1, MCE_WF_EXIT_MODEL = 2 }; /* "merging" / "exit" in Agent.behavior_model */
+#define MCE_YIELD_CAP 12
+typedef struct mce_walk_vehicle { /* agent.py Agent as far as plan / step read and write it */
+  int32_t id, behavior /* MCE_WB_* */, flags /* MCE_WF_* */, seed /* random_yielding_seed */;
+  int32_t commit /* MCS_COMMIT_* */, keep_step, target_lane, yi_n;
+  double x, y, v, vy, a, yaw, l, w;
+  double hull[8];   /* vehicle_pose_to_rect corner order */
+  double idm[6];    /* acc_max acc_min min_dis acc_com thw vd */
+  double rss[6];    /* r_t_ego r_t_other a_min a_max soft_acc soft_dcc */
+  double mobil[3];  /* politeness_factor delta_a bias_a */
+  double yp[13];    /* yielding model weights */
+  double threshold; /* change_intention_threshold */
+  double ax_last;   /* out: the acceleration planned in the last walk */
+  int32_t yi_id[MCE_YIELD_CAP];       /* yielding_intention_to_others: other vehicle's id, */
+  int32_t yi_yielding[MCE_YIELD_CAP]; /* current intention, */
+  double yi_p0[MCE_YIELD_CAP];        /* first probability */
+} mce_walk_vehicle;
+typedef struct mce_walk_result {
+  int32_t stopped_at;  /* slot that needs the host, -1 = reached `last` */
+  int32_t status;      /* 0 ok; 100 + builder status, 200 + decision status, 300 intention table full */
+  int32_t noise_used;  /* np.random.normal(0., 1) draws consumed from `noise` */
+  int32_t mobil_calls; /* laneChangeMobilBehavior calls made: drop-in seeds seed_base .. seed_base + mobil_calls - 1 */
+  int32_t random_used, random_seed; /* Python `random` consumed; every consumer is random.seed(s); random.random(): last s */
+  int32_t moved, reserved;
+} mce_walk_result;
+/* vehicles [n_agents of the last match]: in / out (host).  upload != 0: the array goes to the device first (first call of a
+ * step, or after the host changed a vehicle); otherwise the walk continues on the device's copy.  noise: the block of
+ * np.random.normal(0., 1) draws the builders consume in order; random_first [100]: random.seed(s); random.random() for
+ * s = 0..99.  ids [n_agents]. */
+int mce_walk_step(mce_map* map, mce_walk_vehicle* vehicles, int upload, const int32_t* ids, const double* noise, int n_noise,
+                  const double* random_first, int first, int last, double dt, uint64_t seed_base, mce_walk_result* result);
+/* std::unordered_map<int, T> iteration order after emplacing ids[0..n) in order (n <= 64), as csrc/walk_kernel.cuh restates
+ * it for the device (scene.cpp uses the container itself); order_out[k] = input index of the k-th node.  For tests. */
+int mce_hash_iteration_order(const int32_t* ids, int n, int32_t* order_out);
+
 /* average duration (ms, CUDA events on the launching stream) of the kernels of the last mce_env_match call:
  * out[0] = match + order kernel, out[1] = neighbour kernel */
 int mce_last_kernel_ms(mce_map* map, float* out2);

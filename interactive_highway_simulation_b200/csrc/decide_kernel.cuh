@@ -102,7 +102,7 @@ __device__ __forceinline__ void decide_eval(const SceneDev& sc, const Smem& s, c
   out = o;
 }
 
-__global__ void __launch_bounds__(256, 1) decide_kernel(const SceneDev sc, const DecideParams dp, DecideOut* __restrict__ out) {
+static __global__ void __launch_bounds__(256, 1) decide_kernel(const SceneDev sc, const DecideParams dp, DecideOut* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = threadIdx.x;
   Smem s;

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "env_kernels.cuh"
+#include "walk_kernel.cuh"
 
 namespace {
 
@@ -82,6 +83,9 @@ struct mce_map {
   mce::EnvMapTail* d_tail = nullptr;
   mce::EnvMapBorder* d_border = nullptr;
   mce::EnvLaneInfo* d_info = nullptr;   // Corridor.id / type / v_limit (mce_map_set_lane_info), read by the builders
+  // the device-side walk of the outer step (mce_walk_step): vehicles, ids, attrs [8][n], noise block, random table, result
+  char* d_walk = nullptr; size_t walk_cap = 0; int walk_n = 0;
+  char* h_walk = nullptr;
   // state of the last match (resident)
   int n_agents = 0, n_scenes = 0;
   size_t cap_slots = 0, cap_scenes = 0, cap_arc_on = 0, cap_q = 0;
@@ -204,7 +208,8 @@ int mce_map_create(const mce_corridor* corridors, int n_corridors, int device, m
 int mce_map_destroy(mce_map* m) {
   if (!m) return MCE_OK;
   cudaSetDevice(m->device);
-  void* bufs[] = {m->d_info, m->d_head, m->d_tail, m->d_border, m->d_x, m->d_y, m->d_arc, m->d_arc_on, m->d_nbd, m->d_lane, m->d_order, m->d_start,
+  if (m->h_walk) cudaFreeHost(m->h_walk);
+  void* bufs[] = {m->d_walk, m->d_info, m->d_head, m->d_tail, m->d_border, m->d_x, m->d_y, m->d_arc, m->d_arc_on, m->d_nbd, m->d_lane, m->d_order, m->d_start,
                   m->d_nbi, m->d_q};
   if (m->h_q) cudaFreeHost(m->h_q);
   for (void* b : bufs) if (b) cudaFree(b);
@@ -505,6 +510,76 @@ int mce_build_rollout_scene(mce_map* m, const mce_build_request* request, const 
     if (src != MCS_OK) return efail(src == MCS_ERR_CUDA ? MCE_ERR_CUDA : (src == MCS_ERR_CAPACITY ? MCE_ERR_CAPACITY : MCE_ERR_ARG),
                                     std::string("mcs_scene_create: ") + mcs_last_error());
   }
+  return MCE_OK;
+}
+
+static_assert(sizeof(mce_walk_vehicle) == sizeof(mcw::WalkVehicle) && sizeof(mce_walk_result) == sizeof(mcw::WalkResult),
+              "include/mcsim_env.h and csrc/walk_kernel.cuh describe the same records");
+
+int mce_hash_iteration_order(const int32_t* ids, int n, int32_t* order_out) {
+  if (!ids || !order_out || n < 0 || n > 64) return efail(MCE_ERR_ARG, "bad arguments");
+  int order[64];
+  mcw::hash_iteration_order(ids, n, order);
+  for (int k = 0; k < n; ++k) order_out[k] = order[k];
+  return MCE_OK;
+}
+
+int mce_walk_step(mce_map* m, mce_walk_vehicle* vehicles, int upload, const int32_t* ids, const double* noise, int n_noise,
+                  const double* random_first, int first, int last, double dt, uint64_t seed_base, mce_walk_result* result) {
+  if (!m || !vehicles || !ids || !random_first || !result) return efail(MCE_ERR_ARG, "null argument");
+  if (m->n_scenes == 0) return efail(MCE_ERR_ARG, "mce_walk_step before mce_env_match");
+  if (!m->d_info) return efail(MCE_ERR_ARG, "mce_walk_step before mce_map_set_lane_info");
+  const int n = m->n_agents;
+  if (first < 0 || last > n || first > last || n_noise < 0 || (n_noise > 0 && !noise)) return efail(MCE_ERR_ARG, "bad range");
+  ENV_TRY(cudaSetDevice(m->device));
+  // layout of the walk buffer (device and pinned mirror alike): vehicles | attrs [8][n] | ids | random table | result | noise
+  const size_t b_veh = sizeof(mcw::WalkVehicle) * (size_t)n, b_attr = 64 * (size_t)n, b_ids = ((size_t)n * 4 + 15) & ~size_t(15);
+  const size_t o_attr = b_veh, o_ids = o_attr + b_attr, o_rnd = o_ids + b_ids, o_res = o_rnd + 800, o_noise = o_res + 64;
+  const size_t total = o_noise + (size_t)(n_noise > 4096 ? n_noise : 4096) * 8;
+  if (total > m->walk_cap) {
+    if (m->d_walk) cudaFree(m->d_walk);
+    if (m->h_walk) cudaFreeHost(m->h_walk);
+    m->d_walk = nullptr; m->h_walk = nullptr; m->walk_cap = 0;
+    ENV_TRY(cudaMalloc(&m->d_walk, total));
+    ENV_TRY(cudaMallocHost(&m->h_walk, total));
+    m->walk_cap = total;
+    upload = 1;
+  }
+  if (m->walk_n != n) upload = 1;
+  m->walk_n = n;
+  cudaStream_t s = m->stream;
+  if (upload) {
+    std::memcpy(m->h_walk, vehicles, b_veh);
+    double* at = reinterpret_cast<double*>(m->h_walk + o_attr);
+    for (int i = 0; i < n; ++i) {
+      const mce_walk_vehicle& v = vehicles[i];
+      at[i] = v.x; at[(size_t)n + i] = v.y; at[2 * (size_t)n + i] = v.v; at[3 * (size_t)n + i] = v.vy; at[4 * (size_t)n + i] = v.a;
+      at[5 * (size_t)n + i] = v.l; at[6 * (size_t)n + i] = v.w; at[7 * (size_t)n + i] = v.idm[5];
+    }
+    std::memcpy(m->h_walk + o_ids, ids, (size_t)n * 4);
+    std::memcpy(m->h_walk + o_rnd, random_first, 800);
+    ENV_TRY(cudaMemcpyAsync(m->d_walk, m->h_walk, o_res, cudaMemcpyHostToDevice, s));
+  }
+  if (n_noise > 0) {
+    std::memcpy(m->h_walk + o_noise, noise, (size_t)n_noise * 8);
+    ENV_TRY(cudaMemcpyAsync(m->d_walk + o_noise, m->h_walk + o_noise, (size_t)n_noise * 8, cudaMemcpyHostToDevice, s));
+  }
+  mcw::WalkParams wp;
+  wp.first = first; wp.last = last; wp.scene = 0; wp.dt = dt; wp.seed_base = seed_base; wp.n_noise = n_noise;
+  constexpr int decide_bytes = 11808;      // rollout_kernel's shared-memory region of a 64-slot rollout without histories (capi.cu)
+  const size_t smem = ((sizeof(mcw::WalkShared) + 15) & ~size_t(15)) + decide_bytes + (size_t)n * 36 + 64;
+  ENV_TRY(cudaFuncSetAttribute(mcw::walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mcw::walk_kernel<<<1, 128, smem, s>>>(m->d_head, m->d_tail, m->d_border, m->d_info, n, m->d_lane, m->d_arc, m->d_order, m->d_start,
+                                        reinterpret_cast<mcw::WalkVehicle*>(m->d_walk), reinterpret_cast<const int32_t*>(m->d_walk + o_ids),
+                                        reinterpret_cast<double*>(m->d_walk + o_attr), reinterpret_cast<const double*>(m->d_walk + o_noise),
+                                        reinterpret_cast<const double*>(m->d_walk + o_rnd), wp,
+                                        reinterpret_cast<mcw::WalkResult*>(m->d_walk + o_res), decide_bytes);
+  ENV_TRY(cudaGetLastError());
+  ENV_TRY(cudaMemcpyAsync(m->h_walk, m->d_walk, b_veh, cudaMemcpyDeviceToHost, s));
+  ENV_TRY(cudaMemcpyAsync(m->h_walk + o_res, m->d_walk + o_res, sizeof(mcw::WalkResult), cudaMemcpyDeviceToHost, s));
+  ENV_TRY(cudaStreamSynchronize(s));
+  std::memcpy(vehicles, m->h_walk, b_veh);
+  std::memcpy(result, m->h_walk + o_res, sizeof(mce_walk_result));
   return MCE_OK;
 }
 

@@ -157,7 +157,7 @@ struct LineView {
 
 // ---- match_agents_on_corridor + agents_in_corridor_by_arc_length (environment.py:85-101, 135-143) --------------------
 // grid = scenes; dynamic shared memory: n doubles (arc) + n ints (lane)
-__global__ void __launch_bounds__(kBT) env_match_kernel(const EnvMapHead* __restrict__ gmap, const double* __restrict__ x,
+static __global__ void __launch_bounds__(kBT) env_match_kernel(const EnvMapHead* __restrict__ gmap, const double* __restrict__ x,
                                                         const double* __restrict__ y, int n, int32_t* __restrict__ lane_out,
                                                         double* __restrict__ arc_out, int32_t* __restrict__ order_out,
                                                         int32_t* __restrict__ start_out, double* __restrict__ arc_on_lane_out) {
@@ -286,7 +286,7 @@ __device__ __forceinline__ void neighbor_row(const EnvMapHead& m, int n, const i
 // ---- front_agent / following_agent / neighbor_around_agent (environment.py:166-251) ---------------------------------
 // One thread per query.  q_scene == nullptr: every slot of every scene at the matched positions (grid.y = scene);
 // otherwise a list of (scene, slot, x, y) queries against the resident vectors of the last match.
-__global__ void __launch_bounds__(kBT) env_neighbors_kernel(const EnvMapHead* __restrict__ gmap, int n,
+static __global__ void __launch_bounds__(kBT) env_neighbors_kernel(const EnvMapHead* __restrict__ gmap, int n,
                                                             const int32_t* __restrict__ lane, const double* __restrict__ arc,
                                                             const int32_t* __restrict__ order, const int32_t* __restrict__ start,
                                                             const int32_t* __restrict__ q_scene, const int32_t* __restrict__ q_slot,
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kBT) env_neighbors_kernel(const EnvMapHead* __
 
 // ---- LineSimplified(extend_line_both_sides(center, 1000)).to_frenet_frame (type.py:307-317) --------------------------
 // center_line: project on the corridor's own centre line instead (LineString(center).project / .distance)
-__global__ void __launch_bounds__(kBT) env_frenet_kernel(const EnvMapTail* __restrict__ gmap, int ref_lane, bool center_line,
+static __global__ void __launch_bounds__(kBT) env_frenet_kernel(const EnvMapTail* __restrict__ gmap, int ref_lane, bool center_line,
                                                          const double* __restrict__ x, const double* __restrict__ y, int n,
                                                          double* __restrict__ s_out, double* __restrict__ d_out) {
   __shared__ EnvMapTail m;
@@ -348,8 +348,28 @@ __global__ void __launch_bounds__(kBT) env_frenet_kernel(const EnvMapTail* __res
   d_out[i] = d;
 }
 
+// utility.py:88-98 for one vehicle on corridors[l].centerSimplified; k = index of the yaw / cos / sin entry of the new position
+__device__ __forceinline__ void step_along_path_fn(const EnvMapTail& m, int l, double px, double py, double v, double ax, double vy,
+                                                   double dt, double& x_new, double& y_new, double& v_out, int& k) {
+  LineView lv{m.cpath[l], m.cdis[l], m.n_center[l], m.cs_len[l]};
+  double s, dis;
+  project_distance(m.cs[l], m.n_cs[l], px, py, s, dis);
+  const int sign = (dis > 0.0 && lv.side_of(s, px, py) > 0) ? 1 : -1;   // is_left_of: a point on the line is not left
+  const double d = sign > 0 ? dis : -dis;
+  const double s_new = s + v * dt;
+  const double d_new = d + vy * dt;
+  double v_new = v + ax * dt;
+  v_new = v_new > 0.0 ? v_new : 0.0;
+  k = lv.yaw_index(s_new);
+  double fx, fy;
+  lv.point_at(s_new, fx, fy);
+  x_new = fx - d_new * m.csin[l][k];            // offset_point utility.py:83-85
+  y_new = fy + d_new * m.ccos[l][k];
+  v_out = v_new;
+}
+
 // ---- utility.py:88-98 step_along_path on corridors[ref_lane[i]].centerSimplified ------------------------------------
-__global__ void __launch_bounds__(kBT) env_step_kernel(const EnvMapTail* __restrict__ gmap, const int32_t* __restrict__ ref_lane,
+static __global__ void __launch_bounds__(kBT) env_step_kernel(const EnvMapTail* __restrict__ gmap, const int32_t* __restrict__ ref_lane,
                                                        const double* __restrict__ x, const double* __restrict__ y,
                                                        const double* __restrict__ v, const double* __restrict__ ax,
                                                        const double* __restrict__ vy, double dt, int n, double* __restrict__ x_out,
@@ -360,38 +380,12 @@ __global__ void __launch_bounds__(kBT) env_step_kernel(const EnvMapTail* __restr
   __syncthreads();
   const int i = blockIdx.x * kBT + threadIdx.x;
   if (i >= n) return;
-  const int l = ref_lane[i];
-  const double px = x[i], py = y[i];
-  LineView lv{m.cpath[l], m.cdis[l], m.n_center[l], m.cs_len[l]};
-  double s, dis;
-  project_distance(m.cs[l], m.n_cs[l], px, py, s, dis);
-  const int sign = (dis > 0.0 && lv.side_of(s, px, py) > 0) ? 1 : -1;   // is_left_of: a point on the line is not left
-  const double d = sign > 0 ? dis : -dis;
-  const double s_new = s + v[i] * dt;
-  const double d_new = d + vy[i] * dt;
-  double v_new = v[i] + ax[i] * dt;
-  v_new = v_new > 0.0 ? v_new : 0.0;
-  const int k = lv.yaw_index(s_new);
-  double fx, fy;
-  lv.point_at(s_new, fx, fy);
-  x_out[i] = fx - d_new * m.csin[l][k];            // offset_point utility.py:83-85
-  y_out[i] = fy + d_new * m.ccos[l][k];
-  v_out[i] = v_new;
-  yaw_out[i] = m.cyaw[l][k];
+  int k;
+  step_along_path_fn(m, ref_lane[i], x[i], y[i], v[i], ax[i], vy[i], dt, x_out[i], y_out[i], v_out[i], k);
+  yaw_out[i] = m.cyaw[ref_lane[i]][k];
 }
 
-// ---- corridor.centerSimplified.signed_distance (type.py:307-315, behaviors.py:20) and Corridor.distance_to_corridor_end
-// (type.py:180-181) of n points, each on its own corridor ---------------------------------------------------------------
-__global__ void __launch_bounds__(kBT) env_center_kernel(const EnvMapBorder* __restrict__ gmap, const int32_t* __restrict__ lane,
-                                                         const double* __restrict__ x, const double* __restrict__ y, int n,
-                                                         double* __restrict__ d_out, double* __restrict__ end_out) {
-  __shared__ EnvMapBorder m;
-  stage(&m, gmap);
-  __syncthreads();
-  const int i = blockIdx.x * kBT + threadIdx.x;
-  if (i >= n) return;
-  const int l = lane[i];
-  const double px = x[i], py = y[i];
+__device__ __forceinline__ void center_distance_fn(const EnvMapBorder& m, int l, double px, double py, double& signed_d, double& to_end) {
   double s, dis;
   project_distance(m.cs[l], m.n_cs[l], px, py, s, dis);
   double d = 0.0;
@@ -399,8 +393,21 @@ __global__ void __launch_bounds__(kBT) env_center_kernel(const EnvMapBorder* __r
     LineView lv{m.cpath[l], m.cdis[l], m.n_center[l], m.cs_len[l]};
     d = lv.side_of(s, px, py) > 0 ? dis : -dis;
   }
-  d_out[i] = d;
-  end_out[i] = m.cs_len[l] - s;
+  signed_d = d;
+  to_end = m.cs_len[l] - s;
+}
+
+// ---- corridor.centerSimplified.signed_distance (type.py:307-315, behaviors.py:20) and Corridor.distance_to_corridor_end
+// (type.py:180-181) of n points, each on its own corridor ---------------------------------------------------------------
+static __global__ void __launch_bounds__(kBT) env_center_kernel(const EnvMapBorder* __restrict__ gmap, const int32_t* __restrict__ lane,
+                                                         const double* __restrict__ x, const double* __restrict__ y, int n,
+                                                         double* __restrict__ d_out, double* __restrict__ end_out) {
+  __shared__ EnvMapBorder m;
+  stage(&m, gmap);
+  __syncthreads();
+  const int i = blockIdx.x * kBT + threadIdx.x;
+  if (i >= n) return;
+  center_distance_fn(m, lane[i], x[i], y[i], d_out[i], end_out[i]);
 }
 
 // shapely: do the closed segments AB and CD share a point
@@ -429,20 +436,8 @@ __device__ __forceinline__ double seg_seg_distance(double ax, double ay, double 
   return best;
 }
 
-// ---- Corridor.distance_to_border(hull, direction) (type.py:183-206; environment.py:113-115 dis_to_lane_border):
-// < 0 = how far the hull has passed the border on that side, otherwise Polygon(hull).distance(border line) ------------
-__global__ void __launch_bounds__(kBT) env_border_kernel(const EnvMapBorder* __restrict__ gmap, const int32_t* __restrict__ lane,
-                                                         const int32_t* __restrict__ side, const double* __restrict__ hull, size_t row,
-                                                         int n, double* __restrict__ out) {
-  __shared__ EnvMapBorder m;
-  stage(&m, gmap);
-  __syncthreads();
-  const int i = blockIdx.x * kBT + threadIdx.x;
-  if (i >= n) return;
-  const int l = lane[i], sd = side[i];                       // 0 = "left", 1 = "right"
-  double hx[4], hy[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { hx[k] = hull[(size_t)(2 * k) * row + i]; hy[k] = hull[(size_t)(2 * k + 1) * row + i]; }
+// Corridor.distance_to_border(hull, direction) for one hull (corner order of vehicle_pose_to_rect); sd: 0 = "left", 1 = "right"
+__device__ __forceinline__ double border_distance_fn(const EnvMapBorder& m, int l, int sd, const double* hx, const double* hy) {
   const double (*simp)[2] = m.simp[sd][l];
   const int ns = m.n_simp[sd][l];
   LineView lv{m.path[sd][l], m.dis[sd][l], m.n_path[sd][l], m.simp_len[sd][l]};
@@ -458,13 +453,13 @@ __global__ void __launch_bounds__(kBT) env_border_kernel(const EnvMapBorder* __r
       worst = dis > worst ? dis : worst;
     }
   }
-  if (pass) { out[i] = -worst; return; }
+  if (pass) return -worst;
   // Polygon(hull).distance(LineString): 0 when a vertex of the line lies inside the hull, else the nearest edge pair
   double shell[4][2];
 #pragma unroll
   for (int k = 0; k < 4; ++k) { shell[k][0] = hx[k]; shell[k][1] = hy[k]; }
   for (int k = 0; k < ns; ++k)
-    if (within(shell, 4, simp[k][0], simp[k][1])) { out[i] = 0.0; return; }
+    if (within(shell, 4, simp[k][0], simp[k][1])) return 0.0;
   double best = 0.0;
   bool have = false;
   for (int e = 0; e < 4; ++e) {
@@ -474,9 +469,26 @@ __global__ void __launch_bounds__(kBT) env_border_kernel(const EnvMapBorder* __r
       if (!have || d < best) { best = d; have = true; }
     }
   }
-  out[i] = best;
+  return best;
 }
 
+
+
+// ---- Corridor.distance_to_border(hull, direction) (type.py:183-206; environment.py:113-115 dis_to_lane_border):
+// < 0 = how far the hull has passed the border on that side, otherwise Polygon(hull).distance(border line) ------------
+static __global__ void __launch_bounds__(kBT) env_border_kernel(const EnvMapBorder* __restrict__ gmap, const int32_t* __restrict__ lane,
+                                                         const int32_t* __restrict__ side, const double* __restrict__ hull, size_t row,
+                                                         int n, double* __restrict__ out) {
+  __shared__ EnvMapBorder m;
+  stage(&m, gmap);
+  __syncthreads();
+  const int i = blockIdx.x * kBT + threadIdx.x;
+  if (i >= n) return;
+  double hx[4], hy[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { hx[k] = hull[(size_t)(2 * k) * row + i]; hy[k] = hull[(size_t)(2 * k + 1) * row + i]; }
+  out[i] = border_distance_fn(m, lane[i], side[i], hx, hy);
+}
 
 // ---- mcs_wrapper.py:24-283 — the three builders of the inner simulator's scene, on the device ----------------------
 // One block per request.  Thread 0 walks the reference's selection logic over the resident match tables (the neighbour
@@ -710,7 +722,7 @@ __device__ __forceinline__ void build_scene_block(const EnvMapHead& H, const Env
 
 // one block per request: stage the map head, the request's scene tables and the current positions, then build
 // Dynamic shared memory: n x (8 arc + 8 x + 8 y + 4 lane + 4 order + 4 spare) bytes + 9 lane starts.
-__global__ void __launch_bounds__(128) env_build_kernel(const EnvMapHead* __restrict__ head, const EnvMapTail* __restrict__ tail,
+static __global__ void __launch_bounds__(128) env_build_kernel(const EnvMapHead* __restrict__ head, const EnvMapTail* __restrict__ tail,
                                                         const EnvMapBorder* __restrict__ border, const EnvLaneInfo* __restrict__ info,
                                                         int n, const int32_t* __restrict__ g_lane, const double* __restrict__ g_arc,
                                                         const int32_t* __restrict__ g_order, const int32_t* __restrict__ g_start,

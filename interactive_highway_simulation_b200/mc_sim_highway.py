@@ -17,7 +17,6 @@ Differences a caller can observe (all documented in DESIGN.md):
   * ``simulationMultiThreadBatch`` (extension) evaluates all candidate actions of one decision in a single launch.
 """
 import ctypes as _C
-import itertools as _it
 
 from . import _abi as _abi
 from . import backend as _backend
@@ -213,7 +212,7 @@ class StatusOneSim:
 # ------------------------------------------------------------------------------------------------ device plumbing
 _device = 0
 _seed_base = 1            # libc's default rand() state is srand(1); a fresh process is reproducible like the reference's
-_calls = _it.count()
+_calls = 0                # calls made since seed(): call k draws from the stream of seed _seed_base + k
 _cache = {"key": None, "scene": None}
 
 
@@ -221,7 +220,7 @@ def seed(s):
     """Fix the random stream of every following call (the reference never seeds libc rand())."""
     global _seed_base, _calls
     _seed_base = int(s) & 0xFFFFFFFFFFFFFFFF
-    _calls = _it.count()
+    _calls = 0
 
 
 def set_device(ordinal):
@@ -238,7 +237,20 @@ def _drop_cache():
 
 def _next_seed():
     # one seed per call; the candidates of a batch take consecutive seeds, exactly what mcs_rollouts gives them (seed + c)
-    return (_seed_base + next(_calls)) & 0xFFFFFFFFFFFFFFFF
+    global _calls
+    _calls += 1
+    return (_seed_base + _calls - 1) & 0xFFFFFFFFFFFFFFFF
+
+
+def _peek_seed():
+    """the seed the next call will take (the device-side walk of the outer step makes its laneChangeMobilBehavior calls with
+    consecutive seeds from here and reports how many it made: _advance_seeds)"""
+    return (_seed_base + _calls) & 0xFFFFFFFFFFFFFFFF
+
+
+def _advance_seeds(k):
+    global _calls
+    _calls += int(k)
 
 
 def _pack(map_, agents):

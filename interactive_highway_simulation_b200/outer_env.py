@@ -37,6 +37,42 @@ class BuildRequest(C.Structure):
                 ("ego_rss", C.c_double * 6), ("ego_yp", C.c_double * 7)]
 
 
+class WalkVehicle(C.Structure):
+    """mce_walk_vehicle"""
+    _fields_ = [("id", C.c_int32), ("behavior", C.c_int32), ("flags", C.c_int32), ("seed", C.c_int32),
+                ("commit", C.c_int32), ("keep_step", C.c_int32), ("target_lane", C.c_int32), ("yi_n", C.c_int32),
+                ("x", C.c_double), ("y", C.c_double), ("v", C.c_double), ("vy", C.c_double), ("a", C.c_double), ("yaw", C.c_double),
+                ("l", C.c_double), ("w", C.c_double), ("hull", C.c_double * 8), ("idm", C.c_double * 6), ("rss", C.c_double * 6),
+                ("mobil", C.c_double * 3), ("yp", C.c_double * 13), ("threshold", C.c_double), ("ax_last", C.c_double),
+                ("yi_id", C.c_int32 * 12), ("yi_yielding", C.c_int32 * 12), ("yi_p0", C.c_double * 12)]
+
+
+class WalkResult(C.Structure):
+    """mce_walk_result"""
+    _fields_ = [("stopped_at", C.c_int32), ("status", C.c_int32), ("noise_used", C.c_int32), ("mobil_calls", C.c_int32),
+                ("random_used", C.c_int32), ("random_seed", C.c_int32), ("moved", C.c_int32), ("reserved", C.c_int32)]
+
+
+WALK_BEHAVIORS = {"idm": 1, "idm_mobil_lane_change": 2, "idm_mobil_lane_change_safe": 3, "merging_closest_gap_policy": 4, "exit": 5}
+_random_first = None
+
+
+def random_first_table():
+    """random.seed(s); random.random() for s = 0..99 (every consumer of Python's `random` in the outer step re-seeds with
+    a vehicle's yielding seed and draws once: type.py:75-77, utility.py:136-138); the global stream is left untouched"""
+    global _random_first
+    if _random_first is None:
+        import random
+        state = random.getstate()
+        out = []
+        for s_ in range(100):
+            random.seed(s_)
+            out.append(random.random())
+        random.setstate(state)
+        _random_first = (C.c_double * 100)(*out)
+    return _random_first
+
+
 BUILD_MERGING, BUILD_EXIT, BUILD_LANE_CHANGE = 0, 1, 2
 MCE_BUILD_MAX_AGENTS = 48
 
@@ -69,6 +105,8 @@ def _lib():
         L.mce_center_distance.argtypes = [V, _pi, _pd, _pd, I, _pd, _pd]
         L.mce_border_distance.argtypes = [V, _pi, _pi, _pd, I, _pd]
         L.mce_map_set_lane_info.argtypes = [V, _pi, _pi, _pd, I]
+        L.mce_walk_step.argtypes = [V, C.POINTER(WalkVehicle), I, V, V, I, V, I, I, D, C.c_uint64, C.POINTER(WalkResult)]
+        L.mce_walk_step.restype = I
         L.mce_build_rollout_scene.argtypes = [V, C.POINTER(BuildRequest), V, V, V, I, V, C.POINTER(C.c_int32), V,
                                               C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), I, C.POINTER(V)]
         for f in ("mce_map_set_lane_info", "mce_build_rollout_scene", "mce_center_distance", "mce_border_distance", "mce_map_create", "mce_map_destroy", "mce_env_match", "mce_env_neighbors", "mce_frenet", "mce_project_center",
@@ -239,6 +277,14 @@ class DeviceMap:
         _check(_lib().mce_build_rollout_scene(self._h, request, ids, attrs, pn, nn, cs, nc, ag, na, acts, nact, device,
                                               C.byref(h) if scene else None))
         return cs, nc.value, ag, na.value, list(acts[:nact.value]), (h if scene else None)
+
+    def walk_step(self, vehicles, upload, ids_ptr, noise, first, last, dt, seed_base):
+        """mce_walk_step: the sequential plan-and-move walk over slots [first, last) on the device -> WalkResult"""
+        res = WalkResult()
+        pn, nn = (noise.ctypes.data, len(noise)) if noise is not None and len(noise) else (None, 0)
+        _check(_lib().mce_walk_step(self._h, vehicles, 1 if upload else 0, ids_ptr, pn, nn, C.addressof(random_first_table()),
+                                    first, last, float(dt), seed_base, C.byref(res)))
+        return res
 
     @staticmethod
     def create_scene(corridors, n_corridors, agents, n_agents, device=0):
@@ -447,6 +493,8 @@ class Environment:
         self.matched_agents = {}
         self.matched_agents_sorted_by_arc_length = {}
         self.sim_time = 0
+        self._walk = None
+        self._walk_objs = None
         self.match_agents_on_corridor()
 
     def match_agents_on_corridor(self):                      # environment.py:85-101 — one launch
@@ -466,6 +514,9 @@ class Environment:
                                [a.l for a in objs], [a.w for a in objs], [a.idm_param.vd for a in objs]], np.float64)
         self._ids_p, self._attr_p = self._ids.ctypes.data, self._attr.ctypes.data
         self._mirror_live = False
+        old = self._walk_objs
+        if old is None or len(old) != len(objs) or any(p is not q for p, q in zip(old, objs)):
+            self._walk = None                                 # the slots changed (first match, or a vehicle left the map)
         t = self._tables = self.map.device_map.match(self._x0, self._y0, 1, arc_on_lanes=True)
         for i, a in enumerate(objs):
             lane = int(t.lane[0, i])
@@ -659,8 +710,121 @@ class Environment:
         handle = self.map.device_map.create_scene(cs, nc, ag, na, self.map.device) if scene else None
         return cs, nc, ag, na, actions, handle
 
+    # ---- the sequential walk on the device (mce_walk_step, csrc/walk_kernel.cuh) ----
+    walk_on_device = True          # class-wide switch (tests compare both paths)
+
+    def _walk_record(self, rec, a):
+        from . import _abi as abi
+        ip, rp, mp = a.idm_param, a.rss_param, a.mobil_param
+        rec.id, rec.behavior = int(a.id), WALK_BEHAVIORS.get(a.behavior_model, 0)
+        rec.flags = (1 if "merging" in a.behavior_model else 0) | (2 if "exit" in a.behavior_model else 0)
+        rec.seed = int(a.random_yielding_seed)
+        rec.commit, rec.keep_step, rec.target_lane = abi.COMMITS[a.commit_lane_change], int(a.commit_keep_lane_step), int(a.target_lane_id)
+        rec.x, rec.y, rec.v, rec.vy, rec.a, rec.yaw, rec.l, rec.w = a.x, a.y, a.v, a.vy, a.a, a.yaw, a.l, a.w
+        rec.hull[:] = [c for p in a.hull for c in p]
+        rec.idm[:] = (ip.acc_max, ip.acc_min, ip.min_dis, ip.acc_com, ip.thw, ip.vd)
+        rec.rss[:] = (rp.r_t_ego, rp.r_t_other, rp.a_min, rp.a_max, rp.soft_acc, rp.soft_dcc)
+        rec.mobil[:] = (mp.politeness_factor, mp.delta_a, mp.bias_a)
+        rec.yp[:] = tuple(a.yielding_model.param)
+        rec.threshold = a.change_intention_threshold
+        held = list(a.yielding_intention_to_others.values())
+        if len(held) > 12 or rec.seed < 0 or rec.seed > 99:
+            rec.behavior = 0                                  # beyond what the kernel's tables hold: this vehicle stays on the host
+            held = []
+        rec.yi_n = len(held)
+        for k, it in enumerate(held):
+            rec.yi_id[k], rec.yi_yielding[k], rec.yi_p0[k] = int(it.id), 1 if it.yielding else 0, it.initial_probability
+
+    def _walk_array(self):
+        """The vehicles as mce_walk_vehicle records, slot order.  Built once per set of slots; afterwards the device hands the
+        moved records back every step, and a vehicle somebody else touched (host-planned, behaviour model changed, moved by
+        hand) is written again."""
+        objs = self._objs
+        if self._walk is None:
+            self._walk = (WalkVehicle * len(objs))()
+            for rec, a in zip(self._walk, objs):
+                self._walk_record(rec, a)
+            self._walk_objs = objs
+            self._walk_models = [a.behavior_model for a in objs]
+            return self._walk, True
+        stale = False
+        for i, a in enumerate(objs):
+            rec = self._walk[i]
+            if a.x != rec.x or a.y != rec.y or a.v != rec.v or a.behavior_model != self._walk_models[i]:
+                self._walk_record(rec, a)
+                self._walk_models[i] = a.behavior_model
+                stale = True
+        return self._walk, stale
+
+    def _walk_take(self, i):
+        """vehicle i as the device moved it -> the Python object (what Agent.step and lane_change_behavior_mobil leave behind)"""
+        from . import _abi as abi
+        from .type import YieldingIntention
+        rec, a = self._walk[i], self._objs[i]
+        a.x, a.y, a.v, a.yaw, a.a, a.vy = rec.x, rec.y, rec.v, rec.yaw, rec.a, rec.vy
+        a.acceleration_history.append(a.a)
+        h = rec.hull
+        a.hull = [[h[0], h[1]], [h[2], h[3]], [h[4], h[5]], [h[6], h[7]]]
+        a.state_history.append([a.x, a.y, a.v, a.a])
+        a.commit_lane_change, a.commit_keep_lane_step, a.target_lane_id = abi.COMMIT_NAMES[rec.commit], rec.keep_step, rec.target_lane
+        if rec.yi_n or a.yielding_intention_to_others:
+            held = {}
+            for k in range(rec.yi_n):
+                it = YieldingIntention.__new__(YieldingIntention)
+                it.id, it.initial_probability, it.change_intention_threshold = rec.yi_id[k], rec.yi_p0[k], a.change_intention_threshold
+                it.yielding = bool(rec.yi_yielding[k])
+                held[it.id] = it
+            a.yielding_intention_to_others = held
+        at = self._attr
+        at[0, i] = a.x; at[1, i] = a.y; at[2, i] = a.v; at[3, i] = a.vy; at[4, i] = a.a
+
+    def _step_walk(self, dt):
+        """environment.py:316-323 with the walk on the device: one launch per run of device-plannable vehicles; a vehicle that
+        needs the host (learned behaviours: their rollouts are launches of their own) is planned and moved by the Python
+        path in between, exactly in its turn.  The three host random streams end up where the reference leaves them."""
+        import random
+        from . import mc_sim_highway as ms
+        objs, n = self._objs, len(self._objs)
+        lanes = self._tables.lane[0]
+        self._mirror()
+        self._mirror_live = True
+        try:
+            first = 0
+            while first < n:
+                vehicles, upload = self._walk_array()
+                state = np.random.get_state()
+                noise = np.random.normal(0., 1, min(4096, 48 * (n - first)))
+                res = self.map.device_map.walk_step(vehicles, upload, self._ids_p, noise, first, n, dt, ms._peek_seed())
+                np.random.set_state(state)
+                if res.status:
+                    raise EnvError(-3 if res.status in (101, 300) else -1, "device walk of the outer step failed (status %d)" % res.status)
+                if res.noise_used:
+                    np.random.normal(0., 1, res.noise_used)
+                if res.random_used:
+                    random.seed(res.random_seed)
+                    random.random()
+                ms._advance_seeds(res.mobil_calls)
+                stop = res.stopped_at if res.stopped_at >= 0 else n
+                for i in range(first, stop):
+                    if lanes[i] >= 0:
+                        self._walk_take(i)
+                if stop < n:                                  # this vehicle's plan needs the host
+                    a = objs[stop]
+                    a.step(a.plan(self), dt)
+                    i, at = stop, self._attr
+                    at[0, i] = a.x; at[1, i] = a.y; at[2, i] = a.v; at[3, i] = a.vy; at[4, i] = a.a
+                first = stop + 1
+            for a in list(self.agents.values()):
+                self.set_flag(a)
+        finally:
+            self._mirror_live = False
+        self.match_agents_on_corridor()
+        self.sim_time += dt
+
     def step(self, dt):                                      # environment.py:316-323
         """Plan and move the vehicles one after the other against the lane vectors of the last match, then re-match."""
+        if self.walk_on_device and self._tables is not None and hasattr(self.map.device_map, "walk_step"):
+            return self._step_walk(dt)
         self._mirror()
         self._mirror_live = True
         try:

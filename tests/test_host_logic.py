@@ -205,3 +205,28 @@ def test_corridor_host_values_and_statistics_trimming():
     st.remove_invalid_data([1])
     # the reference ranges every later list over the ALREADY shortened utility_ego: one sample removed, one more cut off the end
     assert st.utility_ego == [1, 3, 4] and st.comfort_ego == [5, 7] and st.epoch_and_ego_id_history == [[0, 1], [0, 3]]
+
+
+def test_hash_iteration_order_restatement_equals_the_container(backend_lib):
+    """csrc/walk_kernel.cuh restates the list / bucket discipline of libstdc++'s std::unordered_map<int, T> for the device
+    (visit order of the inner simulator's agents and corridors); scene.cpp uses the container itself.  Same order for random
+    id sets of every size up to 64 (bucket growth 13 -> 29 -> 59 -> 127), colliding and negative ids included."""
+    from interactive_highway_simulation_b200 import backend
+    lib = backend_lib.lib()
+    lib.mce_hash_iteration_order.restype = C.c_int
+    rng = random.Random(11)
+    cs = (abi.Corridor * 1)()
+    cs[0].id = 1; cs[0].type = 0
+    cs[0].left[:] = [-1000, 3.5, 5000, 3.5]; cs[0].right[:] = [-1000, 0, 5000, 0]; cs[0].center[:] = [-1000, 1.75, 5000, 1.75]
+    for n in list(range(1, 65)) + [13, 14, 29, 30, 59, 60]:
+        for pool in (range(0, 70), range(0, 400), range(-200, 2000), [13 * k for k in range(200)]):
+            ids = rng.sample(list(pool), n)
+            arr = (C.c_int32 * n)(*ids)
+            got = (C.c_int32 * n)()
+            assert lib.mce_hash_iteration_order(arr, n, got) == 0
+            agents = (abi.Agent * n)()
+            for k, a in enumerate(agents):
+                a.id = ids[k]; a.x = 10.0 * k; a.y = 1.0; a.l = 4.8; a.w = 2.0; a.v = 10.0; a.vd = 12.0
+                a.idm[:] = (1.6, 2.0, -3.0, -2.0, -8.0, 1.2); a.rss[:] = (0.7, 0.4, -6.0, -6.0, 1.8, 1.2)
+            want = backend.prepare_host(cs, agents)["agent_order"]
+            assert list(got) == want, (n, ids)
