@@ -567,7 +567,8 @@ int mce_walk_step(mce_map* m, mce_walk_vehicle* vehicles, int upload, const int3
   mcw::WalkParams wp;
   wp.first = first; wp.last = last; wp.scene = 0; wp.dt = dt; wp.seed_base = seed_base; wp.n_noise = n_noise;
   constexpr int decide_bytes = 11808;      // rollout_kernel's shared-memory region of a 64-slot rollout without histories (capi.cu)
-  const size_t smem = ((sizeof(mcw::WalkShared) + 15) & ~size_t(15)) + decide_bytes + (size_t)n * 36 + 64;
+  const size_t smem = ((sizeof(mcw::WalkShared) + 15) & ~size_t(15)) + decide_bytes + (size_t)n * 224 + 128;
+  if (smem > 200 * 1024) return efail(MCE_ERR_CAPACITY, "too many vehicles for the device walk's shared-memory tables");
   ENV_TRY(cudaFuncSetAttribute(mcw::walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mcw::walk_kernel<<<1, 128, smem, s>>>(m->d_head, m->d_tail, m->d_border, m->d_info, n, m->d_lane, m->d_arc, m->d_order, m->d_start,
                                         reinterpret_cast<mcw::WalkVehicle*>(m->d_walk), reinterpret_cast<const int32_t*>(m->d_walk + o_ids),

@@ -523,6 +523,7 @@ __device__ __forceinline__ void to_frenet(const EnvMapTail& t, int ref_lane, dou
 // lines — which run at shared-memory latency there); attrs [8][n] / ids: global; out: global or shared.
 struct BuildScratch {
   int item_slot[kBuildMaxAgents], item_beh[kBuildMaxAgents];
+  double item_arc[kBuildMaxAgents];
   int corr_lane[MCE_MAX_LANES];
   int n_items, n_corr, n_act, status, ref_lane;
   int acts[4];
@@ -530,12 +531,23 @@ struct BuildScratch {
   double cs[MCE_MAX_LANES][6], cd[MCE_MAX_LANES][6];
 };
 
+// What a caller that walks the vehicles one after the other (walk_kernel.cuh) keeps per vehicle, so that the selection does
+// not project again what it projected for another vehicle: the neighbour row and the arc length on the own lane at the
+// vehicle's CURRENT position; stale bit 1 (row) / 4 (arc) = the vehicle has moved since: compute, store, clear.
+struct BuildCache {
+  int32_t* nb_idx;      // [n][MCE_NEIGHBORS]
+  double* nb_dis;       // [n][MCE_NEIGHBORS]
+  double* arc_now;      // [n]
+  int32_t* stale;       // [n]
+};
+
 __device__ __forceinline__ void build_scene_block(const EnvMapHead& H, const EnvMapTail* __restrict__ tail,
                                                   const EnvMapBorder* __restrict__ border, const EnvLaneInfo* __restrict__ info, int n,
                                                   const int32_t* lane, const double* arc, const int32_t* order, const int32_t* start,
                                                   const double* ax, const double* ay, const mce_build_request& rq,
                                                   const int32_t* __restrict__ ids, const double* __restrict__ attrs,
-                                                  const double* __restrict__ noise, int n_noise, BuildScratch& w, BuildOut& out) {
+                                                  const double* __restrict__ noise, int n_noise, BuildScratch& w, BuildOut& out,
+                                                  const BuildCache* cache = nullptr) {
   int (&item_slot)[kBuildMaxAgents] = w.item_slot;
   int (&item_beh)[kBuildMaxAgents] = w.item_beh;
   int (&corr_lane)[MCE_MAX_LANES] = w.corr_lane;
@@ -557,6 +569,17 @@ __device__ __forceinline__ void build_scene_block(const EnvMapHead& H, const Env
     auto gap = [&](int slot) { if (slot >= 0 && n_act < 4) acts[n_act++] = ids[slot]; };
     // sorted_agents_on_corridor_within_range_of_vehicle (environment.py:145-156): the vehicles matched on lane l whose arc
     // length on that lane's centre line is within 80 m of the ego's, by arc length (ties in dict order)
+    auto row_of = [&](int slot, int* idx, double* dis) {     // neighbor_row at the vehicle's current position
+      if (cache && !(cache->stale[slot] & 1)) {
+        for (int k = 0; k < MCE_NEIGHBORS; ++k) { idx[k] = cache->nb_idx[slot * MCE_NEIGHBORS + k]; dis[k] = cache->nb_dis[slot * MCE_NEIGHBORS + k]; }
+        return;
+      }
+      neighbor_row(H, n, lane, arc, order, start, 0, slot, ax[slot], ay[slot], idx, dis);
+      if (cache) {
+        for (int k = 0; k < MCE_NEIGHBORS; ++k) { cache->nb_idx[slot * MCE_NEIGHBORS + k] = idx[k]; cache->nb_dis[slot * MCE_NEIGHBORS + k] = dis[k]; }
+        cache->stale[slot] &= ~1;
+      }
+    };
     auto within_range = [&](int l, int beh) {
       double e, d;
       project_distance(H.center[l], H.n_center[l], ax[ego], ay[ego], e, d);
@@ -564,25 +587,26 @@ __device__ __forceinline__ void build_scene_block(const EnvMapHead& H, const Env
       for (int j = 0; j < n; ++j) {
         if (lane[j] != l) continue;
         double a;
-        project_distance(H.center[l], H.n_center[l], ax[j], ay[j], a, d);
+        if (cache && !(cache->stale[j] & 4)) a = cache->arc_now[j];
+        else {
+          project_distance(H.center[l], H.n_center[l], ax[j], ay[j], a, d);
+          if (cache) { cache->arc_now[j] = a; cache->stale[j] &= ~4; }
+        }
         if (!(fabs(a - e) <= 80.0)) continue;
         if (n_items >= kBuildMaxAgents - 1) { status = 1; return; }
         // insertion by arc length, stable
         int p = n_items;
-        while (p > first) {
-          double ap;
-          project_distance(H.center[l], H.n_center[l], ax[item_slot[p - 1]], ay[item_slot[p - 1]], ap, d);
-          if (!(ap > a)) break;
-          item_slot[p] = item_slot[p - 1]; item_beh[p] = item_beh[p - 1]; --p;
+        while (p > first && w.item_arc[p - 1] > a) {
+          item_slot[p] = item_slot[p - 1]; item_beh[p] = item_beh[p - 1]; w.item_arc[p] = w.item_arc[p - 1]; --p;
         }
-        item_slot[p] = j; item_beh[p] = beh; n_items++;
+        item_slot[p] = j; item_beh[p] = beh; w.item_arc[p] = a; n_items++;
       }
     };
     if (ego_lane < 0) status = 3;
     else {
       int idx[MCE_NEIGHBORS];
       double dis[MCE_NEIGHBORS];
-      neighbor_row(H, n, lane, arc, order, start, 0, ego, ax[ego], ay[ego], idx, dis);
+      row_of(ego, idx, dis);
       if (rq.kind == 0) {                                   // merging_mcs_sim_from_env, mcs_wrapper.py:24-75
         const int left = H.left[ego_lane];
         if (left < 0) status = 2;
@@ -609,7 +633,7 @@ __device__ __forceinline__ void build_scene_block(const EnvMapHead& H, const Env
           int i2[MCE_NEIGHBORS];
           double d2[MCE_NEIGHBORS];
           const int f = idx[MCE_FRONT];
-          neighbor_row(H, n, lane, arc, order, start, 0, f, ax[f], ay[f], i2, d2);
+          row_of(f, i2, d2);
           if (i2[MCE_FRONT] >= 0) add(i2[MCE_FRONT], MCS_BEH_IDM_LC);
         }
         if (idx[MCE_BACK] >= 0) add(idx[MCE_BACK], MCS_BEH_IDM_LC);
