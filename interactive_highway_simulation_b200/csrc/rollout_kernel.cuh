@@ -736,6 +736,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
     double centerY = 0.0, vLimit = 0.0;
     int ycand[5];
     int nY = 0;
+    if (tid == 0) s.flags[1] = 0;     // the movers' queue of this step's lane match (its last reader was before the step's end)
     if (hasLane) {
       const LaneDev& L = sc.lanes[lane];
       centerY = L.centerY; vLimit = L.vLimit;
@@ -959,15 +960,24 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
       if (isEgo && lane >= 0 && s.flags[0] == 0) s.flags[0] = sc.lanes[lane].id == targetLane ? 1 : 0;
     }
     if (kMerge && isEgo) s.flags[2] = beh;
-    // one barrier publishes the new x / v / lane and the ego's arrival, and tells whether any membership changed
+    if (live && lane != laneBefore) {
+      // a mover queues itself for the splice below: slot, old position, old lane, new lane
+      const int slot = atomicAdd(&s.flags[1], 1);
+      s.tasks[slot] = k | (laneBefore >= 0 ? myPos : 0) << 8 | (laneBefore < 0 ? 0xff : laneBefore) << 16 | (lane < 0 ? 0xff : lane) << 24;
+    }
+    // one barrier publishes the new x / v / lane, the movers' queue and the ego's arrival, and tells whether any membership changed
     const int anyChanged = sub_sync_or<NPS, G == 1>(sub, changed ? 1 : 0);
     const bool egoReached = s.flags[0] != 0;
     if (anyChanged) {
       // The reference rebuilds every lane vector (members in visit order) and std::sorts it by x (0x10be30-0x10c1a5):
       // the result is "members ordered by (x, slot)".  Vehicles that kept their lane are already in that order unless
       // two of them passed through each other since the last rebuild, so the usual case only has to splice the few
-      // movers in: rank = old rank - leavers ahead + arrivals ahead.  An order inversion anywhere falls back to ranking
-      // every vehicle against every other one.
+      // movers (queued above) in.  In the coordinates of the old concatenated vector a mover is two events: it leaves
+      // position q (everything behind q moves up one) and it is inserted in front of position `ins` of its new lane's
+      // old vector (everything from `ins` on moves back one).  The movers' searches run on the first threads of the
+      // rollout side by side (one mover per thread, not one divergent search per warp that owns a mover); every other
+      // vehicle adds up the events in front of it: integer compares only.  An order inversion anywhere falls back to
+      // ranking every vehicle against every other one.
       const int newLane = live ? (int)s.lane[k] : 0xff;
       const int oldL = laneBefore < 0 ? 0xff : laneBefore;
       const bool inVec = live && oldL != 0xff;
@@ -978,11 +988,33 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
         const double xp = s.x[pj];
         inversion = xp > x || (xp == x && pj > k);
       }
-      if (k == 0) s.flags[1] = 0;
+      const int nm = s.flags[1];
+      int* ev = (int*)s.mob;        // [np] event words of the movers (the MOBIL results were consumed in part B)
+      int myIns = 0xffff, myRec = 0;
+      if (tid < nm) {
+        myRec = s.tasks[tid];
+        const int mk = myRec & 0xff, mpos = myRec >> 8 & 0xff, mold = myRec >> 16 & 0xff, mnew = myRec >> 24 & 0xff;
+        if (mnew != 0xff) {
+          // members of the destination lane with a smaller (x, slot) key: binary search in its (ordered) old vector
+          const int lo = laneStart[mnew], cntL = laneStart[mnew + 1] - lo;
+          const double xm = s.x[mk];
+          int first = 0, len = cntL;
+          while (len > 0) {
+            const int half = len >> 1, mid = first + half;
+            const int j = s.vec[lo + mid];
+            const double xj = s.x[j];
+            if (xj < xm || (xj == xm && j < mk)) { first = mid + 1; len = len - half - 1; }
+            else len = half;
+          }
+          myIns = lo + first;
+        }
+        ev[tid] = (mold != 0xff ? mpos + 1 : 0xffff) | myIns << 16;
+      }
       if (k < MCS_MAX_LANES + 1) s.scan[16 + k] = 0;
       const int anyInv = sub_sync_or<NPS, G == 1>(sub, inversion ? 1 : 0);
-      int rank = 0;
+      int* nextStart = laneStart == s.cnt ? s.cnt + 16 : s.cnt;
       if (anyInv) {
+        int rank = 0;
         if (newLane != 0xff) {
           for (int j = 0; j < n; ++j) {
             const double xj = s.x[j];
@@ -990,60 +1022,70 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
           }
           atomicAdd(&s.scan[16 + newLane], 1);
         }
-      } else {
-        if (mover) {
-          const int slot = atomicAdd(&s.flags[1], 1);
-          s.tasks[slot] = k | (inVec ? myPos : 0) << 8 | oldL << 16 | newLane << 24;
-        }
         sub_sync<NPS, G == 1>(sub);
-        const int nm = s.flags[1];
-        if (!mover && inVec) {
-          rank = myPos - laneStart[oldL];
-          for (int q = 0; q < nm; ++q) {
-            const int rec = s.tasks[q];
-            const int mk = rec & 0xff, mpos = rec >> 8 & 0xff, mold = rec >> 16 & 0xff, mnew = rec >> 24 & 0xff;
-            if (mold == oldL && mpos < myPos) rank--;
-            if (mnew == oldL) { const double xm = s.x[mk]; rank += (xm < x || (xm == x && mk < k)) ? 1 : 0; }
-          }
-        } else if (mover && newLane != 0xff) {
-          // members of the destination lane with a smaller (x, slot) key: binary search in its (ordered) old vector
-          const int lo = laneStart[newLane], cntL = laneStart[newLane + 1] - lo;
-          int first = 0, len = cntL;
-          while (len > 0) {
-            const int half = len >> 1, mid = first + half;
-            const int j = s.vec[lo + mid];
-            const double xj = s.x[j];
-            if (xj < x || (xj == x && j < k)) { first = mid + 1; len = len - half - 1; }
-            else len = half;
-          }
-          rank = first;
-          for (int q = 0; q < nm; ++q) {
-            const int rec = s.tasks[q];
-            const int mk = rec & 0xff, mpos = rec >> 8 & 0xff, mold = rec >> 16 & 0xff, mnew = rec >> 24 & 0xff;
-            if (mold == newLane && mpos < lo + first) rank--;
-            if (mnew == newLane && mk != k) { const double xm = s.x[mk]; rank += (xm < x || (xm == x && mk < k)) ? 1 : 0; }
-          }
-        }
-        if (newLane != 0xff && (mover || !inVec)) atomicAdd(&s.scan[16 + newLane], 1);      // arrivals
-        if (mover && inVec) atomicSub(&s.scan[16 + oldL], 1);                               // leavers
-      }
-      sub_sync<NPS, G == 1>(sub);
-      // every thread derives the new lane starts itself (≤ 8 lanes) and places its vehicle; the shared copy goes to the
-      // other buffer, so one barrier publishes the vectors and the starts together
-      int* nextStart = laneStart == s.cnt ? s.cnt + 16 : s.cnt;
-      {
+        // every thread derives the new lane starts itself (≤ 8 lanes) and places its vehicle; the shared copy goes to the
+        // other buffer, so one barrier publishes the vectors and the starts together
         int run = 0, myStart = 0;
         for (int j = 0; j < sc.n_lanes; ++j) {
-          const int c = anyInv ? s.scan[16 + j] : (laneStart[j + 1] - laneStart[j]) + s.scan[16 + j];
+          const int c = s.scan[16 + j];
           if (j == newLane) myStart = run;
           if (k == 0) nextStart[j] = run;
           run += c;
         }
         if (k == 0) nextStart[sc.n_lanes] = run;
         if (newLane != 0xff) { myPos = myStart + rank; s.vec[myPos] = (uint8_t)k; }
+      } else {
+        if (inVec && !mover) {
+          int d = 0;
+#pragma unroll 1
+          for (int q = 0; q < nm; ++q) {
+            const int e = ev[q];
+            d += ((e >> 16) <= myPos ? 1 : 0) - ((e & 0xffff) <= myPos ? 1 : 0);
+          }
+          myPos += d;
+          s.vec[myPos] = (uint8_t)k;
+        }
+        if (tid < nm && myIns != 0xffff) {
+          // the mover this thread looks after: its own removal and the other movers' events in front of its insertion point;
+          // arrivals at the same point go by (new lane, x, slot) — a lane's end is the next lane's start
+          const int mk = myRec & 0xff, mnew = myRec >> 24 & 0xff;
+          const double xm = s.x[mk];
+          int pos = myIns;
+#pragma unroll 1
+          for (int q = 0; q < nm; ++q) {
+            const int e = ev[q];
+            pos -= (e & 0xffff) <= myIns ? 1 : 0;
+            const int insq = e >> 16;
+            if (q == tid || insq > myIns) continue;
+            bool ahead = insq < myIns;
+            if (!ahead) {
+              const int rq = s.tasks[q];
+              const int qk = rq & 0xff, qnew = rq >> 24 & 0xff;
+              if (qnew != mnew) ahead = qnew < mnew;
+              else { const double xq = s.x[qk]; ahead = xq < xm || (xq == xm && qk < mk); }
+            }
+            pos += ahead ? 1 : 0;
+          }
+          s.vec[pos] = (uint8_t)mk;
+          s.pos[mk] = (uint8_t)pos;
+        }
+        // new lane starts: old start + arrivals into - departures from the lanes in front (a few threads of the second warp,
+        // next to the movers' threads of the first)
+        constexpr int kStartBase = NPS >= 64 ? 32 : 0;
+        if (tid >= kStartBase && tid <= kStartBase + sc.n_lanes) {
+          const int j = tid - kStartBase;
+          int st = laneStart[j];
+#pragma unroll 1
+          for (int q = 0; q < nm; ++q) {
+            const int rq = s.tasks[q];
+            st += ((rq >> 24 & 0xff) < j ? 1 : 0) - ((rq >> 16 & 0xff) < j ? 1 : 0);
+          }
+          nextStart[j] = st;
+        }
       }
       laneStart = nextStart;
       sub_sync<NPS, G == 1>(sub);
+      if (!anyInv && mover && newLane != 0xff) myPos = s.pos[k];
     }
     // ================= termination (0x10edd0-0x10ee10) =================
     const int gapSlot = (kMerge && isEgo) ? s.flags[4] : -1;
