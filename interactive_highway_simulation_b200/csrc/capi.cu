@@ -26,7 +26,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
   } while (0)
 
 size_t rollout_smem_bytes(int n_pad, int steps) {
-  size_t doubles = (size_t)n_pad * (4 + 6 + 6 + 3 + 2) + 4 * (size_t)((steps + 2) & ~1) + 16;
+  size_t doubles = (size_t)n_pad * (4 + 6 + 6 + 3 + 2) + 4 * (size_t)((steps + 2) & ~1) + 16 + 4;
   size_t ints = 32 + 32 + 8 + (size_t)n_pad;
   return doubles * 8 + ints * 4 + 5 * (size_t)n_pad;
 }
@@ -236,7 +236,8 @@ int stage_candidates(mcs_scene* sc, const mcs_candidate* cands, int n_cand, int*
 // on the merging lane, yielding ones next to it, plain IDM / MOBIL elsewhere) — neighbouring pieces are merged,
 // smallest combined size first, until the pieces fit the warps, and every piece starts on a warp boundary.  Divergent
 // behaviour code then runs on different warps side by side instead of in series inside one warp.
-void thread_slots(const mcs::SceneHost& h, int pad, unsigned char* out) {
+// `reserve` threads at the end of the rollout carry no vehicle (the ego's helper warp of rollout_kernel<..., kHelper>).
+void thread_slots(const mcs::SceneHost& h, int pad, unsigned char* out, int reserve = 0) {
   struct Piece { int first, count; };
   std::vector<Piece> pieces;
   for (int k = 0; k < h.n; ++k) {
@@ -244,7 +245,7 @@ void thread_slots(const mcs::SceneHost& h, int pad, unsigned char* out) {
     const bool cut = pieces.empty() || lane != h.i[(size_t)mcs::I_LANE * h.n_pad + k - 1] || pieces.back().count == 32;
     if (cut) pieces.push_back(Piece{k, 1}); else pieces.back().count++;
   }
-  const int warps = pad / 32;
+  const int warps = (pad - reserve) / 32;
   auto need = [&]() { int w = 0; for (const Piece& p : pieces) w += (p.count + 31) / 32; return w; };
   while (pieces.size() > 1 && need() > warps) {
     size_t best = 0;
@@ -313,7 +314,7 @@ int upload_scene(mcs_scene* sc, int pad, int slot_table = 0) {
     memcpy(c->h_stage + bf + bi, h.lane_vec.data(), (size_t)h.n_pad);
   }
   if (slot_table == 1) bundle_slots(h, pad, c->h_stage + bf + bi + ((bv + 15) & ~(size_t)15));
-  else thread_slots(h, pad, c->h_stage + bf + bi + ((bv + 15) & ~(size_t)15));
+  else thread_slots(h, pad, c->h_stage + bf + bi + ((bv + 15) & ~(size_t)15), slot_table == 2 ? 32 : 0);
   if (total > sc->blob_cap) {
     if (sc->d_blob) CUDA_TRY(cudaFreeAsync(sc->d_blob, c->stream));
     sc->d_blob = nullptr; sc->blob_cap = 0; sc->dev.n_pad = 0;
@@ -386,15 +387,27 @@ int rollout_threads(const mcs_scene* sc, long long rollouts, bool traj, bool mer
 template <bool kMerge, int NPS>
 struct BlockThreads { static constexpr int value = NPS == 256 ? (kMerge ? MCS_FULL_MERGE_BLOCK : MCS_FULL_LC_BLOCK) : (kMerge && NPS == 128 ? MCS_HALF_MERGE_BLOCK : (kMerge && NPS >= 64 ? MCS_QUARTER_MERGE_BLOCK : 256)); };
 
-template <bool kTraj, bool kMerge, int NPS, int BT>
+// The ego's helper warp (rollout_kernel<..., kHelper>): merging / exit launches whose rollouts are 128 or 256 threads wide and
+// leave the last warp free (64-thread rollouts share blocks of 8 or 14: two named barriers per rollout do not fit the 16 of a
+// block).  MCS_NO_HELPER=1 switches it off (tests run both ways; the records are identical).
+bool wants_helper(const mcs_scene* sc, int pad, bool traj, bool merge) {
+  if (!merge || traj || pad < 128 || sc->host.n > pad - 32) return false;
+  if (const char* e = getenv("MCS_NO_HELPER")) if (atoi(e)) return false;
+  return true;
+}
+
+template <bool kTraj, bool kMerge, int NPS, int BT, bool kHelper = false>
 int launch_bt(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& lp) {
+  if constexpr (!kHelper && !kTraj && kMerge && NPS >= 128) {
+    if (sc->slot_table == 2) return launch_bt<kTraj, kMerge, NPS, BT, true>(sc, grid, region, lp);
+  }
   constexpr int G = BT / NPS;       // rollouts per thread block
   static_assert(G >= 1 && G <= 15, "one named barrier per rollout of a block");
   const size_t smem = region * G;
   if (smem > sc->ctx->smem_per_block) return fail(MCS_ERR_CAPACITY, "horizon too long: one rollout's histories do not fit shared memory");
   grid.x = (grid.x + G - 1) / G;
-  CUDA_TRY(cudaFuncSetAttribute(mcs::rollout_kernel<kTraj, kMerge, NPS, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mcs::rollout_kernel<kTraj, kMerge, NPS, BT><<<grid, dim3(BT), smem, sc->ctx->stream>>>(sc->dev, sc->ctx->d_cand, lp, (int)region);
+  CUDA_TRY(cudaFuncSetAttribute(mcs::rollout_kernel<kTraj, kMerge, NPS, BT, kHelper>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mcs::rollout_kernel<kTraj, kMerge, NPS, BT, kHelper><<<grid, dim3(BT), smem, sc->ctx->stream>>>(sc->dev, sc->ctx->d_cand, lp, (int)region);
   CUDA_TRY(cudaGetLastError());
   return MCS_OK;
 }
@@ -524,7 +537,10 @@ int launch_rollouts(mcs_scene* sc, int n_cand, const mcs_sim_param* sp, uint64_t
     CUDA_TRY(cudaMemcpyAsync(&sc->ctx->h_small->err, sc->ctx->d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, sc->ctx->stream));
     return MCS_OK;
   }
-  rc = upload_scene(sc, rollout_threads(sc, (long long)count * n_cand, d_traj != nullptr, merge != 0));
+  {
+    const int pad = rollout_threads(sc, (long long)count * n_cand, d_traj != nullptr, merge != 0);
+    rc = upload_scene(sc, pad, wants_helper(sc, pad, d_traj != nullptr, merge != 0) ? 2 : 0);
+  }
   if (rc != MCS_OK) return rc;
   size_t smem = (rollout_smem_bytes(sc->dev.n_pad, sp->steps) + 15) & ~(size_t)15;   // one rollout's region
   dim3 grid((unsigned)count, (unsigned)n_cand);

@@ -566,7 +566,7 @@ int mce_walk_step(mce_map* m, mce_walk_vehicle* vehicles, int upload, const int3
   }
   mcw::WalkParams wp;
   wp.first = first; wp.last = last; wp.scene = 0; wp.dt = dt; wp.seed_base = seed_base; wp.n_noise = n_noise;
-  constexpr int decide_bytes = 11808;      // rollout_kernel's shared-memory region of a 64-slot rollout without histories (capi.cu)
+  constexpr int decide_bytes = 11840;      // rollout_kernel's shared-memory region of a 64-slot rollout without histories (capi.cu)
   const size_t smem = ((sizeof(mcw::WalkShared) + 15) & ~size_t(15)) + decide_bytes + (size_t)n * 224 + 128;
   if (smem > 200 * 1024) return efail(MCE_ERR_CAPACITY, "too many vehicles for the device walk's shared-memory tables");
   ENV_TRY(cudaFuncSetAttribute(mcw::walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -103,6 +103,7 @@ struct Smem {
   double* vhist;   // [steps+2] ego speed history, turned into per-state utilities at the end
   double* thist;   // [steps+2] ego thwRatioHistory
   double* red;     // [16] reduction scratch
+  double* ego;     // [4] helper-warp hand-over: the ego's y; its planned ax, vy and "a lane on that side exists" (kHelper)
   int* scan;       // [32] warp totals of the two per-step scans (8 + 8), lane counters of the re-ranking (16..)
   int* cnt;        // [2][16] lane starts, double-buffered across rebuilds
   int* flags;      // [8] per-rollout scalars: 0 ego reached its target lane, 1 movers queued, 2 ego behaviour, 3 thw samples,
@@ -136,6 +137,7 @@ __device__ __forceinline__ void carve_smem(Smem& s, unsigned char* p, int np, in
   s.rss = (double*)p; p += sizeof(double) * 3 * np;
   s.acc = (double*)p; p += sizeof(double) * 2 * np;
   s.red = (double*)p; p += sizeof(double) * 16;
+  s.ego = (double*)p; p += sizeof(double) * 4;
   s.scan = (int*)p; p += sizeof(int) * 32;
   s.cnt = (int*)p; p += sizeof(int) * 32;
   s.flags = (int*)p; p += sizeof(int) * 8;
@@ -555,11 +557,19 @@ __device__ __forceinline__ int sub_sync_or(int sub, int pred) {
   return r;
 }
 
+// Barrier of a rollout's working threads when its last warp is the ego's helper (kHelper: NPS - 32 threads, ids behind the
+// G full-rollout barriers); the plain rollout barrier otherwise.
+template <int NPS, bool kWholeBlock, bool kHelper, int G>
+__device__ __forceinline__ void work_sync(int sub) {
+  if (!kHelper) sub_sync<NPS, kWholeBlock>(sub);
+  else asm volatile("bar.sync %0, %1;" ::"r"(G + 1 + sub), "n"(NPS - 32) : "memory");
+}
+
 // exclusive scan over the NPS threads of one rollout of small per-thread counts (< 2^BITS): one warp vote per bit.
 // `flag` is OR-ed over the rollout and comes back in bit 16 of `total`.
-template <int NPS, bool kWholeBlock, int BITS>
+template <int NPS, bool kWholeBlock, int BITS, bool kHelper = false, int G = 1>
 __device__ __forceinline__ int block_exclusive_scan_small(int v, bool flag, int* scratch, int& total, int k, int sub) {
-  constexpr int NW = NPS / 32;
+  constexpr int NW = NPS / 32 - (kHelper ? 1 : 0);
   const int lane = k & 31, w = k >> 5;
   const unsigned below = (1u << lane) - 1u;
   int excl = 0, wtot = 0;
@@ -571,7 +581,7 @@ __device__ __forceinline__ int block_exclusive_scan_small(int v, bool flag, int*
   }
   if (__any_sync(0xffffffffu, flag)) wtot |= 1 << 16;
   if (lane == 0) scratch[w] = wtot;
-  sub_sync<NPS, kWholeBlock>(sub);
+  work_sync<NPS, kWholeBlock, kHelper, G>(sub);
   int base = 0, tot = 0;
 #pragma unroll
   for (int q = 0; q < NW; ++q) {
@@ -590,7 +600,10 @@ namespace mcs {
 
 // kMerge: the scene has a merging/exit lane or vehicle, or a candidate names a gap — yielding intentions and the gap
 // behaviours are compiled in.  The plain lane-change instantiation carries none of their registers.
-template <bool kTraj, bool kMerge, int NPS, int BT>
+// kHelper: the rollout's last warp carries no vehicles (the host's thread -> slot table leaves it empty) and runs the ego's
+// gap execution — customizedMergingBehavior, the longest dependent chain of a merging / exit step, which reads the
+// pre-step state only and draws nothing — next to the other warps' whole plan phase instead of inside it.
+template <bool kTraj, bool kMerge, int NPS, int BT, bool kHelper = false>
 // resident 256-thread-equivalents per SM the register allocation aims at: 3 (80 registers) for the lane-change path —
 // the kernel is latency-bound, the third block hides more than its few spills cost (measured 6.26e9 -> 7.06e9
 // vehicle-steps/s) — and 2 (128 registers) for the much larger merging instantiation
@@ -620,6 +633,9 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
   constexpr int G = BT / NPS;                          // rollouts per thread block
   const int sub = threadIdx.x / NPS;                   // which of them this warp belongs to
   const int tid = threadIdx.x - sub * NPS;             // thread within the rollout: warp votes, task loops
+  static_assert(!kHelper || (kMerge && NPS >= 64 && 2 * G + 1 <= 15), "helper warp: merging instantiation, a spare warp, barrier ids");
+  const bool helper = kHelper && tid >= NPS - 32;      // the ego's helper warp
+  constexpr int NPW = kHelper ? NPS - 32 : NPS;        // working threads of a rollout
   // Vehicle slot of this thread.  Slots keep the reference's visit order and every shared array is indexed by slot; the
   // threads follow the slots in increasing order, so scans over threads are scans over slots, but when a rollout has
   // spare warps the host leaves gaps so that vehicles that start on different lanes — i.e. run different behaviour code
@@ -681,6 +697,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
   sub_sync<NPS, G == 1>(sub);
   if (k < laneStart[sc.n_lanes]) s.pos[s.vec[k]] = (uint8_t)k;
   if (isEgo) {
+    if (kHelper) s.ego[0] = y;
     s.flags[2] = beh;                   // the ego's current behaviour: `exit` vehicles are yielding candidates (0x104c90)
     s.flags[4] = cd.gap_slot;           // Agent::targetGapId as a slot; < 0 = last gap
     s.flags[5] = lp.steps;              // < lp.steps once the ego has reached its target lane (StatusOneSim::finish)
@@ -710,6 +727,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
 
   bool running = true;
   int window = 0;   // steps left until the block's next alignment point
+  int hGap = cd.gap_slot;   // helper warp: Agent::targetGapId as a slot (the helper re-targets it, below)
   while (true) {
     if (G > 1) {
       // the rollouts of a block start every MCS_ALIGN_STEPS-th step together, so their warps run through the same code at
@@ -725,6 +743,60 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
       }
     } else if (!(lp.steps > step)) {
       break;
+    }
+    if (kHelper && helper) {
+      // ---- the ego's helper warp: customizedMergingBehavior on the pre-step state, side by side with the plan of everybody else
+      if (tid == NPS - 32) {
+        const int eg = cd.ego_slot;
+        const int elane = s.lane[eg], ebeh = s.flags[2];
+        if (elane != 0xff && (ebeh == MCS_BEH_MERGING || ebeh == MCS_BEH_EXIT) && s.flags[0] == 0) {
+          const int lo = laneStart[elane], cnt = laneStart[elane + 1] - lo;
+          MergeSelf me;
+          me.k = eg; me.lane = elane; me.x = s.x[eg]; me.y = s.ego[0]; me.v = s.v[eg]; me.l = s.l[eg];
+          const int fpos = lane_upper(s, lo, cnt, me.x);          // frontAgent 0xe2670, as the reference searches it
+          me.front = fpos < cnt ? (int)s.vec[lo + fpos] : -1;
+          me.w = F[(size_t)F_W * np + eg];
+          me.rss.rTOther = F[(size_t)F_RSS_RTOTHER * np + eg]; me.rss.rTEgo = s.rss[eg]; me.rss.aMin = s.rss[np + eg];
+          me.rss.aMax = s.rss[2 * np + eg]; me.rss.dSoft = F[(size_t)F_RSS_DSOFT * np + eg];
+          me.idm = load_idm(s, np, eg);
+          double hax = 0.0, havy = 0.0;
+          const bool okSide = merging_behavior(s, sc, laneStart, me, s.vd[eg], true, false, cd.action == MCS_ACT_LEFT, hGap, hax, havy);
+          s.ego[1] = hax; s.ego[2] = havy; s.ego[3] = okSide ? 1.0 : 0.0;
+        }
+      }
+      sub_sync<NPS, G == 1>(sub);                                   // the plan is done: the ego picks its action up
+      const int anyChangedH = sub_sync_or<NPS, G == 1>(sub, 0);     // moved and matched
+      const bool egoReachedH = s.flags[0] != 0;
+      if (anyChangedH) {
+        const int anyInvH = sub_sync_or<NPS, G == 1>(sub, 0);
+        if (anyInvH) sub_sync<NPS, G == 1>(sub);
+        laneStart = laneStart == s.cnt ? s.cnt + 16 : s.cnt;
+        sub_sync<NPS, G == 1>(sub);
+      }
+      if (tid == NPS - 32 && hGap >= 0) {
+        // the gap's rear vehicle left the target lane: re-target to the last vehicle of that lane behind it, else the
+        // last gap (matchAgentsOnCorridor 0x10c320-0x10c39d)
+        const int gl = s.lane[hGap];
+        if (gl == 0xff) s.flags[6] = 1;
+        else if (sc.lanes[gl].id != cd.target_lane_id) {
+          int tl = -1;
+          for (int j = 0; j < sc.n_lanes; ++j) if (sc.lanes[j].id == cd.target_lane_id) tl = j;
+          if (tl < 0) s.flags[6] = 1;
+          else {
+            const int lo = laneStart[tl], cnt = laneStart[tl + 1] - lo;
+            const double gx = s.x[hGap];
+            int found = -1;
+            for (int q = cnt - 1; q >= 0; --q) {
+              const int o = s.vec[lo + q];
+              if (gx > s.x[o]) { found = o; break; }
+            }
+            hGap = found;
+          }
+        }
+      }
+      step++;
+      if (egoReachedH && lp.min_steps <= step - 1) { if (G > 1) { running = false; continue; } else break; }
+      continue;
     }
     // ================= plan, part A: own-lane search, IDM, draw counts =================
     double ax = 0.0, avy = 0.0;
@@ -779,7 +851,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
     int nTasks;
     {
       int total;
-      const int pos = block_exclusive_scan_small<NPS, G == 1, 1>(needMobil ? 1 : 0, inversion, s.scan, total, tid, sub);
+      const int pos = block_exclusive_scan_small<NPS, G == 1, 1, kHelper, G>(needMobil ? 1 : 0, inversion, s.scan, total, tid, sub);
       nTasks = total & 0xffff;
       ordered = (total >> 16) == 0;
       if (hasLane) {
@@ -795,7 +867,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
       }
       if (needMobil) s.tasks[pos] = k | (front & 0xff) << 8 | (back & 0xff) << 16 | ((front < 0) ? 1 << 24 : 0) | ((back < 0) ? 1 << 25 : 0);
     }
-    sub_sync<NPS, G == 1>(sub);
+    work_sync<NPS, G == 1, kHelper, G>(sub);
     // sub-task slot = part * ceil32(nTasks) + i: every warp runs one part only, and the five parts run on five warps
     // side by side instead of queueing up on the first ones
     const int nT32 = (nTasks + 31) & ~31;
@@ -803,7 +875,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
     // (u * ceil(2^16 / m)) >> 16 == u / m for u < 64 (error < 64 / 2^16 < 1 / m)
     const unsigned magic = (nT32 == 32 ? 65536u : nT32 == 64 ? 32768u : nT32 == 96 ? 21846u : nT32 == 128 ? 16384u
                             : nT32 == 160 ? 13108u : nT32 == 192 ? 10923u : nT32 == 224 ? 9363u : 8192u);
-    for (int t = tid; t < MOBIL_PARTS * nT32; t += NPS) {
+    for (int t = tid; t < MOBIL_PARTS * nT32; t += NPW) {
       const int part = (int)(((unsigned)t >> 5) * magic >> 16), ti = t - part * nT32;
       if (ti >= nTasks) continue;
       const int rec = s.tasks[ti];
@@ -812,7 +884,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
       const int vb = (rec >> 25 & 1) ? -1 : (rec >> 16 & 0xff);
       mobil_geometry(s, sc, laneStart, np, vk, vf, vb, part, ordered);
     }
-    sub_sync<NPS, G == 1>(sub);
+    work_sync<NPS, G == 1, kHelper, G>(sub);
     // draw counts: [noise][MOBIL decision draw]
     bool mobilDraw = false;
     if (needMobil) {
@@ -825,7 +897,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
     nDraw = nY + (noise ? 1 : 0) + (mobilDraw ? 1 : 0);
     int totalDraws;
     // nDraw <= 5 yielding candidates + noise + MOBIL draw
-    const uint64_t drawBase = (uint64_t)drawCtr + (uint64_t)block_exclusive_scan_small<NPS, G == 1, kMerge ? 3 : 2>(nDraw, false, s.scan + 8, totalDraws, tid, sub);
+    const uint64_t drawBase = (uint64_t)drawCtr + (uint64_t)block_exclusive_scan_small<NPS, G == 1, kMerge ? 3 : 2, kHelper, G>(nDraw, false, s.scan + 8, totalDraws, tid, sub);
     drawCtr += (uint32_t)totalDraws;
 
     // ================= plan, part B: actions =================
@@ -839,7 +911,9 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
         s.thist[s.flags[3]++] = thwPush;
       }
       avy = centering_vy(y, centerY);
-      if (kMerge && (mode == 3 || mode == 4)) {
+      if (kHelper && mode == 3) {
+        // the helper warp computes this step's gap execution; the action is picked up behind the barrier below
+      } else if (kMerge && (mode == 3 || mode == 4)) {
         MergeSelf me;
         me.k = k; me.lane = lane; me.front = front; me.x = x; me.y = y; me.v = v; me.l = el;
         me.w = F[(size_t)F_W * np + k];
@@ -847,8 +921,9 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
         me.rss.dSoft = F[(size_t)F_RSS_DSOFT * np + k];
         me.idm = pe;
         // mode 3: the ego executes its gap (customizedMerging); mode 4: a non-ego `merging` vehicle picks the closest gap to the left
-        const bool okSide = merging_behavior(s, sc, laneStart, me, evd, mode == 3, false, mode == 3 ? cd.action == MCS_ACT_LEFT : true,
-                                             mode == 3 ? s.flags[4] : -1, ax, avy);
+        const bool fixedGap = !kHelper && mode == 3;
+        const bool okSide = merging_behavior(s, sc, laneStart, me, evd, fixedGap, false, fixedGap ? cd.action == MCS_ACT_LEFT : true,
+                                             fixedGap ? s.flags[4] : -1, ax, avy);
         if (!okSide) { s.flags[6] = 1; ax = 0.0; avy = 0.0; }
       } else if (mode == 1 || mode == 2) {
         // One idmAccFrontBack call per vehicle and step: the branches only choose its operands.
@@ -920,6 +995,10 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
       }
     }
     sub_sync<NPS, G == 1>(sub);   // every read of the pre-step x / v is done
+    if (kHelper && mode == 3) {
+      if (s.ego[3] != 0.0) { ax = s.ego[1]; avy = s.ego[2]; }
+      else { s.flags[6] = 1; ax = 0.0; avy = 0.0; }
+    }
 
     // ================= integrate (0x10ea36-0x10eb80) =================
     double acc = 0.0;
@@ -932,7 +1011,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
       }
       s.x[k] = x; s.v[k] = v;
       s.acc[k] = s.acc[k] + fabs(acc); s.acc[np + k] = s.acc[np + k] + v;
-      if (isEgo) { s.chist[step + 1] = acc; s.vhist[step + 1] = v; }
+      if (isEgo) { s.chist[step + 1] = acc; s.vhist[step + 1] = v; if (kHelper) s.ego[0] = y; }
       if (kTraj) {
         double* t = lp.traj + ((((size_t)cand * lp.count + ridx) * n + inputIdx) * (size_t)(lp.steps + 1) + step + 1) * 4;
         t[0] = x; t[1] = y; t[2] = v; t[3] = acc;
@@ -1088,7 +1167,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
       if (!anyInv && mover && newLane != 0xff) myPos = s.pos[k];
     }
     // ================= termination (0x10edd0-0x10ee10) =================
-    const int gapSlot = (kMerge && isEgo) ? s.flags[4] : -1;
+    const int gapSlot = (kMerge && !kHelper && isEgo) ? s.flags[4] : -1;
     if (kMerge && isEgo && gapSlot >= 0) {
       // the gap's rear vehicle left the target lane: re-target to the last vehicle of that lane behind it, else the
       // last gap (matchAgentsOnCorridor 0x10c320-0x10c39d)

@@ -636,6 +636,42 @@ def test_bundle_kernel_equals_rollout_kernel(gpu, monkeypatch, kind):
         ds.close()
 
 
+@pytest.mark.parametrize("kind", ["merging", "exit", "exit_200"])
+def test_helper_warp_equals_inline_gap_execution(gpu, monkeypatch, kind):
+    """rollout_kernel<..., kHelper>: the ego's customizedMergingBehavior (and the re-targeting of its gap) on the rollout's spare
+    warp, next to the other warps' plan phase, against the same kernel with the gap execution inline (MCS_NO_HELPER=1):
+    byte-identical outcome records on 128- and 256-thread rollouts, own blocks and shared 768-thread blocks."""
+    rng = random.Random(2024)
+    if kind == "merging":
+        s, ego = random_scene(rng, n_agents=40, lane_types=["merging", "main", "main", "main"], ego_behavior="merging", ego_lane=0,
+                              spacing=(3, 40))
+        ids = [a["id"] for a in s.agents if 3.5 <= a["y"] < 7.0]
+        cands = [(ego, "left", -1)] + [(ego, "left", g) for g in ids[:3]]
+    else:
+        n = 200 if kind == "exit_200" else 60
+        s, ego = random_scene(rng, n_agents=n, lane_types=["exit", "main", "main", "main"], ego_behavior="exit", ego_lane=1,
+                              spacing=(3, 40))
+        ids = [a["id"] for a in s.agents if a["y"] < 3.5]
+        cands = [(ego, "right", -1)] + [(ego, "right", g) for g in ids[:3]]
+    cand = (abi.Candidate * len(cands))(*[abi.Candidate(e, abi.ACTIONS[a], g, 0) for e, a, g in cands])
+    sp = abi.SimParam(0.3, 50, 10)
+    monkeypatch.setenv("MCS_KERNEL", "rollout")
+    ds = gpu.DeviceScene(s.c_corridors(), s.c_agents())
+    try:
+        for threads in ((256,) if kind == "exit_200" else (128, 256)):
+            monkeypatch.setenv("MCS_ROLLOUT_THREADS", str(threads))
+            for count in (3, 700):
+                monkeypatch.setenv("MCS_NO_HELPER", "1")
+                want = bytes(ds.rollouts_range(cand, sp, 515, 0, count))
+                assert any(want[i * 64:(i + 1) * 64] != want[:64] for i in range(1, count))
+                monkeypatch.delenv("MCS_NO_HELPER")
+                got = bytes(ds.rollouts_range(cand, sp, 515, 0, count))
+                bad = [i for i in range(len(cands) * count) if got[i * 64:(i + 1) * 64] != want[i * 64:(i + 1) * 64]]
+                assert not bad, (kind, threads, count, len(bad), bad[:5])
+    finally:
+        ds.close()
+
+
 @pytest.mark.parametrize("kind", ["lane_change", "merging"])
 def test_long_horizon_in_a_large_launch(gpu, kind):
     """A long horizon makes the per-rollout shared-memory region large; a launch big enough to share thread blocks must
