@@ -318,23 +318,29 @@ __device__ __forceinline__ void side_leader_follower(const Smem& s, const int* l
 // Everything mobil_decide needs from the seven sub-tasks of one vehicle
 struct MobilGeo { double accNewL, accNewR, dNewL, dNewR, deltaOld; int mf; };
 
-// one sub-task.  kStore: the result goes to the vehicle's cell of the shared arrays (the task queue of rollout_kernel);
-// otherwise it comes back in `value` (parts 0, 1, 3, 4, 6) or `mfOut` (parts 2, 5: the side's flag bits)
+// the side lane of vehicle k a MOBIL evaluation looks at (side 0 = left, 1 = right): is there a main lane, and who would be
+// k's leader / follower on it — ONE search per vehicle and side, shared by the side's three sub-tasks
+__device__ __forceinline__ bool mobil_side_neighbours(const Smem& s, const SceneDev& sc, const int* laneStart, int k, int side,
+                                                      bool ordered, int& leader, int& follower) {
+  const LaneDev& L = sc.lanes[s.lane[k]];
+  const int sl = side == 0 ? L.leftIdx : L.rightIdx;
+  leader = -1; follower = -1;
+  const bool can = sl >= 0 && sc.lanes[sl].type == MCS_LANE_MAIN;
+  if (can) side_leader_follower(s, laneStart, sl, s.x[k], ordered, leader, follower);
+  return can;
+}
+
+// one sub-task, given the side's neighbours (part 0: can = true, no neighbours).  kStore: the result goes to the vehicle's
+// cell of the shared arrays (the task queue of rollout_kernel); otherwise it comes back in `value` (parts 0, 1, 3, 4, 6) or
+// `mfOut` (parts 2, 5: the side's flag bits)
 template <bool kStore>
-__device__ __forceinline__ void mobil_geometry_core(const Smem& s, const SceneDev& sc, const int* laneStart, int np, int k,
-                                                    int front, int back, int part, bool ordered, double& value, int& mfOut) {
+__device__ __forceinline__ void mobil_sub_task(const Smem& s, const SceneDev& sc, int np, int k, int front, int back, int part,
+                                               bool can, int leader, int follower, double& value, int& mfOut) {
   const LaneDev& L = sc.lanes[s.lane[k]];
   // Which IDM evaluation is this sub-task?  Parts 0, 3, 6 are all "what does vehicle j lose when k drives between it
   // and F" (j = old follower / would-be follower on the left / right); parts 1, 3 are k's own acceleration behind the
   // side lane's leader plus the two RSS gates.  Branches only select the operands; each formula is instantiated once.
   const int side = part > 3 ? 1 : 0, sub = part == 0 ? 2 : (part - 1) - 3 * side;   // sub 0: own IDM, 1: RSS gates, 2: follower delta
-  int leader = -1, follower = -1;
-  bool can = true;
-  if (part != 0) {
-    const int sl = side == 0 ? L.leftIdx : L.rightIdx;
-    can = sl >= 0 && sc.lanes[sl].type == MCS_LANE_MAIN;
-    if (can) side_leader_follower(s, laneStart, sl, s.x[k], ordered, leader, follower);
-  }
   if (sub == 0) {
     double accNew = 0.0;
     if (can) {
@@ -400,12 +406,20 @@ __device__ __forceinline__ void mobil_geometry_core(const Smem& s, const SceneDe
   if (kStore) s.mob[(part == 0 ? 4 : 2 + side) * np + k] = delta; else value = delta;
 }
 
-// the sub-task as the task queue of rollout_kernel runs it
-__device__ __forceinline__ void mobil_geometry(const Smem& s, const SceneDev& sc, const int* laneStart, int np, int k,
-                                               int front, int back, int part, bool ordered) {
-  double value;
-  int mf;
-  mobil_geometry_core<true>(s, sc, laneStart, np, k, front, back, part, ordered, value, mf);
+// A task of rollout_kernel's queue: sub-tasks [first, last) of one side lane (`side` 0 / 1: the vehicle's own acceleration
+// there, the two RSS gates, the new follower's loss — sub-tasks 1-3 / 4-6 of laneChangeBehaviorMOBIL behind ONE search for
+// the side's leader / follower), or with side < 0 the old follower's loss (sub-task 0; first = 2, last = 3).
+__device__ __forceinline__ void mobil_task(const Smem& s, const SceneDev& sc, const int* laneStart, int np, int k, int front,
+                                           int back, int side, int first, int last, bool ordered) {
+  int leader = -1, follower = -1;
+  const bool can = side < 0 ? true : mobil_side_neighbours(s, sc, laneStart, k, side, ordered, leader, follower);
+  const int base = side < 0 ? -2 : 1 + 3 * side;     // part = base + sub
+#pragma unroll 1
+  for (int sub = first; sub < last; ++sub) {
+    double value;
+    int mf;
+    mobil_sub_task<true>(s, sc, np, k, front, back, base + sub, can, leader, follower, value, mf);
+  }
 }
 __device__ __forceinline__ MobilGeo load_mobil_geo(const Smem& s, int np, int k) {
   MobilGeo g;
@@ -419,11 +433,14 @@ __device__ __forceinline__ MobilGeo mobil_geometry_all(const Smem& s, const Scen
                                                        int front, int back) {
   MobilGeo g;
   g.accNewL = g.accNewR = g.dNewL = g.dNewR = g.deltaOld = 0.0; g.mf = 0;
+  int leader = -1, follower = -1;
+  bool can = true;
 #pragma unroll 1
   for (int part = 0; part < MOBIL_PARTS; ++part) {
     double value = 0.0;
     int mf = 0;
-    mobil_geometry_core<false>(s, sc, laneStart, np, k, front, back, part, false, value, mf);
+    if (part == 1 || part == 4) can = mobil_side_neighbours(s, sc, laneStart, k, part == 4 ? 1 : 0, false, leader, follower);
+    mobil_sub_task<false>(s, sc, np, k, front, back, part, can, leader, follower, value, mf);
     if (part == 0) g.deltaOld = value;
     else if (part == 1) g.accNewL = value;
     else if (part == 3) g.dNewL = value;
@@ -868,21 +885,52 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
       if (needMobil) s.tasks[pos] = k | (front & 0xff) << 8 | (back & 0xff) << 16 | ((front < 0) ? 1 << 24 : 0) | ((back < 0) ? 1 << 25 : 0);
     }
     work_sync<NPS, G == 1, kHelper, G>(sub);
-    // sub-task slot = part * ceil32(nTasks) + i: every warp runs one part only, and the five parts run on five warps
-    // side by side instead of queueing up on the first ones
-    const int nT32 = (nTasks + 31) & ~31;
+    // The seven sub-tasks of a queued vehicle can run as 7, 5 or 3 tasks: every sub-task alone (each side sub-task behind
+    // its own search; shortest chain, most warps), per side [own acceleration + RSS gates] and [new follower's loss], or
+    // per side all three behind one search (longest chain, fewest warps).  Groups of like tasks start on warp
+    // boundaries.  The kernel is latency-bound per step: a rollout with eight warps finishes the seven short tasks soonest
+    // (measured, scripts/config_times.py / kernel_time.py: configs[3] 16.3 ms with 7 tasks, 17.7 with 5, 18.4 with 3;
+    // configs[4] 1.057 / 1.061 / 1.032e10), a rollout with one to four warps the few long ones (24 vehicles x 5 x 4096
+    // rollouts: 3.87 / 3.07 / 2.90 ms; configs[2] x 512 rollouts on 128 threads: 1.096 / 1.054 / 1.067 ms).
+    constexpr int split = NPS >= 256 ? 7 : (NPS >= 128 ? 5 : 3);
+    const int w1 = (nTasks + 31) >> 5, nSide = 2 * nTasks, w2 = (nSide + 31) >> 5, nT32 = w1 << 5, nSide32 = w2 << 5;
     // part = t / nT32 without the integer-division sequence: nT32 = 32 m with m <= 8, t / 32 < 64, and
     // (u * ceil(2^16 / m)) >> 16 == u / m for u < 64 (error < 64 / 2^16 < 1 / m)
     const unsigned magic = (nT32 == 32 ? 65536u : nT32 == 64 ? 32768u : nT32 == 96 ? 21846u : nT32 == 128 ? 16384u
                             : nT32 == 160 ? 13108u : nT32 == 192 ? 10923u : nT32 == 224 ? 9363u : 8192u);
-    for (int t = tid; t < MOBIL_PARTS * nT32; t += NPW) {
-      const int part = (int)(((unsigned)t >> 5) * magic >> 16), ti = t - part * nT32;
-      if (ti >= nTasks) continue;
+    const int baseOld = split == 5 ? 2 * nSide32 : nSide32;       // where the old-follower tasks start (splits 5 and 3)
+    const int nSlots = split == 7 ? 7 * nT32 : baseOld + nTasks;
+    for (int t = tid; t < nSlots; t += NPW) {
+      int side = -1, ti = 0, first = 2, last = 3;
+      if constexpr (split == 7) {
+        const int part = (int)(((unsigned)t >> 5) * magic >> 16);
+        ti = t - part * nT32;
+        if (ti >= nTasks) continue;
+        const int rec = s.tasks[ti];
+        const int vk = rec & 0xff;
+        const int vf = (rec >> 24 & 1) ? -1 : (rec >> 8 & 0xff);
+        const int vb = (rec >> 25 & 1) ? -1 : (rec >> 16 & 0xff);
+        int leader = -1, follower = -1, mf;
+        double value;
+        const bool can = part == 0 ? true : mobil_side_neighbours(s, sc, laneStart, vk, part > 3 ? 1 : 0, ordered, leader, follower);
+        mobil_sub_task<true>(s, sc, np, vk, vf, vb, part, can, leader, follower, value, mf);
+        continue;
+      } else if (t >= baseOld) {
+        side = -1; ti = t - baseOld; first = 2; last = 3;
+      } else {
+        const int second = t >= nSide32 ? 1 : 0;      // split 5: the group of the new followers' losses
+        const int q = t - second * nSide32;
+        if (q >= nSide) continue;
+        side = q >= nTasks ? 1 : 0;
+        ti = q - side * nTasks;
+        first = second ? 2 : 0;
+        last = (split == 5 && !second) ? 2 : 3;
+      }
       const int rec = s.tasks[ti];
       const int vk = rec & 0xff;
       const int vf = (rec >> 24 & 1) ? -1 : (rec >> 8 & 0xff);
       const int vb = (rec >> 25 & 1) ? -1 : (rec >> 16 & 0xff);
-      mobil_geometry(s, sc, laneStart, np, vk, vf, vb, part, ordered);
+      mobil_task(s, sc, laneStart, np, vk, vf, vb, side, first, last, ordered);
     }
     work_sync<NPS, G == 1, kHelper, G>(sub);
     // draw counts: [noise][MOBIL decision draw]

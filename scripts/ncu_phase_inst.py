@@ -14,15 +14,24 @@ for r in rows:
         g = lambda k: int(d.get(k, "0")) if d.get(k, "0").isdigit() else 0
         p = per[(cur, int(r[0]))]
         p[0] += g("Instructions Executed"); p[1] += g("Thread Instructions Executed"); p[2] += g("# Samples")
-phases = [  # (name, file, lo, hi)
-    ("mcs_div", "rollout_kernel.cuh", 76, 87), ("idm_acc", "rollout_kernel.cuh", 156, 210), ("search", "rollout_kernel.cuh", 212, 241),
-    ("rss_safe", "rollout_kernel.cuh", 243, 262), ("lc_prob", "rollout_kernel.cuh", 264, 274), ("centering", "rollout_kernel.cuh", 276, 283),
-    ("rss_emerg", "rollout_kernel.cuh", 285, 294), ("side_lf", "rollout_kernel.cuh", 300, 309), ("mobil_geo", "rollout_kernel.cuh", 321, 414),
-    ("mobil_decide", "rollout_kernel.cuh", 438, 501), ("sync/scan", "rollout_kernel.cuh", 537, 586), ("init", "rollout_kernel.cuh", 615, 712),
-    ("loophead", "rollout_kernel.cuh", 713, 728), ("partA", "rollout_kernel.cuh", 729, 776), ("scan1+front", "rollout_kernel.cuh", 777, 797),
-    ("tasks", "rollout_kernel.cuh", 798, 814), ("drawcount", "rollout_kernel.cuh", 815, 829), ("partB", "rollout_kernel.cuh", 830, 921),
-    ("integrate", "rollout_kernel.cuh", 922, 940), ("match", "rollout_kernel.cuh", 941, 964), ("rebuild", "rollout_kernel.cuh", 965, 1047),
-    ("termination", "rollout_kernel.cuh", 1048, 1076), ("stats", "rollout_kernel.cuh", 1077, 1172)]
+import os, re
+SRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "interactive_highway_simulation_b200", "csrc", "rollout_kernel.cuh")
+marks = [  # (phase, regex of the line that starts it) in file order
+    ("mcs_div", r"double mcs_div\("), ("smem", r"void carve_smem\("), ("idm_acc", r"double idm_acc\("), ("search", r"int lane_upper\("),
+    ("rss_safe", r"bool rss_safe\("), ("lc_prob", r"void lane_change_probability\("), ("centering", r"double centering_vy\("),
+    ("rss_emerg", r"bool rss_emergency\("), ("side_lf", r"void side_leader_follower\("), ("mobil_geo", r"void mobil_geometry_core\("),
+    ("mobil_decide", r"void mobil_decide\("), ("cust_lc", r"void customized_lane_change\("), ("sync/scan", r"void sub_sync\("),
+    ("init", r"void __launch_bounds__"), ("loophead", r"^  while \(true\) \{"), ("helper", r"if \(kHelper && helper\) \{"),
+    ("partA", r"=+ plan, part A"), ("scan1+front", r"// compaction: queue MOBIL tasks"), ("tasks", r"// sub-task slot = part"),
+    ("drawcount", r"// draw counts:"), ("partB", r"=+ plan, part B"), ("integrate", r"=+ integrate"), ("match", r"=+ matchAgentsOnCorridor"),
+    ("rebuild", r"^    if \(anyChanged\) \{"), ("termination", r"=+ termination"), ("stats", r"=+ outcome statistics")]
+lines = open(SRC).read().split("\n")
+phases, at = [], 0
+for name, rx in marks:
+    for i in range(at, len(lines)):
+        if re.search(rx, lines[i]):
+            phases.append([name, "rollout_kernel.cuh", i + 1, len(lines)]); at = i + 1; break
+for a, b in zip(phases, phases[1:]): a[3] = b[2] - 1
 agg = collections.OrderedDict((p[0], [0, 0, 0]) for p in phases)
 other = collections.defaultdict(lambda: [0, 0, 0])
 for (f, ln), v in per.items():

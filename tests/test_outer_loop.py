@@ -94,13 +94,45 @@ def test_evaluation_epochs_host_logic_reproduces_the_reference_trace(monkeypatch
     assert inner.k == len(rec["calls"]) and worst < 1e-9
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("tag", sorted(EVALUATIONS))
-def test_evaluation_epochs_on_the_device_reproduce_the_reference_trace(backend_lib, tag):
+def stream_states():
+    """where the three host random streams stand: numpy's global stream, Python's `random`, the drop-in's seed sequence"""
+    import random
+    import numpy as np
     from interactive_highway_simulation_b200 import mc_sim_highway as ms
+    st = np.random.get_state()
+    return (st[1].tobytes(), st[2], st[3], st[4]), random.getstate(), ms._peek_seed()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("walk", ["device_walk", "host_walk"])
+@pytest.mark.parametrize("tag", sorted(EVALUATIONS))
+def test_evaluation_epochs_on_the_device_reproduce_the_reference_trace(backend_lib, monkeypatch, tag, walk):
+    """Both forms of the sequential step: the walk of the vehicles on the device (mce_walk_step: one launch per run of
+    device-plannable vehicles) and on the host (one launch per query)."""
+    from interactive_highway_simulation_b200 import mc_sim_highway as ms, outer_env
+    monkeypatch.setattr(outer_env.Environment, "walk_on_device", walk == "device_walk")
     ms.seed(2000 + EVALUATIONS[tag][1])
     _, worst = run_evaluation(tag, load_scenario(tag))
     assert worst < 1e-9        # kernels == oracle bit for bit, inner answers == reference bit for bit
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", sorted(EVALUATIONS))
+def test_device_walk_leaves_the_random_streams_where_the_host_walk_does(backend_lib, monkeypatch, tag):
+    """The walk kernel consumes numpy's, Python's and the drop-in's streams in the reference's order: after the same steps
+    every vehicle AND all three stream states equal the host path's."""
+    from interactive_highway_simulation_b200 import mc_sim_highway as ms, outer_env
+    ends = []
+    for on_device in (True, False):
+        monkeypatch.setattr(outer_env.Environment, "walk_on_device", on_device)
+        ms.seed(2000 + EVALUATIONS[tag][1])
+        env, _ = run_evaluation(tag, load_scenario(tag))
+        vehicles = sorted((a.id, a.x, a.y, a.v, a.a, a.vy, a.commit_lane_change, a.commit_keep_lane_step, a.target_lane_id,
+                           tuple(sorted((k, it.yielding, it.initial_probability) for k, it in a.yielding_intention_to_others.items())))
+                          for a in list(env.agents.values()) + list(env.removed_agents.values()))
+        ends.append((vehicles, stream_states()))
+    assert ends[0][0] == ends[1][0]
+    assert ends[0][1] == ends[1][1]
 
 
 @pytest.mark.parametrize("tag", ["test_scene", "lane_change_learned", "merging_learned"])
@@ -117,9 +149,11 @@ def test_outer_loop_host_logic_reproduces_the_reference_trace(monkeypatch, tag):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("walk", ["device_walk", "host_walk"])
 @pytest.mark.parametrize("tag", ["test_scene", "lane_change_learned", "merging_learned"])
-def test_outer_loop_on_the_device_reproduces_the_reference_trace(backend_lib, tag):
-    from interactive_highway_simulation_b200 import mc_sim_highway as ms, simulation_multilane as sim_mod
+def test_outer_loop_on_the_device_reproduces_the_reference_trace(backend_lib, monkeypatch, tag, walk):
+    from interactive_highway_simulation_b200 import mc_sim_highway as ms, outer_env, simulation_multilane as sim_mod
+    monkeypatch.setattr(outer_env.Environment, "walk_on_device", walk == "device_walk")
     rec = load_scenario(tag)
     overrides, seed = learned_overrides(sim_mod, tag)
     ms.seed(1000 + seed)
