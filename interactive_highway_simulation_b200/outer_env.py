@@ -15,7 +15,9 @@ import ctypes as C
 
 import numpy as np
 
+from . import _abi as abi
 from . import backend
+from .type import YieldingIntention
 
 MCE_MAX_LANES, MCE_MAX_POINTS, MCE_MAX_AGENTS, MCE_NEIGHBORS = 8, 16, 1024, 10
 LEFT_FF, LEFT_F, LEFT_B, LEFT_BB, FRONT, BACK, RIGHT_FF, RIGHT_F, RIGHT_B, RIGHT_BB = range(10)
@@ -159,6 +161,7 @@ class DeviceMap:
         self._pods = corridor_pods(list(corridors))
         self.n_lanes = len(self._pods)
         self.center_cache = {}                               # (lane, x, y) -> (signed centre distance, distance to the end)
+        self.center_fill = None                              # pending batch of the last match (Environment), run on first use
         self._build_out = None
         self._step_io = None
         self._h = C.c_void_p()
@@ -258,7 +261,6 @@ class DeviceMap:
         """mce_build_rollout_scene: one of mcs_wrapper's builders on the device.  Returns (corridors, agents, actions, handle):
         ctypes arrays of abi.Corridor / abi.Agent cut to their lengths (None unless `records`), the candidate gap ids, and
         the handle of the marshalled inner scene (None unless `scene`; the caller owns it: backend.DeviceScene.adopt)."""
-        from . import _abi as abi
         # `ids` / `attrs`: numpy arrays (int32 [n], float64 [8][n]) or raw addresses of such arrays (a caller in a loop
         # caches them).  The record arrays are the map's own and are overwritten by the next call.
         if self._build_out is None:
@@ -370,6 +372,11 @@ class Corridor:
         key = (self.lane_index, float(point[0]), float(point[1]))
         cache = self.device_map.center_cache
         if key not in cache:
+            fill = getattr(self.device_map, "center_fill", None)
+            if fill is not None:                             # the step's batch for every matched vehicle, on first use
+                self.device_map.center_fill = None
+                fill()
+        if key not in cache:
             if len(cache) > 65536:                           # a map used without an Environment never gets its cache reset
                 cache.clear()
             d, e = self.device_map.center_distance([key[0]], [key[1]], [key[2]])
@@ -455,7 +462,6 @@ class Map:
         self.device_map = DeviceMap(list(self.corridors.values()), device)
         for k, c in enumerate(self.corridors.values()):
             c.device_map, c.lane_index = self.device_map, k
-        from . import _abi as abi
         self.device_map.set_lane_info([int(c.id) for c in self.corridors.values()],
                                       [abi.LANE_TYPES.get(c.type, abi.LANE_OTHER) for c in self.corridors.values()],
                                       [float(c.v_limit) for c in self.corridors.values()])
@@ -534,15 +540,20 @@ class Environment:
             members = t.order[0, t.start[0, lane]:t.start[0, lane + 1]]
             self.matched_agents_sorted_by_arc_length[cid] = [[float(t.arc[0, j]), objs[j]] for j in members]
         # centre-line distances of every matched vehicle at its matched position, one launch (read by idm_behavior and the
-        # yielding model during the sequential loop; a vehicle that has moved since is asked for again)
-        on = [i for i in range(len(objs)) if t.lane[0, i] >= 0]
-        cache = self.map.device_map.center_cache
-        cache.clear()
-        if on:
-            lanes = [int(t.lane[0, i]) for i in on]
-            d, e = self.map.device_map.center_distance(lanes, self._x0[on], self._y0[on])
-            for k, i in enumerate(on):
-                cache[(lanes[k], float(self._x0[i]), float(self._y0[i]))] = (float(d[k]), float(e[k]))
+        # yielding model during the sequential loop on the host; a vehicle that has moved since is asked for again).  The
+        # launch waits for its first reader: a step whose vehicles are all walked on the device never asks.
+        dm = self.map.device_map
+        dm.center_cache.clear()
+        x0, y0 = self._x0, self._y0
+
+        def fill():
+            on = [i for i in range(len(objs)) if t.lane[0, i] >= 0]
+            if on:
+                lanes = [int(t.lane[0, i]) for i in on]
+                d, e = dm.center_distance(lanes, x0[on], y0[on])
+                for k, i in enumerate(on):
+                    dm.center_cache[(lanes[k], float(x0[i]), float(y0[i]))] = (float(d[k]), float(e[k]))
+        dm.center_fill = fill
 
     def corridor_for_agent(self, idx):                       # environment.py:103-112
         if idx not in self.agents or idx not in self.matched_agents:
@@ -675,7 +686,6 @@ class Environment:
         (the caller owns it: backend.DeviceScene.adopt)."""
         if agent.id not in self._slot or agent.id not in self.matched_agents:
             raise EnvError(-1, "agent %r is not matched on any corridor" % (agent.id,))
-        from . import _abi as abi
         ip, mp, yp = agent.idm_param, agent.mobil_param, agent.yielding_param
         merging_model = "merging" in agent.behavior_model
         rq = BuildRequest()
@@ -714,7 +724,6 @@ class Environment:
     walk_on_device = True          # class-wide switch (tests compare both paths)
 
     def _walk_record(self, rec, a):
-        from . import _abi as abi
         ip, rp, mp = a.idm_param, a.rss_param, a.mobil_param
         rec.id, rec.behavior = int(a.id), WALK_BEHAVIORS.get(a.behavior_model, 0)
         rec.flags = (1 if "merging" in a.behavior_model else 0) | (2 if "exit" in a.behavior_model else 0)
@@ -758,8 +767,6 @@ class Environment:
 
     def _walk_take(self, i):
         """vehicle i as the device moved it -> the Python object (what Agent.step and lane_change_behavior_mobil leave behind)"""
-        from . import _abi as abi
-        from .type import YieldingIntention
         rec, a = self._walk[i], self._objs[i]
         a.x, a.y, a.v, a.yaw, a.a, a.vy = rec.x, rec.y, rec.v, rec.yaw, rec.a, rec.vy
         a.acceleration_history.append(a.a)
