@@ -19,10 +19,10 @@ SRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 marks = [  # (phase, regex of the line that starts it) in file order
     ("mcs_div", r"double mcs_div\("), ("smem", r"void carve_smem\("), ("idm_acc", r"double idm_acc\("), ("search", r"int lane_upper\("),
     ("rss_safe", r"bool rss_safe\("), ("lc_prob", r"void lane_change_probability\("), ("centering", r"double centering_vy\("),
-    ("rss_emerg", r"bool rss_emergency\("), ("side_lf", r"void side_leader_follower\("), ("mobil_geo", r"void mobil_geometry_core\("),
+    ("rss_emerg", r"bool rss_emergency\("), ("side_lf", r"void side_leader_follower\("), ("mobil_geo", r"void mobil_sub_task\("),
     ("mobil_decide", r"void mobil_decide\("), ("cust_lc", r"void customized_lane_change\("), ("sync/scan", r"void sub_sync\("),
     ("init", r"void __launch_bounds__"), ("loophead", r"^  while \(true\) \{"), ("helper", r"if \(kHelper && helper\) \{"),
-    ("partA", r"=+ plan, part A"), ("scan1+front", r"// compaction: queue MOBIL tasks"), ("tasks", r"// sub-task slot = part"),
+    ("partA", r"=+ plan, part A"), ("scan1+front", r"// compaction: queue MOBIL tasks"), ("tasks", r"// The seven sub-tasks of a queued vehicle"),
     ("drawcount", r"// draw counts:"), ("partB", r"=+ plan, part B"), ("integrate", r"=+ integrate"), ("match", r"=+ matchAgentsOnCorridor"),
     ("rebuild", r"^    if \(anyChanged\) \{"), ("termination", r"=+ termination"), ("stats", r"=+ outcome statistics")]
 lines = open(SRC).read().split("\n")
