@@ -888,11 +888,13 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
     // The seven sub-tasks of a queued vehicle can run as 7, 5 or 3 tasks: every sub-task alone (each side sub-task behind
     // its own search; shortest chain, most warps), per side [own acceleration + RSS gates] and [new follower's loss], or
     // per side all three behind one search (longest chain, fewest warps).  Groups of like tasks start on warp
-    // boundaries.  The kernel is latency-bound per step: a rollout with eight warps finishes the seven short tasks soonest
-    // (measured, scripts/config_times.py / kernel_time.py: configs[3] 16.3 ms with 7 tasks, 17.7 with 5, 18.4 with 3;
-    // configs[4] 1.057 / 1.061 / 1.032e10), a rollout with one to four warps the few long ones (24 vehicles x 5 x 4096
-    // rollouts: 3.87 / 3.07 / 2.90 ms; configs[2] x 512 rollouts on 128 threads: 1.096 / 1.054 / 1.067 ms).
-    constexpr int split = NPS >= 256 ? 7 : (NPS >= 128 ? 5 : 3);
+    // boundaries.  The kernel is latency-bound per step: a merging / exit rollout with seven or eight warps finishes the
+    // seven short tasks soonest (measured, scripts/config_times.py / kernel_time.py: configs[3] 16.3 ms with 7 tasks, 17.7
+    // with 5, 18.4 with 3), the 256-vehicle lane-change rollout is as fast with 5 as with 7 at 6 % fewer instructions
+    // (configs[4] 1.057 / 1.061 / 1.032e10 vehicle-steps/s, 64.7 -> 60.9 warp instructions per vehicle-step), a rollout with
+    // one to four warps wants the few long ones (24 vehicles x 5 x 4096 rollouts: 3.87 / 3.07 / 2.90 ms; configs[2] x 512
+    // rollouts on 128 threads: 1.096 / 1.054 / 1.067 ms).
+    constexpr int split = NPS >= 256 ? (kMerge ? 7 : 5) : (NPS >= 128 ? 5 : 3);
     const int w1 = (nTasks + 31) >> 5, nSide = 2 * nTasks, w2 = (nSide + 31) >> 5, nT32 = w1 << 5, nSide32 = w2 << 5;
     // part = t / nT32 without the integer-division sequence: nT32 = 32 m with m <= 8, t / 32 < 64, and
     // (u * ceil(2^16 / m)) >> 16 == u / m for u < 64 (error < 64 / 2^16 < 1 / m)
