@@ -74,7 +74,15 @@ __host__ __device__ inline void hash_iteration_order(const int32_t* ids, int n, 
   int next[64];
   int bucket_before[127];
   int head = -1, n_bkt = 13, bbegin_bkt = -1;
-  auto bkt_of = [&](int idx, int nb) { return (int)((unsigned long long)(long long)ids[idx] % (unsigned long long)nb); };
+  // std::hash<int> is the identity on the sign-extended value; ids are non-negative in every scene of the reference, and a
+  // 32-bit remainder by one of the four bucket counts is a multiply and a shift (the 64-bit remainder is a ~100-instruction
+  // routine on the device, once per emplace and re-link of the walk's serial path)
+  auto bkt_of = [&](int idx, int nb) {
+    const int id = ids[idx];
+    if (id < 0) return (int)((unsigned long long)(long long)id % (unsigned long long)nb);
+    const unsigned u = (unsigned)id;
+    return (int)(nb == 13 ? u % 13u : nb == 29 ? u % 29u : nb == 59 ? u % 59u : u % 127u);
+  };
   for (int b = 0; b < 127; ++b) bucket_before[b] = -2;
   auto link = [&](int node, int nb) {
     const int b = bkt_of(node, nb);
