@@ -158,3 +158,99 @@ def evaluate_recorded_exit_scene(path, sim, ego_policy, epoch_id, ego_id, statis
     statistics.epoch_and_ego_id_history.append([epoch_id, ego_id])
     _ego_and_others(sim, ego_id, statistics)
     return print_output + statistics.__repr__() + "\n"
+
+
+# ---- many evaluations side by side ------------------------------------------------------------------------------------
+# The scripts' main loops (evaluation_merging.py:108-140, evaluation_lane_change.py:103-140, evaluation_exit.py:107-150) call
+# evaluate_recorded_*_scene once per (epoch, ego, policy), 500 epochs one after the other.  An evaluation is a sequential outer
+# loop of ~100 steps — a chain of small, latency-bound launches and the host bookkeeping of ~25 vehicles; the evaluations
+# themselves are independent, so they shard: evaluate_scenes_parallel runs them in worker processes, task i on device
+# devices[i % len(devices)], and merges the statistics in task order.  Each task seeds the three random streams itself
+# (numpy's, Python's, the drop-in's), so a task's result does not depend on which worker or GPU runs it or on what ran
+# before it — unlike the scripts' single run, where evaluation k starts from the stream positions evaluation k-1 left
+# behind.  Measured (scripts/eval_parallel.py): the shard unit is the GPU, not the host core — worker processes that share
+# ONE GPU do not overlap (their contexts time-slice the device, and an evaluation keeps it occupied ~2/3 of the time:
+# 5.5 evaluations/s with 1 worker, 5.8 with 15), workers on different GPUs scale with the number of GPUs.
+
+def _new_statistics(kind):
+    return LaneChangeStatistics() if kind == "lane_change" else MergingAndExitStatistics()
+
+
+def _evaluate_task(task):
+    """One (epoch, ego, policy) evaluation in a worker: (kind, path, policy, epoch_id, ego_id, max_fall_back_ratio, seed, dt, steps,
+    device) -> (console text, the statistics object's fields)."""
+    import random
+    from . import mc_sim_highway as ms
+    kind, path, policy, epoch_id, ego_id, ratio, seed, dt, steps, device = task
+    if _WORKER_DEVICE is not None:
+        device = _WORKER_DEVICE                       # a pool worker stays on the GPU it was given
+    random.seed(seed); np.random.seed(seed); ms.seed(seed)
+    sim = Simulation(None, SimulationParameter(dt, steps, render=False, write_gif=False, scenario=kind))
+    sim.device = device
+    st = _new_statistics(kind)
+    if kind == "merging":
+        text = evaluate_recorded_merging_scene(path, sim, policy, epoch_id, st, ratio)
+    elif kind == "lane_change":
+        text = evaluate_recorded_lc_scene(path, sim, policy, epoch_id, ego_id, st)
+    else:
+        text = evaluate_recorded_exit_scene(path, sim, policy, epoch_id, ego_id, st, ratio)
+    return text, dict(st.__dict__)
+
+
+def merge_statistics(kind, parts):
+    """The statistics object a single run over the same tasks in the same order would have built: lists concatenated,
+    counters summed."""
+    total = _new_statistics(kind)
+    for part in parts:
+        for name, value in part.items():
+            if isinstance(value, list):
+                getattr(total, name).extend(value)
+            elif isinstance(value, (int, float)) and not isinstance(value, bool):
+                setattr(total, name, getattr(total, name) + value)
+    return total
+
+
+_WORKER_DEVICE = None
+
+
+def _bind_worker(counter, devices):
+    global _WORKER_DEVICE
+    with counter.get_lock():
+        k = counter.value
+        counter.value += 1
+    _WORKER_DEVICE = devices[k % len(devices)]
+
+
+class EvaluationPool:
+    """Worker processes for evaluate_scenes_parallel, spawned once: a worker keeps its CUDA context and the loaded library,
+    and is bound to one GPU (worker k to devices[k % len(devices)])."""
+
+    def __init__(self, workers, devices=(0,)):
+        import multiprocessing
+        ctx = multiprocessing.get_context("spawn")
+        self.workers = workers
+        self._pool = ctx.Pool(workers, initializer=_bind_worker, initargs=(ctx.Value("i", 0), list(devices)))
+
+    def run(self, tasks):
+        return self._pool.map(_evaluate_task, tasks, chunksize=1)
+
+    def close(self):
+        self._pool.close()
+        self._pool.join()
+
+
+def evaluate_scenes_parallel(kind, tasks, workers=None, pool=None, dt=0.2, steps=100, devices=(0,)):
+    """tasks: [(path, policy, epoch_id, ego_id, max_fall_back_ratio, seed)] -> ([console texts], merged statistics).
+    devices: the GPUs of the pool's workers (default worker count: one per device); a pool passed in keeps its own."""
+    devices = list(devices)
+    full = [(kind, path, policy, epoch_id, ego_id, ratio, seed, dt, steps, devices[0])
+            for path, policy, epoch_id, ego_id, ratio, seed in tasks]
+    own = pool is None
+    if own:
+        pool = EvaluationPool(workers or min(len(full), len(devices)), devices)
+    try:
+        results = pool.run(full)
+    finally:
+        if own:
+            pool.close()
+    return [r[0] for r in results], merge_statistics(kind, [r[1] for r in results])

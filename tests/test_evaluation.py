@@ -127,3 +127,33 @@ def test_evaluate_recorded_scene_on_the_device(backend_lib, tmp_path, rec, k):
     st = fresh_statistics(ev_mod, rec["kind"])
     sim, text = evaluate(ev_mod, rec, k, path, st)
     check(ev_mod, rec, k, text, st, sim, 0.0)
+
+
+def test_merge_statistics_concatenates_lists_and_sums_counters():
+    from interactive_highway_simulation_b200 import evaluation as ev_mod
+    a, b = ev_mod.LaneChangeStatistics(), ev_mod.LaneChangeStatistics()
+    a.utility_ego += [0.5]; a.num_lane_change += 2; a.num_fallback += 1; a.lane_id_history += [3]
+    b.utility_ego += [0.7, 0.9]; b.num_lane_change += 1; b.lane_id_history += [1, 2]
+    total = ev_mod.merge_statistics("lane_change", [dict(a.__dict__), dict(b.__dict__)])
+    assert total.utility_ego == [0.5, 0.7, 0.9] and total.num_lane_change == 3 and total.num_fallback == 1
+    assert total.lane_id_history == [3, 1, 2]
+
+
+@pytest.mark.gpu
+def test_parallel_evaluations_equal_the_same_tasks_one_after_the_other(backend_lib, tmp_path):
+    """evaluate_scenes_parallel: worker processes sharing the GPU, every task seeding its own random streams — texts and
+    merged statistics identical to running the same tasks in this process in task order."""
+    from interactive_highway_simulation_b200 import evaluation as ev_mod
+    rec = [r for r in RECORDS if r["kind"] == "lane_change"][0]
+    path = write_scene(rec, tmp_path)
+    egos = rec["ego_candidates"][:3]
+    tasks = [(path, policy, 0, ego, 1.0, 40 + i) for i, (ego, policy) in
+             enumerate([(e, p) for e in egos for p in ("lane_change_learned", "idm_mobil_lane_change_safe")])]
+    texts, total = ev_mod.evaluate_scenes_parallel("lane_change", tasks, workers=3, steps=25, devices=[0])
+    want_texts, parts = [], []
+    for t in tasks:
+        text, part = ev_mod._evaluate_task(("lane_change",) + t[:5] + (t[5], 0.2, 25, 0))
+        want_texts.append(text); parts.append(part)
+    want = ev_mod.merge_statistics("lane_change", parts)
+    assert texts == want_texts
+    assert total.__dict__ == want.__dict__ and len(total.utility_ego) == len(tasks)
