@@ -583,7 +583,7 @@ __device__ __forceinline__ void work_sync(int sub) {
 }
 
 // exclusive scan over the NPS threads of one rollout of small per-thread counts (< 2^BITS): one warp vote per bit.
-// `flag` is OR-ed over the rollout and comes back in bit 16 of `total`.
+// `flag` is OR-ed over the rollout and comes back in bits 16.. of `total` (nonzero = set somewhere).
 template <int NPS, bool kWholeBlock, int BITS, bool kHelper = false, int G = 1>
 __device__ __forceinline__ int block_exclusive_scan_small(int v, bool flag, int* scratch, int& total, int k, int sub) {
   constexpr int NW = NPS / 32 - (kHelper ? 1 : 0);
@@ -599,16 +599,27 @@ __device__ __forceinline__ int block_exclusive_scan_small(int v, bool flag, int*
   if (__any_sync(0xffffffffu, flag)) wtot |= 1 << 16;
   if (lane == 0) scratch[w] = wtot;
   work_sync<NPS, kWholeBlock, kHelper, G>(sub);
+  // the warp totals come in with two 16-byte loads (the scratch rows are 16-byte aligned and zero beyond the rollout's
+  // warps); the flags add up in bits 16.. (at most eight of them), the counts below them
+  int c[8];
+  {
+    const int4 a = *reinterpret_cast<const int4*>(scratch);
+    c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w;
+    if (NW > 4) {
+      const int4 b = *reinterpret_cast<const int4*>(scratch + 4);
+      c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+    } else {
+      c[4] = c[5] = c[6] = c[7] = 0;
+    }
+  }
   int base = 0, tot = 0;
 #pragma unroll
   for (int q = 0; q < NW; ++q) {
-    const int c = scratch[q];
-    if (q < w) base += c & 0xffff;
-    tot += c & 0xffff;
-    tot |= c & 0x10000;
+    base += q < w ? c[q] : 0;
+    tot += c[q];
   }
   total = tot;
-  return base + excl;
+  return (base & 0xffff) + excl;
 }
 
 }  // namespace mcs
@@ -711,6 +722,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
   int myPos = 0;                // its position in s.vec
   if (k <= sc.n_lanes) laneStart[k] = sc.lane_start[k];
   if (k < 8) s.flags[k] = 0;
+  if (tid < 32) s.scan[tid] = 0;       // warp totals of the scans: zero beyond the rollout's working warps
   sub_sync<NPS, G == 1>(sub);
   if (k < laneStart[sc.n_lanes]) s.pos[s.vec[k]] = (uint8_t)k;
   if (isEgo) {
