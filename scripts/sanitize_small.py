@@ -23,3 +23,12 @@ print("merging", [f.successRate for f in feats])
 o = sc.decide_fixed_gap(ego, abi.ACTIONS["left"], gaps[1]); print("fixed gap", o.ax, o.vy)
 o = sc.decide_closest_gap(ego, abi.ACTIONS["left"]); print("closest gap", o.ax, o.vy)
 sc.close()
+# exit scene of 200 vehicles: the helper-warp instantiation, first in blocks of its own, then three rollouts per 768-thread block
+c, a, ego, gaps = synthetic.exit_scene(200, 0)
+sc = backend.DeviceScene(c, a)
+cands = (abi.Candidate * len(gaps))(*[abi.Candidate(ego, abi.ACTIONS["right"], g, 0) for g in gaps])
+feats, _ = sc.rollouts(cands, abi.SimParam(0.3, 12, 4), 1, 3)
+print("exit, own blocks", [f.successRate for f in feats])
+ms, vs = sc.rollouts_device(cands, abi.SimParam(0.3, 8, 4), 3, 0, 120)
+print("exit, shared blocks", ms, vs)
+sc.close()
