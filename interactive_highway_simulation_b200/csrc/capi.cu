@@ -646,6 +646,7 @@ int mcs_scene_create(const mcs_corridor* corridors, int n_corridors, const mcs_a
     const mcs::LaneHost& L = h.lanes[j];
     d.lanes[j] = mcs::LaneDev{L.leftY, L.rightY, L.centerY, L.vLimit, L.endX, L.startX, L.id, L.type, L.leftIdx, L.rightIdx, L.leftmost, 0};
   }
+  mcs::lane_neighbour_bits(d.lanes, h.n_lanes);
   *out = sc;
   return MCS_OK;
 }

@@ -36,8 +36,9 @@ namespace mcs {
 
 struct LaneDev {
   double leftY, rightY, centerY, vLimit, endX, startX;
-  int id, type, leftIdx, rightIdx, leftmost, pad;
+  int id, type, leftIdx, rightIdx, leftmost, nb /* LANE_NB_*: what the neighbour lanes are (lane_neighbour_bits) */;
 };
+enum { LANE_NB_LEFT_MAIN = 1, LANE_NB_RIGHT_MAIN = 2, LANE_NB_RIGHT_MERGING = 4 };
 
 struct SceneDev {
   int n, n_pad, n_lanes, has_exit_lanes;
@@ -48,6 +49,20 @@ struct SceneDev {
   int lane_start[MCS_MAX_LANES + 1];
   LaneDev lanes[MCS_MAX_LANES];
 };
+
+struct SceneDev;
+// per lane, once per scene: is the left / right neighbour a main lane, is the right one a merging lane — the plan asks every
+// vehicle every step, and the answer through lanes[lanes[l].leftIdx].type is two dependent constant-bank loads
+template <class Lanes>
+__host__ __device__ inline void lane_neighbour_bits(Lanes& lanes, int n_lanes) {
+  for (int j = 0; j < n_lanes; ++j) {
+    int nb = 0;
+    if (lanes[j].leftIdx >= 0 && lanes[lanes[j].leftIdx].type == MCS_LANE_MAIN) nb |= LANE_NB_LEFT_MAIN;
+    if (lanes[j].rightIdx >= 0 && lanes[lanes[j].rightIdx].type == MCS_LANE_MAIN) nb |= LANE_NB_RIGHT_MAIN;
+    if (lanes[j].rightIdx >= 0 && lanes[lanes[j].rightIdx].type == MCS_LANE_MERGING) nb |= LANE_NB_RIGHT_MERGING;
+    lanes[j].nb = nb;
+  }
+}
 
 struct CandDev { int ego_slot, action, gap_id, target_lane_id, ok, gap_slot /* slot of gap_id, -1 = last gap */, pad[2]; };
 
@@ -325,7 +340,7 @@ __device__ __forceinline__ bool mobil_side_neighbours(const Smem& s, const Scene
   const LaneDev& L = sc.lanes[s.lane[k]];
   const int sl = side == 0 ? L.leftIdx : L.rightIdx;
   leader = -1; follower = -1;
-  const bool can = sl >= 0 && sc.lanes[sl].type == MCS_LANE_MAIN;
+  const bool can = (L.nb & (side == 0 ? LANE_NB_LEFT_MAIN : LANE_NB_RIGHT_MAIN)) != 0;
   if (can) side_leader_follower(s, laneStart, sl, s.x[k], ordered, leader, follower);
   return can;
 }
@@ -852,9 +867,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
         else s.flags[6] = 1;
       } else if (beh == MCS_BEH_IDM_LC) {
         mode = 1; noise = true;
-        const bool canL = L.leftIdx >= 0 && sc.lanes[L.leftIdx].type == MCS_LANE_MAIN;
-        const bool canR = L.rightIdx >= 0 && sc.lanes[L.rightIdx].type == MCS_LANE_MAIN;
-        needMobil = !(commit == MCS_COMMIT_KEEP_LANE && keepStep <= 9) && (canL || canR);
+        needMobil = !(commit == MCS_COMMIT_KEEP_LANE && keepStep <= 9) && (L.nb & (LANE_NB_LEFT_MAIN | LANE_NB_RIGHT_MAIN)) != 0;
       } else if (beh == MCS_BEH_IDM) {
         mode = 1; noise = true;
       } else if (beh == MCS_BEH_MERGING) {
@@ -866,8 +879,8 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
         if (mode == 1) {
           // yielding candidates: neighbours on a merging lane to the right (0x104469), `exit` vehicles on the main lane to
           // the left (0x1044df) — inside a rollout only the ego can still be an `exit` vehicle
-          if (L.rightIdx >= 0 && sc.lanes[L.rightIdx].type == MCS_LANE_MERGING) nY = side_vector(s, laneStart, L.rightIdx, x, ycand);
-          if (sc.has_exit_lanes && L.leftIdx >= 0 && sc.lanes[L.leftIdx].type == MCS_LANE_MAIN) {
+          if (L.nb & LANE_NB_RIGHT_MERGING) nY = side_vector(s, laneStart, L.rightIdx, x, ycand);
+          if (sc.has_exit_lanes && (L.nb & LANE_NB_LEFT_MAIN)) {
             const int eg = cd.ego_slot;
             if (eg != k && s.lane[eg] == L.leftIdx && s.flags[2] == MCS_BEH_EXIT) ycand[nY++] = eg;
           }

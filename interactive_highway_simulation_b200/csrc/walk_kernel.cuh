@@ -132,7 +132,7 @@ __device__ inline void prep_orders(const mce::BuildOut& b, double* F, int32_t* I
     const mcs_corridor& c = b.corridors[lorder[k]];
     mcs::LaneDev& L = sc.lanes[k];
     L.leftY = c.left[1]; L.rightY = c.right[1]; L.centerY = c.center[1]; L.vLimit = c.v_limit; L.endX = c.center[2]; L.startX = c.center[0];
-    L.id = c.id; L.type = c.type; L.leftIdx = -1; L.rightIdx = -1; L.leftmost = 0; L.pad = 0;
+    L.id = c.id; L.type = c.type; L.leftIdx = -1; L.rightIdx = -1; L.leftmost = 0; L.nb = 0;
     // neighbours by centre y: the nearest lane above / below
     double best_up = 0.0, best_dn = 0.0;
     for (int j = 0; j < nc; ++j) {
@@ -144,6 +144,7 @@ __device__ inline void prep_orders(const mce::BuildOut& b, double* F, int32_t* I
     if (L.leftIdx < 0) leftmost = k;
   }
   if (leftmost >= 0) sc.lanes[leftmost].leftmost = 1;
+  mcs::lane_neighbour_bits(sc.lanes, nc);
   int32_t ids[64];
   for (int k = 0; k < na; ++k) ids[k] = b.agents[k].id;
   hash_iteration_order(ids, na, visit);
