@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 384 ? 2 : 1) bundle_kernel(const
     lane = I[(size_t)I_LANE * np + k]; beh = I[(size_t)I_BEH * np + k]; commit = I[(size_t)I_COMMIT * np + k];
     keepStep = I[(size_t)I_KEEPSTEP * np + k]; targetLane = I[(size_t)I_TARGETLANE * np + k];
     inputIdx = I[(size_t)I_INPUT * np + k];
-    aggressive = ((double)mcs_rand31(key, (uint64_t)inputIdx) / 2147483647.0) > 0.8;     // Agent ctor draw 0xf89e6
+    aggressive = (mcs_unit31(mcs_rand31(key, (uint64_t)inputIdx))) > 0.8;     // Agent ctor draw 0xf89e6
     if (isEgo) targetLane = cd.target_lane_id;
   }
   if (active) {
@@ -310,14 +310,14 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 384 ? 2 : 1) bundle_kernel(const
               axY = MCS_MAXSD(py.accMin, r);
             }
             ax = MCS_MINSD(axY, axFront);
-            if (noise) ax = ax + ((double)mcs_rand31(key, drawBase + (uint64_t)nY) / 2147483647.0 - 0.5);
+            if (noise) ax = ax + (mcs_unit31(mcs_rand31(key, drawBase + (uint64_t)nY)) - 0.5);
             if (emergency) ax = aMin;
             if (beh == MCS_BEH_IDM_LC && !isEgo) {
               // laneChangeBehaviorMOBIL 0xf42d0, decision part
               if (commit == MCS_COMMIT_KEEP_LANE && keepStep <= 9) {
                 keepStep = keepStep + 1;
               } else if (needMobil) {
-                const double u = (double)mcs_rand31(key, drawBase + (uint64_t)nY + 1) / 2147483647.0;
+                const double u = mcs_unit31(mcs_rand31(key, drawBase + (uint64_t)nY + 1));
                 MobilState ms{commit, keepStep, targetLane};
                 mobil_decide(geo, sc, np, k, lane, v, el, aMin, F[(size_t)F_YP_PF * np + k], F[(size_t)F_YP_DA * np + k],
                              F[(size_t)F_YP_BA * np + k], /*mode=*/(step == 0) ? 0 : 1, aggressive, F + (size_t)F_PRIOR_L * np, u, ms, ax, avy);

@@ -75,7 +75,7 @@ __device__ __forceinline__ void decide_eval(const SceneDev& sc, const Smem& s, c
         const int bpos = lane_reverse(s, lo, cnt, x);
         const int back = bpos > 0 ? (int)s.vec[lo + bpos - 1] : -1;
         const MobilGeo geo = mobil_geometry_all(s, sc, laneStart, np, k, front, back);
-        const double u = (double)mcs_rand31(dp.key, (uint64_t)n) / 2147483647.0;
+        const double u = mcs_unit31(mcs_rand31(dp.key, (uint64_t)n));
         mobil_decide(geo, sc, np, k, lane, v, el, aMin, F[(size_t)F_YP_PF * np + k], F[(size_t)F_YP_DA * np + k],
                      F[(size_t)F_YP_BA * np + k], dp.require_rss ? 2 : 3, false, F + (size_t)F_PRIOR_L * np, u, ms, ax, avy);
       }

@@ -101,6 +101,16 @@ __device__ __forceinline__ double mcs_div(double num, double den) {
   return q * 0.0;       // den is 0 or NaN: 1/den is inf or NaN, times zero is the NaN that 0/den would be
 }
 
+// r / 2147483647.0 for a 31-bit draw r (the reference's (double)rand() / RAND_MAX) without the division sequence: with
+// y = RN(1 / c) the product r * y corrected once by its exact remainder, q = fma(fma(-q0, c, r), y, q0), is the correctly
+// rounded quotient — for EVERY r in [0, 2^31), checked exhaustively on the host (tests/test_host_logic.py
+// test_unit_draw_without_division, tests/unit31_check.c).  3 instructions instead of ~14, once per vehicle and step.
+__device__ __forceinline__ double mcs_unit31(int r) {
+  const double c = 2147483647.0, y = 1.0 / 2147483647.0;
+  const double a = (double)r, q0 = a * y;
+  return __fma_rn(__fma_rn(-q0, c, a), y, q0);
+}
+
 struct IdmP { double accMax, minDis, accMin, accCom, thw, sq2 /* 2*sqrt(-accMax*accCom), static per vehicle */; };
 
 // shared-memory view of one rollout
@@ -716,7 +726,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
     keepStep = I[(size_t)I_KEEPSTEP * np + k]; targetLane = I[(size_t)I_TARGETLANE * np + k];
     inputIdx = I[(size_t)I_INPUT * np + k];
     // Agent ctor draw (0xf89e6): draw index = position in the INPUT list
-    aggressive = ((double)mcs_rand31(key, (uint64_t)inputIdx) / 2147483647.0) > 0.8;
+    aggressive = (mcs_unit31(mcs_rand31(key, (uint64_t)inputIdx))) > 0.8;
     if (isEgo) targetLane = cd.target_lane_id;
   }
   // stage what neighbours gather
@@ -1052,14 +1062,14 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
           axY = MCS_MAXSD(py.accMin, r);
         }
         ax = MCS_MINSD(axY, axFront);
-        if (noise) ax = ax + ((double)mcs_rand31(key, drawBase + (uint64_t)nY) / 2147483647.0 - 0.5);
+        if (noise) ax = ax + (mcs_unit31(mcs_rand31(key, drawBase + (uint64_t)nY)) - 0.5);
         if (emergency) ax = aMin;
         if (beh == MCS_BEH_IDM_LC && !isEgo) {
           // laneChangeBehaviorMOBIL 0xf42d0, decision part
           if (commit == MCS_COMMIT_KEEP_LANE && keepStep <= 9) {
             keepStep = keepStep + 1;
           } else if (needMobil) {
-            const double u = (double)mcs_rand31(key, drawBase + (uint64_t)nY + 1) / 2147483647.0;
+            const double u = mcs_unit31(mcs_rand31(key, drawBase + (uint64_t)nY + 1));
             MobilState ms{commit, keepStep, targetLane};
             mobil_decide(load_mobil_geo(s, np, k), sc, np, k, lane, v, el, aMin, F[(size_t)F_YP_PF * np + k], F[(size_t)F_YP_DA * np + k],
                          F[(size_t)F_YP_BA * np + k], /*mode=*/(step == 0) ? 0 : 1, aggressive, F + (size_t)F_PRIOR_L * np, u, ms, ax, avy);

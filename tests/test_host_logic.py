@@ -1,6 +1,7 @@
 """Host-side logic of libmcsim_b200.so that needs no GPU: the fixed-order two-level feature reduction
 (runMTimes so:0xc2a6e-0xc2b1f + runMultiThreads so:0xbca08-0xbca92) against the oracle's restatement."""
 import ctypes as C
+import os
 import random
 
 from interactive_highway_simulation_b200 import _abi as abi
@@ -230,3 +231,22 @@ def test_hash_iteration_order_restatement_equals_the_container(backend_lib):
                 a.idm[:] = (1.6, 2.0, -3.0, -2.0, -8.0, 1.2); a.rss[:] = (0.7, 0.4, -6.0, -6.0, 1.8, 1.2)
             want = backend.prepare_host(cs, agents)["agent_order"]
             assert list(got) == want, (n, ids)
+
+
+def test_unit_draw_without_division(tmp_path):
+    """mcs_unit31 (csrc/rollout_kernel.cuh) turns a 31-bit draw into r / 2147483647.0 with one multiplication and two fused
+    multiply-adds instead of the division sequence: identical to the IEEE quotient for EVERY r in [0, 2^31) — all of them
+    are tried here (tests/unit31_check.c, ~3 s with hardware FMA)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "unit31_check.c")
+    exe = str(tmp_path / "unit31_check")
+    with open("/proc/cpuinfo") as f:
+        has_fma = " fma " in f.read()
+    if not has_fma:
+        pytest.skip("no hardware FMA on this host: the exhaustive loop would run on libm's software fma for minutes")
+    subprocess.run(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-o", exe, src, "-lm"], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=600).stdout.strip()
+    assert out == "0", out
