@@ -288,6 +288,43 @@ __device__ MCS_HEAVY_INLINE bool rss_safe(const Smem& s, int leader, int followe
   return !(d > -bGap);
 }
 
+// rssSafe 0xb8950 twice for the same leader / follower — with the vehicle's own RSS parameters (bit 0 of the result) and
+// with the relaxed ones (aMin -10, aMax -1; bit 1), as laneChangeBehaviorMOBIL asks for both.  One pass: the gaps and
+// speeds are fetched once and the four stopping distances are independent chains that overlap in the pipeline, where two
+// calls of rss_safe walk up to eight divisions one behind the other (a MOBIL sub-task's time is the length of its chain).
+// Each distance is the reference's own expression, operation for operation.
+__device__ MCS_HEAVY_INLINE int rss_safe_both(const Smem& s, int leader, int follower, double ex, double ev, double el,
+                                              double rTOther, double rTEgo, double aMin, double aMax) {
+  if (leader < 0 && follower < 0) return 3;
+  const double ev2 = ev * ev;
+  bool failS = false, failR = false;
+  if (leader >= 0) {
+    const double fGap = (s.x[leader] - ex) - (s.l[leader] + el) * 0.5;
+    const double fV = s.v[leader];
+    const double fV2 = fV * fV, evT = ev * rTEgo;
+    double dS = ev2 / (aMin * -2.0) + evT;
+    double dR = ev2 / (-10.0 * -2.0) + evT;
+    dS = dS + fV2 / (aMax + aMax);
+    dR = dR + fV2 / (-1.0 + -1.0);
+    dS = MCS_MAXSD(0.0, dS);
+    dR = MCS_MAXSD(0.0, dR);
+    failS = dS > fGap; failR = dR > fGap;
+  }
+  if (follower >= 0) {
+    const double bGap = (s.l[follower] + el) * 0.5 + (s.x[follower] - ex);
+    const double bV = s.v[follower];
+    const double bV2 = bV * bV, bvT = bV * rTOther;
+    double dS = bV2 / (aMin * -2.0) + bvT;
+    double dR = bV2 / (-10.0 * -2.0) + bvT;
+    dS = dS + ev2 / (aMax + aMax);
+    dR = dR + ev2 / (-1.0 + -1.0);
+    dS = MCS_MAXSD(0.0, dS);
+    dR = MCS_MAXSD(0.0, dR);
+    failS = failS || dS > -bGap; failR = failR || dR > -bGap;
+  }
+  return (failS ? 0 : 1) | (failR ? 0 : 2);
+}
+
 // laneChangeProbability 0xe19f0
 __device__ __forceinline__ void lane_change_probability(double p[3], double q0, double q1, double q2, bool leftOk, bool rightOk) {
   const double wP = MCS_MAXSD(p[2], p[0]) * 1.5 + 0.5;
@@ -384,11 +421,8 @@ __device__ __forceinline__ void mobil_sub_task(const Smem& s, const SceneDev& sc
       const double rTOther = sc.f[(size_t)F_RSS_RTOTHER * np + k], rTEgo = sc.f[(size_t)F_RSS_RTEGO * np + k];
       const double aMin = sc.f[(size_t)F_RSS_AMIN * np + k], aMax = sc.f[(size_t)F_RSS_AMAX * np + k];
       mf = side == 0 ? MF_CAN_L : MF_CAN_R;
-#pragma unroll 1
-      for (int relaxed = 0; relaxed < 2; ++relaxed) {     // strict (Agent+0x118) and relaxed (Agent+0x148: aMin -10, aMax -1) RSS
-        const bool ok = rss_safe(s, leader, follower, ex, ev, el, rTOther, rTEgo, relaxed ? -10.0 : aMin, relaxed ? -1.0 : aMax);
-        if (ok) mf |= (side == 0 ? MF_STRICT_L : MF_STRICT_R) << relaxed;
-      }
+      // strict (Agent+0x118) and relaxed (Agent+0x148: aMin -10, aMax -1) RSS; MF_RELAX_* = MF_STRICT_* << 1
+      mf |= rss_safe_both(s, leader, follower, ex, ev, el, rTOther, rTEgo, aMin, aMax) * (side == 0 ? MF_STRICT_L : MF_STRICT_R);
     }
     if (kStore) s.mflag[side * np + k] = (uint8_t)mf; else mfOut = mf;
     return;
