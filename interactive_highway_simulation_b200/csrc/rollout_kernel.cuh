@@ -1074,6 +1074,8 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
           }
         }
         const double pw = mcs_pow4(v / vdd);
+        // the noise draw (0x104d98) does not depend on the acceleration: it starts here, next to the divisions below
+        const double nz = mcs_unit31(mcs_rand31(key, drawBase + (uint64_t)nY)) - 0.5;
         double axFront = 0.0;
         if (evalIdm) axFront = idm_acc(s, p, f0, f1, bk, x, v, el, pw);
         const bool emergency = front >= 0 && rss_emergency(s, front, x, v, el, rTEgo, aMin, aMax);
@@ -1096,7 +1098,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
           axY = MCS_MAXSD(py.accMin, r);
         }
         ax = MCS_MINSD(axY, axFront);
-        if (noise) ax = ax + (mcs_unit31(mcs_rand31(key, drawBase + (uint64_t)nY)) - 0.5);
+        if (noise) ax = ax + nz;
         if (emergency) ax = aMin;
         if (beh == MCS_BEH_IDM_LC && !isEgo) {
           // laneChangeBehaviorMOBIL 0xf42d0, decision part
