@@ -1208,7 +1208,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
           }
           myIns = lo + first;
         }
-        ev[tid] = (mold != 0xff ? mpos + 1 : 0xffff) | myIns << 16;
+        ev[tid] = (int)((unsigned)(mold != 0xff ? mpos + 1 : 0xffff) | (unsigned)myIns << 16);
       }
       if (k < MCS_MAX_LANES + 1) s.scan[16 + k] = 0;
       const int anyInv = sub_sync_or<NPS, G == 1>(sub, inversion ? 1 : 0);
@@ -1239,8 +1239,8 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
           int d = 0;
 #pragma unroll 1
           for (int q = 0; q < nm; ++q) {
-            const int e = ev[q];
-            d += ((e >> 16) <= myPos ? 1 : 0) - ((e & 0xffff) <= myPos ? 1 : 0);
+            const unsigned e = (unsigned)ev[q];      // [leave + 1 | insert << 16], 0xffff = none
+            d += ((int)(e >> 16) <= myPos ? 1 : 0) - ((int)(e & 0xffffu) <= myPos ? 1 : 0);
           }
           myPos += d;
           s.vec[myPos] = (uint8_t)k;
@@ -1253,9 +1253,9 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
           int pos = myIns;
 #pragma unroll 1
           for (int q = 0; q < nm; ++q) {
-            const int e = ev[q];
-            pos -= (e & 0xffff) <= myIns ? 1 : 0;
-            const int insq = e >> 16;
+            const unsigned e = (unsigned)ev[q];      // [leave + 1 | insert << 16], 0xffff = none
+            pos -= (int)(e & 0xffffu) <= myIns ? 1 : 0;
+            const int insq = (int)(e >> 16);
             if (q == tid || insq > myIns) continue;
             bool ahead = insq < myIns;
             if (!ahead) {
