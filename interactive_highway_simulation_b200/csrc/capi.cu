@@ -25,10 +25,11 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
     if (e_ != cudaSuccess) return fail(MCS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
-size_t rollout_smem_bytes(int n_pad, int steps) {
-  size_t doubles = (size_t)n_pad * (4 + 6 + 6 + 3 + 2) + 4 * (size_t)((steps + 2) & ~1) + 16 + 4;
+// `helper`: the rows of the helper-warp instantiation (carve_smem: hy hax havy | hbeh hok)
+size_t rollout_smem_bytes(int n_pad, int steps, bool helper = false) {
+  size_t doubles = (size_t)n_pad * (4 + 6 + 6 + 3 + 2 + (helper ? 3 : 0)) + 4 * (size_t)((steps + 2) & ~1) + 16 + 4;
   size_t ints = 32 + 32 + 8 + (size_t)n_pad;
-  return doubles * 8 + ints * 4 + 5 * (size_t)n_pad;
+  return doubles * 8 + ints * 4 + (helper ? 7 : 5) * (size_t)n_pad;
 }
 
 // runMTimes 0xc2a6e-0xc2b1f: the means of one group of m rollouts (p[0].ok == 0: setEgo failed, fromNSims = 0)
@@ -314,7 +315,7 @@ int upload_scene(mcs_scene* sc, int pad, int slot_table = 0) {
     memcpy(c->h_stage + bf + bi, h.lane_vec.data(), (size_t)h.n_pad);
   }
   if (slot_table == 1) bundle_slots(h, pad, c->h_stage + bf + bi + ((bv + 15) & ~(size_t)15));
-  else thread_slots(h, pad, c->h_stage + bf + bi + ((bv + 15) & ~(size_t)15), slot_table == 2 ? 32 : 0);
+  else thread_slots(h, pad, c->h_stage + bf + bi + ((bv + 15) & ~(size_t)15), slot_table >= 2 ? 32 : 0);
   if (total > sc->blob_cap) {
     if (sc->d_blob) CUDA_TRY(cudaFreeAsync(sc->d_blob, c->stream));
     sc->d_blob = nullptr; sc->blob_cap = 0; sc->dev.n_pad = 0;
@@ -353,7 +354,12 @@ int rollout_threads(const mcs_scene* sc, long long rollouts, bool traj, bool mer
   }
   if (traj) return t;
   const long long budget = (long long)(merge ? MCS_WIDE_WARPS_PER_SM_MERGE : MCS_WIDE_WARPS_PER_SM) * sc->ctx->n_sm;
-  while (t < 256 && rollouts * (2 * t / 32) <= budget) t *= 2;
+  while (t < 256 && rollouts * (2 * t / 32) <= budget) {
+    // a merging rollout that already has its helper warp (128 threads, <= 96 vehicles) gains nothing from twice the threads
+    // (4 gaps x 64 rollouts x 40 vehicles: 0.51 ms on 128 threads, 0.64 on 256; scripts/cfg1_variants.py)
+    if (merge && t >= 128 && sc->host.n <= t - 32) break;
+    t *= 2;
+  }
   return t;
 }
 
@@ -390,16 +396,22 @@ struct BlockThreads { static constexpr int value = NPS == 256 ? (kMerge ? MCS_FU
 // The ego's helper warp (rollout_kernel<..., kHelper>): merging / exit launches whose rollouts are 128 or 256 threads wide and
 // leave the last warp free (64-thread rollouts share blocks of 8 or 14: two named barriers per rollout do not fit the 16 of a
 // block).  MCS_NO_HELPER=1 switches it off (tests run both ways; the records are identical).
-bool wants_helper(const mcs_scene* sc, int pad, bool traj, bool merge) {
-  if (!merge || traj || pad < 128 || sc->host.n > pad - 32) return false;
-  if (const char* e = getenv("MCS_NO_HELPER")) if (atoi(e)) return false;
-  return true;
+// Returns the thread -> slot table the launch wants: 0 none, 2 helper warp for the ego, 3 helper warp for the ego and the
+// ramp vehicles (scenes that have any).
+int wants_helper(const mcs_scene* sc, int pad, bool traj, bool merge) {
+  if (!merge || traj || pad < 128 || sc->host.n > pad - 32) return 0;
+  if (const char* e = getenv("MCS_NO_HELPER")) if (atoi(e)) return 0;
+  const mcs::SceneHost& h = sc->host;
+  for (int k = 0; k < h.n; ++k)
+    if (h.i[(size_t)mcs::I_BEH * h.n_pad + k] == MCS_BEH_MERGING) return 3;
+  return 2;
 }
 
-template <bool kTraj, bool kMerge, int NPS, int BT, bool kHelper = false>
+template <bool kTraj, bool kMerge, int NPS, int BT, int kHelper = 0>
 int launch_bt(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& lp) {
-  if constexpr (!kHelper && !kTraj && kMerge && NPS >= 128) {
-    if (sc->slot_table == 2) return launch_bt<kTraj, kMerge, NPS, BT, true>(sc, grid, region, lp);
+  if constexpr (kHelper == 0 && !kTraj && kMerge && NPS >= 128) {
+    if (sc->slot_table == 2) return launch_bt<kTraj, kMerge, NPS, BT, 1>(sc, grid, region, lp);
+    if (sc->slot_table == 3) return launch_bt<kTraj, kMerge, NPS, BT, 2>(sc, grid, region, lp);
   }
   constexpr int G = BT / NPS;       // rollouts per thread block
   static_assert(G >= 1 && G <= 15, "one named barrier per rollout of a block");
@@ -539,10 +551,10 @@ int launch_rollouts(mcs_scene* sc, int n_cand, const mcs_sim_param* sp, uint64_t
   }
   {
     const int pad = rollout_threads(sc, (long long)count * n_cand, d_traj != nullptr, merge != 0);
-    rc = upload_scene(sc, pad, wants_helper(sc, pad, d_traj != nullptr, merge != 0) ? 2 : 0);
+    rc = upload_scene(sc, pad, wants_helper(sc, pad, d_traj != nullptr, merge != 0));
   }
   if (rc != MCS_OK) return rc;
-  size_t smem = (rollout_smem_bytes(sc->dev.n_pad, sp->steps) + 15) & ~(size_t)15;   // one rollout's region
+  size_t smem = (rollout_smem_bytes(sc->dev.n_pad, sp->steps, sc->slot_table == 3) + 15) & ~(size_t)15;   // one rollout's region
   dim3 grid((unsigned)count, (unsigned)n_cand);
   // the trajectory-writing variant is a test / Simulation.run() path: one instantiation (the merging superset) serves it
   if (d_traj) rc = launch_one<true, true>(sc, grid, smem, lp);

@@ -128,7 +128,13 @@ struct Smem {
   double* vhist;   // [steps+2] ego speed history, turned into per-state utilities at the end
   double* thist;   // [steps+2] ego thwRatioHistory
   double* red;     // [16] reduction scratch
-  double* ego;     // [4] helper-warp hand-over: the ego's y; its planned ax, vy and "a lane on that side exists" (kHelper)
+  double* ego;     // [4] helper-warp hand-over of the ego (kHelper 1): its y; its planned ax, vy and "a lane on that side exists"
+  // helper warp with ramp vehicles (kHelper 2): what its lanes read of and answer for the vehicles they serve
+  double* hy;      // [n_pad] lateral position of every vehicle (the owner's register copy, published at every integration)
+  double* hax;     // [n_pad] planned acceleration of a served vehicle
+  double* havy;    // [n_pad] planned lateral speed
+  uint8_t* hbeh;   // [n_pad] current behaviour of every vehicle
+  uint8_t* hok;    // [n_pad] 0xff = not served by the helper warp; else "a lane on that side exists" of the last plan
   int* scan;       // [32] warp totals of the two per-step scans (8 + 8), lane counters of the re-ranking (16..)
   int* cnt;        // [2][16] lane starts, double-buffered across rebuilds
   int* flags;      // [8] per-rollout scalars: 0 ego reached its target lane, 1 movers queued, 2 ego behaviour, 3 thw samples,
@@ -152,7 +158,7 @@ constexpr int YIELD_END = 0xffff;
 constexpr int BUNDLE_YCAP = 256;
 
 // shared-memory layout of one rollout (host twin: rollout_smem_bytes in capi.cu)
-__device__ __forceinline__ void carve_smem(Smem& s, unsigned char* p, int np, int steps) {
+__device__ __forceinline__ void carve_smem(Smem& s, unsigned char* p, int np, int steps, bool helper = false) {
   s.x = (double*)p; p += sizeof(double) * np;
   s.v = (double*)p; p += sizeof(double) * np;
   s.l = (double*)p; p += sizeof(double) * np;
@@ -161,6 +167,12 @@ __device__ __forceinline__ void carve_smem(Smem& s, unsigned char* p, int np, in
   s.mob = (double*)p; p += sizeof(double) * 6 * np;
   s.rss = (double*)p; p += sizeof(double) * 3 * np;
   s.acc = (double*)p; p += sizeof(double) * 2 * np;
+  s.hy = s.hax = s.havy = nullptr; s.hbeh = s.hok = nullptr;
+  if (helper) {
+    s.hy = (double*)p; p += sizeof(double) * np;
+    s.hax = (double*)p; p += sizeof(double) * np;
+    s.havy = (double*)p; p += sizeof(double) * np;
+  }
   s.red = (double*)p; p += sizeof(double) * 16;
   s.ego = (double*)p; p += sizeof(double) * 4;
   s.scan = (int*)p; p += sizeof(int) * 32;
@@ -171,6 +183,7 @@ __device__ __forceinline__ void carve_smem(Smem& s, unsigned char* p, int np, in
   s.vec = p; p += np;
   s.mflag = p; p += 2 * np;
   s.pos = p; p += np;      // 5 * np bytes so far, np a multiple of 32: still 8-byte aligned
+  if (helper) { s.hbeh = p; p += np; s.hok = p; p += np; }
   s.ycap = 0; s.yp0 = nullptr; s.ynext = nullptr; s.ykey = nullptr; s.yflag = nullptr;
   // the arrays whose size depends on the horizon come last: everything above sits at a compile-time offset (np is the
   // block-size template constant), so the per-step accesses need no address arithmetic
@@ -690,7 +703,9 @@ namespace mcs {
 // kHelper: the rollout's last warp carries no vehicles (the host's thread -> slot table leaves it empty) and runs the ego's
 // gap execution — customizedMergingBehavior, the longest dependent chain of a merging / exit step, which reads the
 // pre-step state only and draws nothing — next to the other warps' whole plan phase instead of inside it.
-template <bool kTraj, bool kMerge, int NPS, int BT, bool kHelper = false>
+// kHelper 2 (scenes with ramp vehicles): lanes 1 .. 31 of the helper warp also run mergingBehaviorClosestGap of the first 31
+// ramp vehicles — the same kind of chain — and the vehicles pick their actions up like the ego does.
+template <bool kTraj, bool kMerge, int NPS, int BT, int kHelper = 0>
 // resident 256-thread-equivalents per SM the register allocation aims at: 3 (80 registers) for the lane-change path —
 // the kernel is latency-bound, the third block hides more than its few spills cost (measured 6.26e9 -> 7.06e9
 // vehicle-steps/s) — and 2 (128 registers) for the much larger merging instantiation
@@ -722,6 +737,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
   const int tid = threadIdx.x - sub * NPS;             // thread within the rollout: warp votes, task loops
   static_assert(!kHelper || (kMerge && NPS >= 64 && 2 * G + 1 <= 15), "helper warp: merging instantiation, a spare warp, barrier ids");
   const bool helper = kHelper && tid >= NPS - 32;      // the ego's helper warp
+  constexpr bool kRamp = kHelper == 2;                 // ... which also serves the ramp vehicles
   constexpr int NPW = kHelper ? NPS - 32 : NPS;        // working threads of a rollout
   // Vehicle slot of this thread.  Slots keep the reference's visit order and every shared array is indexed by slot; the
   // threads follow the slots in increasing order, so scans over threads are scans over slots, but when a rollout has
@@ -741,7 +757,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
   }
 
   Smem s;
-  carve_smem(s, smem_raw + (G > 1 ? sub * region_bytes : 0), np, lp.steps);
+  carve_smem(s, smem_raw + (G > 1 ? sub * region_bytes : 0), np, lp.steps, kRamp);
   int* laneStart = s.cnt;  // [n_lanes + 1]; flips between s.cnt and s.cnt + 16 at every rebuild
 
   const bool live = k < n;
@@ -782,16 +798,38 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
   if (k <= sc.n_lanes) laneStart[k] = sc.lane_start[k];
   if (k < 8) s.flags[k] = 0;
   if (tid < 32) s.scan[tid] = 0;       // warp totals of the scans: zero beyond the rollout's working warps
+  if (kRamp) { s.hy[k] = y; s.hbeh[k] = (uint8_t)(live ? beh : 0xff); s.hok[k] = 0xff; }
   sub_sync<NPS, G == 1>(sub);
   if (k < laneStart[sc.n_lanes]) s.pos[s.vec[k]] = (uint8_t)k;
+  // The helper warp's lanes 1 .. 31 serve the first 31 ramp vehicles (behaviour `merging`, not the ego) in slot order:
+  // mergingBehaviorClosestGap, like the ego's gap execution, reads the pre-step state only and draws nothing.  A lane
+  // keeps its vehicle for the whole rollout (it idles once the vehicle has reached the main lane).
+  int hSlot = -1;
+  if (kRamp && helper) {
+    const int hl = tid - (NPS - 32);
+    int seen = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int j = base + hl;
+      const unsigned m = __ballot_sync(0xffffffffu, j < n && j != cd.ego_slot && s.hbeh[j] == MCS_BEH_MERGING);
+      const int want = hl - 1 - seen;                    // which set bit of this chunk is mine
+      if (hl >= 1 && hSlot < 0 && want >= 0 && want < __popc(m)) {
+        unsigned mm = m;
+        for (int q = 0; q < want; ++q) mm &= mm - 1;
+        hSlot = base + __ffs(mm) - 1;
+      }
+      seen += __popc(m);
+    }
+    if (hSlot >= 0) s.hok[hSlot] = 1;
+  }
   if (isEgo) {
-    if (kHelper) s.ego[0] = y;
+    if (kHelper == 1) s.ego[0] = y;
     s.flags[2] = beh;                   // the ego's current behaviour: `exit` vehicles are yielding candidates (0x104c90)
     s.flags[4] = cd.gap_slot;           // Agent::targetGapId as a slot; < 0 = last gap
     s.flags[5] = lp.steps;              // < lp.steps once the ego has reached its target lane (StatusOneSim::finish)
   }
   sub_sync<NPS, G == 1>(sub);
   myPos = s.pos[k];
+  const bool served = kRamp && live && s.hok[k] != 0xff;     // this vehicle's closest-gap plan comes from the helper warp
 
   // statistics (Simulation::run 0x10ee71-0x10f49a) accumulated on the fly in history order
   // statistics (Simulation::run 0x10ee71-0x10f49a): per-object sums accumulated on the fly in history order; the ego's own
@@ -834,7 +872,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
     }
     if (kHelper && helper) {
       // ---- the ego's helper warp: customizedMergingBehavior on the pre-step state, side by side with the plan of everybody else
-      if (tid == NPS - 32) {
+      if (!kRamp && tid == NPS - 32) {
         const int eg = cd.ego_slot;
         const int elane = s.lane[eg], ebeh = s.flags[2];
         if (elane != 0xff && (ebeh == MCS_BEH_MERGING || ebeh == MCS_BEH_EXIT) && s.flags[0] == 0) {
@@ -850,6 +888,37 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
           double hax = 0.0, havy = 0.0;
           const bool okSide = merging_behavior(s, sc, laneStart, me, s.vd[eg], true, false, cd.action == MCS_ACT_LEFT, hGap, hax, havy);
           s.ego[1] = hax; s.ego[2] = havy; s.ego[3] = okSide ? 1.0 : 0.0;
+        }
+      }
+      // ---- the helper warp: the gap behaviours on the pre-step state, side by side with the plan of everybody else — lane 0
+      // the ego's customizedMergingBehavior, lanes 1 .. 31 the ramp vehicles' mergingBehaviorClosestGap
+      if (kRamp) {
+        const int eg = cd.ego_slot;
+        int slot = -1;
+        bool fixedGap = false;
+        if (tid == NPS - 32) {
+          const int ebeh = s.flags[2];
+          if (s.lane[eg] != 0xff && (ebeh == MCS_BEH_MERGING || ebeh == MCS_BEH_EXIT) && s.flags[0] == 0) { slot = eg; fixedGap = true; }
+        } else if (hSlot >= 0 && s.hbeh[hSlot] == MCS_BEH_MERGING && s.lane[hSlot] != 0xff) {
+          slot = hSlot;
+        }
+        if (slot >= 0) {
+          const int vlane = s.lane[slot];
+          const int lo = laneStart[vlane], cnt = laneStart[vlane + 1] - lo;
+          MergeSelf me;
+          me.k = slot; me.lane = vlane; me.x = s.x[slot]; me.y = s.hy[slot]; me.v = s.v[slot]; me.l = s.l[slot];
+          const int fpos = lane_upper(s, lo, cnt, me.x);          // frontAgent 0xe2670, as the reference searches it
+          me.front = fpos < cnt ? (int)s.vec[lo + fpos] : -1;
+          me.w = F[(size_t)F_W * np + slot];
+          me.rss.rTOther = F[(size_t)F_RSS_RTOTHER * np + slot]; me.rss.rTEgo = s.rss[slot]; me.rss.aMin = s.rss[np + slot];
+          me.rss.aMax = s.rss[2 * np + slot]; me.rss.dSoft = F[(size_t)F_RSS_DSOFT * np + slot];
+          me.idm = load_idm(s, np, slot);
+          double hax = 0.0, havy = 0.0;
+          // two call sites: each is the behaviour specialised for its kind of gap (the ego's lane walks the code it walked
+          // before the ramp vehicles moved in)
+          const bool okSide = fixedGap ? merging_behavior(s, sc, laneStart, me, s.vd[slot], true, false, cd.action == MCS_ACT_LEFT, hGap, hax, havy)
+                                       : merging_behavior(s, sc, laneStart, me, s.vd[slot], false, false, true, -1, hax, havy);
+          s.hax[slot] = hax; s.havy[slot] = havy; s.hok[slot] = okSide ? 1 : 0;
         }
       }
       sub_sync<NPS, G == 1>(sub);                                   // the plan is done: the ego picks its action up
@@ -937,7 +1006,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
     int nTasks;
     {
       int total;
-      const int pos = block_exclusive_scan_small<NPS, G == 1, 1, kHelper, G>(needMobil ? 1 : 0, inversion, s.scan, total, tid, sub);
+      const int pos = block_exclusive_scan_small<NPS, G == 1, 1, kHelper != 0, G>(needMobil ? 1 : 0, inversion, s.scan, total, tid, sub);
       nTasks = total & 0xffff;
       ordered = (total >> 16) == 0;
       if (hasLane) {
@@ -953,7 +1022,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
       }
       if (needMobil) s.tasks[pos] = k | (front & 0xff) << 8 | (back & 0xff) << 16 | ((front < 0) ? 1 << 24 : 0) | ((back < 0) ? 1 << 25 : 0);
     }
-    work_sync<NPS, G == 1, kHelper, G>(sub);
+    work_sync<NPS, G == 1, kHelper != 0, G>(sub);
     // The seven sub-tasks of a queued vehicle can run as 7, 5 or 3 tasks: every sub-task alone (each side sub-task behind
     // its own search; shortest chain, most warps), per side [own acceleration + RSS gates] and [new follower's loss], or
     // per side all three behind one search (longest chain, fewest warps).  Groups of like tasks start on warp
@@ -1003,7 +1072,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
       const int vb = (rec >> 25 & 1) ? -1 : (rec >> 16 & 0xff);
       mobil_task(s, sc, laneStart, np, vk, vf, vb, side, first, last, ordered);
     }
-    work_sync<NPS, G == 1, kHelper, G>(sub);
+    work_sync<NPS, G == 1, kHelper != 0, G>(sub);
     // draw counts: [noise][MOBIL decision draw]
     bool mobilDraw = false;
     if (needMobil) {
@@ -1016,7 +1085,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
     nDraw = nY + (noise ? 1 : 0) + (mobilDraw ? 1 : 0);
     int totalDraws;
     // nDraw <= 5 yielding candidates + noise + MOBIL draw
-    const uint64_t drawBase = (uint64_t)drawCtr + (uint64_t)block_exclusive_scan_small<NPS, G == 1, kMerge ? 3 : 2, kHelper, G>(nDraw, false, s.scan + 8, totalDraws, tid, sub);
+    const uint64_t drawBase = (uint64_t)drawCtr + (uint64_t)block_exclusive_scan_small<NPS, G == 1, kMerge ? 3 : 2, kHelper != 0, G>(nDraw, false, s.scan + 8, totalDraws, tid, sub);
     drawCtr += (uint32_t)totalDraws;
 
     // ================= plan, part B: actions =================
@@ -1030,8 +1099,8 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
         s.thist[s.flags[3]++] = thwPush;
       }
       avy = centering_vy(y, centerY);
-      if (kHelper && mode == 3) {
-        // the helper warp computes this step's gap execution; the action is picked up behind the barrier below
+      if (kHelper && (mode == 3 || (kRamp && mode == 4 && served))) {
+        // the helper warp computes this step's gap behaviour; the action is picked up behind the barrier below
       } else if (kMerge && (mode == 3 || mode == 4)) {
         MergeSelf me;
         me.k = k; me.lane = lane; me.front = front; me.x = x; me.y = y; me.v = v; me.l = el;
@@ -1116,7 +1185,10 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
       }
     }
     sub_sync<NPS, G == 1>(sub);   // every read of the pre-step x / v is done
-    if (kHelper && mode == 3) {
+    if (kRamp && (mode == 3 || (mode == 4 && served))) {
+      if (s.hok[k] != 0) { ax = s.hax[k]; avy = s.havy[k]; }
+      else { s.flags[6] = 1; ax = 0.0; avy = 0.0; }
+    } else if (kHelper == 1 && mode == 3) {
       if (s.ego[3] != 0.0) { ax = s.ego[1]; avy = s.ego[2]; }
       else { s.flags[6] = 1; ax = 0.0; avy = 0.0; }
     }
@@ -1132,7 +1204,8 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
       }
       s.x[k] = x; s.v[k] = v;
       s.acc[k] = s.acc[k] + fabs(acc); s.acc[np + k] = s.acc[np + k] + v;
-      if (isEgo) { s.chist[step + 1] = acc; s.vhist[step + 1] = v; if (kHelper) s.ego[0] = y; }
+      if (isEgo) { s.chist[step + 1] = acc; s.vhist[step + 1] = v; if (kHelper == 1) s.ego[0] = y; }
+      if (kRamp) s.hy[k] = y;
       if (kTraj) {
         double* t = lp.traj + ((((size_t)cand * lp.count + ridx) * n + inputIdx) * (size_t)(lp.steps + 1) + step + 1) * 4;
         t[0] = x; t[1] = y; t[2] = v; t[3] = acc;
@@ -1156,6 +1229,7 @@ __global__ void __launch_bounds__(BT, MCS_RESIDENT_BLOCKS_OF(BT, NPS, kMerge)) r
           break;
         }
         s.lane[k] = (uint8_t)(lane < 0 ? 0xff : lane);
+        if (kRamp) s.hbeh[k] = (uint8_t)beh;
       }
       if (isEgo && lane >= 0 && s.flags[0] == 0) s.flags[0] = sc.lanes[lane].id == targetLane ? 1 : 0;
     }
