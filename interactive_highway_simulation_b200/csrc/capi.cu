@@ -354,7 +354,9 @@ int rollout_threads(const mcs_scene* sc, long long rollouts, bool traj, bool mer
   }
   if (traj) return t;
   const long long budget = (long long)(merge ? MCS_WIDE_WARPS_PER_SM_MERGE : MCS_WIDE_WARPS_PER_SM) * sc->ctx->n_sm;
-  while (t < 256 && rollouts * (2 * t / 32) <= budget) {
+  // (a merging launch that gets a helper warp at 128 threads may fill one wave of six-rollout blocks)
+  const bool helper128 = merge && t <= 64 && sc->host.n <= 96 && rollouts <= 6LL * sc->ctx->n_sm;
+  while (t < 256 && (rollouts * (2 * t / 32) <= budget || (helper128 && t < 128))) {
     // a merging rollout that already has its helper warp (128 threads, <= 96 vehicles) gains nothing from twice the threads
     // (4 gaps x 64 rollouts x 40 vehicles: 0.51 ms on 128 threads, 0.64 on 256; scripts/cfg1_variants.py)
     if (merge && t >= 128 && sc->host.n <= t - 32) break;
@@ -439,7 +441,10 @@ int launch_np(mcs_scene* sc, dim3 grid, size_t region, const mcs::LaunchParams& 
   if constexpr (kMerge && NPS == 128 && BT != 512) {
     // six 128-thread rollouts per block pay only when every SM gets a full block; smaller launches keep the four-rollout
     // 512-thread blocks (4 gaps x 128 rollouts x 40 vehicles, widened to 128 threads: 0.77 ms there, 1.13 ms in 768-thread blocks)
-    if (rollouts < (long long)sc->ctx->n_sm * (BT / NPS) || region * (BT / NPS) > smem_limit) {
+    // ... unless the four-rollout blocks would need a second wave and the six-rollout ones do not
+    const long long sm = sc->ctx->n_sm;
+    const bool one_wave_of_six = (rollouts + 3) / 4 > sm && (rollouts + 5) / 6 <= sm && region * (BT / NPS) <= smem_limit;
+    if (!one_wave_of_six && (rollouts < sm * (BT / NPS) || region * (BT / NPS) > smem_limit)) {
       if (region * 4 <= smem_limit) return launch_bt<kTraj, kMerge, NPS, 512>(sc, grid, region, lp);
       return launch_bt<kTraj, kMerge, NPS, NPS>(sc, grid, region, lp);
     }
