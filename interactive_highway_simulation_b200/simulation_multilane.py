@@ -19,9 +19,15 @@ class SimulationParameter:                                   # simulation_multil
         self.show_debug_info, self.scenario = show_debug_info, scenario
 
 
+# yaml.safe_load's scanner and parser in C where PyYAML was built with libyaml (the constructors — what turns the scalars
+# into Python values — are the same Python code either way): loading an epoch's two files is a third of a learned-policy
+# evaluation with the pure-Python scanner (0.05 of 0.19 s)
+_SAFE_LOADER = getattr(yaml, "CSafeLoader", yaml.SafeLoader)
+
+
 def load_yaml(path):                                         # simulation_multilane.py:19-22
     with open(path) as infile:
-        return yaml.safe_load(infile)
+        return yaml.load(infile, Loader=_SAFE_LOADER)
 
 
 class Simulation:
