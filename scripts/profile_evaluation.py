@@ -26,4 +26,4 @@ for rep in range(2):
     else:
         ev.evaluate_recorded_exit_scene(path, sim, policy, 0, rec["ego_candidates"][0], st, 1.0)
 pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(38)
+pstats.Stats(pr).sort_stats(sys.argv[2] if len(sys.argv) > 2 else "cumulative").print_stats(38)
